@@ -1,0 +1,133 @@
+/*
+ * mrcnn_roi_b200.h -- extern "C" launcher ABI of libmrcnn_roi_b200.so: the B200 (sm_100a) replacement for
+ * the ROI-stage hot path of miguelalejo/maskrcnn_tf2.
+ *
+ * The reference has no FFI for this path: its four Keras layers (src/layers/mrcnn_layers.py) call stock
+ * TensorFlow ops.  The boundary a maintainer binds is therefore the layer `call` bodies; each entry point
+ * below names the reference lines it replaces.  INTEGRATION.md shows the TF custom-op shim and the ctypes
+ * binding that sit on top of this header.
+ *
+ * Conventions (all entry points):
+ *   - every tensor pointer is DEVICE memory unless the comment says "host"; tensors are dense, row-major,
+ *     fp32 / int32 / uint8 / uint32 as typed; float4-read tensors (boxes, anchors, deltas, feature maps,
+ *     outputs) must be 16-byte aligned (MRCNN_ERR_ALIGN otherwise);
+ *   - the caller owns every buffer including `ws`; launchers never allocate, never keep a pointer after
+ *     returning, never synchronise the host and never touch any stream but `stream` (a cudaStream_t passed
+ *     as void*; NULL = the legacy default stream).  They are re-entrant and hold no mutable globals, so
+ *     one process may drive several GPUs / streams concurrently (cudaSetDevice is the caller's job);
+ *   - outputs are fully written (zero / -1 padding included); `ws` needs no initialisation;
+ *   - return value: 0 = success; negative = argument error (below); positive = a cudaError_t observed by
+ *     cudaGetLastError() after the launches.  No exceptions, no abort, no printf.
+ *   - workspace size queries are pure host functions of the shape arguments.
+ */
+#ifndef MRCNN_ROI_B200_H_
+#define MRCNN_ROI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRCNN_OK 0
+#define MRCNN_ERR_NULL (-1)      /* a required pointer is NULL */
+#define MRCNN_ERR_RANGE (-2)     /* a size/threshold is outside the supported range */
+#define MRCNN_ERR_WORKSPACE (-3) /* ws_bytes smaller than the matching *_workspace_bytes() */
+#define MRCNN_ERR_ALIGN (-4)     /* a vector-accessed pointer is not 16-byte aligned */
+
+/* hard limits of this build */
+#define MRCNN_MAX_SORT 8192      /* K (pre-NMS top-k), NMS candidates M and DetectionTarget proposals P */
+#define MRCNN_MAX_GT 1024        /* DetectionTarget GT instances per image */
+
+const char* mrcnn_roi_b200_version(void);
+const char* mrcnn_status_string(int rc);
+
+/* ---- tf.nn.top_k(scores, K, sorted=True).indices  (mrcnn_layers.py:246) ------------------------------
+ * scores: element (b, a) is at scores[(b*A + a)*stride + offset]; stride/offset let the caller point at
+ * the foreground column of rpn_probs [B,A,2] (stride 2, offset 1) without a slice copy (L:235).
+ * idx [B,K] int32: descending value, ties -> lower index (TF TopKV2).  vals [B,K] optional (NULL ok).
+ * Requires 1 <= K <= min(A, MRCNN_MAX_SORT).  NaN scores are ordered below every number. */
+int mrcnn_topk_workspace_bytes(int B, int A, int K, size_t* bytes);
+int mrcnn_topk_forward(const float* scores, int stride, int offset, int B, int A, int K, int32_t* idx,
+                       float* vals, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- tf.image.non_max_suppression(boxes, scores, max_out, thr)  (mrcnn_layers.py:225,455) -------------
+ * Batched: boxes [B,M,4], scores [B,M]; valid [B] (optional) limits image b to its first valid[b] rows.
+ * keep [B,max_out] int32 indices into the M rows in selection order, -1 padded; count [B].
+ * TF NonMaxSuppressionV3 CPU semantics: candidates score > -inf, order (score desc, index asc), suppressed
+ * iff IoU > thr with IoU = inter/(a_i+a_j-inter) as a true fp32 division, zero-area boxes have IoU 0.
+ * Requires 1 <= M <= MRCNN_MAX_SORT, 0 <= thr <= 1. */
+int mrcnn_nms_workspace_bytes(int B, int M, size_t* bytes);
+int mrcnn_nms_forward(const float* boxes, const float* scores, const int32_t* valid, int B, int M, int max_out,
+                      float thr, int32_t* keep, int32_t* count, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- ProposalLayer.call  (mrcnn_layers.py:233-269, nms 224-231; utils.py:830-869) ----------------------
+ * rpn_probs [B,A,2], rpn_bbox [B,A,4] (raw, multiplied by std_dev inside, L:238), anchors [B,A,4]
+ * normalised.  K = min(pre_nms_limit, A) (L:245).  proposals [B,P,4]: decoded, clipped to [0,1], NMS'ed,
+ * zero-padded rows after the kept ones (L:229-230).
+ * Optional debug outputs (NULL ok): topk_idx [B,K]; keep_idx [B,P] (positions in the top-k order, -1
+ * padded); keep_count [B]; pre_nms_boxes [B,K,4].  std_dev: host pointer to 4 floats. */
+int mrcnn_proposal_workspace_bytes(int B, int A, int pre_nms_limit, int P, size_t* bytes);
+int mrcnn_proposal_forward(const float* rpn_probs, const float* rpn_bbox, const float* anchors, int B, int A,
+                           int pre_nms_limit, int P, const float* std_dev, float nms_thr, float* proposals,
+                           int32_t* topk_idx, int32_t* keep_idx, int32_t* keep_count, float* pre_nms_boxes,
+                           void* ws, size_t ws_bytes, void* stream);
+
+/* ---- PyramidROIAlign.call  (mrcnn_layers.py:583-664; utils.py:825-827) ---------------------------------
+ * boxes [B,N,4] normalised; image_meta [B,meta_len] (only row 0, columns 4..5 = image h,w are read,
+ * L:600); fmaps: host array of 4 device pointers P2..P5, each [B,H[l],W[l],C] NHWC fp32; C % 4 == 0.
+ * out [B,N,ph,pw,C] written directly in input ROI order.  roi_map [B,N] int32 (required; saved for the
+ * backward pass): index 0..3 of the feature map each ROI was sampled from.
+ * map_mode 0 = reference behaviour: map index = first-appearance rank of the ROI's FPN level over the
+ * flattened [B*N] batch (L:613-619,641); 1 = canonical level-2.  denominator: 244.0 in the reference
+ * (L:574).  roi_level [B,N] optional. */
+int mrcnn_roialign_workspace_bytes(int B, int N, size_t* bytes);
+int mrcnn_roialign_forward(const float* boxes, const float* image_meta, int meta_len, const float* const* fmaps,
+                           const int* H, const int* W, int C, int B, int N, int ph, int pw, float denominator,
+                           int map_mode, float* out, int32_t* roi_map, int32_t* roi_level, void* ws,
+                           size_t ws_bytes, void* stream);
+
+/* ---- gradient of PyramidROIAlign w.r.t. the four feature maps (TF CropAndResizeGradImage through the
+ * reference's gather/concat, M:142,168; boxes get no gradient, L:628-629).  grad_fmaps: host array of 4
+ * device pointers, zero-filled by the launcher, then accumulated with fp32 vector atomics. */
+int mrcnn_roialign_backward(const float* grad_out, const float* boxes, const int32_t* roi_map,
+                            float* const* grad_fmaps, const int* H, const int* W, int C, int B, int N, int ph,
+                            int pw, void* stream);
+
+/* ---- DetectionLayer.call + refine_detections  (mrcnn_layers.py:369-524) -------------------------------
+ * rois [B,N,4], probs [B,N,NC], deltas [B,N,NC,4], image_meta [B,meta_len] (window = columns 7..10 of each
+ * row, normalised with image 0's h,w, L:513-515).  use_min_conf mirrors the Python truthiness test at
+ * L:404.  per_class 0 = reference behaviour (one class-agnostic NMS, L:440-468); 1 is rejected
+ * (MRCNN_ERR_RANGE) in this build.  detections [B,max_inst,6] = (y1,x1,y2,x2,class,score), zero padded;
+ * det_count [B] optional.  Requires N <= MRCNN_MAX_SORT. */
+int mrcnn_detection_workspace_bytes(int B, int N, int NC, size_t* bytes);
+int mrcnn_detection_forward(const float* rois, const float* probs, const float* deltas, const float* image_meta,
+                            int meta_len, int B, int N, int NC, const float* std_dev, float min_conf,
+                            int use_min_conf, int max_inst, float nms_thr, int per_class, float* detections,
+                            int32_t* det_count, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- DetectionTargetLayer.call + detection_targets_graph  (mrcnn_layers.py:313-325, 844-1007) ----------
+ * proposals [B,P,4]; gt_class_ids [B,G] int32 (crowds negative); gt_boxes [B,G,4] normalised; gt_masks
+ * [B,MH,MW,G] uint8 (tf.bool layout); rand_keys [B,P] uint32: the injected stand-in for the reference's
+ * unseeded tf.random.shuffle (L:905,910) -- positives / negatives are taken in (key asc, row asc) order.
+ * Outputs: rois [B,T,4], class_ids [B,T] int32, deltas [B,T,4], masks [B,T,mask_h,mask_w] fp32 in {0,1},
+ * all zero padded; counts [B,2] (positives, negatives) optional.  roi_positive_ratio is a double because the
+ * reference evaluates int(T * ratio) and 1.0 / ratio in Python floats (L:904,908).  bbox_std_dev: host
+ * pointer to 4 floats.  Requires P <= MRCNN_MAX_SORT, G <= MRCNN_MAX_GT. */
+int mrcnn_detection_target_workspace_bytes(int B, int P, int G, int T, size_t* bytes);
+int mrcnn_detection_target_forward(const float* proposals, const int32_t* gt_class_ids, const float* gt_boxes,
+                                   const uint8_t* gt_masks, const uint32_t* rand_keys, int B, int P, int G,
+                                   int MH, int MW, int T, double roi_positive_ratio, const float* bbox_std_dev,
+                                   int mask_h, int mask_w, int use_mini_masks, float* rois, int32_t* class_ids,
+                                   float* deltas, float* masks, int32_t* counts, void* ws, size_t ws_bytes,
+                                   void* stream);
+
+/* ---- helpers exported for the parity tests (device arrays of n elements) ------------------------------ */
+int mrcnn_test_expf(const float* x, float* y, int n, void* stream);
+int mrcnn_test_logf(const float* x, float* y, int n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRCNN_ROI_B200_H_ */

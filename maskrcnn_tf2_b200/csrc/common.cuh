@@ -1,0 +1,274 @@
+// common.cuh -- device helpers shared by the ROI-stage kernels (sm_100a).
+//
+// Numerics contract (DESIGN.md "Numerics"): every fp32 operation that the reference performs as a separate
+// TensorFlow op is issued here as an individually rounded IEEE operation (__fadd_rn/__fmul_rn/__fdiv_rn,
+// which nvcc never contracts into FMA), in the reference's order (utils.py:830-869, TF crop_and_resize_op.cc,
+// non_max_suppression_op.cc).  exp/log follow one fixed Cephes-style fmaf sequence so that decoded boxes are
+// bit-identical on any IEEE machine.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mrcnn_roi_b200.h"
+
+#define MRCNN_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace mrcnn {
+
+constexpr int kMaxSort = MRCNN_MAX_SORT;
+
+static inline int last_error() { return (int)cudaGetLastError(); }
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// ---------------------------------------------------------------------------------------------------
+// deterministic exp / log (<= 1 ulp); same operation sequence on every IEEE-754 machine
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float pow2i(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }
+
+__device__ __forceinline__ float det_expf(float x) {
+    if (x != x) return x;
+    if (x > 88.72283935546875f) return __uint_as_float(0x7f800000u);
+    if (x < -103.972076416015625f) return 0.0f;
+    const float m = floorf(__fmaf_rn(x, 1.44269504088896341f, 0.5f));
+    float r = __fmaf_rn(m, -0.693359375f, x);
+    r = __fmaf_rn(m, 2.12194440e-4f, r);
+    float p = 1.9875691500e-4f;
+    p = __fmaf_rn(p, r, 1.3981999507e-3f);
+    p = __fmaf_rn(p, r, 8.3334519073e-3f);
+    p = __fmaf_rn(p, r, 4.1665795894e-2f);
+    p = __fmaf_rn(p, r, 1.6666665459e-1f);
+    p = __fmaf_rn(p, r, 5.0000001201e-1f);
+    const float r2 = __fmul_rn(r, r);
+    float y = __fmaf_rn(p, r2, r);
+    y = __fadd_rn(y, 1.0f);
+    const int mi = (int)m;
+    const int m1 = mi >> 1;
+    const int m2 = mi - m1;
+    return __fmul_rn(__fmul_rn(y, pow2i(m1)), pow2i(m2));
+}
+
+__device__ __forceinline__ float det_logf(float x) {
+    if (x != x) return x;
+    if (x < 0.0f) return __uint_as_float(0x7fc00000u);
+    if (x == 0.0f) return __uint_as_float(0xff800000u);
+    if (x == __uint_as_float(0x7f800000u)) return x;
+    int e = 0;
+    if (x < 1.17549435e-38f) { x = __fmul_rn(x, 8388608.0f); e = -23; }
+    uint32_t u = __float_as_uint(x);
+    e += (int)((u >> 23) & 0xffu) - 126;
+    u = (u & 0x007fffffu) | 0x3f000000u;
+    float m = __uint_as_float(u);
+    if (m < 0.707106781186547524f) { e -= 1; m = __fadd_rn(__fadd_rn(m, m), -1.0f); }
+    else { m = __fadd_rn(m, -1.0f); }
+    const float z = __fmul_rn(m, m);
+    float p = 7.0376836292e-2f;
+    p = __fmaf_rn(p, m, -1.1514610310e-1f);
+    p = __fmaf_rn(p, m, 1.1676998740e-1f);
+    p = __fmaf_rn(p, m, -1.2420140846e-1f);
+    p = __fmaf_rn(p, m, 1.4249322787e-1f);
+    p = __fmaf_rn(p, m, -1.6668057665e-1f);
+    p = __fmaf_rn(p, m, 2.0000714765e-1f);
+    p = __fmaf_rn(p, m, -2.4999993993e-1f);
+    p = __fmaf_rn(p, m, 3.3333331174e-1f);
+    float y = __fmul_rn(__fmul_rn(m, z), p);
+    const float fe = (float)e;
+    y = __fmaf_rn(fe, -2.12194440e-4f, y);
+    y = __fmaf_rn(-0.5f, z, y);
+    float r = __fadd_rn(m, y);
+    r = __fmaf_rn(fe, 0.693359375f, r);
+    return r;
+}
+
+// Eigen static_cast<int32>(float) on x86 (cvttss2si): NaN / out of range -> INT32_MIN
+__device__ __forceinline__ int32_t cast_i32_x86(float v) {
+    if (!(v >= -2147483648.0f && v < 2147483648.0f)) return (int32_t)0x80000000;
+    return (int32_t)v;  // truncation
+}
+
+// ---------------------------------------------------------------------------------------------------
+// utils.py:830-851 apply_box_deltas_graph (deltas already multiplied by std_dev) + utils.py:854-869 clip
+// boxes are (y1, x1, y2, x2) in a float4 (x, y, z, w)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 apply_box_deltas(float4 b, float4 d) {
+    float height = __fsub_rn(b.z, b.x);
+    float width = __fsub_rn(b.w, b.y);
+    float cy = __fadd_rn(b.x, __fmul_rn(0.5f, height));
+    float cx = __fadd_rn(b.y, __fmul_rn(0.5f, width));
+    cy = __fadd_rn(cy, __fmul_rn(d.x, height));
+    cx = __fadd_rn(cx, __fmul_rn(d.y, width));
+    height = __fmul_rn(height, det_expf(d.z));
+    width = __fmul_rn(width, det_expf(d.w));
+    float4 o;
+    o.x = __fsub_rn(cy, __fmul_rn(0.5f, height));
+    o.y = __fsub_rn(cx, __fmul_rn(0.5f, width));
+    o.z = __fadd_rn(o.x, height);
+    o.w = __fadd_rn(o.y, width);
+    return o;
+}
+
+__device__ __forceinline__ float4 scale_deltas(float4 d, float4 sd) {
+    return make_float4(__fmul_rn(d.x, sd.x), __fmul_rn(d.y, sd.y), __fmul_rn(d.z, sd.z), __fmul_rn(d.w, sd.w));
+}
+
+__device__ __forceinline__ float4 clip_box(float4 b, float4 w) {  // w = (wy1, wx1, wy2, wx2)
+    b.x = fmaxf(fminf(b.x, w.z), w.x);
+    b.y = fmaxf(fminf(b.y, w.w), w.y);
+    b.z = fmaxf(fminf(b.z, w.z), w.x);
+    b.w = fmaxf(fminf(b.w, w.w), w.y);
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// order-preserving key for fp32 scores: a > b  <=>  key(a) > key(b); -0 == +0; NaN lowest
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t score_key(float x) {
+    if (x != x) return 0u;
+    const uint32_t u = __float_as_uint(__fadd_rn(x, 0.0f));  // -0 -> +0
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_score(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+constexpr uint32_t kKeyNegInf = 0x007fffffu;  // score_key(-inf)
+
+__device__ __forceinline__ uint64_t make_composite(uint32_t key, uint32_t idx) {
+    return ((uint64_t)key << 32) | (uint64_t)(0xffffffffu - idx);  // sort descending: key desc, idx asc
+}
+__device__ __forceinline__ uint32_t composite_idx(uint64_t c) { return 0xffffffffu - (uint32_t)c; }
+__device__ __forceinline__ uint32_t composite_key(uint64_t c) { return (uint32_t)(c >> 32); }
+
+// in-place bitonic sort of n (power of two) elements in shared memory, descending; all threads of the block
+template <typename T>
+__device__ __forceinline__ void block_bitonic_sort_desc(T* s, int n) {
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int p = i | j;
+                const bool desc = ((i & k) == 0);
+                const T a = s[i], b = s[p];
+                if ((a < b) == desc) { s[i] = b; s[p] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// TF NonMaxSuppressionV3 IoU test "inter / (a_i + a_j - inter) > thr" (non_max_suppression_op.cc IOU()).
+// Boxes are min/max-normalised corners with precomputed areas; callers guarantee both areas > 0.
+// The division is only executed when the multiplicative screen lands within 2^-21 relative of the
+// threshold; outside that band the screen provably agrees with the rounded quotient.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool iou_gt(const float4& bi, float ai, const float4& bj, float aj, float thr) {
+    const float iy0 = fmaxf(bi.x, bj.x), ix0 = fmaxf(bi.y, bj.y);
+    const float iy1 = fminf(bi.z, bj.z), ix1 = fminf(bi.w, bj.w);
+    const float dh = fmaxf(__fsub_rn(iy1, iy0), 0.0f);
+    const float dw = fmaxf(__fsub_rn(ix1, ix0), 0.0f);
+    const float inter = __fmul_rn(dh, dw);
+    const float uni = __fsub_rn(__fadd_rn(ai, aj), inter);
+    const float t = __fmul_rn(thr, uni);
+    const float d = __fsub_rn(inter, t);
+    bool res = d > 0.0f;
+    if (fabsf(d) <= __fmul_rn(t, 4.76837158203125e-07f)) res = __fdiv_rn(inter, uni) > thr;
+    return res;
+}
+
+// TF IOU(): corners normalised with min/max; returns area in `area`
+__device__ __forceinline__ float4 normalise_box(float4 b, float& area) {
+    float4 n;
+    n.x = fminf(b.x, b.z);
+    n.y = fminf(b.y, b.w);
+    n.z = fmaxf(b.x, b.z);
+    n.w = fmaxf(b.y, b.w);
+    area = __fmul_rn(__fsub_rn(n.z, n.x), __fsub_rn(n.w, n.y));
+    return n;
+}
+
+// TF crop_and_resize sampling tap along one axis (crop_and_resize_op.cc)
+struct Tap {
+    int lo, hi;
+    float lerp;
+    bool valid;
+};
+__device__ __forceinline__ Tap make_tap(float c1, float c2, int size, int crop, int t, float scale) {
+    Tap r;
+    float in;
+    if (crop > 1) in = __fadd_rn(__fmul_rn(c1, (float)(size - 1)), __fmul_rn((float)t, scale));
+    else in = (float)(0.5 * (double)__fadd_rn(c1, c2) * (double)(size - 1));
+    r.valid = (in >= 0.0f && in <= (float)(size - 1));
+    r.lo = r.valid ? (int)floorf(in) : 0;
+    r.hi = r.valid ? (int)ceilf(in) : 0;
+    r.lerp = __fsub_rn(in, (float)r.lo);
+    return r;
+}
+__device__ __forceinline__ float crop_scale(float c1, float c2, int size, int crop) {
+    return (crop > 1) ? __fdiv_rn(__fmul_rn(__fsub_rn(c2, c1), (float)(size - 1)), (float)(crop - 1)) : 0.0f;
+}
+
+// block-wide exclusive scan of one int per thread (blockDim.x <= 1024, multiple of 32); returns the
+// exclusive prefix, writes the block total to *total.  `warp_sums` = 32 ints of shared memory.
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    __syncthreads();  // protect warp_sums reuse
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = (lane < nwarps) ? warp_sums[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += n;
+        }
+        warp_sums[lane] = wi - w;  // exclusive warp offsets
+        if (lane == 31) *total = wi;
+    }
+    __syncthreads();
+    return warp_sums[warp] + incl - v;
+}
+
+// ---- internal launchers shared between translation units (hidden visibility) -----------------------
+struct NmsEpilogue {
+    int mode;                    // 0 = indices, 1 = proposal boxes, 2 = detection rows
+    // mode 0
+    const int32_t* orig_idx;     // [B,M] sorted position -> original row (NULL = identity)
+    int32_t* keep;               // [B,max_out]
+    int32_t* count;              // [B]
+    // mode 1
+    float4* proposals;           // [B,max_out]
+    // mode 2
+    const float4* refined;       // [B,N] boxes by original row
+    const float* scores;         // [B,N]
+    const int32_t* class_ids;    // [B,N]
+    float* detections;           // [B,max_out,6]
+    int N;
+};
+
+// boxes_sorted [B,M] in candidate order; valid [B] or NULL (= M); mask scratch [B,M,ceil(M/64)] u64
+__attribute__((visibility("hidden"))) int launch_nms_sorted(const float4* boxes_sorted, const int32_t* valid, int B,
+                                                            int M, int max_out, float thr, uint64_t* mask,
+                                                            const NmsEpilogue& epi, cudaStream_t stream);
+__attribute__((visibility("hidden"))) size_t nms_mask_bytes(int B, int M);
+
+struct TopkDecode {              // optional fused epilogue of the top-k final kernel (ProposalLayer)
+    const float4* anchors;       // [B,A]
+    const float4* deltas;        // [B,A] raw
+    float4 std_dev;
+    float4* boxes_sorted;        // [B,K]
+    float4* pre_nms_boxes;       // [B,K] optional copy
+};
+__attribute__((visibility("hidden"))) size_t topk_ws_bytes(int B);
+__attribute__((visibility("hidden"))) int launch_topk(const float* scores, int stride, int offset, int B, int A, int K,
+                                                      int32_t* idx, float* vals, const TopkDecode* dec, void* ws,
+                                                      cudaStream_t stream);
+
+}  // namespace mrcnn

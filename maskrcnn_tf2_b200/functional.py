@@ -1,0 +1,235 @@
+"""Tensor-level entry points: torch CUDA tensors in, torch CUDA tensors out, all work done by the C-ABI launchers.
+
+Every function is asynchronous on torch's current stream and never synchronises the host.  Workspaces are cached
+per (op, shape, device) so repeated calls (and CUDA-graph capture) do not allocate.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import c_float, c_int, c_size_t, c_void_p, check, ptr
+
+_ws_cache = {}
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t, dtype, name, ndim=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name}: expected a CUDA tensor (the ROI-stage kernels have no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name}: expected {ndim} dimensions, got shape {tuple(t.shape)}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _workspace(key, nbytes, device):
+    key = key + (device.index,)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def _query(fn, *args):
+    out = c_size_t(0)
+    check(fn(*args, ctypes.byref(out)), fn.__name__)
+    return out.value
+
+
+def det_expf(x):
+    x = _req(x, torch.float32, "x")
+    y = torch.empty_like(x)
+    check(_lib.lib().mrcnn_test_expf(ptr(x), ptr(y), x.numel(), _stream()), "mrcnn_test_expf")
+    return y
+
+
+def det_logf(x):
+    x = _req(x, torch.float32, "x")
+    y = torch.empty_like(x)
+    check(_lib.lib().mrcnn_test_logf(ptr(x), ptr(y), x.numel(), _stream()), "mrcnn_test_logf")
+    return y
+
+
+def topk(scores, k, column=None, return_values=False):
+    """tf.nn.top_k(scores, k, sorted=True).indices per row.  scores [B,A], or [B,A,S] with `column` selecting
+    one of the S interleaved columns (e.g. the foreground probability of rpn_probs)."""
+    L = _lib.lib()
+    if column is None:
+        scores = _req(scores, torch.float32, "scores", 2)
+        stride, offset = 1, 0
+    else:
+        scores = _req(scores, torch.float32, "scores", 3)
+        stride, offset = scores.shape[2], int(column)
+    B, A = scores.shape[0], scores.shape[1]
+    k = int(k)
+    nbytes = _query(L.mrcnn_topk_workspace_bytes, B, A, k)
+    ws = _workspace(("topk", B, A, k), nbytes, scores.device)
+    idx = torch.empty((B, k), dtype=torch.int32, device=scores.device)
+    vals = torch.empty((B, k), dtype=torch.float32, device=scores.device) if return_values else None
+    check(L.mrcnn_topk_forward(ptr(scores), stride, offset, B, A, k, ptr(idx), ptr(vals), ptr(ws), ws.numel(),
+                               _stream()), "mrcnn_topk_forward")
+    return (idx, vals) if return_values else idx
+
+
+def nms(boxes, scores, max_output_size, iou_threshold, valid=None):
+    """Batched tf.image.non_max_suppression.  boxes [B,M,4], scores [B,M] -> keep [B,max_out] (-1 padded), count [B]."""
+    L = _lib.lib()
+    boxes = _req(boxes, torch.float32, "boxes", 3)
+    scores = _req(scores, torch.float32, "scores", 2)
+    B, M = scores.shape
+    if valid is not None:
+        valid = _req(valid, torch.int32, "valid", 1)
+    nbytes = _query(L.mrcnn_nms_workspace_bytes, B, M)
+    ws = _workspace(("nms", B, M), nbytes, boxes.device)
+    keep = torch.empty((B, int(max_output_size)), dtype=torch.int32, device=boxes.device)
+    count = torch.empty((B,), dtype=torch.int32, device=boxes.device)
+    check(L.mrcnn_nms_forward(ptr(boxes), ptr(scores), ptr(valid), B, M, int(max_output_size),
+                              c_float(float(iou_threshold)), ptr(keep), ptr(count), ptr(ws), ws.numel(), _stream()),
+          "mrcnn_nms_forward")
+    return keep, count
+
+
+def proposal_forward(rpn_probs, rpn_bbox, anchors, pre_nms_limit, proposal_count, std_dev, nms_threshold,
+                     debug=False):
+    """ProposalLayer.call.  Returns proposals [B,P,4]; with debug=True a dict with the intermediate indices too."""
+    L = _lib.lib()
+    rpn_probs = _req(rpn_probs, torch.float32, "rpn_probs", 3)
+    rpn_bbox = _req(rpn_bbox, torch.float32, "rpn_bbox", 3)
+    anchors = _req(anchors, torch.float32, "anchors", 3)
+    B, A, two = rpn_probs.shape
+    if two != 2 or tuple(rpn_bbox.shape) != (B, A, 4) or tuple(anchors.shape) != (B, A, 4):
+        raise ValueError("expected rpn_probs [B,A,2], rpn_bbox [B,A,4], anchors [B,A,4]")
+    P = int(proposal_count)
+    K = min(int(pre_nms_limit), A)
+    dev = rpn_probs.device
+    nbytes = _query(L.mrcnn_proposal_workspace_bytes, B, A, int(pre_nms_limit), P)
+    ws = _workspace(("proposal", B, A, K, P), nbytes, dev)
+    proposals = torch.empty((B, P, 4), dtype=torch.float32, device=dev)
+    tk = ki = kc = pb = None
+    if debug:
+        tk = torch.empty((B, K), dtype=torch.int32, device=dev)
+        ki = torch.empty((B, P), dtype=torch.int32, device=dev)
+        kc = torch.empty((B,), dtype=torch.int32, device=dev)
+        pb = torch.empty((B, K, 4), dtype=torch.float32, device=dev)
+    check(L.mrcnn_proposal_forward(ptr(rpn_probs), ptr(rpn_bbox), ptr(anchors), B, A, int(pre_nms_limit), P,
+                                   _lib.float4(std_dev), c_float(float(nms_threshold)), ptr(proposals), ptr(tk),
+                                   ptr(ki), ptr(kc), ptr(pb), ptr(ws), ws.numel(), _stream()),
+          "mrcnn_proposal_forward")
+    if debug:
+        return dict(proposals=proposals, topk_idx=tk, keep_idx=ki, keep_count=kc, pre_nms_boxes=pb)
+    return proposals
+
+
+def _map_args(maps):
+    if len(maps) != 4:
+        raise ValueError("PyramidROIAlign needs exactly four feature maps (P2..P5)")
+    maps = [_req(m, torch.float32, f"feature_maps[{i}]", 4) for i, m in enumerate(maps)]
+    ptrs = (c_void_p * 4)(*[m.data_ptr() for m in maps])
+    Hs = (c_int * 4)(*[m.shape[1] for m in maps])
+    Ws = (c_int * 4)(*[m.shape[2] for m in maps])
+    return maps, ptrs, Hs, Ws
+
+
+def roialign_forward(boxes, image_meta, feature_maps, pool_shape, denominator=244.0, map_mode=0,
+                     return_level=False):
+    """PyramidROIAlign.call.  Returns (pooled [B,N,ph,pw,C], roi_map [B,N]) (+ roi_level when asked)."""
+    L = _lib.lib()
+    boxes = _req(boxes, torch.float32, "boxes", 3)
+    image_meta = _req(image_meta, torch.float32, "image_meta", 2)
+    maps, ptrs, Hs, Ws = _map_args(feature_maps)
+    B, N, _ = boxes.shape
+    C = maps[0].shape[3]
+    for m in maps:
+        if m.shape[0] != B or m.shape[3] != C:
+            raise ValueError("feature maps must be [B,H,W,C] with the batch size of `boxes` and equal C")
+    ph, pw = int(pool_shape[0]), int(pool_shape[1])
+    dev = boxes.device
+    out = torch.empty((B, N, ph, pw, C), dtype=torch.float32, device=dev)
+    roi_map = torch.empty((B, N), dtype=torch.int32, device=dev)
+    roi_level = torch.empty((B, N), dtype=torch.int32, device=dev) if return_level else None
+    check(L.mrcnn_roialign_forward(ptr(boxes), ptr(image_meta), image_meta.shape[1], ptrs, Hs, Ws, C, B, N, ph, pw,
+                                   c_float(float(denominator)), int(map_mode), ptr(out), ptr(roi_map), ptr(roi_level),
+                                   None, 0, _stream()), "mrcnn_roialign_forward")
+    if return_level:
+        return out, roi_map, roi_level
+    return out, roi_map
+
+
+def roialign_backward(grad_out, boxes, roi_map, fmap_shapes):
+    """Feature-map gradients of PyramidROIAlign: list of four [B,H,W,C] tensors."""
+    L = _lib.lib()
+    grad_out = _req(grad_out, torch.float32, "grad_out", 5)
+    boxes = _req(boxes, torch.float32, "boxes", 3)
+    roi_map = _req(roi_map, torch.int32, "roi_map", 2)
+    B, N, ph, pw, C = grad_out.shape
+    grads = [torch.empty(tuple(s), dtype=torch.float32, device=grad_out.device) for s in fmap_shapes]
+    ptrs = (c_void_p * 4)(*[g.data_ptr() for g in grads])
+    Hs = (c_int * 4)(*[s[1] for s in fmap_shapes])
+    Ws = (c_int * 4)(*[s[2] for s in fmap_shapes])
+    check(L.mrcnn_roialign_backward(ptr(grad_out), ptr(boxes), ptr(roi_map), ptrs, Hs, Ws, C, B, N, ph, pw,
+                                    _stream()), "mrcnn_roialign_backward")
+    return grads
+
+
+def detection_forward(rois, probs, deltas, image_meta, bbox_std_dev, min_confidence, max_instances, nms_threshold,
+                      return_count=False):
+    """DetectionLayer.call -> detections [B,max_instances,6]."""
+    L = _lib.lib()
+    rois = _req(rois, torch.float32, "rois", 3)
+    probs = _req(probs, torch.float32, "mrcnn_class", 3)
+    deltas = _req(deltas, torch.float32, "mrcnn_bbox", 4)
+    image_meta = _req(image_meta, torch.float32, "image_meta", 2)
+    B, N, NC = probs.shape
+    if tuple(rois.shape) != (B, N, 4) or tuple(deltas.shape) != (B, N, NC, 4):
+        raise ValueError("expected rois [B,N,4], mrcnn_class [B,N,NC], mrcnn_bbox [B,N,NC,4]")
+    dev = rois.device
+    nbytes = _query(L.mrcnn_detection_workspace_bytes, B, N, NC)
+    ws = _workspace(("detection", B, N, NC), nbytes, dev)
+    det = torch.empty((B, int(max_instances), 6), dtype=torch.float32, device=dev)
+    cnt = torch.empty((B,), dtype=torch.int32, device=dev) if return_count else None
+    use_conf = 1 if min_confidence else 0
+    check(L.mrcnn_detection_forward(ptr(rois), ptr(probs), ptr(deltas), ptr(image_meta), image_meta.shape[1], B, N,
+                                    NC, _lib.float4(bbox_std_dev), c_float(float(min_confidence or 0.0)), use_conf,
+                                    int(max_instances), c_float(float(nms_threshold)), 0, ptr(det), ptr(cnt), ptr(ws),
+                                    ws.numel(), _stream()), "mrcnn_detection_forward")
+    return (det, cnt) if return_count else det
+
+
+def detection_target_forward(proposals, gt_class_ids, gt_boxes, gt_masks, rand_keys, train_rois_per_image,
+                             roi_positive_ratio, bbox_std_dev, mask_shape, use_mini_masks=False, return_counts=False):
+    """DetectionTargetLayer.call -> rois [B,T,4], class_ids [B,T] int32, deltas [B,T,4], masks [B,T,mh,mw]."""
+    L = _lib.lib()
+    proposals = _req(proposals, torch.float32, "proposals", 3)
+    gt_class_ids = _req(gt_class_ids, torch.int32, "gt_class_ids", 2)
+    gt_boxes = _req(gt_boxes, torch.float32, "gt_boxes", 3)
+    gt_masks = _req(gt_masks, torch.uint8, "gt_masks", 4)
+    rand_keys = _req(rand_keys, torch.int32, "rand_keys", 2)  # raw 32 bits, compared as unsigned
+    B, P, _ = proposals.shape
+    G = gt_class_ids.shape[1]
+    _, MH, MW, G2 = gt_masks.shape
+    if G2 != G or tuple(gt_boxes.shape) != (B, G, 4) or tuple(rand_keys.shape) != (B, P):
+        raise ValueError("expected gt_boxes [B,G,4], gt_masks [B,MH,MW,G], rand_keys [B,P]")
+    T = int(train_rois_per_image)
+    mh, mw = int(mask_shape[0]), int(mask_shape[1])
+    dev = proposals.device
+    nbytes = _query(L.mrcnn_detection_target_workspace_bytes, B, P, G, T)
+    ws = _workspace(("dtarget", B, P, G, T), nbytes, dev)
+    rois = torch.empty((B, T, 4), dtype=torch.float32, device=dev)
+    cls = torch.empty((B, T), dtype=torch.int32, device=dev)
+    dl = torch.empty((B, T, 4), dtype=torch.float32, device=dev)
+    masks = torch.empty((B, T, mh, mw), dtype=torch.float32, device=dev)
+    counts = torch.empty((B, 2), dtype=torch.int32, device=dev) if return_counts else None
+    check(L.mrcnn_detection_target_forward(ptr(proposals), ptr(gt_class_ids), ptr(gt_boxes), ptr(gt_masks),
+                                           ptr(rand_keys), B, P, G, MH, MW, T, ctypes.c_double(roi_positive_ratio),
+                                           _lib.float4(bbox_std_dev), mh, mw, 1 if use_mini_masks else 0, ptr(rois),
+                                           ptr(cls), ptr(dl), ptr(masks), ptr(counts), ptr(ws), ws.numel(), _stream()),
+          "mrcnn_detection_target_forward")
+    if return_counts:
+        return rois, cls, dl, masks, counts
+    return rois, cls, dl, masks

@@ -1,0 +1,160 @@
+"""The reference's ROI-stage Keras layer API (src/layers/mrcnn_layers.py) on top of the B200 launchers.
+
+Same class names, constructor arguments, `call(inputs)` argument order, output shapes, layer names and error
+behaviour as the reference, so code written against `mrcnnl.ProposalLayer(...)([...])` reads the same here.  The
+host language of the reference is Python/TF2 and TensorFlow is not installable in this image, so the tensors are
+torch CUDA tensors (device memory + streams only); the TensorFlow custom-op shim that binds the very same
+launchers is in tf_shim/ (see INTEGRATION.md).  There is no CPU path: CPU tensors raise.
+"""
+import numpy as np
+import torch
+
+from . import functional as F
+
+
+class _Layer:
+    """Minimal stand-in for tf.keras.layers.Layer: name, build(), __call__ -> call(), get_config()."""
+
+    def __init__(self, name=None, **kwargs):
+        self.name = name
+        self.built = False
+        self._kwargs = kwargs
+
+    def build(self, input_shape):
+        self.built = True
+
+    def __call__(self, inputs, **kwargs):
+        if not self.built:
+            self.build(None)
+        return self.call(inputs, **kwargs)
+
+    def get_config(self):
+        return {"name": self.name}
+
+
+class ProposalLayer(_Layer):
+    """mrcnn_layers.py:202-280.  inputs = [rpn_probs [B,A,2], rpn_bbox [B,A,4], anchors [B,A,4]] ->
+    proposals [B, proposal_count, 4] in normalised coordinates, zero padded."""
+
+    def __init__(self, proposal_count, config, name='roi', **kwargs):
+        super().__init__(name=name, **kwargs)
+        self.config = config
+        self.proposal_count = proposal_count
+        self.nms_threshold = self.config['rpn_nms_threshold']
+
+    def call(self, inputs, **kwargs):
+        rpn_probs, rpn_bbox, anchors = inputs[0], inputs[1], inputs[2]
+        return F.proposal_forward(rpn_probs, rpn_bbox, anchors, self.config['pre_nms_limit'], self.proposal_count,
+                                  np.asarray(self.config['rpn_bbox_std_dev'], dtype=np.float32), self.nms_threshold)
+
+    def compute_output_shape(self, input_shape):
+        return None, self.proposal_count, 4
+
+
+class _PyramidROIAlignFn(torch.autograd.Function):
+    """Feature maps receive CropAndResizeGradImage gradients; boxes and image_meta receive none (L:628-629)."""
+
+    @staticmethod
+    def forward(ctx, boxes, image_meta, pool_shape, denominator, map_mode, *feature_maps):
+        out, roi_map = F.roialign_forward(boxes, image_meta, feature_maps, pool_shape, denominator, map_mode)
+        ctx.save_for_backward(boxes, roi_map)
+        ctx.shapes = [tuple(m.shape) for m in feature_maps]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        boxes, roi_map = ctx.saved_tensors
+        grads = F.roialign_backward(grad_out.contiguous(), boxes, roi_map, ctx.shapes)
+        return (None, None, None, None, None) + tuple(grads)
+
+
+class PyramidROIAlign(_Layer):
+    """mrcnn_layers.py:553-671.  inputs = [boxes [B,N,4], image_meta [B,meta], P2, P3, P4, P5] ->
+    [B, N, pool_h, pool_w, C].  `denominator` keeps the reference's 244.0 default (L:574); `map_mode=0` keeps
+    its first-appearance level->map assignment (L:613-619), `map_mode=1` selects the canonical level-2."""
+
+    def __init__(self, pool_shape, denominator=244.0, name='roi_align', map_mode=0, **kwargs):
+        super().__init__(name=name, **kwargs)
+        self.pool_shape = tuple(pool_shape)
+        self.denominator = denominator
+        self.map_mode = map_mode
+
+    def call(self, inputs, **kwargs):
+        boxes, image_meta = inputs[0], inputs[1]
+        feature_maps = list(inputs[2:])
+        return _PyramidROIAlignFn.apply(boxes, image_meta, self.pool_shape, self.denominator, self.map_mode,
+                                        *feature_maps)
+
+    def compute_output_shape(self, input_shape):
+        return input_shape[0][:2] + self.pool_shape + (input_shape[2][-1],)
+
+
+class DetectionLayer(_Layer):
+    """mrcnn_layers.py:343-531.  inputs = [rois [B,N,4], mrcnn_class [B,N,NC], mrcnn_bbox [B,N,NC,4],
+    image_meta [B,meta]] -> [batch_size, detection_max_instances, 6] = (y1,x1,y2,x2,class_id,score)."""
+
+    def __init__(self, proposals, detection_min_confidence, detection_max_instances, detection_nms_threshold,
+                 bbox_std_dev, images_per_gpu, batch_size, name='mrcnn_detection', **kwargs):
+        super().__init__(name=name, **kwargs)
+        self.detection_min_confidence = detection_min_confidence
+        self.detection_max_instances = detection_max_instances
+        self.detection_nms_threshold = detection_nms_threshold
+        self.bbox_std_dev = bbox_std_dev
+        self.batch_size = batch_size
+        self.proposals = proposals
+        self.images_per_gpu = images_per_gpu
+
+    def call(self, inputs, **kwargs):
+        rois, mrcnn_class, mrcnn_bbox, image_meta = inputs[0], inputs[1], inputs[2], inputs[3]
+        if rois.shape[1] != self.proposals:
+            # the reference builds tf.range(self.proposals) indices (L:388-391) and fails on a mismatch
+            raise ValueError(f"DetectionLayer built for {self.proposals} proposals, got {rois.shape[1]}")
+        det = F.detection_forward(rois, mrcnn_class, mrcnn_bbox, image_meta,
+                                  np.asarray(self.bbox_std_dev, dtype=np.float32), self.detection_min_confidence,
+                                  self.detection_max_instances, self.detection_nms_threshold)
+        return det.reshape(self.batch_size, self.detection_max_instances, 6)  # L:524
+
+    def compute_output_shape(self, input_shape):
+        return None, self.detection_max_instances, 6
+
+
+class DetectionTargetLayer(_Layer):
+    """mrcnn_layers.py:283-340.  inputs = [proposals [B,P,4], gt_class_ids [B,G] int32, gt_boxes [B,G,4],
+    gt_masks [B,H,W,G] bool/uint8] -> [rois [B,T,4], target_class_ids [B,T], target_deltas [B,T,4],
+    target_mask [B,T,mh,mw]].
+
+    The reference subsamples with an unseeded tf.random.shuffle (L:905,910).  Here the permutation comes from one
+    uint32 key per proposal row: drawn from `generator` (a torch.Generator on the device; default: torch's global
+    CUDA generator), or injected through call(..., rand_keys=...) for reproducible tests."""
+
+    def __init__(self, config, name='proposal_targets', generator=None, **kwargs):
+        super().__init__(name=name, **kwargs)
+        self.config = config
+        self.generator = generator
+
+    def call(self, inputs, rand_keys=None, **kwargs):
+        proposals, gt_class_ids, gt_boxes, gt_masks = inputs[0], inputs[1], inputs[2], inputs[3]
+        if proposals.shape[1] <= 0:
+            raise ValueError("roi_assertion: DetectionTargetLayer needs at least one proposal (L:866-868)")
+        if gt_masks.dtype == torch.bool:
+            gt_masks = gt_masks.view(torch.uint8)
+        if gt_class_ids.dtype != torch.int32:
+            gt_class_ids = gt_class_ids.to(torch.int32)  # Keras casts to the Input dtype (model.py:424)
+        if rand_keys is None:
+            B, P = proposals.shape[0], proposals.shape[1]
+            rand_keys = torch.randint(-2 ** 31, 2 ** 31, (B, P), dtype=torch.int64, device=proposals.device,
+                                      generator=self.generator).to(torch.int32)
+        cfg = self.config
+        rois, cls, deltas, masks = F.detection_target_forward(
+            proposals, gt_class_ids, gt_boxes, gt_masks, rand_keys, cfg['train_rois_per_image'],
+            cfg['roi_positive_ratio'], np.asarray(cfg['bbox_std_dev'], dtype=np.float32), cfg['mask_shape'],
+            bool(cfg['use_mini_masks']))
+        return [rois, cls, deltas, masks]
+
+    def compute_output_shape(self, input_shape):
+        T = self.config['train_rois_per_image']
+        return [(None, T, 4), (None, T), (None, T, 4),
+                (None, T, self.config['mask_shape'][0], self.config['mask_shape'][1])]
+
+    def compute_mask(self, inputs, mask=None):
+        return [None, None, None, None]
