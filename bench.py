@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""ROI-stage benchmark (BASELINE.json: "ROI-stage images/sec (Proposal+ROIAlign+Detection)").
+
+A step = one pass of the inference ROI stage over one batch of synthetic COCO-shape input on each GPU:
+    ProposalLayer -> PyramidROIAlign 7x7 (N=1000) -> DetectionLayer -> PyramidROIAlign 14x14 (N=100)
+(the classifier / mask heads between them stay in TensorFlow and are represented by their synthetic outputs).
+
+    python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU under torchrun for N>1)
+    python bench.py --impl reference ...                      the reference arm: the CPU restatement of the
+                                                              reference's TF path (oracle/), all host threads
+
+Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for how each field is obtained.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "roi_stage_images_per_sec"
+UNIT = "images/s"
+WORKLOAD = "configs[1]: COCO-shape ResNet-101 FPN ROI stage, batch 8/GPU, 1024x1024, A=261888, 6000 pre-NMS / " \
+           "1000 post-NMS RoIs, 81-class DetectionLayer, clustered RPN regime"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
+    ap.add_argument("--img-size", type=int, default=1024)
+    ap.add_argument("--num-classes", type=int, default=81)
+    ap.add_argument("--regime", default="clustered", choices=["clustered", "iid"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bound on the CPU baseline sample")
+    return ap.parse_args()
+
+
+def algorithmic_bytes(img_size, n_rois, ph, pw, C=256):
+    """SURVEY.md 8(d) / BASELINE.md section 3: ROIAlign forward bytes per image."""
+    maps = sum((img_size // s) ** 2 * C * 4 for s in (4, 8, 16, 32))
+    out = n_rois * ph * pw * C * 4
+    return out + min(4 * out, maps) + 16 * n_rois
+
+
+def stage_bytes(img_size, A, K=6000, P=1000, NC=81, D=100):
+    prop = A * 8 + 2 * K * 16 + P * 16
+    det = P * 16 + P * NC * 4 + P * NC * 16 + D * 24
+    return prop + det + algorithmic_bytes(img_size, P, 7, 7) + algorithmic_bytes(img_size, D, 14, 14)
+
+
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons during the timed region (NVML; nvidia-smi as fallback)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _sample_nvml(self):
+        nv = self.nv
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+        for bit, name in names.items():
+            if bits & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        import subprocess
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        out = subprocess.check_output(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                       "--format=csv,noheader,nounits"], timeout=5).decode().strip().split(",")
+        self.samples.append(int(out[0]))
+        self.max_mhz = int(out[1])
+        for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], out[2:]):
+            if v.strip().lower() == "active":
+                self.reasons.add(name)
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                if self.nv is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
+            except Exception:
+                pass
+            self._stop_evt.wait(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_stage(oracle, x, cfg):
+    """The reference's CPU path for one batch (oracle = restatement of the TF kernels + layer control flow)."""
+    import numpy as np
+    S = float(cfg["img_size"])
+    r = oracle.proposal_layer(x["rpn_probs"], x["rpn_bbox"], x["anchors"], cfg["pre_nms_limit"],
+                              cfg["post_nms_rois_inference"], cfg["rpn_bbox_std_dev"], cfg["rpn_nms_threshold"])
+    oracle.pyramid_roi_align(r["proposals"], S, S, x["feature_maps"], (7, 7))
+    d = oracle.detection_layer(r["proposals"], x["mrcnn_class"], x["mrcnn_bbox"], x["image_meta"], cfg["bbox_std_dev"],
+                               cfg["detection_min_confidence"], cfg["detection_max_instances"],
+                               cfg["detection_nms_threshold"])
+    oracle.pyramid_roi_align(np.ascontiguousarray(d["detections"][..., :4]), S, S, x["feature_maps"], (14, 14))
+    return d["detections"]
+
+
+def time_cpu(x, cfg, batch, max_seconds, steps=None, warmup=1):
+    """Times the oracle on the host cores.  Returns (images/s, seconds per batch, reps, threads)."""
+    import oracle
+    threads = os.cpu_count() or 1
+    oracle.set_num_threads(threads)
+    for _ in range(warmup):
+        cpu_stage(oracle, x, cfg)
+    times = []
+    t_begin = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        cpu_stage(oracle, x, cfg)
+        times.append(time.perf_counter() - t0)
+        if steps is not None:
+            if len(times) >= steps:
+                break
+        elif time.perf_counter() - t_begin > max_seconds or len(times) >= 30:
+            break
+    times.sort()
+    med = times[len(times) // 2]
+    return batch / med, med, len(times), threads
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path.  TensorFlow (tensorflow==2.2-2.5,
+    the reference's only implementation) cannot be installed here, so this is the oracle port, all host threads."""
+    if rank != 0:
+        return
+    from maskrcnn_tf2_b200 import make_config, synth
+    cfg = make_config(img_size=args.img_size, num_classes=args.num_classes, batch_size=args.batch)
+    x = synth.inference_batch(2, args.batch, img_size=args.img_size, num_classes=args.num_classes, regime=args.regime)
+    ips, sec, reps, threads = time_cpu(x, cfg, args.batch, args.cpu_seconds, steps=args.steps, warmup=max(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": reps,
+        "warmup": max(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_step": args.batch, "regime": args.regime,
+                   "note": "CPU restatement of the reference's TF path (TensorFlow unavailable offline); one process, "
+                           "OpenMP over images/ROIs"},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{reps} x the full batch of {args.batch} images, median"},
+        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from maskrcnn_tf2_b200 import functional as F
+    from maskrcnn_tf2_b200 import make_config, synth
+    from maskrcnn_tf2_b200.layers import DetectionLayer, ProposalLayer, PyramidROIAlign
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the ROI-stage kernels have no CPU path "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, S, NC = args.batch, args.img_size, args.num_classes
+    cfg = make_config(img_size=S, num_classes=NC, batch_size=B)
+    # distinct images per rank (weak scaling: every GPU processes its own B images per step)
+    x = synth.inference_batch(2, B, img_size=S, num_classes=NC, regime=args.regime, first_image=rank * B)
+    A = x["anchors"].shape[1]
+
+    def pin(a):
+        return torch.from_numpy(a).pin_memory()
+    host = {k: pin(v) for k, v in x.items() if k != "feature_maps"}
+    host_maps = [pin(f) for f in x["feature_maps"]]
+    d = {k: v.to(dev) for k, v in host.items()}
+    d_maps = [f.to(dev) for f in host_maps]
+    anchors = d["anchors"]           # model constant (AnchorsLayer's non-trainable variable): always resident
+
+    proposal = ProposalLayer(cfg["post_nms_rois_inference"], cfg)
+    align7 = PyramidROIAlign([cfg["pool_size"]] * 2, name="roi_align_classifier")
+    align14 = PyramidROIAlign([cfg["mask_pool_size"]] * 2, name="roi_align_mask")
+    detect = DetectionLayer(cfg["post_nms_rois_inference"], cfg["detection_min_confidence"],
+                            cfg["detection_max_instances"], cfg["detection_nms_threshold"], cfg["bbox_std_dev"], B, B)
+    KERNELS_PER_STEP = 6 + 2 + 4 + 2   # proposal (4 top-k + mask + sweep), align7 (prep + fwd), detection, align14
+    ev7 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+
+    def stage(t, maps, step=None):
+        rois = proposal([t["rpn_probs"], t["rpn_bbox"], anchors])
+        if step is not None:
+            ev7[step][0].record()
+        pooled = align7([rois, t["image_meta"]] + maps)
+        if step is not None:
+            ev7[step][1].record()
+        det = detect([rois, t["mrcnn_class"], t["mrcnn_bbox"], t["image_meta"]])
+        mask_pooled = align14([det[..., :4].contiguous(), t["image_meta"]] + maps)
+        return rois, pooled, det, mask_pooled
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: inputs in HBM (713 MB of feature maps per step >> 126 MB L2) ----
+    for _ in range(max(args.warmup, 3)):
+        stage(d, d_maps)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        outs = stage(d, d_maps, i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    ms7 = sorted(a.elapsed_time(b) for a, b in ev7)
+    ms7_avg = sum(ms7) / len(ms7)
+
+    # ---- end to end: pinned host inputs -> H2D every step, detections -> host every step ----
+    e2e = None
+    if not args.no_e2e:
+        dd = {k: torch.empty_like(v, device=dev) for k, v in host.items() if k != "anchors"}
+        dm = [torch.empty_like(f, device=dev) for f in host_maps]
+        det_host = torch.empty((B, cfg["detection_max_instances"], 6), dtype=torch.float32).pin_memory()
+        h2d = sum(v.numel() * v.element_size() for k, v in host.items() if k != "anchors") + \
+            sum(f.numel() * f.element_size() for f in host_maps)
+        d2h = det_host.numel() * det_host.element_size()
+
+        def e2e_step():
+            for k in dd:
+                dd[k].copy_(host[k], non_blocking=True)
+            for a, b in zip(dm, host_maps):
+                a.copy_(b, non_blocking=True)
+            o = stage(dd, dm)
+            det_host.copy_(o[2], non_blocking=True)
+            torch.cuda.current_stream().synchronize()     # the caller reads the detections
+
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        t_e2e = time.perf_counter() - t0
+
+    # ---- max over ranks ----
+    if world > 1:
+        tt = torch.tensor([ms_total, t_e2e if e2e is None and not args.no_e2e else 0.0, ms7_avg], device=dev,
+                          dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total, t_e2e_max, ms7_avg = tt[0].item(), tt[1].item(), tt[2].item()
+        if not args.no_e2e:
+            t_e2e = t_e2e_max
+    value = world * B * args.steps / (ms_total * 1e-3)
+    if not args.no_e2e:
+        e2e = {"value": world * B * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+               "note": "pinned host inputs copied to HBM and detections read back every step; anchors stay resident"}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        bytes7 = B * algorithmic_bytes(S, cfg["post_nms_rois_inference"], 7, 7)
+        achieved = bytes7 / (ms7_avg * 1e-3) / 1e9
+        cpu = None
+        if not args.no_cpu_baseline:
+            ips, sec, reps, threads = time_cpu(x, cfg, B, args.cpu_seconds)
+            cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{reps} x the full batch of {B} images (whole stage), median; oracle/ C restatement of "
+                             "the reference's TF CPU path with OpenMP"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "img_size": S, "anchors": A, "regime": args.regime,
+                       "l2": "inputs larger than L2 (feature maps 89 MB/image, 713 MB/step per GPU vs 126 MB L2)",
+                       "stage_algorithmic_bytes_per_image": stage_bytes(S, A, NC=NC),
+                       "stage_hbm_gbs": world * B * stage_bytes(S, A, NC=NC) * args.steps / (ms_total * 1e-3) / 1e9},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": KERNELS_PER_STEP * args.steps,
+            "roofline": {"bound": "hbm", "kernel": "roialign_fwd_kernel<2> (7x7, N=1000, +prep)", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "ms_per_launch": ms7_avg,
+                         "algorithmic_bytes_per_launch": bytes7},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

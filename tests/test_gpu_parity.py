@@ -1,0 +1,436 @@
+"""Parity of the CUDA path (through the extern "C" launchers) against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): top-k and NMS indices bit-exact; decoded boxes, ROIAlign values and ROIAlign
+gradients within 1e-5 relative / 1e-6 absolute.  Because the kernels issue the oracle's fp32 operation sequence,
+everything except the atomically accumulated gradients is in fact compared bit-exactly here.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import random_boxes
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6     # north_star tolerance for floating-point outputs
+SD = np.array([0.1, 0.1, 0.2, 0.2], np.float32)
+
+
+@pytest.fixture(scope="module")
+def F():
+    from maskrcnn_tf2_b200 import functional
+    return functional
+
+
+def T(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_exp_log_bit_exact(F, orc, dev):
+    rng = np.random.default_rng(100)
+    x = np.concatenate([rng.uniform(-104, 89, 5000), rng.standard_normal(5000) * 3,
+                        [0, -0.0, 88.72, 88.73, -103.9, -104.1, np.inf, -np.inf, np.nan]]).astype(np.float32)
+    got = N(F.det_expf(T(x, dev)))
+    assert np.array_equal(got, orc.expf(x), equal_nan=True)
+    x = np.concatenate([np.exp(rng.uniform(-100, 88, 5000)), rng.uniform(0.5, 2, 5000),
+                        [0, 1, 1e-40, 1e-45, np.inf, -1, np.nan]]).astype(np.float32)
+    got = N(F.det_logf(T(x, dev)))
+    assert np.array_equal(got, orc.logf(x), equal_nan=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,A,K,kind", [
+    (2, 5000, 600, "normal"), (3, 70000, 6000, "softmax"), (1, 8192, 8192, "normal"), (2, 300, 300, "quant"),
+    (2, 40000, 6000, "quant"), (1, 30000, 6000, "allequal"), (1, 20000, 3000, "twovalues"), (1, 33, 1, "normal"),
+    (1, 50000, 6000, "saturated"),
+])
+def test_topk_indices_bit_exact(F, orc, dev, B, A, K, kind):
+    rng = np.random.default_rng(101)
+    if kind == "normal":
+        s = rng.standard_normal((B, A)).astype(np.float32)
+    elif kind == "softmax":
+        z = 2 * rng.standard_normal((B, A, 2))
+        s = (np.exp(z[..., 1]) / np.exp(z).sum(-1)).astype(np.float32)
+    elif kind == "quant":
+        s = (np.round(rng.uniform(0, 1, (B, A)) * 256) / 256).astype(np.float32)
+    elif kind == "allequal":
+        s = np.full((B, A), 0.75, np.float32)
+    elif kind == "twovalues":     # > 8192 candidates share all 32 key bits with the K-th element
+        s = np.where(rng.uniform(0, 1, (B, A)) < 0.05, 0.9, 0.3).astype(np.float32)
+    else:                         # probabilities saturating at 1.0 (ties at the top) and at 0
+        s = (1 / (1 + np.exp(-rng.standard_normal((B, A)) * 30))).astype(np.float32)
+    idx, vals = F.topk(T(s, dev), K, return_values=True)
+    idx, vals = N(idx), N(vals)
+    for b in range(B):
+        ref = orc.topk(s[b], K)
+        assert np.array_equal(idx[b], ref)
+        assert np.array_equal(vals[b], s[b][ref])
+
+
+def test_topk_strided_column_and_special_values(F, orc, dev):
+    rng = np.random.default_rng(102)
+    probs = rng.uniform(0, 1, (2, 9000, 2)).astype(np.float32)
+    probs[0, 5, 1] = -0.0
+    probs[0, 6, 1] = 0.0
+    probs[0, 7, 1] = -np.inf
+    probs[1, :50, 1] = np.inf
+    idx = N(F.topk(T(probs, dev), 8000, column=1))
+    for b in range(2):
+        assert np.array_equal(idx[b], orc.topk(probs[b, :, 1], 8000))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def _check_nms(F, orc, dev, boxes, scores, max_out, thr, valid=None):
+    keep, count = F.nms(T(boxes, dev), T(scores, dev), max_out, thr,
+                        None if valid is None else T(np.asarray(valid, np.int32), dev))
+    keep, count = N(keep), N(count)
+    for b in range(boxes.shape[0]):
+        n = boxes.shape[1] if valid is None else valid[b]
+        ref = orc.nms(boxes[b, :n], scores[b, :n], max_out, thr)
+        assert count[b] == len(ref)
+        assert np.array_equal(keep[b, :len(ref)], ref)
+        assert np.all(keep[b, len(ref):] == -1)
+
+
+@pytest.mark.parametrize("M,clusters,thr,max_out", [
+    (64, 3, 0.5, 64), (65, 3, 0.5, 10), (1000, 10, 0.3, 100), (1000, 0, 0.7, 1000), (6000, 40, 0.7, 1000),
+    (6000, 20, 0.7, 2000), (8192, 60, 0.5, 8192), (300, 5, 0.0, 300), (300, 5, 1.0, 300), (1, 0, 0.5, 5),
+])
+def test_nms_keep_indices_bit_exact(F, orc, dev, M, clusters, thr, max_out):
+    rng = np.random.default_rng(103 + M)
+    B = 3
+    boxes = np.stack([random_boxes(rng, M, clusters=clusters) for _ in range(B)])
+    scores = rng.uniform(0, 1, (B, M)).astype(np.float32)
+    _check_nms(F, orc, dev, boxes, scores, max_out, thr)
+
+
+def test_nms_ties_degenerate_boxes_and_valid_counts(F, orc, dev):
+    rng = np.random.default_rng(104)
+    B, M = 4, 700
+    boxes = np.stack([random_boxes(rng, M, clusters=6) for _ in range(B)])
+    scores = (np.round(rng.uniform(0, 1, (B, M)) * 16) / 16).astype(np.float32)     # heavy score ties
+    boxes[:, 100:140] = boxes[:, 0:40]                                             # exact duplicates
+    boxes[:, 200:220, 2] = boxes[:, 200:220, 0]                                     # zero height
+    boxes[:, 300:320] = boxes[:, 300:320][:, :, [2, 3, 0, 1]]                       # flipped corners
+    scores[0, 10:20] = -np.inf
+    scores[1, 30:35] = np.nan
+    scores[2, :] = 0.5                                                              # all tied
+    _check_nms(F, orc, dev, boxes, scores, 200, 0.5)
+    _check_nms(F, orc, dev, boxes, scores, 200, 0.5, valid=[0, 1, 64, 650])
+
+
+def test_nms_chain_dependency_inside_one_tile(F, orc, dev):
+    # 64 boxes in a sliding row: every box overlaps only its immediate neighbours above the threshold, so the
+    # in-tile resolution has the longest possible decide chain (keep, drop, keep, drop ...)
+    M = 256
+    x = np.arange(M, dtype=np.float32) * 0.003
+    boxes = np.stack([np.zeros(M, np.float32) + 0.1, x, np.zeros(M, np.float32) + 0.2, x + 0.01], 1)[None]
+    scores = (1.0 - np.arange(M, dtype=np.float32) / M)[None]
+    _check_nms(F, orc, dev, boxes.astype(np.float32), scores.astype(np.float32), M, 0.5)
+
+
+def test_nms_property_idempotent_full_size(F, dev):
+    # size-independent property at BASELINE size: NMS over the kept boxes keeps all of them, in order
+    rng = np.random.default_rng(105)
+    B, M = 8, 6000
+    boxes = np.stack([random_boxes(rng, M, clusters=50) for _ in range(B)])
+    scores = rng.uniform(0, 1, (B, M)).astype(np.float32)
+    tb, ts = T(boxes, dev), T(scores, dev)
+    keep, count = F.nms(tb, ts, 1000, 0.7)
+    keep, count = N(keep), N(count)
+    kb = np.zeros((B, 1000, 4), np.float32)
+    ks = np.full((B, 1000), -np.inf, np.float32)
+    for b in range(B):
+        kb[b, :count[b]] = boxes[b, keep[b, :count[b]]]
+        ks[b, :count[b]] = scores[b, keep[b, :count[b]]]
+        assert np.all(np.diff(ks[b, :count[b]]) <= 0)                               # selection order = score order
+    keep2, count2 = F.nms(T(kb, dev), T(ks, dev), 1000, 0.7)
+    keep2, count2 = N(keep2), N(count2)
+    assert np.array_equal(count2, count)
+    for b in range(B):
+        assert np.array_equal(keep2[b, :count[b]], np.arange(count[b]))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def _proposal_inputs(regime, B, img_size=1024, seed=2000):
+    from maskrcnn_tf2_b200 import synth
+    a = synth.pyramid_anchors(img_size)
+    probs, bbox = [], []
+    for b in range(B):
+        p, d = synth.rpn_outputs(np.random.default_rng(seed + b), a, regime, img_size)
+        probs.append(p); bbox.append(d)
+    return np.stack(probs), np.stack(bbox), np.ascontiguousarray(np.broadcast_to(a, (B,) + a.shape))
+
+
+@pytest.mark.parametrize("regime,img_size,P", [("iid", 1024, 1000), ("clustered", 1024, 1000), ("clustered", 512, 2000),
+                                               ("iid", 256, 1000)])
+def test_proposal_layer_bit_exact_coco_shape(F, orc, dev, regime, img_size, P):
+    B = 2
+    probs, bbox, anchors = _proposal_inputs(regime, B, img_size)
+    ref = orc.proposal_layer(probs, bbox, anchors, 6000, P, SD, 0.7)
+    got = F.proposal_forward(T(probs, dev), T(bbox, dev), T(anchors, dev), 6000, P, SD, 0.7, debug=True)
+    assert np.array_equal(N(got["topk_idx"]), ref["topk_idx"])
+    assert np.array_equal(N(got["pre_nms_boxes"]), ref["pre_nms_boxes"])          # decode + clip bit-exact
+    assert np.array_equal(N(got["keep_count"]), ref["keep_count"])
+    assert np.array_equal(N(got["keep_idx"]), ref["keep_idx"])
+    assert np.array_equal(N(got["proposals"]), ref["proposals"])
+    plain = F.proposal_forward(T(probs, dev), T(bbox, dev), T(anchors, dev), 6000, P, SD, 0.7)
+    assert np.array_equal(N(plain), ref["proposals"])
+
+
+def test_proposal_layer_small_anchor_set_and_padding(F, orc, dev):
+    rng = np.random.default_rng(106)
+    B, A = 3, 500                                   # A < pre_nms_limit -> K = A (L:245); P > survivors -> zero rows
+    probs = rng.uniform(0, 1, (B, A, 2)).astype(np.float32)
+    bbox = rng.standard_normal((B, A, 4)).astype(np.float32)
+    anchors = np.stack([random_boxes(rng, A, clusters=4) for _ in range(B)])
+    ref = orc.proposal_layer(probs, bbox, anchors, 6000, 1000, SD, 0.7)
+    got = F.proposal_forward(T(probs, dev), T(bbox, dev), T(anchors, dev), 6000, 1000, SD, 0.7, debug=True)
+    assert np.array_equal(N(got["proposals"]), ref["proposals"])
+    assert np.array_equal(N(got["keep_idx"]), ref["keep_idx"])
+    assert np.all(ref["keep_count"] < 1000)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def _roi_boxes(rng, B, Nr, pad=0, wild=0):
+    side = np.exp(rng.uniform(np.log(16), np.log(900), (B, Nr))) / 1024.0
+    ar = np.exp(rng.uniform(-0.7, 0.7, (B, Nr)))
+    h, w = np.minimum(side * ar, 1.0), np.minimum(side / ar, 1.0)
+    y1, x1 = rng.uniform(0, 1, (B, Nr)) * (1 - h), rng.uniform(0, 1, (B, Nr)) * (1 - w)
+    boxes = np.stack([y1, x1, y1 + h, x1 + w], -1).astype(np.float32)
+    if wild:      # partially / fully outside the image, flipped, degenerate
+        boxes[:, :wild] += rng.uniform(-0.6, 0.6, (B, wild, 4)).astype(np.float32)
+    if pad:
+        boxes[:, -pad:] = 0.0
+    return boxes
+
+
+def _meta(B, size, nc=81):
+    from maskrcnn_tf2_b200 import synth
+    return synth.image_meta(B, size, nc)
+
+
+@pytest.mark.parametrize("B,Nr,C,pool,sizes,pad,wild,mode", [
+    (2, 50, 256, (7, 7), (64, 32, 16, 8), 5, 10, 0),
+    (3, 33, 256, (14, 14), (32, 16, 8, 4), 0, 8, 0),
+    (2, 40, 128, (7, 7), (40, 20, 10, 5), 3, 6, 1),
+    (1, 20, 512, (3, 5), (16, 8, 4, 2), 2, 4, 0),
+    (2, 25, 24, (7, 7), (16, 8, 4, 2), 2, 5, 0),           # generic channel count
+    (2, 16, 256, (1, 1), (16, 8, 4, 2), 1, 3, 0),           # crop size 1: box-centre sampling
+    (1, 30, 256, (28, 28), (32, 16, 8, 4), 0, 0, 1),
+])
+def test_roialign_forward_bit_exact(F, orc, dev, B, Nr, C, pool, sizes, pad, wild, mode):
+    rng = np.random.default_rng(107 + Nr)
+    boxes = _roi_boxes(rng, B, Nr, pad, wild)
+    fm = [rng.standard_normal((B, s, s, C)).astype(np.float32) for s in sizes]
+    ref = orc.pyramid_roi_align(boxes, 1024.0, 1024.0, fm, pool, map_mode=mode)
+    out, roi_map, level = F.roialign_forward(T(boxes, dev), T(_meta(B, 1024), dev), [T(f, dev) for f in fm], pool,
+                                             map_mode=mode, return_level=True)
+    assert np.array_equal(N(level), ref["level"])
+    assert np.array_equal(N(roi_map), ref["roi_map"])
+    assert np.array_equal(N(out), ref["out"])            # well inside 1e-5 rel / 1e-6 abs: bit-exact
+
+
+def test_roialign_first_appearance_depends_on_batch_composition(F, orc, dev):
+    # quirk Q2: the same ROI is sampled from a different map when an earlier image changes the level order
+    rng = np.random.default_rng(108)
+    fm = [rng.standard_normal((2, s, s, 256)).astype(np.float32) for s in (32, 16, 8, 4)]
+    big, small = [0.1, 0.1, 0.9, 0.9], [0.4, 0.4, 0.43, 0.43]
+    for first in (big, small):
+        boxes = np.array([[first, big], [small, big]], np.float32)
+        ref = orc.pyramid_roi_align(boxes, 1024.0, 1024.0, fm, (7, 7))
+        out, roi_map = F.roialign_forward(T(boxes, dev), T(_meta(2, 1024), dev), [T(f, dev) for f in fm], (7, 7))
+        assert np.array_equal(N(roi_map), ref["roi_map"]) and np.array_equal(N(out), ref["out"])
+
+
+def test_roialign_forward_coco_shape_one_image(F, orc, dev):
+    rng = np.random.default_rng(109)
+    boxes = _roi_boxes(rng, 1, 1000, pad=300, wild=20)
+    fm = [rng.standard_normal((1, s, s, 256)).astype(np.float32) for s in (256, 128, 64, 32)]
+    ref = orc.pyramid_roi_align(boxes, 1024.0, 1024.0, fm, (7, 7))
+    out, roi_map = F.roialign_forward(T(boxes, dev), T(_meta(1, 1024), dev), [T(f, dev) for f in fm], (7, 7))
+    assert np.array_equal(N(roi_map), ref["roi_map"])
+    assert np.array_equal(N(out), ref["out"])
+
+
+@pytest.mark.parametrize("B,Nr,C,pool,sizes,pad,wild", [
+    (2, 60, 256, (7, 7), (64, 32, 16, 8), 6, 10),
+    (2, 40, 256, (14, 14), (32, 16, 8, 4), 0, 6),
+    (1, 30, 24, (7, 7), (16, 8, 4, 2), 4, 5),
+    (1, 400, 256, (7, 7), (8, 4, 4, 2), 0, 0),     # heavy fan-in: 400 ROIs accumulate into tiny maps
+])
+def test_roialign_backward_within_tolerance(F, orc, dev, B, Nr, C, pool, sizes, pad, wild):
+    rng = np.random.default_rng(110 + Nr)
+    boxes = _roi_boxes(rng, B, Nr, pad, wild)
+    shapes = [(B, s, s, C) for s in sizes]
+    g = rng.standard_normal((B, Nr) + pool + (C,)).astype(np.float32)
+    ref = orc.pyramid_roi_align_grad(g, boxes, 1024.0, 1024.0, shapes)
+    fm = [torch.zeros(s, device=dev) for s in shapes]
+    _, roi_map = F.roialign_forward(T(boxes, dev), T(_meta(B, 1024), dev), fm, pool)
+    grads = F.roialign_backward(T(g, dev), T(boxes, dev), roi_map, shapes)
+    for l in range(4):
+        got = N(grads[l])
+        # fp32 accumulation order differs (atomics): tolerance relative to the accumulated magnitude
+        scale = np.maximum(np.abs(ref[l]), orc.pyramid_roi_align_grad(np.abs(g), boxes, 1024.0, 1024.0, shapes)[l])
+        assert np.all(np.abs(got - ref[l]) <= ATOL + RTOL * scale)
+
+
+def test_roialign_adjoint_property_full_size(F, dev):
+    # <roialign(X), G> == <X, roialign_backward(G)> at COCO shape (linearity / adjointness, size independent)
+    torch.manual_seed(0)
+    B, Nr = 2, 1000
+    rng = np.random.default_rng(111)
+    boxes = T(_roi_boxes(rng, B, Nr, pad=100, wild=10), dev)
+    fm = [torch.randn((B, s, s, 256), device=dev) for s in (256, 128, 64, 32)]
+    out, roi_map = F.roialign_forward(boxes, T(_meta(B, 1024), dev), fm, (7, 7))
+    g = torch.randn_like(out)
+    grads = F.roialign_backward(g, boxes, roi_map, [tuple(f.shape) for f in fm])
+    lhs = (out.double() * g.double()).sum().item()
+    rhs = sum((f.double() * gr.double()).sum().item() for f, gr in zip(fm, grads))
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), (out.double().abs() * g.double().abs()).sum().item() * 1e-2)
+    out2, _ = F.roialign_forward(boxes, T(_meta(B, 1024), dev), [2.0 * f for f in fm], (7, 7))
+    assert torch.equal(out2, 2.0 * out)                   # exact linearity under power-of-two scaling
+
+
+def test_pyramid_roi_align_layer_autograd(orc, dev):
+    from maskrcnn_tf2_b200.layers import PyramidROIAlign
+    rng = np.random.default_rng(112)
+    B, Nr = 2, 30
+    boxes = _roi_boxes(rng, B, Nr, pad=3)
+    fm_np = [rng.standard_normal((B, s, s, 256)).astype(np.float32) for s in (32, 16, 8, 4)]
+    fm = [T(f, dev).requires_grad_(True) for f in fm_np]
+    layer = PyramidROIAlign([7, 7], name="roi_align_classifier")
+    out = layer([T(boxes, dev), T(_meta(B, 1024), dev)] + fm)
+    w = rng.standard_normal(out.shape).astype(np.float32)
+    (out * T(w, dev)).sum().backward()
+    ref = orc.pyramid_roi_align_grad(w, boxes, 1024.0, 1024.0, [f.shape for f in fm_np])
+    for l in range(4):
+        assert np.allclose(N(fm[l].grad), ref[l], rtol=1e-4, atol=1e-5)
+    assert layer.compute_output_shape([(None, Nr, 4), (None, 93), (None, 32, 32, 256)]) == (None, Nr, 7, 7, 256)
+
+
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,Nr,NC,min_conf,D", [(2, 1000, 81, 0.7, 100), (3, 400, 2, 0.7, 100), (2, 1000, 81, 0.0, 100),
+                                                (1, 37, 5, 0.3, 10), (2, 1000, 81, 0.05, 100)])
+def test_detection_layer_bit_exact(F, orc, dev, B, Nr, NC, min_conf, D):
+    from maskrcnn_tf2_b200 import synth
+    rng = np.random.default_rng(113 + Nr)
+    rois = np.stack([random_boxes(rng, Nr, clusters=12) for _ in range(B)])
+    rois[:, -Nr // 10:] = 0.0                                     # zero-padded proposals flow through (Q5)
+    probs, deltas = synth.head_outputs(rng, B, Nr, NC)
+    deltas *= 0.5
+    meta = synth.image_meta(B, 1024, NC)
+    meta[-1, 7:11] = (64, 128, 960, 896)                          # letter-boxed window on the last image
+    ref = orc.detection_layer(rois, probs, deltas, meta, SD, min_conf, D, 0.3)
+    det, cnt = F.detection_forward(T(rois, dev), T(probs, dev), T(deltas, dev), T(meta, dev), SD, min_conf, D, 0.3,
+                                   return_count=True)
+    assert np.array_equal(N(cnt), ref["count"])
+    assert np.array_equal(N(det), ref["detections"])
+
+
+def test_detection_layer_class_api(orc, dev):
+    from maskrcnn_tf2_b200 import synth
+    from maskrcnn_tf2_b200.layers import DetectionLayer
+    rng = np.random.default_rng(114)
+    B, Nr, NC = 2, 200, 6
+    rois = np.stack([random_boxes(rng, Nr, clusters=5) for _ in range(B)])
+    probs, deltas = synth.head_outputs(rng, B, Nr, NC)
+    meta = synth.image_meta(B, 512, NC)
+    layer = DetectionLayer(proposals=Nr, detection_min_confidence=0.7, detection_max_instances=50,
+                           detection_nms_threshold=0.3, bbox_std_dev=SD, images_per_gpu=B, batch_size=B)
+    out = layer([T(rois, dev), T(probs, dev), T(deltas, dev), T(meta, dev)])
+    assert tuple(out.shape) == (B, 50, 6) and layer.name == "mrcnn_detection"
+    ref = orc.detection_layer(rois, probs, deltas, meta, SD, 0.7, 50, 0.3)
+    assert np.array_equal(N(out), ref["detections"])
+    with pytest.raises(ValueError):
+        layer([T(rois[:, :10], dev), T(probs[:, :10], dev), T(deltas[:, :10], dev), T(meta, dev)])
+
+
+# ---------------------------------------------------------------------------------------------------------
+def _target_inputs(rng, B, P, G, MH, mini=False, n_real=8):
+    props = np.stack([random_boxes(rng, P, min_size=0.04, max_size=0.5, clusters=10) for _ in range(B)])
+    props[:, -P // 8:] = 0.0
+    gtb = np.zeros((B, G, 4), np.float32)
+    gtc = np.zeros((B, G), np.int32)
+    for b in range(B):
+        pick = rng.choice(P - P // 8, n_real, replace=False)
+        gtb[b, :n_real] = props[b, pick] + rng.normal(0, 0.004, (n_real, 4)).astype(np.float32)
+        gtc[b, :n_real] = rng.integers(1, 81, n_real)
+    gtc[0, n_real - 1] *= -1                                      # crowd
+    masks = (rng.uniform(0, 1, (B, MH, MH, G)) < 0.5).astype(np.uint8)
+    keys = rng.integers(0, 2 ** 32, (B, P), dtype=np.uint64).astype(np.uint32)
+    return props, gtc, gtb, masks, keys
+
+
+@pytest.mark.parametrize("B,P,G,T_,MH,mini", [(2, 2000, 100, 200, 128, False), (3, 300, 10, 64, 56, False),
+                                              (2, 1000, 100, 200, 32, True), (1, 8192, 100, 512, 64, False)])
+def test_detection_target_layer_bit_exact(F, orc, dev, B, P, G, T_, MH, mini):
+    rng = np.random.default_rng(115 + P)
+    props, gtc, gtb, masks, keys = _target_inputs(rng, B, P, G, MH, mini)
+    ref = orc.detection_target_layer(props, gtc, gtb, masks, keys, T_, 0.33, SD, (28, 28), use_mini_masks=mini)
+    rois, cls, deltas, mk, counts = F.detection_target_forward(
+        T(props, dev), T(gtc, dev), T(gtb, dev), T(masks, dev), T(keys.view(np.int32), dev), T_, 0.33, SD, (28, 28),
+        use_mini_masks=mini, return_counts=True)
+    assert np.array_equal(N(counts), ref["counts"])
+    assert np.array_equal(N(rois), ref["rois"])
+    assert np.array_equal(N(cls), ref["class_ids"])
+    assert np.array_equal(N(deltas), ref["deltas"])
+    assert np.array_equal(N(mk), ref["masks"])
+    assert ref["counts"][:, 0].min() > 0
+
+
+def test_detection_target_layer_edge_cases(F, orc, dev):
+    rng = np.random.default_rng(116)
+    props, gtc, gtb, masks, keys = _target_inputs(rng, 3, 200, 6, 32, n_real=5)
+    gtc[1, :] = 0          # image 1: no usable GT -> no positives, no negatives (count 0), all-zero outputs
+    gtb[2, :] = 0          # image 2: all GT rows are zero padding
+    props[0, :] = 0        # image 0: only padded proposals
+    ref = orc.detection_target_layer(props, gtc, gtb, masks, keys, 40, 0.33, SD, (28, 28))
+    out = F.detection_target_forward(T(props, dev), T(gtc, dev), T(gtb, dev), T(masks, dev),
+                                     T(keys.view(np.int32), dev), 40, 0.33, SD, (28, 28), return_counts=True)
+    for got, name in zip(out, ["rois", "class_ids", "deltas", "masks", "counts"]):
+        assert np.array_equal(N(got), ref[name])
+    assert ref["counts"].sum() == 0
+
+
+def test_detection_target_layer_class_api_and_seeded_generator(dev):
+    from maskrcnn_tf2_b200 import make_config
+    from maskrcnn_tf2_b200.layers import DetectionTargetLayer
+    rng = np.random.default_rng(117)
+    props, gtc, gtb, masks, _ = _target_inputs(rng, 2, 500, 20, 64)
+    cfg = make_config(train_rois_per_image=100)
+    outs = []
+    for _ in range(2):
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(7)
+        layer = DetectionTargetLayer(cfg, name="detection_targets_layer", generator=gen)
+        outs.append(layer([T(props, dev), T(gtc, dev), T(gtb, dev), T(masks, dev).bool()]))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)                      # same seed -> same subsample (the reference is unseeded, Q8)
+    rois, cls, deltas, mk = outs[0]
+    assert tuple(rois.shape) == (2, 100, 4) and tuple(mk.shape) == (2, 100, 28, 28) and cls.dtype == torch.int32
+    assert layer.compute_mask(None) == [None] * 4
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_proposal_layer_class_api_and_errors(orc, dev):
+    from maskrcnn_tf2_b200 import make_config
+    from maskrcnn_tf2_b200._lib import MrcnnError
+    from maskrcnn_tf2_b200.layers import ProposalLayer
+    probs, bbox, anchors = _proposal_inputs("clustered", 1, 256)
+    cfg = make_config(img_size=256)
+    layer = ProposalLayer(proposal_count=cfg['post_nms_rois_inference'], config=cfg)
+    out = layer([T(probs, dev), T(bbox, dev), T(anchors, dev)])
+    ref = orc.proposal_layer(probs, bbox, anchors, 6000, 1000, SD, 0.7)
+    assert layer.name == "roi" and np.array_equal(N(out), ref["proposals"])
+    assert layer.compute_output_shape(None) == (None, 1000, 4)
+    with pytest.raises(TypeError):
+        layer([torch.from_numpy(probs), torch.from_numpy(bbox), torch.from_numpy(anchors)])   # CPU tensors: no fallback
+    bad = make_config(img_size=256, pre_nms_limit=9000)
+    with pytest.raises(MrcnnError):
+        ProposalLayer(1000, bad)([T(probs, dev), T(bbox, dev), T(anchors, dev)])               # K > MRCNN_MAX_SORT
