@@ -253,11 +253,10 @@ struct NmsEpilogue {
     int N;
 };
 
-// boxes_sorted [B,M] in candidate order; valid [B] or NULL (= M); mask scratch [B,M,ceil(M/64)] u64
+// boxes_sorted [B,M] in candidate order; valid [B] or NULL (= M)
 __attribute__((visibility("hidden"))) int launch_nms_sorted(const float4* boxes_sorted, const int32_t* valid, int B,
-                                                            int M, int max_out, float thr, uint64_t* mask,
-                                                            const NmsEpilogue& epi, cudaStream_t stream);
-__attribute__((visibility("hidden"))) size_t nms_mask_bytes(int B, int M);
+                                                            int M, int max_out, float thr, const NmsEpilogue& epi,
+                                                            cudaStream_t stream);
 
 struct TopkDecode {              // optional fused epilogue of the top-k final kernel (ProposalLayer)
     const float4* anchors;       // [B,A]

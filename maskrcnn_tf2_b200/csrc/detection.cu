@@ -4,7 +4,7 @@
 //                             window normalised with image 0's shape, L:513-515), keep flag (L:402-414)
 //   detection_sort_kernel   : CTA per image -- kept ROIs ordered by (score desc, ROI index asc), i.e. the
 //                             candidate order of the NMS at L:455
-//   nms.cu mask + sweep     : ONE class-agnostic NMS (quirk Q3, L:440-468) with the detection epilogue that
+//   nms.cu nms_lazy_kernel  : ONE class-agnostic NMS (quirk Q3, L:440-468) with the detection epilogue that
 //                             packs [y1,x1,y2,x2,class,score] and zero-pads (L:494-500).  The two O(n^2)
 //                             broadcast intersections (L:411-414, 475-478) and the final top_k (L:486-490) are
 //                             identities on this ordering and have no kernel.
@@ -93,12 +93,10 @@ struct DetWs {
     float4* boxes_sorted;
     int32_t* orig_idx;
     int32_t* ncand;
-    uint64_t* mask;
 };
 static size_t det_ws_bytes(int B, int N) {
     const size_t bn = (size_t)B * N;
-    return 2 * align_up(bn * sizeof(float4), 256) + 4 * align_up(bn * 4, 256) + align_up((size_t)B * 4, 256) +
-           nms_mask_bytes(B, N);
+    return 2 * align_up(bn * sizeof(float4), 256) + 4 * align_up(bn * 4, 256) + align_up((size_t)B * 4, 256);
 }
 
 }  // namespace mrcnn
@@ -133,8 +131,7 @@ MRCNN_EXPORT int mrcnn_detection_forward(const float* rois, const float* probs, 
     w.class_ids = (int32_t*)p;   p += align_up(bn * 4, 256);
     w.keep_key = (uint32_t*)p;   p += align_up(bn * 4, 256);
     w.orig_idx = (int32_t*)p;    p += align_up(bn * 4, 256);
-    w.ncand = (int32_t*)p;       p += align_up((size_t)B * 4, 256);
-    w.mask = (uint64_t*)p;
+    w.ncand = (int32_t*)p;
 
     const float4 sd = make_float4(std_dev[0], std_dev[1], std_dev[2], std_dev[3]);
     detection_refine_kernel<<<dim3((N + 7) / 8, B), 256, 0, st>>>((const float4*)rois, probs, (const float4*)deltas,
@@ -157,5 +154,5 @@ MRCNN_EXPORT int mrcnn_detection_forward(const float* rois, const float* probs, 
     epi.detections = detections;
     epi.count = det_count;
     epi.N = N;
-    return launch_nms_sorted(w.boxes_sorted, w.ncand, B, N, max_inst, nms_thr, w.mask, epi, st);
+    return launch_nms_sorted(w.boxes_sorted, w.ncand, B, N, max_inst, nms_thr, epi, st);
 }

@@ -1,158 +1,183 @@
 // nms.cu -- batched greedy hard NMS with TF NonMaxSuppressionV3 (CPU kernel) semantics.
 // Replaces tf.image.non_max_suppression at mrcnn_layers.py:225 (RPN, thr 0.7) and :455 (detections, thr 0.3).
 //
-// Three stages, all asynchronous on one stream:
-//   1. (generic entry only) per-image sort of the candidates by (score desc, index asc);
-//   2. nms_mask_kernel: 64x64 tiles of the upper-triangular "IoU > thr" bit matrix, column boxes staged in
-//      shared memory, one 64-bit word per (row, column tile); diagonal tiles are computed symmetric;
-//   3. nms_sweep_kernel: one CTA per image walks the tiles in order.  Inside a tile the keep/suppress
-//      decisions are resolved by a warp with ballots (fixed-point over the symmetric diagonal block: a
-//      candidate is kept once every earlier overlapping candidate is decided-removed, removed once one is
-//      decided-kept); the rows of the kept boxes are then OR-ed into the per-word "removed" registers.
-//      Stops as soon as max_out boxes are kept.
+// nms_lazy_kernel: a thread-block CLUSTER of 1..8 CTAs (1024 threads each) per image; every CTA stages the image's
+// candidate boxes (already in candidate order) in its own shared memory.  Candidates are consumed in 64-box
+// tiles; for a tile only the IoU tests that can matter are evaluated:
+//   (a) kept-so-far x tile: the kept list is dealt round-robin to all warps of the cluster (shared-memory
+//       broadcast reads) against the tile's 64 candidates (two per lane); each CTA ORs its warps' ballots into a
+//       64-bit word and stores it into its slot in every CTA of the cluster (distributed shared memory);
+//   (b) the tile's own symmetric 64x64 block (two rows per warp, ballot per row), redundantly per CTA;
+//   (c) after one cluster barrier every CTA resolves the in-tile decisions identically with ballots (fixed
+//       point: a candidate is kept once every earlier overlapping candidate is decided-removed, removed once one
+//       is decided-kept) and appends the kept ones to its own copy of the kept list.
+// Work is sum_t kept(t) * 64 + M * 64 pair tests instead of the M^2/2 of a full bit matrix, nothing is written
+// to global memory but the result, and the loop stops as soon as max_out boxes are kept.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace mrcnn {
 
-constexpr int kTile = 64;
-constexpr int kSweepThreads = 128;  // one removed-word per thread: up to 128 * 64 = 8192 candidates
+#ifdef MRCNN_NMS_PROFILE   // debug build only (scripts/profile_nms.py): per-phase cycle counters of cluster 0
+__device__ long long g_nms_prof[8];
+#define PROF_DECL long long p_t0 = clock64(), p_acc[4] = {0, 0, 0, 0}; int p_tiles = 0
+#define PROF_MARK(i) do { const long long p_now = clock64(); p_acc[i] += p_now - p_t0; p_t0 = p_now; } while (0)
+#define PROF_TILE ++p_tiles
+#define PROF_DUMP do { if (blockIdx.x == 0 && threadIdx.x == 0) { for (int q = 0; q < 4; ++q) g_nms_prof[q] = p_acc[q]; \
+                       g_nms_prof[4] = p_tiles; g_nms_prof[5] = nkept; } } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(i)
+#define PROF_TILE
+#define PROF_DUMP
+#endif
 
-size_t nms_mask_bytes(int B, int M) {
-    const size_t words = (size_t)((M + kTile - 1) / kTile);
-    return align_up((size_t)B * M * words * sizeof(uint64_t), 256);
+constexpr int kTile = 64;
+constexpr int kNmsThreads = 1024;
+constexpr int kNmsWarps = kNmsThreads / 32;
+
+static size_t nms_smem_bytes(int M, int max_out) {
+    return (size_t)M * (sizeof(float4) + sizeof(float)) + (size_t)(max_out < M ? max_out : M) * sizeof(int32_t);
 }
 
-__global__ void __launch_bounds__(kTile)
-nms_mask_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ valid, int M, int words, float thr,
-                uint64_t* __restrict__ mask) {
-    const int c = blockIdx.x, r = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
-    if (c < r) return;
-    const int n = valid ? min(max(valid[b], 0), M) : M;
-    if (r * kTile >= n || c * kTile >= n) return;
-    __shared__ float4 cb[kTile];
-    __shared__ float ca[kTile];
-    const float4* bx = boxes + (size_t)b * M;
-    {
-        const int j = c * kTile + tid;
-        float4 nb = make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f);  // never overlaps, never ambiguous
-        float a = 1.0f;
-        if (j < n) {
-            float aj;
-            const float4 t = normalise_box(__ldg(bx + j), aj);
-            if (aj > 0.0f) { nb = t; a = aj; }  // TF: area <= 0 -> IoU 0
-        }
-        cb[tid] = nb;
-        ca[tid] = a;
-    }
-    __syncthreads();
-    const int i = r * kTile + tid;
-    if (i >= n) return;
-    float ai;
-    const float4 bi = normalise_box(__ldg(bx + i), ai);
-    uint64_t bits = 0;
-    if (ai > 0.0f) {
-        const int ncol = min(kTile, n - c * kTile);
-#pragma unroll 8
-        for (int j = 0; j < ncol; ++j) {
-            if (iou_gt(bi, ai, cb[j], ca[j], thr)) bits |= (1ull << j);
-        }
-        if (c == r) bits &= ~(1ull << tid);
-    }
-    mask[((size_t)b * M + i) * words + c] = bits;
+// cluster barrier with release / acquire ordering of the distributed-shared-memory stores that precede it
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 __device__ __forceinline__ uint64_t ballot64(bool lo, bool hi) {
     return (uint64_t)__ballot_sync(0xffffffffu, lo) | ((uint64_t)__ballot_sync(0xffffffffu, hi) << 32);
 }
 
-__global__ void __launch_bounds__(kSweepThreads)
-nms_sweep_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ valid, int M, int words, int max_out,
-                 const uint64_t* __restrict__ mask, NmsEpilogue epi) {
-    extern __shared__ int32_t sel[];  // min(max_out, M) selected sorted positions
-    __shared__ uint64_t s_cur, s_kept;
-    __shared__ int s_total;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+__global__ void __launch_bounds__(kNmsThreads, 1)
+nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ valid, int M, int max_out, float thr,
+                NmsEpilogue epi) {
+    extern __shared__ __align__(16) unsigned char nms_smem[];
+    float4* sb = reinterpret_cast<float4*>(nms_smem);          // [M] min/max-normalised corners
+    float* sa = reinterpret_cast<float*>(sb + M);               // [M] areas
+    int32_t* sel = reinterpret_cast<int32_t*>(sa + M);          // [min(max_out, M)] kept candidate positions
+    __shared__ uint64_t diag[kTile];
+    __shared__ unsigned long long s_parts[2][8];                // [tile parity][source CTA]: written by the peers
+    __shared__ unsigned long long s_part;                       // this CTA's partial of the current tile
+    __shared__ int s_nkept;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int csize = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
+    const int b = blockIdx.x / csize, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = valid ? min(max(valid[b], 0), M) : M;
     const int tiles = (n + kTile - 1) / kTile;
-    const uint64_t* mk = mask + (size_t)b * M * words;
-    uint64_t my_removed = 0;  // removed bits of word `tid`
-    int total = 0;
-    // warp 0 keeps the diagonal words of the next tile in flight
-    uint64_t nlo = 0, nhi = 0;
-    if (tid < 32 && tiles > 0) {
-        if (lane < n) nlo = __ldg(mk + (size_t)lane * words);
-        if (lane + 32 < n) nhi = __ldg(mk + (size_t)(lane + 32) * words);
+    const float4* bx = boxes + (size_t)b * M;
+    const float4 kNone = make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f);  // overlaps nothing, never ambiguous
+    for (int i = tid; i < n; i += kNmsThreads) {
+        float a;
+        float4 t = normalise_box(__ldg(bx + i), a);
+        if (!(a > 0.0f)) { t = kNone; a = 1.0f; }  // TF: area <= 0 -> IoU 0 with everything
+        sb[i] = t;
+        sa[i] = a;
     }
-    for (int t = 0; t < tiles && total < max_out; ++t) {
-        if (tid == t) s_cur = my_removed;
+    if (tid == 0) { s_part = 0ull; s_nkept = 0; }
+    cluster.sync();  // every CTA of the cluster is resident before a peer stores into its shared memory
+    int nkept = 0;
+    const int gwarp = crank * kNmsWarps + warp, gstride = csize * kNmsWarps;
+    PROF_DECL;
+    for (int t = 0; t < tiles && nkept < max_out; ++t) {
+        PROF_TILE;
+        const int base = t * kTile;
+        const int c0 = base + lane, c1 = c0 + 32;
+        const float4 b0 = (c0 < n) ? sb[c0] : kNone, b1 = (c1 < n) ? sb[c1] : kNone;
+        const float a0 = (c0 < n) ? sa[c0] : 1.0f, a1 = (c1 < n) ? sa[c1] : 1.0f;
+        // (a) kept-so-far x tile, this warp's share of the kept list
+        bool r0 = false, r1 = false;
+        for (int k = gwarp; k < nkept; k += gstride) {
+            const int ki = sel[k];
+            const float4 bk = sb[ki];
+            const float ak = sa[ki];
+            r0 |= iou_gt(bk, ak, b0, a0, thr);
+            r1 |= iou_gt(bk, ak, b1, a1, thr);
+        }
+        const uint64_t hit = ballot64(r0, r1);
+        if (lane == 0 && hit) {  // two native 32-bit shared atomics (a 64-bit OR would be a CAS loop)
+            unsigned* sp = reinterpret_cast<unsigned*>(&s_part);
+            if ((unsigned)hit) atomicOr(sp, (unsigned)hit);
+            if ((unsigned)(hit >> 32)) atomicOr(sp + 1, (unsigned)(hit >> 32));
+        }
+        // (b) symmetric in-tile block: rows 2*warp, 2*warp+1
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int i = 2 * warp + rr;
+            const int ci = base + i;
+            const float4 bi = (ci < n) ? sb[ci] : kNone;
+            const float ai = (ci < n) ? sa[ci] : 1.0f;
+            const uint64_t row = ballot64(iou_gt(bi, ai, b0, a0, thr), iou_gt(bi, ai, b1, a1, thr)) & ~(1ull << i);
+            if (lane == 0) diag[i] = row;
+        }
         __syncthreads();
-        if (tid < 32) {
-            const uint64_t rlo = nlo, rhi = nhi;
-            if (t + 1 < tiles) {  // prefetch next diagonal block
-                const int r0 = (t + 1) * kTile + lane, r1 = r0 + 32;
-                nlo = (r0 < n) ? __ldg(mk + (size_t)r0 * words + t + 1) : 0ull;
-                nhi = (r1 < n) ? __ldg(mk + (size_t)r1 * words + t + 1) : 0ull;
-            }
-            const int rem = n - t * kTile;
+        PROF_MARK(0);
+        if (warp == 0) {  // store this CTA's partial into its slot in every CTA of the cluster (DSMEM)
+            const unsigned long long part = s_part;
+            if (lane < csize) *cluster.map_shared_rank(&s_parts[t & 1][crank], lane) = part;
+            __syncwarp();
+            if (lane == 0) s_part = 0ull;
+        }
+        cluster_barrier();
+        PROF_MARK(1);
+        // (c) in-tile resolution, identical in every CTA
+        if (warp == 0) {
+            const int rem = n - base;
             const uint64_t validbits = (rem >= kTile) ? ~0ull : ((1ull << rem) - 1ull);
-            uint64_t und = ~s_cur & validbits, kept = 0;
-            const uint64_t blk0 = rlo & ((1ull << lane) - 1ull);          // earlier overlapping candidates
-            const uint64_t blk1 = rhi & ((1ull << (lane + 32)) - 1ull);
+            uint64_t removed = 0;
+            for (int r = 0; r < csize; ++r) removed |= (uint64_t)s_parts[t & 1][r];
+            uint64_t und = ~removed & validbits, kept = 0;
+            const uint64_t blk0 = diag[lane] & ((1ull << lane) - 1ull);            // earlier overlapping candidates
+            const uint64_t blk1 = diag[lane + 32] & ((1ull << (lane + 32)) - 1ull);
             while (und) {
                 const bool u0 = (und >> lane) & 1ull, u1 = (und >> (lane + 32)) & 1ull;
-                const bool d0 = u0 && (blk0 & kept), d1 = u1 && (blk1 & kept);          // removed
+                const bool d0 = u0 && (blk0 & kept), d1 = u1 && (blk1 & kept);              // removed
                 const bool k0 = u0 && !d0 && !(blk0 & und), k1 = u1 && !d1 && !(blk1 & und);  // kept
                 const uint64_t nk = ballot64(k0, k1), nd = ballot64(d0, d1);
                 kept |= nk;
                 und &= ~(nk | nd);
             }
-            const int room = max_out - total;
+            const int room = max_out - nkept;
             while (__popcll(kept) > room) kept &= ~(1ull << (63 - __clzll(kept)));
-            if ((kept >> lane) & 1ull) sel[total + __popcll(kept & ((1ull << lane) - 1ull))] = t * kTile + lane;
-            if ((kept >> (lane + 32)) & 1ull)
-                sel[total + __popcll(kept & ((1ull << (lane + 32)) - 1ull))] = t * kTile + lane + 32;
-            if (lane == 0) { s_kept = kept; s_total = total + __popcll(kept); }
+            if ((kept >> lane) & 1ull) sel[nkept + __popcll(kept & ((1ull << lane) - 1ull))] = c0;
+            if ((kept >> (lane + 32)) & 1ull) sel[nkept + __popcll(kept & ((1ull << (lane + 32)) - 1ull))] = c1;
+            __syncwarp();
+            // the slots of parity (t & 1) are next overwritten by peers after the cluster barrier of tile t + 1
+            if (lane == 0) s_nkept = nkept + __popcll(kept);
         }
+        PROF_MARK(2);
         __syncthreads();
-        uint64_t kept = s_kept;
-        total = s_total;
-        if (total >= max_out) break;
-        if (tid > t && tid < tiles) {
-            const uint64_t* col = mk + (size_t)t * kTile * words + tid;
-            while (kept) {  // up to 4 independent row loads in flight
-                const int j0 = __ffsll((long long)kept) - 1; kept &= kept - 1;
-                uint64_t v = __ldg(col + (size_t)j0 * words);
-                if (kept) { const int j1 = __ffsll((long long)kept) - 1; kept &= kept - 1; v |= __ldg(col + (size_t)j1 * words); }
-                if (kept) { const int j2 = __ffsll((long long)kept) - 1; kept &= kept - 1; v |= __ldg(col + (size_t)j2 * words); }
-                if (kept) { const int j3 = __ffsll((long long)kept) - 1; kept &= kept - 1; v |= __ldg(col + (size_t)j3 * words); }
-                my_removed |= v;
-            }
-        }
+        nkept = s_nkept;
+        PROF_MARK(3);
     }
-    __syncthreads();
-    total = (tiles > 0) ? s_total : 0;
+    PROF_DUMP;
+    cluster.sync();  // no CTA leaves while a peer could still address its shared memory
+    if (crank != 0) return;
+    const int total = nkept;
     // ---- epilogue: fixed-size padded outputs, no host round trip --------------------------------
     if (epi.mode == 0) {
-        for (int r = tid; r < max_out; r += blockDim.x) {
+        for (int r = tid; r < max_out; r += kNmsThreads) {
             int32_t v = -1;
             if (r < total) v = epi.orig_idx ? epi.orig_idx[(size_t)b * M + sel[r]] : sel[r];
             epi.keep[(size_t)b * max_out + r] = v;
         }
         if (tid == 0 && epi.count) epi.count[b] = total;
     } else if (epi.mode == 1) {  // ProposalLayer.nms L:227-230: gather + zero pad
-        for (int r = tid; r < max_out; r += blockDim.x) {
-            epi.proposals[(size_t)b * max_out + r] =
-                (r < total) ? boxes[(size_t)b * M + sel[r]] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = tid; r < max_out; r += kNmsThreads) {
+            epi.proposals[(size_t)b * max_out + r] = (r < total) ? __ldg(bx + sel[r]) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (epi.keep) epi.keep[(size_t)b * max_out + r] = (r < total) ? sel[r] : -1;
         }
         if (tid == 0 && epi.count) epi.count[b] = total;
     } else {  // refine_detections L:494-500: [y1,x1,y2,x2,class,score] rows + zero pad
-        for (int r = tid; r < max_out; r += blockDim.x) {
+        for (int r = tid; r < max_out; r += kNmsThreads) {
             float* o = epi.detections + ((size_t)b * max_out + r) * 6;
             if (r < total) {
                 const int i = epi.orig_idx[(size_t)b * M + sel[r]];
-                const float4 bx = epi.refined[(size_t)b * epi.N + i];
-                o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+                const float4 v = epi.refined[(size_t)b * epi.N + i];
+                o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
                 o[4] = (float)epi.class_ids[(size_t)b * epi.N + i];
                 o[5] = epi.scores[(size_t)b * epi.N + i];
             } else {
@@ -163,17 +188,35 @@ nms_sweep_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ v
     }
 }
 
+// cluster size: spread one image over as many SMs as the batch leaves free (148 SMs, 1 CTA per SM), at most the
+// portable maximum of 8; small candidate sets do not amortise the cluster barrier
+static int nms_cluster_size(int B, int M) {
+    if (M <= 2048) return 1;
+    int cs = 1;
+    while (cs < 8 && (long long)B * (cs * 2) <= 148) cs *= 2;
+    return cs;
+}
+
 int launch_nms_sorted(const float4* boxes_sorted, const int32_t* valid, int B, int M, int max_out, float thr,
-                      uint64_t* mask, const NmsEpilogue& epi, cudaStream_t stream) {
-    const int words = (M + kTile - 1) / kTile;
-    const dim3 grid(words, words, B);
-    nms_mask_kernel<<<grid, kTile, 0, stream>>>(boxes_sorted, valid, M, words, thr, mask);
-    const size_t smem = (size_t)(max_out < M ? max_out : M) * sizeof(int32_t);  // never more than M kept
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
-    nms_sweep_kernel<<<B, kSweepThreads, smem, stream>>>(boxes_sorted, valid, M, words, max_out, mask, epi);
+                      const NmsEpilogue& epi, cudaStream_t stream) {
+    const size_t smem = nms_smem_bytes(M, max_out);
+    cudaError_t e = cudaFuncSetAttribute(nms_lazy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int cs = nms_cluster_size(B, M);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * cs));
+    cfg.blockDim = dim3(kNmsThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, nms_lazy_kernel, boxes_sorted, valid, M, max_out, thr, epi);
+    if (e != cudaSuccess) return (int)e;
     return last_error();
 }
 
@@ -215,16 +258,21 @@ struct NmsWs {
     float4* boxes_sorted;
     int32_t* orig_idx;
     int32_t* ncand;
-    uint64_t* mask;
 };
 static size_t nms_ws_bytes(int B, int M) {
     return align_up((size_t)B * M * sizeof(float4), 256) + align_up((size_t)B * M * sizeof(int32_t), 256) +
-           align_up((size_t)B * sizeof(int32_t), 256) + nms_mask_bytes(B, M);
+           align_up((size_t)B * sizeof(int32_t), 256);
 }
 
 }  // namespace mrcnn
 
 using namespace mrcnn;
+
+#ifdef MRCNN_NMS_PROFILE
+MRCNN_EXPORT int mrcnn_debug_nms_profile(long long* host_out8) {
+    return (int)cudaMemcpyFromSymbol(host_out8, g_nms_prof, sizeof(long long) * 8);
+}
+#endif
 
 MRCNN_EXPORT int mrcnn_nms_workspace_bytes(int B, int M, size_t* bytes) {
     if (!bytes) return MRCNN_ERR_NULL;
@@ -245,8 +293,7 @@ MRCNN_EXPORT int mrcnn_nms_forward(const float* boxes, const float* scores, cons
     char* p = (char*)ws;
     w.boxes_sorted = (float4*)p; p += align_up((size_t)B * M * sizeof(float4), 256);
     w.orig_idx = (int32_t*)p;    p += align_up((size_t)B * M * sizeof(int32_t), 256);
-    w.ncand = (int32_t*)p;       p += align_up((size_t)B * sizeof(int32_t), 256);
-    w.mask = (uint64_t*)p;
+    w.ncand = (int32_t*)p;
     const int sort_n = next_pow2(M < 32 ? 32 : M);
     const size_t smem = (size_t)sort_n * sizeof(uint64_t);
     if (smem > 48 * 1024) {
@@ -259,5 +306,5 @@ MRCNN_EXPORT int mrcnn_nms_forward(const float* boxes, const float* scores, cons
     epi.orig_idx = w.orig_idx;
     epi.keep = keep;
     epi.count = count;
-    return launch_nms_sorted(w.boxes_sorted, w.ncand, B, M, max_out, thr, w.mask, epi, st);
+    return launch_nms_sorted(w.boxes_sorted, w.ncand, B, M, max_out, thr, epi, st);
 }

@@ -1,7 +1,7 @@
 // proposal.cu -- ProposalLayer.call (mrcnn_layers.py:233-269) as one asynchronous launch sequence:
 //   top-k over the foreground column of rpn_probs (L:235,246)  -> topk.cu (hist, hist, compact, final)
 //   gather + std-dev scale + decode + clip (L:238,247-261)      -> fused into the top-k final kernel
-//   NMS 0.7 + gather + zero pad (L:224-231,268)                 -> nms.cu (mask, sweep with proposal epilogue)
+//   NMS 0.7 + gather + zero pad (L:224-231,268)                 -> nms.cu (nms_lazy_kernel, proposal epilogue)
 // No per-image Python loop (utils.batch_slice, utils.py:738-772): the whole batch is one grid per kernel.
 #include "common.cuh"
 
@@ -11,10 +11,9 @@ namespace {
 struct ProposalWs {
     void* topk;
     float4* boxes_sorted;  // [B,K]
-    uint64_t* mask;        // [B,K,ceil(K/64)]
 };
 size_t proposal_ws_bytes(int B, int K) {
-    return align_up(topk_ws_bytes(B), 256) + align_up((size_t)B * K * sizeof(float4), 256) + nms_mask_bytes(B, K);
+    return align_up(topk_ws_bytes(B), 256) + align_up((size_t)B * K * sizeof(float4), 256);
 }
 }  // namespace
 
@@ -42,8 +41,7 @@ MRCNN_EXPORT int mrcnn_proposal_forward(const float* rpn_probs, const float* rpn
     ProposalWs w;
     char* p = (char*)ws;
     w.topk = p;                  p += align_up(topk_ws_bytes(B), 256);
-    w.boxes_sorted = (float4*)p; p += align_up((size_t)B * K * sizeof(float4), 256);
-    w.mask = (uint64_t*)p;
+    w.boxes_sorted = (float4*)p;
 
     TopkDecode dec;
     dec.anchors = (const float4*)anchors;
@@ -59,5 +57,5 @@ MRCNN_EXPORT int mrcnn_proposal_forward(const float* rpn_probs, const float* rpn
     epi.proposals = (float4*)proposals;
     epi.keep = keep_idx;
     epi.count = keep_count;
-    return launch_nms_sorted(w.boxes_sorted, nullptr, B, K, P, nms_thr, w.mask, epi, st);
+    return launch_nms_sorted(w.boxes_sorted, nullptr, B, K, P, nms_thr, epi, st);
 }

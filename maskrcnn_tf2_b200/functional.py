@@ -153,9 +153,11 @@ def roialign_forward(boxes, image_meta, feature_maps, pool_shape, denominator=24
     out = torch.empty((B, N, ph, pw, C), dtype=torch.float32, device=dev)
     roi_map = torch.empty((B, N), dtype=torch.int32, device=dev)
     roi_level = torch.empty((B, N), dtype=torch.int32, device=dev) if return_level else None
+    nbytes = _query(L.mrcnn_roialign_workspace_bytes, B, N)
+    ws = _workspace(("roialign", B, N, ph, pw), nbytes, dev)
     check(L.mrcnn_roialign_forward(ptr(boxes), ptr(image_meta), image_meta.shape[1], ptrs, Hs, Ws, C, B, N, ph, pw,
                                    c_float(float(denominator)), int(map_mode), ptr(out), ptr(roi_map), ptr(roi_level),
-                                   None, 0, _stream()), "mrcnn_roialign_forward")
+                                   ptr(ws), ws.numel(), _stream()), "mrcnn_roialign_forward")
     if return_level:
         return out, roi_map, roi_level
     return out, roi_map

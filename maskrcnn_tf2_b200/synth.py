@@ -111,23 +111,29 @@ def _iou_matrix(a, b):
     return inter / (aa[:, None] + ab[None, :] - inter + 1e-12)
 
 
-def rpn_outputs(rng, anchors, regime, img_size, std_dev=(0.1, 0.1, 0.2, 0.2), n_gt=20):
+# (objects, delta noise, logit noise): 'clustered' = busy COCO image, NMS keeps 1000 after examining ~3500 of the
+# 6000 candidates (~70 % suppressed); 'sparse' = few objects, ~200 survivors of all 6000 (zero padding exercised)
+_REGIMES = {"clustered": (40, 0.15, 1.0), "sparse": (20, 0.05, 0.5)}
+
+
+def rpn_outputs(rng, anchors, regime, img_size, std_dev=(0.1, 0.1, 0.2, 0.2)):
     """One image's rpn_probs [A,2] and raw rpn_bbox [A,4].
     regime 'iid': softmax(2 N(0,1)), N(0,0.5) deltas -- NMS nearly trivial (best case).
-    regime 'clustered': what a trained RPN emits -- objectness follows the best IoU with n_gt objects and the
-    deltas regress towards them, so proposals pile up and NMS suppresses most of them (headline case)."""
+    regime 'clustered' / 'sparse': what a trained RPN emits -- objectness follows the best IoU with a set of
+    objects and the deltas regress towards them, so proposals pile up and NMS suppresses most of them."""
     A = anchors.shape[0]
     if regime == 'iid':
         probs = _softmax(2.0 * rng.standard_normal((A, 2), dtype=np.float32)).astype(np.float32)
         bbox = (0.5 * rng.standard_normal((A, 4), dtype=np.float32)).astype(np.float32)
         return probs, bbox
+    n_gt, delta_noise, logit_noise = _REGIMES[regime]
     gt_px, _ = gt_instances(rng, img_size, n_real=n_gt, max_gt=n_gt)
     gt = norm_boxes(gt_px, img_size).astype(np.float64)
     an = anchors.astype(np.float64)
     iou = _iou_matrix(an, gt)
     best = iou.argmax(axis=1)
     miou = iou[np.arange(A), best]
-    logit = 12.0 * miou - 4.0 + 0.5 * rng.standard_normal(A)
+    logit = 12.0 * miou - 4.0 + logit_noise * rng.standard_normal(A)
     p = 1.0 / (1.0 + np.exp(-logit))
     probs = np.stack([1.0 - p, p], axis=1).astype(np.float32)
     g = gt[best]
@@ -137,7 +143,7 @@ def rpn_outputs(rng, anchors, regime, img_size, std_dev=(0.1, 0.1, 0.2, 0.2), n_
                   ((g[:, 1] + 0.5 * gw) - (an[:, 1] + 0.5 * aw)) / aw,
                   np.log(gh / ah), np.log(gw / aw)], axis=1)
     t = np.clip(t, -4.0, 4.0)
-    d = 0.8 * t + 0.05 * rng.standard_normal((A, 4))
+    d = 0.8 * t + delta_noise * rng.standard_normal((A, 4))
     bbox = (d / np.asarray(std_dev, dtype=np.float64)).astype(np.float32)
     return probs, bbox
 

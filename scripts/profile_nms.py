@@ -1,0 +1,24 @@
+"""Per-phase cycle counters of nms_lazy_kernel (debug build `make -C maskrcnn_tf2_b200/csrc prof`)."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from maskrcnn_tf2_b200 import _lib
+_lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), "libmrcnn_roi_b200_prof.so")
+from maskrcnn_tf2_b200 import functional as F, synth
+L = _lib.lib()
+L.mrcnn_debug_nms_profile.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+regime = sys.argv[2] if len(sys.argv) > 2 else "clustered"
+a = synth.pyramid_anchors(1024)
+pr, bb = zip(*[synth.rpn_outputs(np.random.default_rng(2000 + b), a, regime, 1024) for b in range(B)])
+t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+probs, bbox, anch = t(np.stack(pr)), t(np.stack(bb)), t(np.broadcast_to(a, (B,) + a.shape))
+for _ in range(3):
+    out = F.proposal_forward(probs, bbox, anch, 6000, 1000, [0.1, 0.1, 0.2, 0.2], 0.7, debug=True)
+torch.cuda.synchronize()
+buf = (ctypes.c_longlong * 8)()
+L.mrcnn_debug_nms_profile(buf)
+v = list(buf)
+tiles = max(v[4], 1)
+print(f"B={B} {regime}: tiles {v[4]} kept {v[5]}  cycles/tile: pairs+diag {v[0]/tiles:.0f}  dsmem+cluster barrier {v[1]/tiles:.0f}  "
+      f"resolve {v[2]/tiles:.0f}  cta barrier {v[3]/tiles:.0f}  total {sum(v[:4])/tiles:.0f}")

@@ -55,8 +55,8 @@ def test_version_and_status_strings(lib):
 def test_workspace_queries_are_pure_host_functions(lib):
     n = ctypes.c_size_t(0)
     assert lib.mrcnn_proposal_workspace_bytes(8, 261888, 6000, 1000, ctypes.byref(n)) == 0
-    # top-k scratch + sorted boxes + the 6000 x 94-word bit matrix per image
-    assert n.value >= 8 * 6000 * 94 * 8
+    # top-k scratch (two 8192-entry candidate lists per image) + the sorted boxes
+    assert n.value >= 8 * (2 * 8192 * 8 + 6000 * 16)
     assert lib.mrcnn_topk_workspace_bytes(2, 1000, 100, ctypes.byref(n)) == 0 and n.value > 0
     assert lib.mrcnn_nms_workspace_bytes(2, 1000, ctypes.byref(n)) == 0 and n.value > 0
     assert lib.mrcnn_detection_workspace_bytes(8, 1000, 81, ctypes.byref(n)) == 0 and n.value > 0
@@ -88,11 +88,13 @@ def test_launchers_reject_bad_arguments_without_launching(lib):
     maps = (ctypes.c_void_p * 4)(0x1000, 0x2000, 0x3000, 0x4000)
     hw = (ctypes.c_int * 4)(8, 4, 2, 1)
     assert lib.mrcnn_roialign_forward(fake, fake, 93, maps, hw, hw, 255, 1, 10, 7, 7, 244.0, 0, fake, fake, None,
-                                      None, 0, None) == -2                                      # C % 4 != 0
+                                      fake, 1 << 20, None) == -2                                # C % 4 != 0
     assert lib.mrcnn_roialign_forward(fake, fake, 93, maps, hw, hw, 256, 1, 10, 7, 7, 244.0, 2, fake, fake, None,
-                                      None, 0, None) == -2                                      # map_mode
+                                      fake, 1 << 20, None) == -2                                # map_mode
     assert lib.mrcnn_roialign_forward(fake, fake, 93, maps, hw, hw, 256, 1, 10, 7, 7, 244.0, 0, fake, None, None,
-                                      None, 0, None) == -1                                      # roi_map required
+                                      fake, 1 << 20, None) == -1                                # roi_map required
+    assert lib.mrcnn_roialign_forward(fake, fake, 93, maps, hw, hw, 256, 1, 10, 7, 7, 244.0, 0, fake, fake, None,
+                                      fake, 16, None) == -3                                     # workspace
     assert lib.mrcnn_roialign_backward(fake, fake, fake, maps, hw, hw, 256, 1, 10, 0, 7, None) == -2
     assert lib.mrcnn_detection_forward(fake, fake, fake, fake, 93, 1, 1000, 81, std, 0.7, 1, 100, 0.3, 1, fake, None,
                                        fake, 1 << 30, None) == -2                               # per_class unsupported

@@ -167,8 +167,8 @@ def _proposal_inputs(regime, B, img_size=1024, seed=2000):
     return np.stack(probs), np.stack(bbox), np.ascontiguousarray(np.broadcast_to(a, (B,) + a.shape))
 
 
-@pytest.mark.parametrize("regime,img_size,P", [("iid", 1024, 1000), ("clustered", 1024, 1000), ("clustered", 512, 2000),
-                                               ("iid", 256, 1000)])
+@pytest.mark.parametrize("regime,img_size,P", [("iid", 1024, 1000), ("clustered", 1024, 1000), ("sparse", 1024, 1000),
+                                               ("clustered", 512, 2000), ("iid", 256, 1000)])
 def test_proposal_layer_bit_exact_coco_shape(F, orc, dev, regime, img_size, P):
     B = 2
     probs, bbox, anchors = _proposal_inputs(regime, B, img_size)

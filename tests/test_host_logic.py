@@ -80,12 +80,13 @@ def test_synthetic_regimes_exercise_nms_differently(orc):
     from maskrcnn_tf2_b200 import synth
     a = synth.pyramid_anchors(512)
     kept = {}
-    for regime in ("iid", "clustered"):
+    for regime in ("iid", "clustered", "sparse"):
         p, d = synth.rpn_outputs(np.random.default_rng(5), a, regime, 512)
         assert p.shape == (65472, 2) and np.allclose(p.sum(1), 1.0, atol=1e-6)
         r = orc.proposal_layer(p[None], d[None], a[None], 6000, 1000, [0.1, 0.1, 0.2, 0.2], 0.7)
         kept[regime] = int(r["keep_count"][0])
-    assert kept["iid"] == 1000 and kept["clustered"] < 700      # clustered: heavy suppression, zero padding exercised
+    assert kept["iid"] == 1000 and kept["sparse"] < 700      # sparse: heavy suppression, zero padding exercised
+    assert kept["clustered"] > kept["sparse"]
 
 
 def test_shard_ranges_cover_the_batch_once():
