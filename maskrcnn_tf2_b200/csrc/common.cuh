@@ -156,6 +156,68 @@ __device__ __forceinline__ void block_bitonic_sort_desc(T* s, int n) {
     }
 }
 
+// Register-blocked bitonic sort, descending, of 1024*E 64-bit keys held E per thread (thread t owns ranks
+// t*E .. t*E+E-1) by a 1024-thread block.  Compare distances below E stay in registers, distances inside a warp
+// use shuffles, and only the log2(32) remaining distances per merge level go through shared memory (double
+// buffered: one __syncthreads per such stage; per-thread rows padded by 16 bytes against bank conflicts).
+// xch: 2 * 1024 * (E + 2) uint64_t of shared memory.
+template <int E, int J>
+__device__ __forceinline__ void sort_local_stage(uint64_t (&v)[E], int k, int t, int log_e) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        if ((e & J) == 0 && (e | J) < E) {
+            const bool desc = (((t << log_e) | e) & k) == 0;
+            const uint64_t a = v[e], b = v[e | J];
+            if ((a < b) == desc) { v[e] = b; v[e | J] = a; }
+        }
+    }
+}
+
+template <int E>
+__device__ __forceinline__ void block_sort_desc_blocked(uint64_t (&v)[E], uint64_t* xch) {
+    constexpr int LOG_E = (E == 1) ? 0 : (E == 2) ? 1 : (E == 4) ? 2 : 3;
+    constexpr int N = 1024 * E;
+    constexpr int ROW = E + 2;
+    const int t = threadIdx.x;
+    int buf = 0;
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32 * E) {  // partner element lives in another warp
+                const int dm = j >> LOG_E;
+                uint64_t* mine = xch + (size_t)buf * (1024 * ROW) + (size_t)t * ROW;
+#pragma unroll
+                for (int e = 0; e < E; ++e) mine[e] = v[e];
+                __syncthreads();
+                const uint64_t* theirs = xch + (size_t)buf * (1024 * ROW) + (size_t)(t ^ dm) * ROW;
+                const bool lower = (t & dm) == 0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const uint64_t p = theirs[e];
+                    const bool desc = (((t << LOG_E) | e) & k) == 0;
+                    const bool take_max = (lower == desc);
+                    v[e] = take_max ? (v[e] > p ? v[e] : p) : (v[e] < p ? v[e] : p);
+                }
+                buf ^= 1;
+            } else if (j >= E) {  // partner lane in the same warp
+                const int lm = j >> LOG_E;
+                const bool lower = (t & lm) == 0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const uint64_t p = __shfl_xor_sync(0xffffffffu, v[e], lm);
+                    const bool desc = (((t << LOG_E) | e) & k) == 0;
+                    const bool take_max = (lower == desc);
+                    v[e] = take_max ? (v[e] > p ? v[e] : p) : (v[e] < p ? v[e] : p);
+                }
+            } else {  // both elements in this thread's registers (compile-time register indices)
+                if (j == 4) sort_local_stage<E, 4>(v, k, t, LOG_E);
+                else if (j == 2) sort_local_stage<E, 2>(v, k, t, LOG_E);
+                else sort_local_stage<E, 1>(v, k, t, LOG_E);
+            }
+        }
+    }
+}
+constexpr size_t block_sort_xch_bytes(int E) { return 2 * 1024 * (size_t)(E + 2) * sizeof(uint64_t); }
+
 // ---------------------------------------------------------------------------------------------------
 // TF NonMaxSuppressionV3 IoU test "inter / (a_i + a_j - inter) > thr" (non_max_suppression_op.cc IOU()).
 // Boxes are min/max-normalised corners with precomputed areas; callers guarantee both areas > 0.

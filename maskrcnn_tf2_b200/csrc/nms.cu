@@ -2,17 +2,19 @@
 // Replaces tf.image.non_max_suppression at mrcnn_layers.py:225 (RPN, thr 0.7) and :455 (detections, thr 0.3).
 //
 // nms_lazy_kernel: a thread-block CLUSTER of 1..8 CTAs (1024 threads each) per image; every CTA stages the image's
-// candidate boxes (already in candidate order) in its own shared memory.  Candidates are consumed in 64-box
-// tiles; for a tile only the IoU tests that can matter are evaluated:
-//   (a) kept-so-far x tile: the kept list is dealt round-robin to all warps of the cluster (shared-memory
-//       broadcast reads) against the tile's 64 candidates (two per lane); each CTA ORs its warps' ballots into a
-//       64-bit word and stores it into its slot in every CTA of the cluster (distributed shared memory);
-//   (b) the tile's own symmetric 64x64 block (two rows per warp, ballot per row), redundantly per CTA;
-//   (c) after one cluster barrier every CTA resolves the in-tile decisions identically with ballots (fixed
-//       point: a candidate is kept once every earlier overlapping candidate is decided-removed, removed once one
-//       is decided-kept) and appends the kept ones to its own copy of the kept list.
-// Work is sum_t kept(t) * 64 + M * 64 pair tests instead of the M^2/2 of a full bit matrix, nothing is written
-// to global memory but the result, and the loop stops as soon as max_out boxes are kept.
+// candidate boxes (already in candidate order) in its own shared memory and walks the candidates in 64-box tiles.
+// Only the IoU tests that can matter are evaluated, and the cluster never blocks on a barrier inside the loop:
+//   far(t)  = tile t's candidates suppressed by boxes kept in tiles <= t-2.  The kept list is dealt round-robin to
+//             the 31 worker warps of every CTA of the cluster one iteration ahead of its use; each CTA sends its
+//             64-bit partial to every peer with st.async (distributed shared memory store that completes a
+//             transaction on the receiver's mbarrier), so the exchange overlaps the previous tile's resolution;
+//   near(t) = suppressed by the boxes kept in tile t-1: at most 64 x 64 tests, done locally by every CTA;
+//   diag(t) = the tile's own symmetric 64x64 block, computed one iteration ahead by the worker warps;
+//   resolve = warp 0 of every CTA decides the tile identically with ballots (fixed point over diag: a candidate is
+//             kept once every earlier overlapping candidate is decided-removed, removed once one is decided-kept)
+//             and appends the kept ones to the CTA's copy of the kept list.
+// Work is sum_t kept(t) * 64 + M * 64 pair tests instead of the M^2/2 of a full bit matrix, nothing is written to
+// global memory but the result, and the loop stops as soon as max_out boxes are kept.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -38,18 +40,51 @@ __device__ long long g_nms_prof[8];
 constexpr int kTile = 64;
 constexpr int kNmsThreads = 1024;
 constexpr int kNmsWarps = kNmsThreads / 32;
+constexpr int kWorkers = kNmsWarps - 1;  // warps 1..31 run one tile ahead of warp 0
 
 static size_t nms_smem_bytes(int M, int max_out) {
     return (size_t)M * (sizeof(float4) + sizeof(float)) + (size_t)(max_out < M ? max_out : M) * sizeof(int32_t);
 }
 
-// cluster barrier with release / acquire ordering of the distributed-shared-memory stores that precede it
-__device__ __forceinline__ void cluster_barrier() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
 __device__ __forceinline__ uint64_t ballot64(bool lo, bool hi) {
     return (uint64_t)__ballot_sync(0xffffffffu, lo) | ((uint64_t)__ballot_sync(0xffffffffu, hi) << 32);
+}
+
+// ---- mbarrier / distributed-shared-memory primitives (sm_90+ PTX) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arm(uint32_t bar, uint32_t tx_bytes) {  // one arrival + expected bytes
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx_bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+// 8-byte store into a peer CTA's shared memory that completes 8 transaction bytes on the peer's mbarrier
+__device__ __forceinline__ void st_async_u64(uint32_t peer_addr, uint64_t v, uint32_t peer_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                 ::"r"(peer_addr), "l"(v), "r"(peer_bar) : "memory");
+}
+__device__ __forceinline__ void named_barrier(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void or_into(unsigned long long* word, uint64_t bits) {  // two native 32-bit shared atomics
+    unsigned* w = reinterpret_cast<unsigned*>(word);
+    if ((unsigned)bits) atomicOr(w, (unsigned)bits);
+    if ((unsigned)(bits >> 32)) atomicOr(w + 1, (unsigned)(bits >> 32));
 }
 
 __global__ void __launch_bounds__(kNmsThreads, 1)
@@ -59,9 +94,12 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
     float4* sb = reinterpret_cast<float4*>(nms_smem);          // [M] min/max-normalised corners
     float* sa = reinterpret_cast<float*>(sb + M);               // [M] areas
     int32_t* sel = reinterpret_cast<int32_t*>(sa + M);          // [min(max_out, M)] kept candidate positions
-    __shared__ uint64_t diag[kTile];
-    __shared__ unsigned long long s_parts[2][8];                // [tile parity][source CTA]: written by the peers
-    __shared__ unsigned long long s_part;                       // this CTA's partial of the current tile
+    __shared__ uint64_t diag[2][kTile];                         // [tile parity]
+    __shared__ unsigned long long s_far[4][8];                  // [tile & 3][source CTA], written by the peers
+    __shared__ unsigned long long s_near[2];                    // [tile parity]
+    __shared__ unsigned long long s_farpart;                    // this CTA's partial of far(t+1)
+    __shared__ __align__(8) uint64_t s_bar[4];                  // mbarriers, [tile & 3]: a peer can run at most two
+                                                                // tiles ahead, so four phases never alias
     __shared__ int s_nkept;
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
@@ -77,61 +115,55 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
         sb[i] = t;
         sa[i] = a;
     }
-    if (tid == 0) { s_part = 0ull; s_nkept = 0; }
-    cluster.sync();  // every CTA of the cluster is resident before a peer stores into its shared memory
-    int nkept = 0;
-    const int gwarp = crank * kNmsWarps + warp, gstride = csize * kNmsWarps;
-    PROF_DECL;
-    for (int t = 0; t < tiles && nkept < max_out; ++t) {
-        PROF_TILE;
-        const int base = t * kTile;
-        const int c0 = base + lane, c1 = c0 + 32;
-        const float4 b0 = (c0 < n) ? sb[c0] : kNone, b1 = (c1 < n) ? sb[c1] : kNone;
-        const float a0 = (c0 < n) ? sa[c0] : 1.0f, a1 = (c1 < n) ? sa[c1] : 1.0f;
-        // (a) kept-so-far x tile, this warp's share of the kept list
-        bool r0 = false, r1 = false;
-        for (int k = gwarp; k < nkept; k += gstride) {
-            const int ki = sel[k];
-            const float4 bk = sb[ki];
-            const float ak = sa[ki];
-            r0 |= iou_gt(bk, ak, b0, a0, thr);
-            r1 |= iou_gt(bk, ak, b1, a1, thr);
-        }
-        const uint64_t hit = ballot64(r0, r1);
-        if (lane == 0 && hit) {  // two native 32-bit shared atomics (a 64-bit OR would be a CAS loop)
-            unsigned* sp = reinterpret_cast<unsigned*>(&s_part);
-            if ((unsigned)hit) atomicOr(sp, (unsigned)hit);
-            if ((unsigned)(hit >> 32)) atomicOr(sp + 1, (unsigned)(hit >> 32));
-        }
-        // (b) symmetric in-tile block: rows 2*warp, 2*warp+1
+    const uint32_t bar_base = smem_u32(&s_bar[0]);
+    const uint32_t far_bytes = (uint32_t)csize * 8u;  // one 64-bit partial from every CTA of the cluster
+    if (tid == 0) {
+        s_near[0] = 0ull; s_near[1] = 0ull; s_farpart = 0ull; s_nkept = 0;
+        for (int j = 0; j < 4; ++j) mbar_init(bar_base + 8u * j, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int j = 1; j < 4; ++j) mbar_arm(bar_base + 8u * j, far_bytes);  // far(1..3); far(4) is armed in tile 0
+    }
+    __syncthreads();
+    // diag(0): rows 2*warp, 2*warp+1 of tile 0
+    {
+        const float4 b0 = (lane < n) ? sb[lane] : kNone, b1 = (lane + 32 < n) ? sb[lane + 32] : kNone;
+        const float a0 = (lane < n) ? sa[lane] : 1.0f, a1 = (lane + 32 < n) ? sa[lane + 32] : 1.0f;
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             const int i = 2 * warp + rr;
-            const int ci = base + i;
-            const float4 bi = (ci < n) ? sb[ci] : kNone;
-            const float ai = (ci < n) ? sa[ci] : 1.0f;
+            const float4 bi = (i < n) ? sb[i] : kNone;
+            const float ai = (i < n) ? sa[i] : 1.0f;
             const uint64_t row = ballot64(iou_gt(bi, ai, b0, a0, thr), iou_gt(bi, ai, b1, a1, thr)) & ~(1ull << i);
-            if (lane == 0) diag[i] = row;
+            if (lane == 0) diag[0][i] = row;
         }
-        __syncthreads();
-        PROF_MARK(0);
-        if (warp == 0) {  // store this CTA's partial into its slot in every CTA of the cluster (DSMEM)
-            const unsigned long long part = s_part;
-            if (lane < csize) *cluster.map_shared_rank(&s_parts[t & 1][crank], lane) = part;
-            __syncwarp();
-            if (lane == 0) s_part = 0ull;
-        }
-        cluster_barrier();
-        PROF_MARK(1);
-        // (c) in-tile resolution, identical in every CTA
+    }
+    cluster.sync();  // every CTA of the cluster is resident and its mbarriers are initialised before any st.async
+    int nkept = 0, t = 0;
+    PROF_DECL;
+    for (; t < tiles && nkept < max_out; ++t) {
+        PROF_TILE;
+        const int p = t & 1, q = p ^ 1;
+        const int base = t * kTile;
+        const int nkept_before = nkept;  // boxes kept in tiles <= t-1
         if (warp == 0) {
+            // ---- far(t) (from the peers) | near(t) (local) -> resolve tile t ----
+            uint64_t removed = (uint64_t)s_near[p];
+            const uint32_t bar_t = bar_base + 8u * (uint32_t)(t & 3);
+            if (t >= 1) {  // barrier (t & 3) serves tiles t&3, t&3 + 4, ...; tile 0 has no far set
+                mbar_wait(bar_t, (uint32_t)(((t >> 2) - ((t & 3) == 0 ? 1 : 0)) & 1));
+                for (int r = 0; r < csize; ++r) removed |= (uint64_t)s_far[t & 3][r];
+            }
+            __syncwarp();
+            if (lane == 0) {
+                s_near[p] = 0ull;            // next accumulated for tile t+2, after a CTA barrier
+                mbar_arm(bar_t, far_bytes);  // far(t+4) arrives during iteration t+3
+            }
+            PROF_MARK(0);
             const int rem = n - base;
             const uint64_t validbits = (rem >= kTile) ? ~0ull : ((1ull << rem) - 1ull);
-            uint64_t removed = 0;
-            for (int r = 0; r < csize; ++r) removed |= (uint64_t)s_parts[t & 1][r];
             uint64_t und = ~removed & validbits, kept = 0;
-            const uint64_t blk0 = diag[lane] & ((1ull << lane) - 1ull);            // earlier overlapping candidates
-            const uint64_t blk1 = diag[lane + 32] & ((1ull << (lane + 32)) - 1ull);
+            const uint64_t blk0 = diag[p][lane] & ((1ull << lane) - 1ull);            // earlier overlapping candidates
+            const uint64_t blk1 = diag[p][lane + 32] & ((1ull << (lane + 32)) - 1ull);
             while (und) {
                 const bool u0 = (und >> lane) & 1ull, u1 = (und >> (lane + 32)) & 1ull;
                 const bool d0 = u0 && (blk0 & kept), d1 = u1 && (blk1 & kept);              // removed
@@ -142,19 +174,75 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
             }
             const int room = max_out - nkept;
             while (__popcll(kept) > room) kept &= ~(1ull << (63 - __clzll(kept)));
-            if ((kept >> lane) & 1ull) sel[nkept + __popcll(kept & ((1ull << lane) - 1ull))] = c0;
-            if ((kept >> (lane + 32)) & 1ull) sel[nkept + __popcll(kept & ((1ull << (lane + 32)) - 1ull))] = c1;
-            __syncwarp();
-            // the slots of parity (t & 1) are next overwritten by peers after the cluster barrier of tile t + 1
+            if ((kept >> lane) & 1ull) sel[nkept + __popcll(kept & ((1ull << lane) - 1ull))] = base + lane;
+            if ((kept >> (lane + 32)) & 1ull)
+                sel[nkept + __popcll(kept & ((1ull << (lane + 32)) - 1ull))] = base + lane + 32;
             if (lane == 0) s_nkept = nkept + __popcll(kept);
+            PROF_MARK(1);
+        } else if (t + 1 < tiles) {
+            // ---- worker warps, one tile ahead: this CTA's share of far(t+1) and diag(t+1) ----
+            const int nbase = base + kTile;
+            const int c0 = nbase + lane, c1 = c0 + 32;
+            const float4 b0 = (c0 < n) ? sb[c0] : kNone, b1 = (c1 < n) ? sb[c1] : kNone;
+            const float a0 = (c0 < n) ? sa[c0] : 1.0f, a1 = (c1 < n) ? sa[c1] : 1.0f;
+            bool r0 = false, r1 = false;
+            for (int k = crank * kWorkers + (warp - 1); k < nkept_before; k += csize * kWorkers) {
+                const int ki = sel[k];
+                const float4 bk = sb[ki];
+                const float ak = sa[ki];
+                r0 |= iou_gt(bk, ak, b0, a0, thr);
+                r1 |= iou_gt(bk, ak, b1, a1, thr);
+            }
+            const uint64_t hit = ballot64(r0, r1);
+            if (lane == 0 && hit) or_into(&s_farpart, hit);
+            for (int i = warp - 1; i < kTile; i += kWorkers) {
+                const int ci = nbase + i;
+                const float4 bi = (ci < n) ? sb[ci] : kNone;
+                const float ai = (ci < n) ? sa[ci] : 1.0f;
+                const uint64_t row = ballot64(iou_gt(bi, ai, b0, a0, thr), iou_gt(bi, ai, b1, a1, thr)) & ~(1ull << i);
+                if (lane == 0) diag[q][i] = row;
+            }
+            named_barrier(1, kWorkers * 32);  // all partials of this CTA are in s_farpart
+            if (warp == 1) {
+                const unsigned long long part = s_farpart;
+                __syncwarp();
+                if (lane < csize)
+                    st_async_u64(mapa_u32(smem_u32(&s_far[(t + 1) & 3][crank]), (uint32_t)lane), part,
+                                 mapa_u32(bar_base + 8u * (uint32_t)((t + 1) & 3), (uint32_t)lane));
+                if (lane == 0) s_farpart = 0ull;
+            }
         }
-        PROF_MARK(2);
         __syncthreads();
         nkept = s_nkept;
+        PROF_MARK(2);
+        // ---- near(t+1): boxes kept in tile t x tile t+1, every CTA for itself ----
+        if (t + 1 < tiles && nkept < max_out) {
+            const int nbase = base + kTile;
+            const int c0 = nbase + lane, c1 = c0 + 32;
+            bool r0 = false, r1 = false;
+            if (nkept_before + warp < nkept) {
+                const float4 b0 = (c0 < n) ? sb[c0] : kNone, b1 = (c1 < n) ? sb[c1] : kNone;
+                const float a0 = (c0 < n) ? sa[c0] : 1.0f, a1 = (c1 < n) ? sa[c1] : 1.0f;
+                for (int k = nkept_before + warp; k < nkept; k += kNmsWarps) {
+                    const int ki = sel[k];
+                    const float4 bk = sb[ki];
+                    const float ak = sa[ki];
+                    r0 |= iou_gt(bk, ak, b0, a0, thr);
+                    r1 |= iou_gt(bk, ak, b1, a1, thr);
+                }
+            }
+            const uint64_t hit = ballot64(r0, r1);
+            if (lane == 0 && hit) or_into(&s_near[q], hit);
+        }
+        __syncthreads();
         PROF_MARK(3);
     }
     PROF_DUMP;
-    cluster.sync();  // no CTA leaves while a peer could still address its shared memory
+    // far(t) was sent during the last iteration but never consumed: drain it, so that no st.async is in flight
+    // towards this CTA when it exits; the cluster barrier then keeps every CTA alive until its peers have drained
+    if (warp == 0 && t >= 1 && t < tiles)
+        mbar_wait(bar_base + 8u * (uint32_t)(t & 3), (uint32_t)(((t >> 2) - ((t & 3) == 0 ? 1 : 0)) & 1));
+    cluster.sync();
     if (crank != 0) return;
     const int total = nkept;
     // ---- epilogue: fixed-size padded outputs, no host round trip --------------------------------

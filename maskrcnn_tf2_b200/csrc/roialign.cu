@@ -2,8 +2,8 @@
 //
 // forward = roialign_prep_kernel: FPN level per ROI (L:596-607, utils.py:825-827) and, per level, the first
 //           flattened index at which it appears (tf.unique order over the whole batch, L:613-615, quirk Q2);
-//         + roialign_fwd_kernel (<= 32 output bins per CTA, one warp per bin): each warp turns the four
-//           first-appearance indices into its ROI's map index, then TF CropAndResize bilinear sampling
+//         + roialign_fwd_kernel (one warp per output row of a ROI): each warp turns the four first-appearance
+//           indices into its ROI's map index and walks the bins of its row with TF CropAndResize bilinear sampling
 //           (crop_and_resize_op.cc; called at L:641) with 128-bit channel-vectorised NHWC loads, written straight
 //           into [B,N,ph,pw,C] in input ROI order -- the reference's concat / top_k re-sort / gather passes
 //           (L:644-659) have no counterpart here because nothing is ever out of order.
@@ -28,7 +28,6 @@ struct GradTable {
 
 constexpr int kPrepThreads = 256;
 constexpr int kRoiThreads = 256;   // 8 warps per CTA
-constexpr int kBinsPerCta = 32;    // upper bound; bins are split evenly over ceil(bins / 32) CTAs per ROI
 
 __device__ __forceinline__ int roi_level_of(float4 b, float denom) {
     const float h = __fsub_rn(b.z, b.x);
@@ -61,76 +60,91 @@ roialign_prep_kernel(const float4* __restrict__ boxes, const float* __restrict__
     }
 }
 
-struct RoiParams {
-    const float* base;  // feature map of this ROI's image
-    float y1, x1, y2, x2, hs, ws;
-    int H, W;
+// Sampling geometry of one ROI on its feature map, computed once per warp (all lanes redundantly, no divergence):
+// TF crop_and_resize_op.cc evaluates in_y = y1*(H-1) + y*height_scale per output row (and the box centre when the
+// crop has a single row); y0 / x0 hold the y- and x-independent terms so a bin costs one multiply and one add.
+struct RoiGeom {
+    float y0, x0, hs, ws;  // in_y = y0 + y * hs, in_x = x0 + x * ws (individually rounded, as TF)
+    int H, W, m;
 };
 
-// per-warp (redundant, divergence-free) ROI setup: level -> map index through the first-appearance table
-template <typename Table>
-__device__ __forceinline__ int roi_setup(const float4* __restrict__ boxes, const int32_t* __restrict__ level_ws,
-                                         const int* __restrict__ first, int map_mode, const Table& tbl, int f, int ph,
-                                         int pw, RoiParams& p, size_t& image_offset, int N, int C) {
-    const int level = level_ws[f];
-    int m = level - 2;  // map_mode 1
-    if (map_mode == 0) {  // rank of this level in first-appearance order (L:613-619)
-        const int4 fa = *reinterpret_cast<const int4*>(first);
-        const int mine = (level == 2) ? fa.x : (level == 3) ? fa.y : (level == 4) ? fa.z : fa.w;
-        m = (fa.x < mine) + (fa.y < mine) + (fa.z < mine) + (fa.w < mine);
-    }
-    p.H = (m == 0) ? tbl.H[0] : (m == 1) ? tbl.H[1] : (m == 2) ? tbl.H[2] : tbl.H[3];
-    p.W = (m == 0) ? tbl.W[0] : (m == 1) ? tbl.W[1] : (m == 2) ? tbl.W[2] : tbl.W[3];
-    image_offset = (size_t)(f / N) * p.H * p.W * C;
-    const float4 b = __ldg(boxes + f);
-    p.y1 = b.x; p.x1 = b.y; p.y2 = b.z; p.x2 = b.w;
-    p.hs = crop_scale(b.x, b.z, p.H, ph);
-    p.ws = crop_scale(b.y, b.w, p.W, pw);
-    return m;
+__device__ __forceinline__ RoiGeom roi_geom(float4 b, int m, const int (&Hs)[4], const int (&Ws)[4], int ph, int pw) {
+    RoiGeom g;
+    g.m = m;
+    g.H = (m == 0) ? Hs[0] : (m == 1) ? Hs[1] : (m == 2) ? Hs[2] : Hs[3];
+    g.W = (m == 0) ? Ws[0] : (m == 1) ? Ws[1] : (m == 2) ? Ws[2] : Ws[3];
+    if (ph > 1) { g.hs = crop_scale(b.x, b.z, g.H, ph); g.y0 = __fmul_rn(b.x, (float)(g.H - 1)); }
+    else { g.hs = 0.0f; g.y0 = (float)(0.5 * (double)__fadd_rn(b.x, b.z) * (double)(g.H - 1)); }
+    if (pw > 1) { g.ws = crop_scale(b.y, b.w, g.W, pw); g.x0 = __fmul_rn(b.y, (float)(g.W - 1)); }
+    else { g.ws = 0.0f; g.x0 = (float)(0.5 * (double)__fadd_rn(b.y, b.w) * (double)(g.W - 1)); }
+    return g;
 }
 
-template <int VPL>  // float4 vectors per lane: C == VPL * 128; VPL == 0 -> generic C
-__global__ void __launch_bounds__(kRoiThreads)
+struct AxisTap {
+    int lo, hi;
+    float lerp;
+    bool valid;
+};
+__device__ __forceinline__ AxisTap axis_tap(float c0, float scale, int t, int size) {
+    AxisTap r;
+    const float in = __fadd_rn(c0, __fmul_rn((float)t, scale));
+    r.valid = (in >= 0.0f && in <= (float)(size - 1));
+    const float fl = floorf(in);
+    r.lo = r.valid ? (int)fl : 0;
+    r.hi = r.valid ? (int)ceilf(in) : 0;
+    r.lerp = __fsub_rn(in, fl);
+    return r;
+}
+
+// map index of a ROI from its level and the four first-appearance indices (L:613-619), or level-2 (map_mode 1)
+__device__ __forceinline__ int roi_map_index(int level, const int* __restrict__ first, int map_mode) {
+    if (map_mode != 0) return level - 2;
+    const int4 fa = *reinterpret_cast<const int4*>(first);
+    const int mine = (level == 2) ? fa.x : (level == 3) ? fa.y : (level == 4) ? fa.z : fa.w;
+    return (fa.x < mine) + (fa.y < mine) + (fa.z < mine) + (fa.w < mine);
+}
+
+// One warp per output ROW (roi f, row y): lanes span the channels with 128-bit accesses, the warp walks the pw
+// bins of its row.  VPL = float4 vectors per lane (C == VPL * 128); VPL == 0 -> any C that is a multiple of 4.
+template <int VPL>
+__global__ void __launch_bounds__(kRoiThreads, 5)
 roialign_fwd_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ level_ws,
                     const int* __restrict__ first, int map_mode, MapTable tbl, int C, int N, int ph, int pw,
-                    int chunks, int per_chunk, float* __restrict__ out, int32_t* __restrict__ roi_map) {
-    const int f = blockIdx.x / chunks, chunk = blockIdx.x - f * chunks;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    RoiParams p;
-    size_t off;
-    const int m = roi_setup(boxes, level_ws, first, map_mode, tbl, f, ph, pw, p, off, N, C);
-    p.base = ((m == 0) ? tbl.ptr[0] : (m == 1) ? tbl.ptr[1] : (m == 2) ? tbl.ptr[2] : tbl.ptr[3]) + off;
-    if (chunk == 0 && threadIdx.x == 0) roi_map[f] = m;
-    const int bins = ph * pw;
-    const int bin_end = min(bins, (chunk + 1) * per_chunk);
+                    int total_rows, float* __restrict__ out, int32_t* __restrict__ roi_map) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (kRoiThreads / 32) + (threadIdx.x >> 5);
+    if (row >= total_rows) return;
+    const int f = row / ph, y = row - f * ph;
+    const int m = roi_map_index(level_ws[f], first, map_mode);
+    const RoiGeom g = roi_geom(__ldg(boxes + f), m, tbl.H, tbl.W, ph, pw);
+    if (y == 0 && lane == 0) roi_map[f] = m;
     const int c4 = C >> 2;
-    float4* orow = reinterpret_cast<float4*>(out) + (size_t)f * bins * c4;
-    for (int bin = chunk * per_chunk + warp; bin < bin_end; bin += kRoiThreads / 32) {
-        const int y = bin / pw, x = bin - y * pw;
-        const Tap ty = make_tap(p.y1, p.y2, p.H, ph, y, p.hs);
-        const Tap tx = make_tap(p.x1, p.x2, p.W, pw, x, p.ws);
-        float4* o = orow + (size_t)bin * c4;
+    const float4* img = reinterpret_cast<const float4*>(
+        ((m == 0) ? tbl.ptr[0] : (m == 1) ? tbl.ptr[1] : (m == 2) ? tbl.ptr[2] : tbl.ptr[3]) +
+        (size_t)(f / N) * g.H * g.W * C);
+    float4* o = reinterpret_cast<float4*>(out) + (size_t)row * pw * c4;
+    const AxisTap ty = axis_tap(g.y0, g.hs, y, g.H);
+    const int top = ty.lo * g.W, bot = ty.hi * g.W;  // pixel index of the two sampled rows
+    const float ly = ty.lerp;
+    for (int x = 0; x < pw; ++x, o += c4) {
+        const AxisTap tx = axis_tap(g.x0, g.ws, x, g.W);
         if (!(ty.valid && tx.valid)) {  // extrapolation_value = 0
             for (int v = lane; v < c4; v += 32) __stcs(o + v, make_float4(0.f, 0.f, 0.f, 0.f));
             continue;
         }
-        const float4* tl = reinterpret_cast<const float4*>(p.base + ((size_t)ty.lo * p.W + tx.lo) * C);
-        const float4* tr = reinterpret_cast<const float4*>(p.base + ((size_t)ty.lo * p.W + tx.hi) * C);
-        const float4* bl = reinterpret_cast<const float4*>(p.base + ((size_t)ty.hi * p.W + tx.lo) * C);
-        const float4* br = reinterpret_cast<const float4*>(p.base + ((size_t)ty.hi * p.W + tx.hi) * C);
-        const float lx = tx.lerp, ly = ty.lerp;
+        const float4* tl = img + (size_t)(top + tx.lo) * c4;
+        const float4* tr = img + (size_t)(top + tx.hi) * c4;
+        const float4* bl = img + (size_t)(bot + tx.lo) * c4;
+        const float4* br = img + (size_t)(bot + tx.hi) * c4;
+        const float lx = tx.lerp;
+        auto lerp1 = [&](float a, float b, float c, float d) {
+            const float t = __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), lx));
+            const float u = __fadd_rn(c, __fmul_rn(__fsub_rn(d, c), lx));
+            return __fadd_rn(t, __fmul_rn(__fsub_rn(u, t), ly));
+        };
         auto lerp4 = [&](const float4& a, const float4& b, const float4& c, const float4& d) {
-            float4 r;
-            float top, bot;
-            top = __fadd_rn(a.x, __fmul_rn(__fsub_rn(b.x, a.x), lx)); bot = __fadd_rn(c.x, __fmul_rn(__fsub_rn(d.x, c.x), lx));
-            r.x = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
-            top = __fadd_rn(a.y, __fmul_rn(__fsub_rn(b.y, a.y), lx)); bot = __fadd_rn(c.y, __fmul_rn(__fsub_rn(d.y, c.y), lx));
-            r.y = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
-            top = __fadd_rn(a.z, __fmul_rn(__fsub_rn(b.z, a.z), lx)); bot = __fadd_rn(c.z, __fmul_rn(__fsub_rn(d.z, c.z), lx));
-            r.z = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
-            top = __fadd_rn(a.w, __fmul_rn(__fsub_rn(b.w, a.w), lx)); bot = __fadd_rn(c.w, __fmul_rn(__fsub_rn(d.w, c.w), lx));
-            r.w = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
-            return r;
+            return make_float4(lerp1(a.x, b.x, c.x, d.x), lerp1(a.y, b.y, c.y, d.y), lerp1(a.z, b.z, c.z, d.z),
+                               lerp1(a.w, b.w, c.w, d.w));
         };
         if (VPL > 0) {
             float4 a[VPL > 0 ? VPL : 1], b[VPL > 0 ? VPL : 1], c[VPL > 0 ? VPL : 1], d[VPL > 0 ? VPL : 1];
@@ -152,39 +166,36 @@ __device__ __forceinline__ void red_add_v4(float* addr, float x, float y, float 
 }
 
 // TF CropAndResizeGradImage: dtop = (1-ly) g; tl += (1-lx) dtop; tr += lx dtop; dbot = ly g; bl += (1-lx) dbot;
-// br += lx dbot -- skipped exactly where the forward pass extrapolated.
+// br += lx dbot -- skipped exactly where the forward pass extrapolated.  One warp per output row, as the forward.
 __global__ void __launch_bounds__(kRoiThreads)
 roialign_bwd_kernel(const float4* __restrict__ grad_out, const float4* __restrict__ boxes,
-                    const int32_t* __restrict__ roi_map, GradTable tbl, int C, int N, int ph, int pw, int chunks,
-                    int per_chunk) {
-    const int f = blockIdx.x / chunks, chunk = blockIdx.x - f * chunks;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                    const int32_t* __restrict__ roi_map, GradTable tbl, int C, int N, int ph, int pw, int total_rows) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (kRoiThreads / 32) + (threadIdx.x >> 5);
+    if (row >= total_rows) return;
+    const int f = row / ph, y = row - f * ph;
     const int m = roi_map[f];
-    const int H = (m == 0) ? tbl.H[0] : (m == 1) ? tbl.H[1] : (m == 2) ? tbl.H[2] : tbl.H[3];
-    const int W = (m == 0) ? tbl.W[0] : (m == 1) ? tbl.W[1] : (m == 2) ? tbl.W[2] : tbl.W[3];
-    float* gbase = ((m == 0) ? tbl.ptr[0] : (m == 1) ? tbl.ptr[1] : (m == 2) ? tbl.ptr[2] : tbl.ptr[3]) +
-                   (size_t)(f / N) * H * W * C;
-    const float4 b = __ldg(boxes + f);
-    const float hs = crop_scale(b.x, b.z, H, ph), ws = crop_scale(b.y, b.w, W, pw);
-    const int bins = ph * pw;
-    const int bin_end = min(bins, (chunk + 1) * per_chunk);
+    const RoiGeom g = roi_geom(__ldg(boxes + f), m, tbl.H, tbl.W, ph, pw);
+    const AxisTap ty = axis_tap(g.y0, g.hs, y, g.H);
+    if (!ty.valid) return;
     const int c4 = C >> 2;
-    const float4* grow = grad_out + (size_t)f * bins * c4;
-    for (int bin = chunk * per_chunk + warp; bin < bin_end; bin += kRoiThreads / 32) {
-        const int y = bin / pw, x = bin - y * pw;
-        const Tap ty = make_tap(b.x, b.z, H, ph, y, hs);
-        const Tap tx = make_tap(b.y, b.w, W, pw, x, ws);
-        if (!(ty.valid && tx.valid)) continue;
-        float* tl = gbase + ((size_t)ty.lo * W + tx.lo) * C;
-        float* tr = gbase + ((size_t)ty.lo * W + tx.hi) * C;
-        float* bl = gbase + ((size_t)ty.hi * W + tx.lo) * C;
-        float* br = gbase + ((size_t)ty.hi * W + tx.hi) * C;
-        const float lx = tx.lerp, ly = ty.lerp;
-        const float wy0 = __fsub_rn(1.0f, ly), wx0 = __fsub_rn(1.0f, lx);
+    float* gimg = ((m == 0) ? tbl.ptr[0] : (m == 1) ? tbl.ptr[1] : (m == 2) ? tbl.ptr[2] : tbl.ptr[3]) +
+                  (size_t)(f / N) * g.H * g.W * C;
+    const float4* gr = grad_out + (size_t)row * pw * c4;
+    const int top = ty.lo * g.W, bot = ty.hi * g.W;
+    const float ly = ty.lerp, wy0 = __fsub_rn(1.0f, ty.lerp);
+    for (int x = 0; x < pw; ++x, gr += c4) {
+        const AxisTap tx = axis_tap(g.x0, g.ws, x, g.W);
+        if (!tx.valid) continue;
+        float* tl = gimg + (size_t)(top + tx.lo) * C;
+        float* tr = gimg + (size_t)(top + tx.hi) * C;
+        float* bl = gimg + (size_t)(bot + tx.lo) * C;
+        float* br = gimg + (size_t)(bot + tx.hi) * C;
+        const float lx = tx.lerp, wx0 = __fsub_rn(1.0f, tx.lerp);
         for (int i = lane; i < c4; i += 32) {
-            const float4 g = __ldcs(grow + (size_t)bin * c4 + i);
-            const float4 dt = make_float4(__fmul_rn(wy0, g.x), __fmul_rn(wy0, g.y), __fmul_rn(wy0, g.z), __fmul_rn(wy0, g.w));
-            const float4 db = make_float4(__fmul_rn(ly, g.x), __fmul_rn(ly, g.y), __fmul_rn(ly, g.z), __fmul_rn(ly, g.w));
+            const float4 v = __ldcs(gr + i);
+            const float4 dt = make_float4(__fmul_rn(wy0, v.x), __fmul_rn(wy0, v.y), __fmul_rn(wy0, v.z), __fmul_rn(wy0, v.w));
+            const float4 db = make_float4(__fmul_rn(ly, v.x), __fmul_rn(ly, v.y), __fmul_rn(ly, v.z), __fmul_rn(ly, v.w));
             red_add_v4(tl + 4 * i, __fmul_rn(wx0, dt.x), __fmul_rn(wx0, dt.y), __fmul_rn(wx0, dt.z), __fmul_rn(wx0, dt.w));
             red_add_v4(tr + 4 * i, __fmul_rn(lx, dt.x), __fmul_rn(lx, dt.y), __fmul_rn(lx, dt.z), __fmul_rn(lx, dt.w));
             red_add_v4(bl + 4 * i, __fmul_rn(wx0, db.x), __fmul_rn(wx0, db.y), __fmul_rn(wx0, db.z), __fmul_rn(wx0, db.w));
@@ -225,7 +236,7 @@ MRCNN_EXPORT int mrcnn_roialign_forward(const float* boxes, const float* image_m
     int rc = check_maps((const void* const*)fmaps, H, W, C);
     if (rc != MRCNN_OK) return rc;
     if (B < 1 || N < 1 || ph < 1 || pw < 1 || meta_len < 6 || (map_mode != 0 && map_mode != 1) ||
-        (long long)B * N > INT_MAX / 64 || !(denominator > 0.0f))
+        (long long)B * N * ph > INT_MAX / 2 || !(denominator > 0.0f))
         return MRCNN_ERR_RANGE;
     if (ws_bytes < roialign_ws_bytes(B, N)) return MRCNN_ERR_WORKSPACE;
     if (!aligned16(boxes) || !aligned16(out) || !aligned16(ws)) return MRCNN_ERR_ALIGN;
@@ -239,12 +250,10 @@ MRCNN_EXPORT int mrcnn_roialign_forward(const float* boxes, const float* image_m
     if (e != cudaSuccess) return (int)e;
     roialign_prep_kernel<<<(BN + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, st>>>(
         (const float4*)boxes, image_meta, BN, denominator, level_ws, first, roi_level);
-    const int bins = ph * pw;
-    const int chunks = (bins + kBinsPerCta - 1) / kBinsPerCta;
-    const int per_chunk = (bins + chunks - 1) / chunks;
-    const int grid = BN * chunks;
+    const int total_rows = BN * ph;
+    const int grid = (total_rows + kRoiThreads / 32 - 1) / (kRoiThreads / 32);
 #define MRCNN_FWD(V) roialign_fwd_kernel<V><<<grid, kRoiThreads, 0, st>>>((const float4*)boxes, level_ws, first, \
-        map_mode, tbl, C, N, ph, pw, chunks, per_chunk, out, roi_map)
+        map_mode, tbl, C, N, ph, pw, total_rows, out, roi_map)
     if (C == 128) MRCNN_FWD(1);
     else if (C == 256) MRCNN_FWD(2);
     else if (C == 512) MRCNN_FWD(4);
@@ -259,7 +268,7 @@ MRCNN_EXPORT int mrcnn_roialign_backward(const float* grad_out, const float* box
     if (!grad_out || !boxes || !roi_map) return MRCNN_ERR_NULL;
     int rc = check_maps((const void* const*)grad_fmaps, H, W, C);
     if (rc != MRCNN_OK) return rc;
-    if (B < 1 || N < 1 || ph < 1 || pw < 1 || (long long)B * N > INT_MAX / 64) return MRCNN_ERR_RANGE;
+    if (B < 1 || N < 1 || ph < 1 || pw < 1 || (long long)B * N * ph > INT_MAX / 2) return MRCNN_ERR_RANGE;
     if (!aligned16(boxes) || !aligned16(grad_out)) return MRCNN_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     GradTable tbl;
@@ -268,10 +277,8 @@ MRCNN_EXPORT int mrcnn_roialign_backward(const float* grad_out, const float* box
         cudaError_t e = cudaMemsetAsync(grad_fmaps[l], 0, (size_t)B * H[l] * W[l] * C * sizeof(float), st);
         if (e != cudaSuccess) return (int)e;
     }
-    const int bins = ph * pw;
-    const int chunks = (bins + kBinsPerCta - 1) / kBinsPerCta;
-    const int per_chunk = (bins + chunks - 1) / chunks;
-    roialign_bwd_kernel<<<B * N * chunks, kRoiThreads, 0, st>>>((const float4*)grad_out, (const float4*)boxes, roi_map,
-                                                                tbl, C, N, ph, pw, chunks, per_chunk);
+    const int total_rows = B * N * ph;
+    roialign_bwd_kernel<<<(total_rows + kRoiThreads / 32 - 1) / (kRoiThreads / 32), kRoiThreads, 0, st>>>(
+        (const float4*)grad_out, (const float4*)boxes, roi_map, tbl, C, N, ph, pw, total_rows);
     return last_error();
 }

@@ -14,7 +14,8 @@ constexpr int kChunk = 4096;        // scores per CTA in the streaming passes
 constexpr int kStreamThreads = 256;
 constexpr int kBins = 4096;
 constexpr int kCtl = 16;            // u32 control words per image
-// ctl: 0 done(pass0) 1 done(pass1) 2 prefix12 3 need1 4 prefix24 5 need2 6 n_above 7 n_bound
+// ctl: 0 done(pass0) 1 done(pass1) 2 prefix12 3 need1 4 prefix (12 or 24 bit) 5 need2 6 n_above 7 n_bound
+//      8 skip-pass-1 flag 9 compaction shift (20 or 8)
 
 struct TopkWs {
     uint32_t* hist;   // [B,4096]
@@ -43,7 +44,81 @@ __device__ __forceinline__ uint32_t load_key(const float* __restrict__ scores, i
     return score_key(__ldg(scores + ((size_t)b * A + a) * stride + offset));
 }
 
-template <int PASS>
+// The streaming passes give every thread kPerThread = 16 scores of its CTA's 4096-score chunk.  MODE 2: scores
+// interleaved two per anchor (rpn_probs [B,A,2]), 8 x 128-bit loads per thread; MODE 1: dense [B,A], 4 x 128-bit
+// loads; MODE 0: any stride, scalar loads.  All loads are issued before the first key is consumed.
+constexpr int kPerThread = kChunk / kStreamThreads;
+
+template <int MODE>
+__device__ __forceinline__ void load_chunk(const float* __restrict__ scores, int stride, int offset, int A, int b,
+                                           int chunk, uint32_t (&key)[kPerThread], int (&idx)[kPerThread]) {
+    const int tid = threadIdx.x;
+    const int base = chunk * kChunk;
+    if (MODE == 2) {
+        const float4* p4 = reinterpret_cast<const float4*>(scores + (size_t)b * A * 2) + (base >> 1);
+        float4 q[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int a = base + (it * kStreamThreads + tid) * 2;
+            q[it] = (a + 1 < A) ? __ldg(p4 + it * kStreamThreads + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a + 1 >= A && a < A) {  // odd tail anchor
+                const float* r = scores + ((size_t)b * A + a) * 2;
+                q[it].x = __ldg(r); q[it].y = __ldg(r + 1);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int a = base + (it * kStreamThreads + tid) * 2;
+            idx[2 * it] = (a < A) ? a : -1;
+            idx[2 * it + 1] = (a + 1 < A) ? a + 1 : -1;
+            key[2 * it] = score_key(offset ? q[it].y : q[it].x);
+            key[2 * it + 1] = score_key(offset ? q[it].w : q[it].z);
+        }
+    } else if (MODE == 1) {
+        const float4* p4 = reinterpret_cast<const float4*>(scores + (size_t)b * A) + (base >> 2);
+        float4 q[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int a = base + (it * kStreamThreads + tid) * 4;
+            if (a + 3 < A) q[it] = __ldg(p4 + it * kStreamThreads + tid);
+            else {
+                const float* r = scores + (size_t)b * A;
+                q[it].x = (a < A) ? __ldg(r + a) : 0.f;
+                q[it].y = (a + 1 < A) ? __ldg(r + a + 1) : 0.f;
+                q[it].z = (a + 2 < A) ? __ldg(r + a + 2) : 0.f;
+                q[it].w = 0.f;
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int a = base + (it * kStreamThreads + tid) * 4;
+            const float f[4] = {q[it].x, q[it].y, q[it].z, q[it].w};
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                idx[4 * it + h] = (a + h < A) ? a + h : -1;
+                key[4 * it + h] = score_key(f[h]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int it = 0; it < kPerThread; ++it) {
+            const int a = base + it * kStreamThreads + tid;
+            idx[it] = (a < A) ? a : -1;
+            key[it] = (a < A) ? load_key(scores, stride, offset, A, b, a) : 0u;
+        }
+    }
+}
+
+static int stream_mode(const float* scores, int stride, int A) {
+    if (!aligned16(scores)) return 0;
+    if (stride == 2 && (A % 2) == 0) return 2;
+    if (stride == 1 && (A % 4) == 0) return 1;
+    return 0;
+}
+
+// ctl[8] = 1: the 12-bit boundary bin plus everything above it fits the sort buffer, pass 1 is skipped and the
+// compaction compares 12-bit prefixes (ctl[9] = shift used by the compaction: 20 or 8)
+template <int PASS, int MODE>
 __global__ void __launch_bounds__(kStreamThreads)
 topk_hist_kernel(const float* __restrict__ scores, int stride, int offset, int A, int K, uint32_t* __restrict__ hist,
                  uint32_t* __restrict__ ctl, int chunks) {
@@ -53,17 +128,18 @@ topk_hist_kernel(const float* __restrict__ scores, int stride, int offset, int A
     const int b = blockIdx.y, tid = threadIdx.x;
     uint32_t* gh = hist + (size_t)b * kBins;
     uint32_t* c = ctl + (size_t)b * kCtl;
+    if (PASS == 1 && c[8]) return;
+    uint32_t key[kPerThread];
+    int idx[kPerThread];
+    load_chunk<MODE>(scores, stride, offset, A, b, blockIdx.x, key, idx);
     for (int i = tid; i < kBins; i += kStreamThreads) sh[i] = 0;
     const uint32_t prefix12 = (PASS == 1) ? c[2] : 0u;
     __syncthreads();
-    const int base = blockIdx.x * kChunk;
-#pragma unroll 4
-    for (int it = 0; it < kChunk / kStreamThreads; ++it) {
-        const int a = base + it * kStreamThreads + tid;
-        if (a < A) {
-            const uint32_t key = load_key(scores, stride, offset, A, b, a);
-            if (PASS == 0) atomicAdd(&sh[key >> 20], 1u);
-            else if ((key >> 20) == prefix12) atomicAdd(&sh[(key >> 8) & 0xfffu], 1u);
+#pragma unroll
+    for (int it = 0; it < kPerThread; ++it) {
+        if (idx[it] >= 0) {
+            if (PASS == 0) atomicAdd(&sh[key[it] >> 20], 1u);
+            else if ((key[it] >> 20) == prefix12) atomicAdd(&sh[(key[it] >> 8) & 0xfffu], 1u);
         }
     }
     __syncthreads();
@@ -89,15 +165,25 @@ topk_hist_kernel(const float* __restrict__ scores, int stride, int offset, int A
     uint32_t above = 0;
     for (int u = tid + 1; u < kStreamThreads; ++u) above += part[u];
     if (above < need && need <= above + tsum) {
-        uint32_t acc = above;
+        uint32_t acc = above, in_bin = 0;
         int digit = 0;
 #pragma unroll
         for (int i = kPer - 1; i >= 0; --i) {
-            if (acc < need && need <= acc + loc[i]) { digit = tid * kPer + i; above = acc; }
+            if (acc < need && need <= acc + loc[i]) { digit = tid * kPer + i; above = acc; in_bin = loc[i]; }
             acc += loc[i];
         }
-        if (PASS == 0) { c[2] = (uint32_t)digit; c[3] = need - above; }
-        else { c[4] = (prefix12 << 12) | (uint32_t)digit; c[5] = need - above; }
+        if (PASS == 0) {
+            c[2] = (uint32_t)digit;
+            c[3] = need - above;
+            if (above + in_bin <= (uint32_t)kMaxSort) {  // whole boundary bin fits: no second pass
+                c[4] = (uint32_t)digit; c[5] = need - above; c[8] = 1u; c[9] = 20u;
+            } else {
+                c[9] = 8u;
+            }
+        } else {
+            c[4] = (prefix12 << 12) | (uint32_t)digit;
+            c[5] = need - above;
+        }
     }
     if (PASS == 0) {
 #pragma unroll
@@ -105,8 +191,9 @@ topk_hist_kernel(const float* __restrict__ scores, int stride, int offset, int A
     }
 }
 
-// candidates above the 24-bit prefix go to `above` (all of them are in the top-K), candidates sharing it
-// go to `bound`; slots are reserved per CTA (one global atomic per list per CTA)
+// candidates above the selected prefix go to `above` (all of them are in the top-K), candidates sharing it go to
+// `bound`; slots are reserved per CTA (one global atomic per list per CTA)
+template <int MODE>
 __global__ void __launch_bounds__(kStreamThreads)
 topk_compact_kernel(const float* __restrict__ scores, int stride, int offset, int A, uint32_t* __restrict__ ctl,
                     uint64_t* __restrict__ above, uint64_t* __restrict__ bound) {
@@ -114,18 +201,18 @@ topk_compact_kernel(const float* __restrict__ scores, int stride, int offset, in
     __shared__ uint32_t n_a, n_b, base_a, base_b;
     const int b = blockIdx.y, tid = threadIdx.x;
     uint32_t* c = ctl + (size_t)b * kCtl;
+    uint32_t key[kPerThread];
+    int idx[kPerThread];
+    load_chunk<MODE>(scores, stride, offset, A, b, blockIdx.x, key, idx);
     if (tid == 0) { n_a = 0; n_b = 0; }
-    const uint32_t p24 = c[4];
+    const uint32_t pfx = c[4], shift = c[9];
     __syncthreads();
-    const int base = blockIdx.x * kChunk;
-#pragma unroll 4
-    for (int it = 0; it < kChunk / kStreamThreads; ++it) {
-        const int a = base + it * kStreamThreads + tid;
-        if (a < A) {
-            const uint32_t key = load_key(scores, stride, offset, A, b, a);
-            const uint32_t k24 = key >> 8;
-            if (k24 > p24) stage[atomicAdd(&n_a, 1u)] = make_composite(key, (uint32_t)a);
-            else if (k24 == p24) stage[kChunk - 1 - atomicAdd(&n_b, 1u)] = make_composite(key, (uint32_t)a);
+#pragma unroll
+    for (int it = 0; it < kPerThread; ++it) {
+        if (idx[it] >= 0) {
+            const uint32_t kp = key[it] >> shift;
+            if (kp > pfx) stage[atomicAdd(&n_a, 1u)] = make_composite(key[it], (uint32_t)idx[it]);
+            else if (kp == pfx) stage[kChunk - 1 - atomicAdd(&n_b, 1u)] = make_composite(key[it], (uint32_t)idx[it]);
         }
     }
     __syncthreads();
@@ -143,13 +230,47 @@ topk_compact_kernel(const float* __restrict__ scores, int stride, int offset, in
     }
 }
 
-// one CTA per image: gather the survivors, sort, emit indices (+ fused ProposalLayer gather/decode/clip)
+// one CTA per image: gather the survivors, sort (register-blocked bitonic), emit indices (+ fused ProposalLayer
+// gather / decode / clip)
+template <int E>
+__device__ __forceinline__ void topk_sort_emit(uint64_t* s, int n, bool in_smem, const uint64_t* ga, int n_above,
+                                               const uint64_t* gb, int A, int K, int b, int32_t* idx_out,
+                                               float* vals_out, const TopkDecode& dec, bool has_dec) {
+    const int tid = threadIdx.x;
+    uint64_t v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = tid * E + e;
+        uint64_t c = 0ull;
+        if (i < n) c = in_smem ? s[i] : (i < n_above ? ga[i] : gb[i - n_above]);
+        v[e] = c;
+    }
+    __syncthreads();  // s[] (if used) is consumed; the exchange buffers alias it
+    block_sort_desc_blocked<E>(v, s);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int r = tid * E + e;
+        if (r >= K) continue;
+        const uint32_t a = composite_idx(v[e]);
+        if (idx_out) idx_out[(size_t)b * K + r] = (int32_t)a;
+        if (vals_out) vals_out[(size_t)b * K + r] = key_score(composite_key(v[e]));
+        if (has_dec) {
+            // L:247-261: gather anchors / deltas by index, scale by std_dev (L:238), decode, clip to [0,1]
+            const float4 an = __ldg(dec.anchors + (size_t)b * A + a);
+            const float4 dl = scale_deltas(__ldg(dec.deltas + (size_t)b * A + a), dec.std_dev);
+            const float4 bx = clip_box(apply_box_deltas(an, dl), make_float4(0.f, 0.f, 1.f, 1.f));
+            dec.boxes_sorted[(size_t)b * K + r] = bx;
+            if (dec.pre_nms_boxes) dec.pre_nms_boxes[(size_t)b * K + r] = bx;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(1024)
 topk_final_kernel(const float* __restrict__ scores, int stride, int offset, int A, int K,
                   const uint32_t* __restrict__ ctl, const uint64_t* __restrict__ above,
                   const uint64_t* __restrict__ bound, int32_t* __restrict__ idx_out, float* __restrict__ vals_out,
                   TopkDecode dec, bool has_dec) {
-    extern __shared__ __align__(16) uint64_t s[];  // sort_n composites
+    extern __shared__ __align__(16) uint64_t s[];  // candidate staging (tie-flood path) / sort exchange buffers
     __shared__ uint32_t h8[256];
     __shared__ int warp_sums[32];
     __shared__ int s_total;
@@ -160,12 +281,12 @@ topk_final_kernel(const float* __restrict__ scores, int stride, int offset, int 
     const uint64_t* ga = above + (size_t)b * kMaxSort;
     const uint64_t* gb = bound + (size_t)b * kMaxSort;
     int n;
+    bool in_smem = false;
     if (n_above + n_bound <= (uint32_t)kMaxSort) {
         n = (int)(n_above + n_bound);
-        for (int i = tid; i < (int)n_above; i += blockDim.x) s[i] = ga[i];
-        for (int i = tid; i < (int)n_bound; i += blockDim.x) s[n_above + i] = gb[i];
     } else {
         // tie flood: resolve the last 8 key bits, then take equal keys in index order
+        in_smem = true;
         for (int i = tid; i < (int)n_above; i += blockDim.x) s[i] = ga[i];
         if (tid < 256) h8[tid] = 0;
         if (tid == 0) s_fill = n_above;
@@ -206,24 +327,10 @@ topk_final_kernel(const float* __restrict__ scores, int stride, int offset, int 
         }
         n = K;
     }
-    const int sort_n = max(32, 1 << (32 - __clz(max(n, 1) - 1)));
-    for (int i = n + tid; i < sort_n; i += blockDim.x) s[i] = 0ull;
-    __syncthreads();
-    block_bitonic_sort_desc(s, sort_n);
-    for (int r = tid; r < K; r += blockDim.x) {
-        const uint64_t comp = s[r];
-        const uint32_t a = composite_idx(comp);
-        if (idx_out) idx_out[(size_t)b * K + r] = (int32_t)a;
-        if (vals_out) vals_out[(size_t)b * K + r] = key_score(composite_key(comp));
-        if (has_dec) {
-            // L:247-261: gather anchors / deltas by index, scale by std_dev (L:238), decode, clip to [0,1]
-            const float4 an = __ldg(dec.anchors + (size_t)b * A + a);
-            const float4 dl = scale_deltas(__ldg(dec.deltas + (size_t)b * A + a), dec.std_dev);
-            const float4 bx = clip_box(apply_box_deltas(an, dl), make_float4(0.f, 0.f, 1.f, 1.f));
-            dec.boxes_sorted[(size_t)b * K + r] = bx;
-            if (dec.pre_nms_boxes) dec.pre_nms_boxes[(size_t)b * K + r] = bx;
-        }
-    }
+    if (n <= 1024) topk_sort_emit<1>(s, n, in_smem, ga, (int)n_above, gb, A, K, b, idx_out, vals_out, dec, has_dec);
+    else if (n <= 2048) topk_sort_emit<2>(s, n, in_smem, ga, (int)n_above, gb, A, K, b, idx_out, vals_out, dec, has_dec);
+    else if (n <= 4096) topk_sort_emit<4>(s, n, in_smem, ga, (int)n_above, gb, A, K, b, idx_out, vals_out, dec, has_dec);
+    else topk_sort_emit<8>(s, n, in_smem, ga, (int)n_above, gb, A, K, b, idx_out, vals_out, dec, has_dec);
 }
 
 int launch_topk(const float* scores, int stride, int offset, int B, int A, int K, int32_t* idx, float* vals,
@@ -233,10 +340,18 @@ int launch_topk(const float* scores, int stride, int offset, int B, int A, int K
     if (e != cudaSuccess) return (int)e;
     const int chunks = (A + kChunk - 1) / kChunk;
     const dim3 grid(chunks, B);
-    topk_hist_kernel<0><<<grid, kStreamThreads, 0, stream>>>(scores, stride, offset, A, K, w.hist, w.ctl, chunks);
-    topk_hist_kernel<1><<<grid, kStreamThreads, 0, stream>>>(scores, stride, offset, A, K, w.hist, w.ctl, chunks);
-    topk_compact_kernel<<<grid, kStreamThreads, 0, stream>>>(scores, stride, offset, A, w.ctl, w.above, w.bound);
-    const size_t smem = (size_t)kMaxSort * sizeof(uint64_t);
+    const int mode = stream_mode(scores, stride, A);
+#define MRCNN_STREAM(M)                                                                                             \
+    do {                                                                                                            \
+        topk_hist_kernel<0, M><<<grid, kStreamThreads, 0, stream>>>(scores, stride, offset, A, K, w.hist, w.ctl, chunks); \
+        topk_hist_kernel<1, M><<<grid, kStreamThreads, 0, stream>>>(scores, stride, offset, A, K, w.hist, w.ctl, chunks); \
+        topk_compact_kernel<M><<<grid, kStreamThreads, 0, stream>>>(scores, stride, offset, A, w.ctl, w.above, w.bound); \
+    } while (0)
+    if (mode == 2) MRCNN_STREAM(2);
+    else if (mode == 1) MRCNN_STREAM(1);
+    else MRCNN_STREAM(0);
+#undef MRCNN_STREAM
+    const size_t smem = block_sort_xch_bytes(8);  // >= kMaxSort * 8: also stages the tie-flood candidates
     e = cudaFuncSetAttribute(topk_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     TopkDecode d{};
