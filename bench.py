@@ -31,8 +31,8 @@ WORKLOAD = "configs[1]: COCO-shape ResNet-101 FPN ROI stage, batch 8/GPU, 1024x1
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
     ap.add_argument("--img-size", type=int, default=1024)
@@ -140,7 +140,7 @@ class ClockSampler(threading.Thread):
                     self._sample_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.02)
+            self._stop_evt.wait(0.002)
 
     def stop(self):
         self._stop_evt.set()

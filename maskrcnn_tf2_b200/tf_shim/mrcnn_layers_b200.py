@@ -1,0 +1,146 @@
+"""Drop-in Keras layers for src/layers/mrcnn_layers.py of miguelalejo/maskrcnn_tf2, backed by libmrcnn_roi_ops.so.
+
+NOT IMPORTABLE IN THIS REPOSITORY'S CI (TensorFlow is not installable in the build image).  Where a CUDA-12
+TensorFlow exists: build tf_shim/mrcnn_roi_ops.cc (see its header), put this file on the reference's import path
+and, in src/layers/mrcnn_layers.py, replace the four class bodies by
+
+    from mrcnn_layers_b200 import ProposalLayer, PyramidROIAlign, DetectionLayer, DetectionTargetLayer
+
+Class names, constructor signatures, layer names, `call` argument order and output shapes are the reference's
+(mrcnn_layers.py:202-280, 283-340, 343-531, 553-671), so mask_rcnn_functional() (model.py:398), fpn_classifier_graph
+/ fpn_mask_graph (mrcnn_layers.py:1145,1215) and the ONNX/TRT surgery that keys on layer names
+(inference_optimize.py:455-465) keep working unchanged.  The same classes, over torch tensors, are what this
+repository tests: maskrcnn_tf2_b200/layers.py.
+"""
+import os
+
+import numpy as np
+import tensorflow as tf
+from tensorflow.keras import layers as tfl
+
+_ops = tf.load_op_library(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmrcnn_roi_ops.so"))
+
+
+@tf.RegisterGradient("MrcnnPyramidRoiAlign")
+def _pyramid_roi_align_grad(op, grad_pooled, _grad_roi_map):
+    # boxes and image_meta receive no gradient (tf.stop_gradient at mrcnn_layers.py:628-629)
+    d2, d3, d4, d5 = _ops.mrcnn_pyramid_roi_align_grad(grad_pooled, op.inputs[0], op.outputs[1], *op.inputs[2:6])
+    return [None, None, d2, d3, d4, d5]
+
+
+# The reference back-propagates mrcnn_bbox_loss through the proposals into rpn_bbox (no stop_gradient at
+# mrcnn_layers.py:227).  This op is not differentiable: proposals are constants for the heads, as
+# in matterport/Mask_RCNN.  Listed under "what comes next" in DESIGN.md.
+tf.no_gradient("MrcnnProposal")
+tf.no_gradient("MrcnnDetection")
+tf.no_gradient("MrcnnDetectionTarget")
+
+
+@tf.keras.utils.register_keras_serializable()
+class ProposalLayer(tfl.Layer):
+    def __init__(self, proposal_count, config, name='roi', **kwargs):
+        super(ProposalLayer, self).__init__(name=name, **kwargs)
+        self.config = config
+        self.proposal_count = proposal_count
+        self.nms_threshold = self.config['rpn_nms_threshold']
+
+    def call(self, inputs, **kwargs):
+        return _ops.mrcnn_proposal(inputs[0], inputs[1], inputs[2], proposal_count=self.proposal_count,
+                                   pre_nms_limit=self.config['pre_nms_limit'], nms_threshold=self.nms_threshold,
+                                   std_dev=[float(v) for v in self.config['rpn_bbox_std_dev']])
+
+    def build(self, input_shape):
+        self.built = True
+        super(ProposalLayer, self).build(input_shape)
+
+    def compute_output_shape(self, input_shape):
+        return None, self.proposal_count, 4
+
+    def get_config(self):
+        return super(ProposalLayer, self).get_config()
+
+
+@tf.keras.utils.register_keras_serializable()
+class PyramidROIAlign(tfl.Layer):
+    def __init__(self, pool_shape, denominator=244.0, name='roi_align', **kwargs):
+        super(PyramidROIAlign, self).__init__(name=name, **kwargs)
+        self.pool_shape = tuple(pool_shape)
+        self.denominator = denominator
+
+    def build(self, input_shape):
+        self.built = True
+        super(PyramidROIAlign, self).build(input_shape)
+
+    def call(self, inputs, **kwargs):
+        pooled, _ = _ops.mrcnn_pyramid_roi_align(inputs[0], inputs[1], *inputs[2:6], pool_height=self.pool_shape[0],
+                                                 pool_width=self.pool_shape[1], denominator=self.denominator,
+                                                 map_mode=0)
+        return pooled
+
+    def compute_output_shape(self, input_shape):
+        return input_shape[0][:2] + self.pool_shape + (input_shape[2][-1],)
+
+    def get_config(self):
+        return super(PyramidROIAlign, self).get_config()
+
+
+@tf.keras.utils.register_keras_serializable()
+class DetectionLayer(tfl.Layer):
+    def __init__(self, proposals, detection_min_confidence, detection_max_instances, detection_nms_threshold,
+                 bbox_std_dev, images_per_gpu, batch_size, name='mrcnn_detection', **kwargs):
+        super(DetectionLayer, self).__init__(name=name, **kwargs)
+        self.detection_min_confidence = detection_min_confidence
+        self.detection_max_instances = detection_max_instances
+        self.detection_nms_threshold = detection_nms_threshold
+        self.bbox_std_dev = bbox_std_dev
+        self.batch_size = batch_size
+        self.proposals = proposals
+        self.images_per_gpu = images_per_gpu
+
+    def build(self, input_shape):
+        self.built = True
+        super(DetectionLayer, self).build(input_shape)
+
+    def call(self, inputs, **kwargs):
+        det = _ops.mrcnn_detection(inputs[0], inputs[1], inputs[2], inputs[3],
+                                   min_confidence=float(self.detection_min_confidence or 0.0),
+                                   use_min_confidence=bool(self.detection_min_confidence),
+                                   max_instances=self.detection_max_instances,
+                                   nms_threshold=self.detection_nms_threshold,
+                                   std_dev=[float(v) for v in np.asarray(self.bbox_std_dev)])
+        return tf.reshape(det, [self.batch_size, self.detection_max_instances, 6])
+
+    def compute_output_shape(self, input_shape):
+        return None, self.detection_max_instances, 6
+
+    def get_config(self):
+        return super(DetectionLayer, self).get_config()
+
+
+@tf.keras.utils.register_keras_serializable()
+class DetectionTargetLayer(tfl.Layer):
+    def __init__(self, config, name='proposal_targets', **kwargs):
+        super(DetectionTargetLayer, self).__init__(name=name, **kwargs)
+        self.config = config
+
+    def call(self, inputs, **kwargs):
+        proposals, gt_class_ids, gt_boxes, gt_masks = inputs[0], inputs[1], inputs[2], inputs[3]
+        shape = tf.shape(proposals)[:2]
+        keys = tf.random.uniform(shape, minval=tf.int32.min, maxval=tf.int32.max, dtype=tf.int32)  # tf.random.shuffle
+        cfg = self.config
+        return list(_ops.mrcnn_detection_target(
+            proposals, tf.cast(gt_class_ids, tf.int32), gt_boxes, tf.cast(gt_masks, tf.bool), keys,
+            train_rois_per_image=cfg['train_rois_per_image'], roi_positive_ratio=cfg['roi_positive_ratio'],
+            mask_height=cfg['mask_shape'][0], mask_width=cfg['mask_shape'][1],
+            use_mini_masks=bool(cfg['use_mini_masks']), std_dev=[float(v) for v in cfg['bbox_std_dev']]))
+
+    def compute_output_shape(self, input_shape):
+        T = self.config['train_rois_per_image']
+        return [(None, T, 4), (None, T), (None, T, 4),
+                (None, T, self.config['mask_shape'][0], self.config['mask_shape'][1])]
+
+    def compute_mask(self, inputs, mask=None):
+        return [None, None, None, None]
+
+    def get_config(self):
+        return super(DetectionTargetLayer, self).get_config()
