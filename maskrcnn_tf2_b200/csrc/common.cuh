@@ -328,6 +328,9 @@ struct TopkDecode {              // optional fused epilogue of the top-k final k
     float4* pre_nms_boxes;       // [B,K] optional copy
 };
 __attribute__((visibility("hidden"))) size_t topk_ws_bytes(int B);
+__attribute__((visibility("hidden"))) int launch_topk_cluster(const float* scores, int stride, int offset, int B, int A,
+                                                              int K, int32_t* idx, float* vals, const TopkDecode* dec,
+                                                              cudaStream_t stream);
 __attribute__((visibility("hidden"))) int launch_topk(const float* scores, int stride, int offset, int B, int A, int K,
                                                       int32_t* idx, float* vals, const TopkDecode* dec, void* ws,
                                                       cudaStream_t stream);

@@ -335,6 +335,12 @@ topk_final_kernel(const float* __restrict__ scores, int stride, int offset, int 
 
 int launch_topk(const float* scores, int stride, int offset, int B, int A, int K, int32_t* idx, float* vals,
                 const TopkDecode* dec, void* ws, cudaStream_t stream) {
+#ifndef MRCNN_TOPK_MULTIKERNEL
+    // default: the single cluster kernel of topk_cluster.cu; the multi-kernel pipeline below (global histograms,
+    // candidate lists in the workspace, one sorting CTA per image) is kept as a build-time alternative
+    (void)ws;
+    return launch_topk_cluster(scores, stride, offset, B, A, K, idx, vals, dec, stream);
+#endif
     TopkWs w = carve(ws, B);
     cudaError_t e = cudaMemsetAsync(w.hist, 0, (size_t)B * (kBins + kCtl) * sizeof(uint32_t), stream);
     if (e != cudaSuccess) return (int)e;
