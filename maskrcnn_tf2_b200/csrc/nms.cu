@@ -9,7 +9,8 @@
 //             64-bit partial to every peer with st.async (distributed shared memory store that completes a
 //             transaction on the receiver's mbarrier), so the exchange overlaps the previous tile's resolution;
 //   near(t) = suppressed by the boxes kept in tile t-1: at most 64 x 64 tests, done locally by every CTA;
-//   diag(t) = the tile's own symmetric 64x64 block, computed one iteration ahead by the worker warps;
+//   diag(t) = the tile's own symmetric 64x64 block: row i is computed one iteration ahead by CTA i % CTAs and
+//             sent to every CTA with the same st.async / mbarrier phase as the far partials;
 //   resolve = warp 0 of every CTA decides the tile identically with ballots (fixed point over diag: a candidate is
 //             kept once every earlier overlapping candidate is decided-removed, removed once one is decided-kept)
 //             and appends the kept ones to the CTA's copy of the kept list.
@@ -94,7 +95,9 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
     float4* sb = reinterpret_cast<float4*>(nms_smem);          // [M] min/max-normalised corners
     float* sa = reinterpret_cast<float*>(sb + M);               // [M] areas
     int32_t* sel = reinterpret_cast<int32_t*>(sa + M);          // [min(max_out, M)] kept candidate positions
-    __shared__ uint64_t diag[2][kTile];                         // [tile parity]
+    __shared__ unsigned long long s_diag[4][kTile];             // [tile & 3][row]: symmetric in-tile block; row i of
+                                                                // tile t+1 is computed by CTA i % csize one tile
+                                                                // ahead and sent to every CTA with st.async
     __shared__ unsigned long long s_far[4][8];                  // [tile & 3][source CTA], written by the peers
     __shared__ unsigned long long s_near[2];                    // [tile parity]
     __shared__ unsigned long long s_farpart;                    // this CTA's partial of far(t+1)
@@ -116,7 +119,8 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
         sa[i] = a;
     }
     const uint32_t bar_base = smem_u32(&s_bar[0]);
-    const uint32_t far_bytes = (uint32_t)csize * 8u;  // one 64-bit partial from every CTA of the cluster
+    // per tile every CTA receives one 64-bit far partial from each CTA and the 64 rows of the tile's diag block
+    const uint32_t far_bytes = (uint32_t)csize * 8u + (uint32_t)kTile * 8u;
     if (tid == 0) {
         s_near[0] = 0ull; s_near[1] = 0ull; s_farpart = 0ull; s_nkept = 0;
         for (int j = 0; j < 4; ++j) mbar_init(bar_base + 8u * j, 1);
@@ -134,7 +138,7 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
             const float4 bi = (i < n) ? sb[i] : kNone;
             const float ai = (i < n) ? sa[i] : 1.0f;
             const uint64_t row = ballot64(iou_gt(bi, ai, b0, a0, thr), iou_gt(bi, ai, b1, a1, thr)) & ~(1ull << i);
-            if (lane == 0) diag[0][i] = row;
+            if (lane == 0) s_diag[0][i] = row;
         }
     }
     cluster.sync();  // every CTA of the cluster is resident and its mbarriers are initialised before any st.async
@@ -162,8 +166,8 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
             const int rem = n - base;
             const uint64_t validbits = (rem >= kTile) ? ~0ull : ((1ull << rem) - 1ull);
             uint64_t und = ~removed & validbits, kept = 0;
-            const uint64_t blk0 = diag[p][lane] & ((1ull << lane) - 1ull);            // earlier overlapping candidates
-            const uint64_t blk1 = diag[p][lane + 32] & ((1ull << (lane + 32)) - 1ull);
+            const uint64_t blk0 = (uint64_t)s_diag[t & 3][lane] & ((1ull << lane) - 1ull);  // earlier overlapping candidates
+            const uint64_t blk1 = (uint64_t)s_diag[t & 3][lane + 32] & ((1ull << (lane + 32)) - 1ull);
             while (und) {
                 const bool u0 = (und >> lane) & 1ull, u1 = (und >> (lane + 32)) & 1ull;
                 const bool d0 = u0 && (blk0 & kept), d1 = u1 && (blk1 & kept);              // removed
@@ -195,12 +199,15 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
             }
             const uint64_t hit = ballot64(r0, r1);
             if (lane == 0 && hit) or_into(&s_farpart, hit);
-            for (int i = warp - 1; i < kTile; i += kWorkers) {
+            const uint32_t bar_n = bar_base + 8u * (uint32_t)((t + 1) & 3);
+            for (int i = crank + csize * (warp - 1); i < kTile; i += csize * kWorkers) {  // this CTA's rows of diag(t+1)
                 const int ci = nbase + i;
                 const float4 bi = (ci < n) ? sb[ci] : kNone;
                 const float ai = (ci < n) ? sa[ci] : 1.0f;
                 const uint64_t row = ballot64(iou_gt(bi, ai, b0, a0, thr), iou_gt(bi, ai, b1, a1, thr)) & ~(1ull << i);
-                if (lane == 0) diag[q][i] = row;
+                if (lane < csize)
+                    st_async_u64(mapa_u32(smem_u32(&s_diag[(t + 1) & 3][i]), (uint32_t)lane), row,
+                                 mapa_u32(bar_n, (uint32_t)lane));
             }
             named_barrier(1, kWorkers * 32);  // all partials of this CTA are in s_farpart
             if (warp == 1) {
