@@ -216,6 +216,26 @@ __device__ __forceinline__ void block_sort_desc_blocked(uint64_t (&v)[E], uint64
         }
     }
 }
+// Sort `sort_n` (power of two, 32..8192) composites held in shared memory `s`, descending, with a 1024-thread
+// block.  Arrays of >= 1024 keys go through the register-blocked network (xch = 2*1024*(E+2) u64 of scratch shared
+// memory that may NOT alias `s`); smaller ones use the in-place shared-memory network.
+__device__ __forceinline__ void block_sort_desc_any(uint64_t* s, int sort_n, uint64_t* xch) {
+    const int t = threadIdx.x;
+    if (sort_n < 1024) { block_bitonic_sort_desc(s, sort_n); return; }
+#define MRCNN_SORT_CASE(E)                                   \
+    {                                                        \
+        uint64_t v[E];                                       \
+        _Pragma("unroll") for (int e = 0; e < E; ++e) v[e] = s[t * E + e]; \
+        block_sort_desc_blocked<E>(v, xch);                  \
+        _Pragma("unroll") for (int e = 0; e < E; ++e) s[t * E + e] = v[e]; \
+        __syncthreads();                                     \
+    }
+    if (sort_n == 1024) MRCNN_SORT_CASE(1)
+    else if (sort_n == 2048) MRCNN_SORT_CASE(2)
+    else if (sort_n == 4096) MRCNN_SORT_CASE(4)
+    else MRCNN_SORT_CASE(8)
+#undef MRCNN_SORT_CASE
+}
 constexpr size_t block_sort_xch_bytes(int E) { return 2 * 1024 * (size_t)(E + 2) * sizeof(uint64_t); }
 
 // ---------------------------------------------------------------------------------------------------

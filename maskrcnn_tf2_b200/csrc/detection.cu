@@ -75,7 +75,7 @@ detection_sort_kernel(const float4* __restrict__ refined, const uint32_t* __rest
     }
     if (local) atomicAdd(&s_n, local);
     __syncthreads();
-    block_bitonic_sort_desc(s, sort_n);
+    block_sort_desc_any(s, sort_n, s + sort_n);
     const int nc = s_n;
     for (int r = tid; r < nc; r += blockDim.x) {
         const int i = (int)composite_idx(s[r]);
@@ -139,7 +139,7 @@ MRCNN_EXPORT int mrcnn_detection_forward(const float* rois, const float* probs, 
                                                                   use_min_conf, w.refined, w.scores, w.class_ids,
                                                                   w.keep_key);
     const int sort_n = next_pow2(N < 32 ? 32 : N);
-    const size_t smem = (size_t)sort_n * sizeof(uint64_t);
+    const size_t smem = (size_t)sort_n * sizeof(uint64_t) + (sort_n >= 1024 ? block_sort_xch_bytes(sort_n / 1024) : 0);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(detection_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;

@@ -337,7 +337,7 @@ nms_sort_kernel(const float4* __restrict__ boxes, const float* __restrict__ scor
     }
     if (local) atomicAdd(&s_n, local);
     __syncthreads();
-    block_bitonic_sort_desc(s, sort_n);
+    block_sort_desc_any(s, sort_n, s + sort_n);
     const int nc = s_n;
     for (int r = tid; r < M; r += blockDim.x) {
         if (r < nc) {
@@ -390,7 +390,7 @@ MRCNN_EXPORT int mrcnn_nms_forward(const float* boxes, const float* scores, cons
     w.orig_idx = (int32_t*)p;    p += align_up((size_t)B * M * sizeof(int32_t), 256);
     w.ncand = (int32_t*)p;
     const int sort_n = next_pow2(M < 32 ? 32 : M);
-    const size_t smem = (size_t)sort_n * sizeof(uint64_t);
+    const size_t smem = (size_t)sort_n * sizeof(uint64_t) + (sort_n >= 1024 ? block_sort_xch_bytes(sort_n / 1024) : 0);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;

@@ -166,24 +166,93 @@ __device__ __forceinline__ void red_add_v4(float* addr, float x, float y, float 
 }
 
 // TF CropAndResizeGradImage: dtop = (1-ly) g; tl += (1-lx) dtop; tr += lx dtop; dbot = ly g; bl += (1-lx) dbot;
-// br += lx dbot -- skipped exactly where the forward pass extrapolated.  One warp per output row, as the forward.
+// br += lx dbot -- skipped exactly where the forward pass extrapolated.
+// One CTA per (ROI, group of <= 8 output rows), one warp per row, lanes over channels.  Contention control:
+//   * a corner whose weight is exactly 0 is not touched (finite gradients: adding 0 changes nothing);
+//   * bins of a row that hit the same pixels (zero width scale) are summed in registers before one reduction;
+//   * ROIs whose taps are constant in both axes (zero-padded ROIs: every bin samples pixel (0,0), quirk Q5) are
+//     summed across the CTA's rows in shared memory and issue ONE reduction per CTA and corner, which keeps the
+//     thousands of padded rows of a training batch from serialising on a single L2 line.
+__device__ __forceinline__ void scatter_corners(float* tl, float* tr, float* bl, float* br, int i, const float4& v,
+                                                float wy0, float ly, float wx0, float lx) {
+    const float4 dt = make_float4(__fmul_rn(wy0, v.x), __fmul_rn(wy0, v.y), __fmul_rn(wy0, v.z), __fmul_rn(wy0, v.w));
+    const float4 db = make_float4(__fmul_rn(ly, v.x), __fmul_rn(ly, v.y), __fmul_rn(ly, v.z), __fmul_rn(ly, v.w));
+    if (wy0 != 0.0f && wx0 != 0.0f)
+        red_add_v4(tl + 4 * i, __fmul_rn(wx0, dt.x), __fmul_rn(wx0, dt.y), __fmul_rn(wx0, dt.z), __fmul_rn(wx0, dt.w));
+    if (wy0 != 0.0f && lx != 0.0f)
+        red_add_v4(tr + 4 * i, __fmul_rn(lx, dt.x), __fmul_rn(lx, dt.y), __fmul_rn(lx, dt.z), __fmul_rn(lx, dt.w));
+    if (ly != 0.0f && wx0 != 0.0f)
+        red_add_v4(bl + 4 * i, __fmul_rn(wx0, db.x), __fmul_rn(wx0, db.y), __fmul_rn(wx0, db.z), __fmul_rn(wx0, db.w));
+    if (ly != 0.0f && lx != 0.0f)
+        red_add_v4(br + 4 * i, __fmul_rn(lx, db.x), __fmul_rn(lx, db.y), __fmul_rn(lx, db.z), __fmul_rn(lx, db.w));
+}
+
 __global__ void __launch_bounds__(kRoiThreads)
 roialign_bwd_kernel(const float4* __restrict__ grad_out, const float4* __restrict__ boxes,
-                    const int32_t* __restrict__ roi_map, GradTable tbl, int C, int N, int ph, int pw, int total_rows) {
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (kRoiThreads / 32) + (threadIdx.x >> 5);
-    if (row >= total_rows) return;
-    const int f = row / ph, y = row - f * ph;
+                    const int32_t* __restrict__ roi_map, GradTable tbl, int C, int N, int ph, int pw, int groups,
+                    int rows_per_group) {
+    extern __shared__ __align__(16) float4 s_acc[];  // [8 warps][C/4], constant-tap ROIs only
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int f = blockIdx.x / groups, grp = blockIdx.x - f * groups;
+    const int y = grp * rows_per_group + warp;
+    const bool has_row = (warp < rows_per_group) && (y < ph);
     const int m = roi_map[f];
     const RoiGeom g = roi_geom(__ldg(boxes + f), m, tbl.H, tbl.W, ph, pw);
-    const AxisTap ty = axis_tap(g.y0, g.hs, y, g.H);
-    if (!ty.valid) return;
     const int c4 = C >> 2;
     float* gimg = ((m == 0) ? tbl.ptr[0] : (m == 1) ? tbl.ptr[1] : (m == 2) ? tbl.ptr[2] : tbl.ptr[3]) +
                   (size_t)(f / N) * g.H * g.W * C;
-    const float4* gr = grad_out + (size_t)row * pw * c4;
+    const bool constant = (g.hs == 0.0f && g.ws == 0.0f);  // CTA-uniform
+    const AxisTap ty = axis_tap(g.y0, g.hs, has_row ? y : 0, g.H);
+    const float4* gr = grad_out + ((size_t)f * ph + (has_row ? y : 0)) * pw * c4;
     const int top = ty.lo * g.W, bot = ty.hi * g.W;
     const float ly = ty.lerp, wy0 = __fsub_rn(1.0f, ty.lerp);
+    if (constant) {
+        const AxisTap tx = axis_tap(g.x0, g.ws, 0, g.W);
+        for (int i = lane; i < c4; i += 32) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_row)
+                for (int x = 0; x < pw; ++x) {
+                    const float4 v = __ldcs(gr + (size_t)x * c4 + i);
+                    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                }
+            s_acc[warp * c4 + i] = acc;
+        }
+        __syncthreads();
+        if (!(ty.valid && tx.valid)) return;  // uniform: the same tap for every bin of the ROI
+        float* tl = gimg + (size_t)(top + tx.lo) * C;
+        float* tr = gimg + (size_t)(top + tx.hi) * C;
+        float* bl = gimg + (size_t)(bot + tx.lo) * C;
+        float* br = gimg + (size_t)(bot + tx.hi) * C;
+        const float lx = tx.lerp, wx0 = __fsub_rn(1.0f, tx.lerp);
+        for (int i = threadIdx.x; i < c4; i += kRoiThreads) {
+            float4 acc = s_acc[i];
+            for (int w = 1; w < kRoiThreads / 32; ++w) {
+                const float4 v = s_acc[w * c4 + i];
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            scatter_corners(tl, tr, bl, br, i, acc, wy0, ly, wx0, lx);
+        }
+        return;
+    }
+    if (!has_row || !ty.valid) return;
+    if (g.ws == 0.0f) {  // every bin of the row hits the same pixels: sum the row first
+        const AxisTap tx = axis_tap(g.x0, g.ws, 0, g.W);
+        if (!tx.valid) return;
+        float* tl = gimg + (size_t)(top + tx.lo) * C;
+        float* tr = gimg + (size_t)(top + tx.hi) * C;
+        float* bl = gimg + (size_t)(bot + tx.lo) * C;
+        float* br = gimg + (size_t)(bot + tx.hi) * C;
+        const float lx = tx.lerp, wx0 = __fsub_rn(1.0f, tx.lerp);
+        for (int i = lane; i < c4; i += 32) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int x = 0; x < pw; ++x) {
+                const float4 v = __ldcs(gr + (size_t)x * c4 + i);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            scatter_corners(tl, tr, bl, br, i, acc, wy0, ly, wx0, lx);
+        }
+        return;
+    }
     for (int x = 0; x < pw; ++x, gr += c4) {
         const AxisTap tx = axis_tap(g.x0, g.ws, x, g.W);
         if (!tx.valid) continue;
@@ -192,15 +261,7 @@ roialign_bwd_kernel(const float4* __restrict__ grad_out, const float4* __restric
         float* bl = gimg + (size_t)(bot + tx.lo) * C;
         float* br = gimg + (size_t)(bot + tx.hi) * C;
         const float lx = tx.lerp, wx0 = __fsub_rn(1.0f, tx.lerp);
-        for (int i = lane; i < c4; i += 32) {
-            const float4 v = __ldcs(gr + i);
-            const float4 dt = make_float4(__fmul_rn(wy0, v.x), __fmul_rn(wy0, v.y), __fmul_rn(wy0, v.z), __fmul_rn(wy0, v.w));
-            const float4 db = make_float4(__fmul_rn(ly, v.x), __fmul_rn(ly, v.y), __fmul_rn(ly, v.z), __fmul_rn(ly, v.w));
-            red_add_v4(tl + 4 * i, __fmul_rn(wx0, dt.x), __fmul_rn(wx0, dt.y), __fmul_rn(wx0, dt.z), __fmul_rn(wx0, dt.w));
-            red_add_v4(tr + 4 * i, __fmul_rn(lx, dt.x), __fmul_rn(lx, dt.y), __fmul_rn(lx, dt.z), __fmul_rn(lx, dt.w));
-            red_add_v4(bl + 4 * i, __fmul_rn(wx0, db.x), __fmul_rn(wx0, db.y), __fmul_rn(wx0, db.z), __fmul_rn(wx0, db.w));
-            red_add_v4(br + 4 * i, __fmul_rn(lx, db.x), __fmul_rn(lx, db.y), __fmul_rn(lx, db.z), __fmul_rn(lx, db.w));
-        }
+        for (int i = lane; i < c4; i += 32) scatter_corners(tl, tr, bl, br, i, __ldcs(gr + i), wy0, ly, wx0, lx);
     }
 }
 
@@ -268,7 +329,7 @@ MRCNN_EXPORT int mrcnn_roialign_backward(const float* grad_out, const float* box
     if (!grad_out || !boxes || !roi_map) return MRCNN_ERR_NULL;
     int rc = check_maps((const void* const*)grad_fmaps, H, W, C);
     if (rc != MRCNN_OK) return rc;
-    if (B < 1 || N < 1 || ph < 1 || pw < 1 || (long long)B * N * ph > INT_MAX / 2) return MRCNN_ERR_RANGE;
+    if (B < 1 || N < 1 || ph < 1 || pw < 1 || (long long)B * N * ph > INT_MAX / 2 || C > 8192) return MRCNN_ERR_RANGE;
     if (!aligned16(boxes) || !aligned16(grad_out)) return MRCNN_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     GradTable tbl;
@@ -277,8 +338,14 @@ MRCNN_EXPORT int mrcnn_roialign_backward(const float* grad_out, const float* box
         cudaError_t e = cudaMemsetAsync(grad_fmaps[l], 0, (size_t)B * H[l] * W[l] * C * sizeof(float), st);
         if (e != cudaSuccess) return (int)e;
     }
-    const int total_rows = B * N * ph;
-    roialign_bwd_kernel<<<(total_rows + kRoiThreads / 32 - 1) / (kRoiThreads / 32), kRoiThreads, 0, st>>>(
-        (const float4*)grad_out, (const float4*)boxes, roi_map, tbl, C, N, ph, pw, total_rows);
+    const int groups = (ph + kRoiThreads / 32 - 1) / (kRoiThreads / 32);
+    const int rows_per_group = (ph + groups - 1) / groups;  // 7x7 -> 1 x 7 rows, 14x14 -> 2 x 7, 28x28 -> 4 x 7
+    const size_t smem = (size_t)(kRoiThreads / 32) * C * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(roialign_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    roialign_bwd_kernel<<<B * N * groups, kRoiThreads, smem, st>>>((const float4*)grad_out, (const float4*)boxes, roi_map,
+                                                                  tbl, C, N, ph, pw, groups, rows_per_group);
     return last_error();
 }

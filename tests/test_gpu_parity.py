@@ -263,6 +263,8 @@ def test_roialign_forward_coco_shape_one_image(F, orc, dev):
     (2, 40, 256, (14, 14), (32, 16, 8, 4), 0, 6),
     (1, 30, 24, (7, 7), (16, 8, 4, 2), 4, 5),
     (1, 400, 256, (7, 7), (8, 4, 4, 2), 0, 0),     # heavy fan-in: 400 ROIs accumulate into tiny maps
+    (2, 600, 256, (14, 14), (16, 8, 4, 2), 520, 0),  # mostly zero-padded ROIs: all their bins hit pixel (0,0)
+    (1, 64, 128, (28, 28), (16, 8, 4, 2), 10, 6),
 ])
 def test_roialign_backward_within_tolerance(F, orc, dev, B, Nr, C, pool, sizes, pad, wild):
     rng = np.random.default_rng(110 + Nr)
