@@ -3,17 +3,19 @@
 //
 // nms_lazy_kernel: a thread-block CLUSTER of 1..8 CTAs (1024 threads each) per image; every CTA stages the image's
 // candidate boxes (already in candidate order) in its own shared memory and walks the candidates in 64-box tiles.
-// Only the IoU tests that can matter are evaluated, and the cluster never blocks on a barrier inside the loop:
-//   far(t)  = tile t's candidates suppressed by boxes kept in tiles <= t-2.  The kept list is dealt round-robin to
-//             the 31 worker warps of every CTA of the cluster one iteration ahead of its use; each CTA sends its
-//             64-bit partial to every peer with st.async (distributed shared memory store that completes a
-//             transaction on the receiver's mbarrier), so the exchange overlaps the previous tile's resolution;
-//   near(t) = suppressed by the boxes kept in tile t-1: at most 64 x 64 tests, done locally by every CTA;
-//   diag(t) = the tile's own symmetric 64x64 block: row i is computed one iteration ahead by CTA i % CTAs and
-//             sent to every CTA with the same st.async / mbarrier phase as the far partials;
-//   resolve = warp 0 of every CTA decides the tile identically with ballots (fixed point over diag: a candidate is
-//             kept once every earlier overlapping candidate is decided-removed, removed once one is decided-kept)
-//             and appends the kept ones to the CTA's copy of the kept list.
+// Only the IoU tests that can matter are evaluated, and neither the cluster nor the CTA blocks on a full barrier
+// inside the loop.  Each CTA is warp-specialised:
+//   worker warps (16..31), up to two tiles ahead of the resolvers:
+//     far(u)  = tile u's candidates suppressed by boxes kept in tiles <= u-2: the kept list is dealt round-robin to
+//               the worker warps of every CTA of the cluster; each CTA sends its 64-bit partial to every peer with
+//               st.async (a distributed-shared-memory store that completes a transaction on the receiver's mbarrier);
+//     diag(u) = the tile's own symmetric 64x64 block: row i is computed by CTA i % CTAs and sent the same way;
+//   resolver warps (0..15), every CTA for itself, identically:
+//     near(u) = suppressed by the boxes kept in tile u-1 (<= 64 x 64 tests);
+//     resolve = warp 0 waits for the tile's mbarrier phase and decides the tile with ballots (fixed point over diag:
+//               a candidate is kept once every earlier overlapping candidate is decided-removed, removed once one is
+//               decided-kept), appends the kept ones to the CTA's copy of the kept list and releases the workers
+//               for tile u+2 through a named barrier.
 // Work is sum_t kept(t) * 64 + M * 64 pair tests instead of the M^2/2 of a full bit matrix, nothing is written to
 // global memory but the result, and the loop stops as soon as max_out boxes are kept.
 #include <cooperative_groups.h>
@@ -41,7 +43,8 @@ __device__ long long g_nms_prof[8];
 constexpr int kTile = 64;
 constexpr int kNmsThreads = 1024;
 constexpr int kNmsWarps = kNmsThreads / 32;
-constexpr int kWorkers = kNmsWarps - 1;  // warps 1..31 run one tile ahead of warp 0
+constexpr int kResolvers = 16;                     // warps 0..15: near + resolve
+constexpr int kWorkers = kNmsWarps - kResolvers;   // warps 16..31: far + diag, ahead of the resolvers
 
 static size_t nms_smem_bytes(int M, int max_out) {
     return (size_t)M * (sizeof(float4) + sizeof(float)) + (size_t)(max_out < M ? max_out : M) * sizeof(int32_t);
@@ -95,15 +98,14 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
     float4* sb = reinterpret_cast<float4*>(nms_smem);          // [M] min/max-normalised corners
     float* sa = reinterpret_cast<float*>(sb + M);               // [M] areas
     int32_t* sel = reinterpret_cast<int32_t*>(sa + M);          // [min(max_out, M)] kept candidate positions
-    __shared__ unsigned long long s_diag[4][kTile];             // [tile & 3][row]: symmetric in-tile block; row i of
-                                                                // tile t+1 is computed by CTA i % csize one tile
-                                                                // ahead and sent to every CTA with st.async
+    __shared__ unsigned long long s_diag[4][kTile];             // [tile & 3][row]: symmetric in-tile block, from the peers
     __shared__ unsigned long long s_far[4][8];                  // [tile & 3][source CTA], written by the peers
     __shared__ unsigned long long s_near[2];                    // [tile parity]
-    __shared__ unsigned long long s_farpart;                    // this CTA's partial of far(t+1)
+    __shared__ unsigned long long s_farpart[2];                 // [tile parity] this CTA's partial of far(u)
     __shared__ __align__(8) uint64_t s_bar[4];                  // mbarriers, [tile & 3]: a peer can run at most two
                                                                 // tiles ahead, so four phases never alias
-    __shared__ int s_nkept;
+    __shared__ int s_nk[4];                                     // [tile & 3] kept count after that tile's resolve
+    __shared__ int s_final[2];
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
     const int b = blockIdx.x / csize, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -122,13 +124,13 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
     // per tile every CTA receives one 64-bit far partial from each CTA and the 64 rows of the tile's diag block
     const uint32_t far_bytes = (uint32_t)csize * 8u + (uint32_t)kTile * 8u;
     if (tid == 0) {
-        s_near[0] = 0ull; s_near[1] = 0ull; s_farpart = 0ull; s_nkept = 0;
-        for (int j = 0; j < 4; ++j) mbar_init(bar_base + 8u * j, 1);
+        s_near[0] = 0ull; s_near[1] = 0ull; s_farpart[0] = 0ull; s_farpart[1] = 0ull;
+        for (int j = 0; j < 4; ++j) { mbar_init(bar_base + 8u * j, 1); s_nk[j] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int j = 1; j < 4; ++j) mbar_arm(bar_base + 8u * j, far_bytes);  // far(1..3); far(4) is armed in tile 0
+        for (int j = 1; j < 4; ++j) mbar_arm(bar_base + 8u * j, far_bytes);  // tiles 1..3; tile 4 is armed in tile 0
     }
     __syncthreads();
-    // diag(0): rows 2*warp, 2*warp+1 of tile 0
+    // diag(0): rows 2*warp, 2*warp+1 of tile 0, every CTA for itself
     {
         const float4 b0 = (lane < n) ? sb[lane] : kNone, b1 = (lane + 32 < n) ? sb[lane + 32] : kNone;
         const float a0 = (lane < n) ? sa[lane] : 1.0f, a1 = (lane + 32 < n) ? sa[lane + 32] : 1.0f;
@@ -144,53 +146,88 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
     cluster.sync();  // every CTA of the cluster is resident and its mbarriers are initialised before any st.async
     int nkept = 0, t = 0;
     PROF_DECL;
-    for (; t < tiles && nkept < max_out; ++t) {
-        PROF_TILE;
-        const int p = t & 1, q = p ^ 1;
-        const int base = t * kTile;
-        const int nkept_before = nkept;  // boxes kept in tiles <= t-1
-        if (warp == 0) {
-            // ---- far(t) (from the peers) | near(t) (local) -> resolve tile t ----
-            uint64_t removed = (uint64_t)s_near[p];
-            const uint32_t bar_t = bar_base + 8u * (uint32_t)(t & 3);
-            if (t >= 1) {  // barrier (t & 3) serves tiles t&3, t&3 + 4, ...; tile 0 has no far set
-                mbar_wait(bar_t, (uint32_t)(((t >> 2) - ((t & 3) == 0 ? 1 : 0)) & 1));
-                for (int r = 0; r < csize; ++r) removed |= (uint64_t)s_far[t & 3][r];
+    if (warp < kResolvers) {
+        // ================= resolver warps: near(t) + resolve(t), tile by tile =================
+        for (; t < tiles && nkept < max_out; ++t) {
+            PROF_TILE;
+            const int p = t & 1;
+            const int base = t * kTile;
+            const int nkept_before = nkept;  // boxes kept in tiles <= t-1
+            if (warp == 0) {
+                uint64_t removed = (uint64_t)s_near[p];
+                const uint32_t bar_t = bar_base + 8u * (uint32_t)(t & 3);
+                if (t >= 1) {  // barrier (t & 3) serves tiles t&3, t&3 + 4, ...; tile 0 has no far set
+                    mbar_wait(bar_t, (uint32_t)(((t >> 2) - ((t & 3) == 0 ? 1 : 0)) & 1));
+                    for (int r = 0; r < csize; ++r) removed |= (uint64_t)s_far[t & 3][r];
+                }
+                PROF_MARK(0);
+                const int rem = n - base;
+                const uint64_t validbits = (rem >= kTile) ? ~0ull : ((1ull << rem) - 1ull);
+                uint64_t und = ~removed & validbits, kept = 0;
+                const uint64_t blk0 = (uint64_t)s_diag[t & 3][lane] & ((1ull << lane) - 1ull);  // earlier overlapping candidates
+                const uint64_t blk1 = (uint64_t)s_diag[t & 3][lane + 32] & ((1ull << (lane + 32)) - 1ull);
+                while (und) {
+                    const bool u0 = (und >> lane) & 1ull, u1 = (und >> (lane + 32)) & 1ull;
+                    const bool d0 = u0 && (blk0 & kept), d1 = u1 && (blk1 & kept);              // removed
+                    const bool k0 = u0 && !d0 && !(blk0 & und), k1 = u1 && !d1 && !(blk1 & und);  // kept
+                    const uint64_t nk = ballot64(k0, k1), nd = ballot64(d0, d1);
+                    kept |= nk;
+                    und &= ~(nk | nd);
+                }
+                const int room = max_out - nkept;
+                while (__popcll(kept) > room) kept &= ~(1ull << (63 - __clzll(kept)));
+                if ((kept >> lane) & 1ull) sel[nkept + __popcll(kept & ((1ull << lane) - 1ull))] = base + lane;
+                if ((kept >> (lane + 32)) & 1ull)
+                    sel[nkept + __popcll(kept & ((1ull << (lane + 32)) - 1ull))] = base + lane + 32;
+                __syncwarp();
+                if (lane == 0) {
+                    s_nk[t & 3] = nkept + __popcll(kept);
+                    s_near[p] = 0ull;            // next accumulated for tile t+2, two resolver barriers later
+                    mbar_arm(bar_t, far_bytes);  // phase of tile t+4
+                }
+                __threadfence_block();
+                // release the workers for tile t+2 (they need the kept list through tile t)
+                if (t + 2 < tiles) asm volatile("bar.arrive %0, %1;" ::"r"(3 + p), "r"(32 + kWorkers * 32) : "memory");
+                PROF_MARK(1);
             }
-            __syncwarp();
-            if (lane == 0) {
-                s_near[p] = 0ull;            // next accumulated for tile t+2, after a CTA barrier
-                mbar_arm(bar_t, far_bytes);  // far(t+4) arrives during iteration t+3
+            named_barrier(1, kResolvers * 32);
+            nkept = s_nk[t & 3];
+            PROF_MARK(2);
+            // near(t+1): boxes kept in tile t x tile t+1
+            if (t + 1 < tiles && nkept < max_out && nkept_before + warp < nkept) {
+                const int c0 = base + kTile + lane, c1 = c0 + 32;
+                const float4 b0 = (c0 < n) ? sb[c0] : kNone, b1 = (c1 < n) ? sb[c1] : kNone;
+                const float a0 = (c0 < n) ? sa[c0] : 1.0f, a1 = (c1 < n) ? sa[c1] : 1.0f;
+                bool r0 = false, r1 = false;
+                for (int k = nkept_before + warp; k < nkept; k += kResolvers) {
+                    const int ki = sel[k];
+                    const float4 bk = sb[ki];
+                    const float ak = sa[ki];
+                    r0 |= iou_gt(bk, ak, b0, a0, thr);
+                    r1 |= iou_gt(bk, ak, b1, a1, thr);
+                }
+                const uint64_t hit = ballot64(r0, r1);
+                if (lane == 0 && hit) or_into(&s_near[p ^ 1], hit);
             }
-            PROF_MARK(0);
-            const int rem = n - base;
-            const uint64_t validbits = (rem >= kTile) ? ~0ull : ((1ull << rem) - 1ull);
-            uint64_t und = ~removed & validbits, kept = 0;
-            const uint64_t blk0 = (uint64_t)s_diag[t & 3][lane] & ((1ull << lane) - 1ull);  // earlier overlapping candidates
-            const uint64_t blk1 = (uint64_t)s_diag[t & 3][lane + 32] & ((1ull << (lane + 32)) - 1ull);
-            while (und) {
-                const bool u0 = (und >> lane) & 1ull, u1 = (und >> (lane + 32)) & 1ull;
-                const bool d0 = u0 && (blk0 & kept), d1 = u1 && (blk1 & kept);              // removed
-                const bool k0 = u0 && !d0 && !(blk0 & und), k1 = u1 && !d1 && !(blk1 & und);  // kept
-                const uint64_t nk = ballot64(k0, k1), nd = ballot64(d0, d1);
-                kept |= nk;
-                und &= ~(nk | nd);
+            named_barrier(1, kResolvers * 32);
+            PROF_MARK(3);
+        }
+    } else {
+        // ================= worker warps: far(u) share + diag(u) rows, u = 1 .. tiles-1 =================
+        const int wk = warp - kResolvers;  // 0..15
+        for (int u = 1; u < tiles; ++u) {
+            int nk = 0;  // boxes kept in tiles <= u-2
+            if (u >= 2) {
+                asm volatile("bar.sync %0, %1;" ::"r"(3 + (u & 1)), "r"(32 + kWorkers * 32) : "memory");
+                nk = s_nk[(u - 2) & 3];
+                if (nk >= max_out) break;  // the resolvers stop after tile u-2
             }
-            const int room = max_out - nkept;
-            while (__popcll(kept) > room) kept &= ~(1ull << (63 - __clzll(kept)));
-            if ((kept >> lane) & 1ull) sel[nkept + __popcll(kept & ((1ull << lane) - 1ull))] = base + lane;
-            if ((kept >> (lane + 32)) & 1ull)
-                sel[nkept + __popcll(kept & ((1ull << (lane + 32)) - 1ull))] = base + lane + 32;
-            if (lane == 0) s_nkept = nkept + __popcll(kept);
-            PROF_MARK(1);
-        } else if (t + 1 < tiles) {
-            // ---- worker warps, one tile ahead: this CTA's share of far(t+1) and diag(t+1) ----
-            const int nbase = base + kTile;
-            const int c0 = nbase + lane, c1 = c0 + 32;
+            const int ubase = u * kTile;
+            const int c0 = ubase + lane, c1 = c0 + 32;
             const float4 b0 = (c0 < n) ? sb[c0] : kNone, b1 = (c1 < n) ? sb[c1] : kNone;
             const float a0 = (c0 < n) ? sa[c0] : 1.0f, a1 = (c1 < n) ? sa[c1] : 1.0f;
             bool r0 = false, r1 = false;
-            for (int k = crank * kWorkers + (warp - 1); k < nkept_before; k += csize * kWorkers) {
+            for (int k = crank * kWorkers + wk; k < nk; k += csize * kWorkers) {
                 const int ki = sel[k];
                 const float4 bk = sb[ki];
                 const float ak = sa[ki];
@@ -198,52 +235,30 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
                 r1 |= iou_gt(bk, ak, b1, a1, thr);
             }
             const uint64_t hit = ballot64(r0, r1);
-            if (lane == 0 && hit) or_into(&s_farpart, hit);
-            const uint32_t bar_n = bar_base + 8u * (uint32_t)((t + 1) & 3);
-            for (int i = crank + csize * (warp - 1); i < kTile; i += csize * kWorkers) {  // this CTA's rows of diag(t+1)
-                const int ci = nbase + i;
+            if (lane == 0 && hit) or_into(&s_farpart[u & 1], hit);
+            const uint32_t bar_u = bar_base + 8u * (uint32_t)(u & 3);
+            for (int i = crank + csize * wk; i < kTile; i += csize * kWorkers) {  // this CTA's rows of diag(u)
+                const int ci = ubase + i;
                 const float4 bi = (ci < n) ? sb[ci] : kNone;
                 const float ai = (ci < n) ? sa[ci] : 1.0f;
                 const uint64_t row = ballot64(iou_gt(bi, ai, b0, a0, thr), iou_gt(bi, ai, b1, a1, thr)) & ~(1ull << i);
                 if (lane < csize)
-                    st_async_u64(mapa_u32(smem_u32(&s_diag[(t + 1) & 3][i]), (uint32_t)lane), row,
-                                 mapa_u32(bar_n, (uint32_t)lane));
+                    st_async_u64(mapa_u32(smem_u32(&s_diag[u & 3][i]), (uint32_t)lane), row, mapa_u32(bar_u, (uint32_t)lane));
             }
-            named_barrier(1, kWorkers * 32);  // all partials of this CTA are in s_farpart
-            if (warp == 1) {
-                const unsigned long long part = s_farpart;
+            named_barrier(2, kWorkers * 32);  // all partials of this CTA are in s_farpart[u & 1]
+            if (wk == 0) {
+                const unsigned long long part = s_farpart[u & 1];
                 __syncwarp();
                 if (lane < csize)
-                    st_async_u64(mapa_u32(smem_u32(&s_far[(t + 1) & 3][crank]), (uint32_t)lane), part,
-                                 mapa_u32(bar_base + 8u * (uint32_t)((t + 1) & 3), (uint32_t)lane));
-                if (lane == 0) s_farpart = 0ull;
+                    st_async_u64(mapa_u32(smem_u32(&s_far[u & 3][crank]), (uint32_t)lane), part, mapa_u32(bar_u, (uint32_t)lane));
+                if (lane == 0) s_farpart[u & 1] = 0ull;  // next used for tile u+2, one worker barrier later
             }
         }
-        __syncthreads();
-        nkept = s_nkept;
-        PROF_MARK(2);
-        // ---- near(t+1): boxes kept in tile t x tile t+1, every CTA for itself ----
-        if (t + 1 < tiles && nkept < max_out) {
-            const int nbase = base + kTile;
-            const int c0 = nbase + lane, c1 = c0 + 32;
-            bool r0 = false, r1 = false;
-            if (nkept_before + warp < nkept) {
-                const float4 b0 = (c0 < n) ? sb[c0] : kNone, b1 = (c1 < n) ? sb[c1] : kNone;
-                const float a0 = (c0 < n) ? sa[c0] : 1.0f, a1 = (c1 < n) ? sa[c1] : 1.0f;
-                for (int k = nkept_before + warp; k < nkept; k += kNmsWarps) {
-                    const int ki = sel[k];
-                    const float4 bk = sb[ki];
-                    const float ak = sa[ki];
-                    r0 |= iou_gt(bk, ak, b0, a0, thr);
-                    r1 |= iou_gt(bk, ak, b1, a1, thr);
-                }
-            }
-            const uint64_t hit = ballot64(r0, r1);
-            if (lane == 0 && hit) or_into(&s_near[q], hit);
-        }
-        __syncthreads();
-        PROF_MARK(3);
     }
+    if (tid == 0) { s_final[0] = t; s_final[1] = nkept; }  // the resolvers' loop state, for everybody
+    __syncthreads();
+    t = s_final[0];
+    nkept = s_final[1];
     PROF_DUMP;
     // far(t) was sent during the last iteration but never consumed: drain it, so that no st.async is in flight
     // towards this CTA when it exits; the cluster barrier then keeps every CTA alive until its peers have drained
