@@ -1,7 +1,7 @@
 // nms.cu -- batched greedy hard NMS with TF NonMaxSuppressionV3 (CPU kernel) semantics.
 // Replaces tf.image.non_max_suppression at mrcnn_layers.py:225 (RPN, thr 0.7) and :455 (detections, thr 0.3).
 //
-// nms_lazy_kernel: a thread-block CLUSTER of 1..8 CTAs (1024 threads each) per image; every CTA stages the image's
+// nms_lazy_kernel: a thread-block CLUSTER of 1..16 CTAs (1024 threads each) per image; every CTA stages the image's
 // candidate boxes (already in candidate order) in its own shared memory and walks the candidates in 64-box tiles.
 // Only the IoU tests that can matter are evaluated, and neither the cluster nor the CTA blocks on a full barrier
 // inside the loop.  Each CTA is warp-specialised:
@@ -99,7 +99,7 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
     float* sa = reinterpret_cast<float*>(sb + M);               // [M] areas
     int32_t* sel = reinterpret_cast<int32_t*>(sa + M);          // [min(max_out, M)] kept candidate positions
     __shared__ unsigned long long s_diag[4][kTile];             // [tile & 3][row]: symmetric in-tile block, from the peers
-    __shared__ unsigned long long s_far[4][8];                  // [tile & 3][source CTA], written by the peers
+    __shared__ unsigned long long s_far[4][16];                 // [tile & 3][source CTA], written by the peers
     __shared__ unsigned long long s_near[2];                    // [tile parity]
     __shared__ unsigned long long s_farpart[2];                 // [tile parity] this CTA's partial of far(u)
     __shared__ __align__(8) uint64_t s_bar[4];                  // mbarriers, [tile & 3]: a peer can run at most two
@@ -298,12 +298,30 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
     }
 }
 
-// cluster size: spread one image over as many SMs as the batch leaves free (148 SMs, 1 CTA per SM), at most the
-// portable maximum of 8; small candidate sets do not amortise the cluster barrier
-static int nms_cluster_size(int B, int M) {
+// cluster size: spread one image over as many SMs as the batch leaves free (148 SMs, 1 CTA per SM): up to the
+// portable maximum of 8, or the non-portable 16 when the driver reports that all B clusters fit at once; small
+// candidate sets do not amortise the exchange
+static int nms_cluster_size(int B, int M, size_t smem) {
     if (M <= 2048) return 1;
     int cs = 1;
     while (cs < 8 && (long long)B * (cs * 2) <= 148) cs *= 2;
+    if (cs == 8 && B * 16 <= 148) {
+        if (cudaFuncSetAttribute(nms_lazy_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(B * 16));
+            cfg.blockDim = dim3(kNmsThreads);
+            cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 16; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, nms_lazy_kernel, &cfg) == cudaSuccess && nclusters >= B)
+                cs = 16;
+        }
+        (void)cudaGetLastError();
+    }
     return cs;
 }
 
@@ -312,7 +330,7 @@ int launch_nms_sorted(const float4* boxes_sorted, const int32_t* valid, int B, i
     const size_t smem = nms_smem_bytes(M, max_out);
     cudaError_t e = cudaFuncSetAttribute(nms_lazy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    const int cs = nms_cluster_size(B, M);
+    const int cs = nms_cluster_size(B, M, smem);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * cs));
     cfg.blockDim = dim3(kNmsThreads);
