@@ -258,6 +258,22 @@ __device__ __forceinline__ bool iou_gt(const float4& bi, float ai, const float4&
     return res;
 }
 
+// Branch-free variant for hot loops: accumulates the multiplicative screen into `hit` and flags `unsure` when a
+// pair lands inside the 2^-21 band; callers re-run the (rare) unsure lanes through iou_gt.
+__device__ __forceinline__ void iou_screen(const float4& bi, float ai, const float4& bj, float aj, float thr, bool& hit,
+                                           bool& unsure) {
+    const float iy0 = fmaxf(bi.x, bj.x), ix0 = fmaxf(bi.y, bj.y);
+    const float iy1 = fminf(bi.z, bj.z), ix1 = fminf(bi.w, bj.w);
+    const float dh = fmaxf(__fsub_rn(iy1, iy0), 0.0f);
+    const float dw = fmaxf(__fsub_rn(ix1, ix0), 0.0f);
+    const float inter = __fmul_rn(dh, dw);
+    const float uni = __fsub_rn(__fadd_rn(ai, aj), inter);
+    const float t = __fmul_rn(thr, uni);
+    const float d = __fsub_rn(inter, t);
+    hit |= d > 0.0f;
+    unsure |= fabsf(d) <= __fmul_rn(t, 4.76837158203125e-07f);
+}
+
 // TF IOU(): corners normalised with min/max; returns area in `area`
 __device__ __forceinline__ float4 normalise_box(float4 b, float& area) {
     float4 n;

@@ -198,13 +198,21 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
                 const int c0 = base + kTile + lane, c1 = c0 + 32;
                 const float4 b0 = (c0 < n) ? sb[c0] : kNone, b1 = (c1 < n) ? sb[c1] : kNone;
                 const float a0 = (c0 < n) ? sa[c0] : 1.0f, a1 = (c1 < n) ? sa[c1] : 1.0f;
-                bool r0 = false, r1 = false;
+                bool r0 = false, r1 = false, u0 = false, u1 = false;
                 for (int k = nkept_before + warp; k < nkept; k += kResolvers) {
                     const int ki = sel[k];
                     const float4 bk = sb[ki];
                     const float ak = sa[ki];
-                    r0 |= iou_gt(bk, ak, b0, a0, thr);
-                    r1 |= iou_gt(bk, ak, b1, a1, thr);
+                    iou_screen(bk, ak, b0, a0, thr, r0, u0);
+                    iou_screen(bk, ak, b1, a1, thr, r1, u1);
+                }
+                if (__any_sync(0xffffffffu, u0 || u1)) {  // a pair within 2^-21 of the threshold: exact division
+                    r0 = false; r1 = false;
+                    for (int k = nkept_before + warp; k < nkept; k += kResolvers) {
+                        const int ki = sel[k];
+                        r0 |= iou_gt(sb[ki], sa[ki], b0, a0, thr);
+                        r1 |= iou_gt(sb[ki], sa[ki], b1, a1, thr);
+                    }
                 }
                 const uint64_t hit = ballot64(r0, r1);
                 if (lane == 0 && hit) or_into(&s_near[p ^ 1], hit);
@@ -226,13 +234,22 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
             const int c0 = ubase + lane, c1 = c0 + 32;
             const float4 b0 = (c0 < n) ? sb[c0] : kNone, b1 = (c1 < n) ? sb[c1] : kNone;
             const float a0 = (c0 < n) ? sa[c0] : 1.0f, a1 = (c1 < n) ? sa[c1] : 1.0f;
-            bool r0 = false, r1 = false;
+            bool r0 = false, r1 = false, u0 = false, u1 = false;
+#pragma unroll 4
             for (int k = crank * kWorkers + wk; k < nk; k += csize * kWorkers) {
                 const int ki = sel[k];
                 const float4 bk = sb[ki];
                 const float ak = sa[ki];
-                r0 |= iou_gt(bk, ak, b0, a0, thr);
-                r1 |= iou_gt(bk, ak, b1, a1, thr);
+                iou_screen(bk, ak, b0, a0, thr, r0, u0);
+                iou_screen(bk, ak, b1, a1, thr, r1, u1);
+            }
+            if (__any_sync(0xffffffffu, u0 || u1)) {  // a pair within 2^-21 of the threshold: exact division
+                r0 = false; r1 = false;
+                for (int k = crank * kWorkers + wk; k < nk; k += csize * kWorkers) {
+                    const int ki = sel[k];
+                    r0 |= iou_gt(sb[ki], sa[ki], b0, a0, thr);
+                    r1 |= iou_gt(sb[ki], sa[ki], b1, a1, thr);
+                }
             }
             const uint64_t hit = ballot64(r0, r1);
             if (lane == 0 && hit) or_into(&s_farpart[u & 1], hit);
