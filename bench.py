@@ -256,7 +256,9 @@ def main():
     align14 = PyramidROIAlign([cfg["mask_pool_size"]] * 2, name="roi_align_mask")
     detect = DetectionLayer(cfg["post_nms_rois_inference"], cfg["detection_min_confidence"],
                             cfg["detection_max_instances"], cfg["detection_nms_threshold"], cfg["bbox_std_dev"], B, B)
-    KERNELS_PER_STEP = 6 + 2 + 4 + 2   # proposal (4 top-k + mask + sweep), align7 (prep + fwd), detection, align14
+    # our kernels per step: proposal (topk_cluster + nms_lazy), align7 (prep + fwd), detection (refine + sort +
+    # nms_lazy), align14 (prep + fwd); the detections[..., :4] slice copy between them is torch's, not counted
+    KERNELS_PER_STEP = 2 + 2 + 3 + 2
     ev7 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
 
     def stage(t, maps, step=None):
@@ -370,7 +372,10 @@ def main():
             "e2e": e2e,
             "gpu_launches": KERNELS_PER_STEP * args.steps,
             "roofline": {"bound": "hbm", "kernel": "roialign_fwd_kernel<2> (7x7, N=1000, +prep)", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at the default config, from
+                         # the ncu --set full capture summarised in profiles/r1_ncu_full_summary.md
+                         "traffic": (712815616 if (B, S, args.regime) == (8, 1024, "clustered") else None),
                          "peak_source": peak_src, "ms_per_launch": ms7_avg,
                          "algorithmic_bytes_per_launch": bytes7, "survey_closed_form_bytes_per_launch": bytes7_upper,
                          "real_rois_per_image": float((np.abs(rois_np).sum(-1) > 0).sum(1).mean())},
