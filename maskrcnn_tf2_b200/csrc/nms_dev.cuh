@@ -1,0 +1,110 @@
+// nms_dev.cuh -- device helpers of the NMS kernel (nms.cu): warp ballots, mbarrier + distributed-shared-memory PTX
+// wrappers, debug cycle counters, output epilogue.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace mrcnn {
+
+#ifdef MRCNN_NMS_PROFILE   // debug build only (scripts/profile_nms.py): per-phase cycle counters of cluster 0
+static __device__ long long g_nms_prof[8];  // one copy per translation unit
+#define PROF_DECL long long p_t0 = clock64(), p_acc[4] = {0, 0, 0, 0}; int p_tiles = 0
+#define PROF_MARK(i) do { const long long p_now = clock64(); p_acc[i] += p_now - p_t0; p_t0 = p_now; } while (0)
+#define PROF_TILE ++p_tiles
+#define PROF_DUMP do { if (blockIdx.x == 0 && threadIdx.x == 0) { for (int q = 0; q < 4; ++q) g_nms_prof[q] = p_acc[q]; \
+                       g_nms_prof[4] = p_tiles; g_nms_prof[5] = nkept; } } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(i)
+#define PROF_TILE
+#define PROF_DUMP
+#endif
+
+constexpr int kTile = 64;
+constexpr int kNmsThreads = 1024;
+constexpr int kNmsWarps = kNmsThreads / 32;
+constexpr int kResolvers = 16;                     // warps 0..15: near + resolve
+constexpr int kWorkers = kNmsWarps - kResolvers;   // warps 16..31: far + diag, ahead of the resolvers
+
+static size_t nms_smem_bytes(int M, int max_out) {
+    return (size_t)M * (sizeof(float4) + sizeof(float)) + (size_t)(max_out < M ? max_out : M) * sizeof(int32_t);
+}
+
+__device__ __forceinline__ uint64_t ballot64(bool lo, bool hi) {
+    return (uint64_t)__ballot_sync(0xffffffffu, lo) | ((uint64_t)__ballot_sync(0xffffffffu, hi) << 32);
+}
+
+// ---- mbarrier / distributed-shared-memory primitives (sm_90+ PTX) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arm(uint32_t bar, uint32_t tx_bytes) {  // one arrival + expected bytes
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx_bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+// 8-byte store into a peer CTA's shared memory that completes 8 transaction bytes on the peer's mbarrier
+__device__ __forceinline__ void st_async_u64(uint32_t peer_addr, uint64_t v, uint32_t peer_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                 ::"r"(peer_addr), "l"(v), "r"(peer_bar) : "memory");
+}
+__device__ __forceinline__ void named_barrier(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void or_into(unsigned long long* word, uint64_t bits) {  // two native 32-bit shared atomics
+    unsigned* w = reinterpret_cast<unsigned*>(word);
+    if ((unsigned)bits) atomicOr(w, (unsigned)bits);
+    if ((unsigned)(bits >> 32)) atomicOr(w + 1, (unsigned)(bits >> 32));
+}
+
+// fixed-size padded outputs, no host round trip; `sel` = kept candidate positions (shared memory), `total` of them
+__device__ __forceinline__ void nms_write_outputs(const NmsEpilogue& epi, const float4* __restrict__ bx, int b, int M,
+                                                  int max_out, int total, const int32_t* sel) {
+    const int tid = threadIdx.x;
+    if (epi.mode == 0) {
+        for (int r = tid; r < max_out; r += kNmsThreads) {
+            int32_t v = -1;
+            if (r < total) v = epi.orig_idx ? epi.orig_idx[(size_t)b * M + sel[r]] : sel[r];
+            epi.keep[(size_t)b * max_out + r] = v;
+        }
+        if (tid == 0 && epi.count) epi.count[b] = total;
+    } else if (epi.mode == 1) {  // ProposalLayer.nms L:227-230: gather + zero pad
+        for (int r = tid; r < max_out; r += kNmsThreads) {
+            epi.proposals[(size_t)b * max_out + r] = (r < total) ? __ldg(bx + sel[r]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (epi.keep) epi.keep[(size_t)b * max_out + r] = (r < total) ? sel[r] : -1;
+        }
+        if (tid == 0 && epi.count) epi.count[b] = total;
+    } else {  // refine_detections L:494-500: [y1,x1,y2,x2,class,score] rows + zero pad
+        for (int r = tid; r < max_out; r += kNmsThreads) {
+            float* o = epi.detections + ((size_t)b * max_out + r) * 6;
+            if (r < total) {
+                const int i = epi.orig_idx[(size_t)b * M + sel[r]];
+                const float4 v = epi.refined[(size_t)b * epi.N + i];
+                o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+                o[4] = (float)epi.class_ids[(size_t)b * epi.N + i];
+                o[5] = epi.scores[(size_t)b * epi.N + i];
+            } else {
+                o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = 0.0f;
+            }
+        }
+        if (tid == 0 && epi.count) epi.count[b] = total;
+    }
+}
+
+
+}  // namespace mrcnn

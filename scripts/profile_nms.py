@@ -3,7 +3,7 @@ import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from maskrcnn_tf2_b200 import _lib
-_lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), "libmrcnn_roi_b200_prof.so")
+_lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), os.environ.get("MRCNN_PROF_LIB", "libmrcnn_roi_b200_prof.so"))
 from maskrcnn_tf2_b200 import functional as F, synth
 L = _lib.lib()
 L.mrcnn_debug_nms_profile.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
@@ -20,5 +20,5 @@ buf = (ctypes.c_longlong * 8)()
 L.mrcnn_debug_nms_profile(buf)
 v = list(buf)
 tiles = max(v[4], 1)
-print(f"B={B} {regime}: tiles {v[4]} kept {v[5]}  cycles/tile: pairs+diag {v[0]/tiles:.0f}  dsmem+cluster barrier {v[1]/tiles:.0f}  "
-      f"resolve {v[2]/tiles:.0f}  cta barrier {v[3]/tiles:.0f}  total {sum(v[:4])/tiles:.0f}")
+print(f"B={B} {regime}: tiles {v[4]} kept {v[5]}  cycles/tile: wait far {v[0]/tiles:.0f}  resolve {v[1]/tiles:.0f}  "
+      f"barrier {v[2]/tiles:.0f}  near+barrier {v[3]/tiles:.0f}  total {sum(v[:4])/tiles:.0f}")
