@@ -74,6 +74,14 @@ int mrcnn_proposal_forward(const float* rpn_probs, const float* rpn_bbox, const 
                            int32_t* topk_idx, int32_t* keep_idx, int32_t* keep_count, float* pre_nms_boxes,
                            void* ws, size_t ws_bytes, void* stream);
 
+/* ---- gradient of ProposalLayer.call w.r.t. rpn_bbox (TF autodiff through L:227 gather, utils.py:854-869 clip,
+ * utils.py:830-851 decode, L:238 scale; the reference has no stop_gradient on the proposals: model.py:155-157,168).
+ * topk_idx [B,K] and keep_idx [B,P] are the tensors mrcnn_proposal_forward returned for the same inputs.
+ * grad_rpn_bbox [B,A,4] is zero-filled by the launcher; anchors and rpn_probs receive no gradient. */
+int mrcnn_proposal_backward(const float* grad_proposals, const float* rpn_bbox, const float* anchors,
+                            const int32_t* topk_idx, const int32_t* keep_idx, int B, int A, int K, int P,
+                            const float* std_dev, float* grad_rpn_bbox, void* stream);
+
 /* ---- PyramidROIAlign.call  (mrcnn_layers.py:583-664; utils.py:825-827) ---------------------------------
  * boxes [B,N,4] normalised; image_meta [B,meta_len] (only row 0, columns 4..5 = image h,w are read,
  * L:600); fmaps: host array of 4 device pointers P2..P5, each [B,H[l],W[l],C] NHWC fp32; C % 4 == 0.

@@ -17,6 +17,61 @@ size_t proposal_ws_bytes(int B, int K) {
 }
 }  // namespace
 
+namespace {
+// one thread per output proposal row: recompute the forward decode of its source anchor, then TF's gradients
+// (tf.minimum passes to x where x <= y, tf.maximum where x >= y; mul / exp in autodiff order)
+__global__ void __launch_bounds__(256)
+proposal_bwd_kernel(const float4* __restrict__ grad_proposals, const float4* __restrict__ rpn_bbox,
+                    const float4* __restrict__ anchors, const int32_t* __restrict__ topk_idx,
+                    const int32_t* __restrict__ keep_idx, int A, int K, int P, float4 sd,
+                    float4* __restrict__ grad_rpn_bbox) {
+    const int b = blockIdx.y, p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int k = keep_idx[(size_t)b * P + p];
+    if (k < 0) return;  // zero-padded row (L:229-230)
+    const int a = topk_idx[(size_t)b * K + k];
+    const float4 an = __ldg(anchors + (size_t)b * A + a);
+    const float4 d = scale_deltas(__ldg(rpn_bbox + (size_t)b * A + a), sd);
+    const float4 g = __ldg(grad_proposals + (size_t)b * P + p);
+    const float height = __fsub_rn(an.z, an.x), width = __fsub_rn(an.w, an.y);
+    float cy = __fadd_rn(an.x, __fmul_rn(0.5f, height)), cx = __fadd_rn(an.y, __fmul_rn(0.5f, width));
+    cy = __fadd_rn(cy, __fmul_rn(d.x, height));
+    cx = __fadd_rn(cx, __fmul_rn(d.y, width));
+    const float eh = det_expf(d.z), ew = det_expf(d.w);
+    const float h2 = __fmul_rn(height, eh), w2 = __fmul_rn(width, ew);
+    const float y1 = __fsub_rn(cy, __fmul_rn(0.5f, h2)), x1 = __fsub_rn(cx, __fmul_rn(0.5f, w2));
+    const float y2 = __fadd_rn(y1, h2), x2 = __fadd_rn(x1, w2);
+    auto pass = [](float v, float gv) { return (v <= 1.0f && fminf(v, 1.0f) >= 0.0f) ? gv : 0.0f; };  // clip to [0,1]
+    const float g0 = pass(y1, g.x), g1 = pass(x1, g.y), g2 = pass(y2, g.z), g3 = pass(x2, g.w);
+    const float gy1 = __fadd_rn(g0, g2), gx1 = __fadd_rn(g1, g3);
+    const float gh2 = __fadd_rn(g2, __fmul_rn(-0.5f, gy1)), gw2 = __fadd_rn(g3, __fmul_rn(-0.5f, gx1));
+    float4 o;
+    o.x = __fmul_rn(__fmul_rn(gy1, height), sd.x);
+    o.y = __fmul_rn(__fmul_rn(gx1, width), sd.y);
+    o.z = __fmul_rn(__fmul_rn(__fmul_rn(gh2, height), eh), sd.z);
+    o.w = __fmul_rn(__fmul_rn(__fmul_rn(gw2, width), ew), sd.w);
+    grad_rpn_bbox[(size_t)b * A + a] = o;  // every anchor is selected at most once
+}
+}  // namespace
+
+MRCNN_EXPORT int mrcnn_proposal_backward(const float* grad_proposals, const float* rpn_bbox, const float* anchors,
+                                         const int32_t* topk_idx, const int32_t* keep_idx, int B, int A, int K, int P,
+                                         const float* std_dev, float* grad_rpn_bbox, void* stream) {
+    if (!grad_proposals || !rpn_bbox || !anchors || !topk_idx || !keep_idx || !std_dev || !grad_rpn_bbox)
+        return MRCNN_ERR_NULL;
+    if (B < 1 || A < 1 || K < 1 || K > A || K > kMaxSort || P < 1) return MRCNN_ERR_RANGE;
+    if (!aligned16(grad_proposals) || !aligned16(rpn_bbox) || !aligned16(anchors) || !aligned16(grad_rpn_bbox))
+        return MRCNN_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(grad_rpn_bbox, 0, (size_t)B * A * 4 * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+    const float4 sd = make_float4(std_dev[0], std_dev[1], std_dev[2], std_dev[3]);
+    proposal_bwd_kernel<<<dim3((P + 255) / 256, B), 256, 0, st>>>((const float4*)grad_proposals, (const float4*)rpn_bbox,
+                                                               (const float4*)anchors, topk_idx, keep_idx, A, K, P, sd,
+                                                               (float4*)grad_rpn_bbox);
+    return last_error();
+}
+
 MRCNN_EXPORT int mrcnn_proposal_workspace_bytes(int B, int A, int pre_nms_limit, int P, size_t* bytes) {
     if (!bytes) return MRCNN_ERR_NULL;
     const int K = pre_nms_limit < A ? pre_nms_limit : A;

@@ -126,6 +126,22 @@ def proposal_forward(rpn_probs, rpn_bbox, anchors, pre_nms_limit, proposal_count
     return proposals
 
 
+def proposal_backward(grad_proposals, rpn_bbox, anchors, topk_idx, keep_idx, std_dev):
+    """Gradient of ProposalLayer.call w.r.t. rpn_bbox [B,A,4] (the reference does not stop it)."""
+    L = _lib.lib()
+    grad_proposals = _req(grad_proposals, torch.float32, "grad_proposals", 3)
+    rpn_bbox = _req(rpn_bbox, torch.float32, "rpn_bbox", 3)
+    anchors = _req(anchors, torch.float32, "anchors", 3)
+    topk_idx = _req(topk_idx, torch.int32, "topk_idx", 2)
+    keep_idx = _req(keep_idx, torch.int32, "keep_idx", 2)
+    B, A, _ = rpn_bbox.shape
+    K, P = topk_idx.shape[1], keep_idx.shape[1]
+    grad = torch.empty_like(rpn_bbox)
+    check(L.mrcnn_proposal_backward(ptr(grad_proposals), ptr(rpn_bbox), ptr(anchors), ptr(topk_idx), ptr(keep_idx), B, A,
+                                    K, P, _lib.float4(std_dev), ptr(grad), _stream()), "mrcnn_proposal_backward")
+    return grad
+
+
 def _map_args(maps):
     if len(maps) != 4:
         raise ValueError("PyramidROIAlign needs exactly four feature maps (P2..P5)")

@@ -32,6 +32,28 @@ class _Layer:
         return {"name": self.name}
 
 
+class _ProposalFn(torch.autograd.Function):
+    """rpn_bbox receives the reference's gradient (no stop_gradient on proposals, model.py:155-157,168 through
+    mrcnn_layers.py:227); rpn_probs and anchors receive none (top_k / NMS indices are not differentiable)."""
+
+    @staticmethod
+    def forward(ctx, rpn_probs, rpn_bbox, anchors, pre_nms_limit, proposal_count, std_dev, nms_threshold):
+        need_grad = ctx.needs_input_grad[1]
+        out = F.proposal_forward(rpn_probs, rpn_bbox, anchors, pre_nms_limit, proposal_count, std_dev, nms_threshold,
+                                 debug=need_grad)
+        if not need_grad:
+            return out
+        ctx.save_for_backward(rpn_bbox, anchors, out["topk_idx"], out["keep_idx"])
+        ctx.std_dev = std_dev
+        return out["proposals"]
+
+    @staticmethod
+    def backward(ctx, grad_proposals):
+        rpn_bbox, anchors, topk_idx, keep_idx = ctx.saved_tensors
+        g = F.proposal_backward(grad_proposals.contiguous(), rpn_bbox, anchors, topk_idx, keep_idx, ctx.std_dev)
+        return None, g, None, None, None, None, None
+
+
 class ProposalLayer(_Layer):
     """mrcnn_layers.py:202-280.  inputs = [rpn_probs [B,A,2], rpn_bbox [B,A,4], anchors [B,A,4]] ->
     proposals [B, proposal_count, 4] in normalised coordinates, zero padded."""
@@ -44,8 +66,8 @@ class ProposalLayer(_Layer):
 
     def call(self, inputs, **kwargs):
         rpn_probs, rpn_bbox, anchors = inputs[0], inputs[1], inputs[2]
-        return F.proposal_forward(rpn_probs, rpn_bbox, anchors, self.config['pre_nms_limit'], self.proposal_count,
-                                  np.asarray(self.config['rpn_bbox_std_dev'], dtype=np.float32), self.nms_threshold)
+        return _ProposalFn.apply(rpn_probs, rpn_bbox, anchors, self.config['pre_nms_limit'], self.proposal_count,
+                                 np.asarray(self.config['rpn_bbox_std_dev'], dtype=np.float32), self.nms_threshold)
 
     def compute_output_shape(self, input_shape):
         return None, self.proposal_count, 4

@@ -158,6 +158,19 @@ def proposal_layer(rpn_probs, rpn_bbox, anchors, pre_nms_limit, proposal_count, 
     return dict(proposals=out, topk_idx=tk, keep_idx=ki, keep_count=kc, pre_nms_boxes=pb)
 
 
+def proposal_layer_grad(grad_proposals, rpn_bbox, anchors, topk_idx, keep_idx, std_dev):
+    """Gradient of ProposalLayer w.r.t. rpn_bbox [B,A,4] (reference behaviour Q7)."""
+    g, bb, an = _f32(grad_proposals), _f32(rpn_bbox), _f32(anchors)
+    tk = np.ascontiguousarray(topk_idx, dtype=np.int32)
+    ki = np.ascontiguousarray(keep_idx, dtype=np.int32)
+    B, A, _ = bb.shape
+    sd = _f32(std_dev)
+    out = np.empty_like(bb)
+    lib().orc_proposal_layer_grad(_p(g, _f32p), _p(bb, _f32p), _p(an, _f32p), _p(tk, _i32p), _p(ki, _i32p), B, A,
+                                  tk.shape[1], ki.shape[1], _p(sd, _f32p), _p(out, _f32p))
+    return out
+
+
 def roi_level(box, img_h, img_w, denominator=244.0):
     b = _f32(box)
     return int(lib().orc_roi_level(_p(b, _f32p), ctypes.c_float(img_h), ctypes.c_float(img_w),

