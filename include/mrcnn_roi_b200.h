@@ -98,10 +98,18 @@ int mrcnn_roialign_forward(const float* boxes, const float* image_meta, int meta
 
 /* ---- gradient of PyramidROIAlign w.r.t. the four feature maps (TF CropAndResizeGradImage through the
  * reference's gather/concat, M:142,168; boxes get no gradient, L:628-629).  grad_fmaps: host array of 4
- * device pointers, zero-filled by the launcher, then accumulated with fp32 vector atomics. */
+ * device pointers; every element is written by the launcher (no pre-clearing needed).
+ * ws != NULL (size from mrcnn_roialign_backward_workspace_bytes): deterministic mode -- every gradient-map pixel
+ * is written once with the sum of its samples in TF CropAndResizeGradImage's own sequential order
+ * ((box, y, x, corner) ascending), bit-identical to the CPU kernel and reproducible run to run.  The exception:
+ * pixels that collect more than 1024 samples or lie under a zero-size ROI (zero-padded ROIs pile thousands of
+ * samples on pixel (0,0)) are accumulated with fp32 vector atomics.
+ * ws == NULL: atomic mode -- zero-fill, then one fp32 vector reduction per sample corner (order not fixed). */
+int mrcnn_roialign_backward_workspace_bytes(int B, int N, int ph, int pw, const int* H, const int* W, int C,
+                                            size_t* bytes);
 int mrcnn_roialign_backward(const float* grad_out, const float* boxes, const int32_t* roi_map,
                             float* const* grad_fmaps, const int* H, const int* W, int C, int B, int N, int ph,
-                            int pw, void* stream);
+                            int pw, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- DetectionLayer.call + refine_detections  (mrcnn_layers.py:369-524) -------------------------------
  * rois [B,N,4], probs [B,N,NC], deltas [B,N,NC,4], image_meta [B,meta_len] (window = columns 7..10 of each

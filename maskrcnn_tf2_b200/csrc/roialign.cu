@@ -7,7 +7,13 @@
 //           (crop_and_resize_op.cc; called at L:641) with 128-bit channel-vectorised NHWC loads, written straight
 //           into [B,N,ph,pw,C] in input ROI order -- the reference's concat / top_k re-sort / gather passes
 //           (L:644-659) have no counterpart here because nothing is ever out of order.
-// backward = memset of the four gradient maps + roialign_bwd_kernel: TF CropAndResizeGradImage scatter with
+// backward (with a workspace) = deterministic pixel-centric gather: count the corner samples that land on every
+//           gradient-map pixel, give each touched pixel a segment of a key list, fill it, then ONE pass over all
+//           pixels writes each of them exactly once -- zeros, or the sum of its samples in TF CropAndResizeGradImage's
+//           own (box, y, x, corner) order, so the result is bit-identical to the sequential CPU kernel and the
+//           713 MB zero-fill and the accumulation are the same HBM write.  Pixels that collect more than 256
+//           samples (zero-padded ROIs pile thousands on pixel (0,0), quirk Q5) fall back to vector atomics.
+// backward (no workspace) = memset of the four gradient maps + roialign_bwd_kernel: scatter with
 //           red.global.add.v4.f32 (one 16-byte reduction per lane and corner).
 #include <limits.h>
 
@@ -173,40 +179,61 @@ __device__ __forceinline__ void red_add_v4(float* addr, float x, float y, float 
 //   * ROIs whose taps are constant in both axes (zero-padded ROIs: every bin samples pixel (0,0), quirk Q5) are
 //     summed across the CTA's rows in shared memory and issue ONE reduction per CTA and corner, which keeps the
 //     thousands of padded rows of a training batch from serialising on a single L2 line.
-__device__ __forceinline__ void scatter_corners(float* tl, float* tr, float* bl, float* br, int i, const float4& v,
+constexpr int kLightMax = 32;       // samples a pixel may collect and still be summed, in TF's order, by one warp
+constexpr int kMediumMax = 1024;    // ... or, thread per channel, by one CTA
+constexpr int kMediumCtas = 296;    // CTAs at the head of the gather grid that walk the list of such pixels
+constexpr uint32_t kConstFlag = 0x80000000u;  // count bit: a constant-tap (zero-size) ROI lands on this pixel
+
+struct PixelSpace {   // global pixel id = base[m] + (b * H[m] + y) * W[m] + x ; base[4] = number of pixels
+    int base[5];
+};
+
+// `count` == nullptr: every corner is scattered (atomic mode).  Otherwise only corners whose pixel was left to the
+// atomic fallback (more than kLightMax samples, or a constant-tap ROI) are; the gather kernel owns the rest.
+__device__ __forceinline__ bool corner_is_ours(const uint32_t* __restrict__ count, int q) {
+    return count == nullptr || __ldg(count + q) > (uint32_t)kMediumMax;
+}
+
+__device__ __forceinline__ void scatter_corners(float* gimg, int C, const uint32_t* __restrict__ count, int qbase,
+                                                int ptl, int ptr_, int pbl, int pbr, int i, const float4& v,
                                                 float wy0, float ly, float wx0, float lx) {
     const float4 dt = make_float4(__fmul_rn(wy0, v.x), __fmul_rn(wy0, v.y), __fmul_rn(wy0, v.z), __fmul_rn(wy0, v.w));
     const float4 db = make_float4(__fmul_rn(ly, v.x), __fmul_rn(ly, v.y), __fmul_rn(ly, v.z), __fmul_rn(ly, v.w));
-    if (wy0 != 0.0f && wx0 != 0.0f)
-        red_add_v4(tl + 4 * i, __fmul_rn(wx0, dt.x), __fmul_rn(wx0, dt.y), __fmul_rn(wx0, dt.z), __fmul_rn(wx0, dt.w));
-    if (wy0 != 0.0f && lx != 0.0f)
-        red_add_v4(tr + 4 * i, __fmul_rn(lx, dt.x), __fmul_rn(lx, dt.y), __fmul_rn(lx, dt.z), __fmul_rn(lx, dt.w));
-    if (ly != 0.0f && wx0 != 0.0f)
-        red_add_v4(bl + 4 * i, __fmul_rn(wx0, db.x), __fmul_rn(wx0, db.y), __fmul_rn(wx0, db.z), __fmul_rn(wx0, db.w));
-    if (ly != 0.0f && lx != 0.0f)
-        red_add_v4(br + 4 * i, __fmul_rn(lx, db.x), __fmul_rn(lx, db.y), __fmul_rn(lx, db.z), __fmul_rn(lx, db.w));
+    if (wy0 != 0.0f && wx0 != 0.0f && corner_is_ours(count, qbase + ptl))
+        red_add_v4(gimg + (size_t)ptl * C + 4 * i, __fmul_rn(wx0, dt.x), __fmul_rn(wx0, dt.y), __fmul_rn(wx0, dt.z), __fmul_rn(wx0, dt.w));
+    if (wy0 != 0.0f && lx != 0.0f && corner_is_ours(count, qbase + ptr_))
+        red_add_v4(gimg + (size_t)ptr_ * C + 4 * i, __fmul_rn(lx, dt.x), __fmul_rn(lx, dt.y), __fmul_rn(lx, dt.z), __fmul_rn(lx, dt.w));
+    if (ly != 0.0f && wx0 != 0.0f && corner_is_ours(count, qbase + pbl))
+        red_add_v4(gimg + (size_t)pbl * C + 4 * i, __fmul_rn(wx0, db.x), __fmul_rn(wx0, db.y), __fmul_rn(wx0, db.z), __fmul_rn(wx0, db.w));
+    if (ly != 0.0f && lx != 0.0f && corner_is_ours(count, qbase + pbr))
+        red_add_v4(gimg + (size_t)pbr * C + 4 * i, __fmul_rn(lx, db.x), __fmul_rn(lx, db.y), __fmul_rn(lx, db.z), __fmul_rn(lx, db.w));
 }
 
 __global__ void __launch_bounds__(kRoiThreads)
 roialign_bwd_kernel(const float4* __restrict__ grad_out, const float4* __restrict__ boxes,
                     const int32_t* __restrict__ roi_map, GradTable tbl, int C, int N, int ph, int pw, int groups,
-                    int rows_per_group) {
+                    int rows_per_group, PixelSpace ps, const uint32_t* __restrict__ count,
+                    const int* __restrict__ heavy_normal) {
     extern __shared__ __align__(16) float4 s_acc[];  // [8 warps][C/4], constant-tap ROIs only
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // gather mode: nothing to do unless a constant-tap ROI exists or some pixel overflowed kMediumMax
+    if (count != nullptr && *heavy_normal == 0) return;
     const int f = blockIdx.x / groups, grp = blockIdx.x - f * groups;
     const int y = grp * rows_per_group + warp;
     const bool has_row = (warp < rows_per_group) && (y < ph);
     const int m = roi_map[f];
     const RoiGeom g = roi_geom(__ldg(boxes + f), m, tbl.H, tbl.W, ph, pw);
     const int c4 = C >> 2;
+    const int b = f / N;
     float* gimg = ((m == 0) ? tbl.ptr[0] : (m == 1) ? tbl.ptr[1] : (m == 2) ? tbl.ptr[2] : tbl.ptr[3]) +
-                  (size_t)(f / N) * g.H * g.W * C;
+                  (size_t)b * g.H * g.W * C;
+    const int qbase = ps.base[m] + b * g.H * g.W;
     const bool constant = (g.hs == 0.0f && g.ws == 0.0f);  // CTA-uniform
     const AxisTap ty = axis_tap(g.y0, g.hs, has_row ? y : 0, g.H);
     const float4* gr = grad_out + ((size_t)f * ph + (has_row ? y : 0)) * pw * c4;
     const int top = ty.lo * g.W, bot = ty.hi * g.W;
     const float ly = ty.lerp, wy0 = __fsub_rn(1.0f, ty.lerp);
-    if (constant) {
+    if (constant) {  // its pixels carry kConstFlag, so in gather mode they are always ours
         const AxisTap tx = axis_tap(g.x0, g.ws, 0, g.W);
         for (int i = lane; i < c4; i += 32) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -219,10 +246,6 @@ roialign_bwd_kernel(const float4* __restrict__ grad_out, const float4* __restric
         }
         __syncthreads();
         if (!(ty.valid && tx.valid)) return;  // uniform: the same tap for every bin of the ROI
-        float* tl = gimg + (size_t)(top + tx.lo) * C;
-        float* tr = gimg + (size_t)(top + tx.hi) * C;
-        float* bl = gimg + (size_t)(bot + tx.lo) * C;
-        float* br = gimg + (size_t)(bot + tx.hi) * C;
         const float lx = tx.lerp, wx0 = __fsub_rn(1.0f, tx.lerp);
         for (int i = threadIdx.x; i < c4; i += kRoiThreads) {
             float4 acc = s_acc[i];
@@ -230,18 +253,15 @@ roialign_bwd_kernel(const float4* __restrict__ grad_out, const float4* __restric
                 const float4 v = s_acc[w * c4 + i];
                 acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
             }
-            scatter_corners(tl, tr, bl, br, i, acc, wy0, ly, wx0, lx);
+            scatter_corners(gimg, C, nullptr, qbase, top + tx.lo, top + tx.hi, bot + tx.lo, bot + tx.hi, i, acc, wy0, ly,
+                            wx0, lx);
         }
         return;
     }
     if (!has_row || !ty.valid) return;
-    if (g.ws == 0.0f) {  // every bin of the row hits the same pixels: sum the row first
+    if (g.ws == 0.0f && count == nullptr) {  // every bin of the row hits the same pixels: sum the row first
         const AxisTap tx = axis_tap(g.x0, g.ws, 0, g.W);
         if (!tx.valid) return;
-        float* tl = gimg + (size_t)(top + tx.lo) * C;
-        float* tr = gimg + (size_t)(top + tx.hi) * C;
-        float* bl = gimg + (size_t)(bot + tx.lo) * C;
-        float* br = gimg + (size_t)(bot + tx.hi) * C;
         const float lx = tx.lerp, wx0 = __fsub_rn(1.0f, tx.lerp);
         for (int i = lane; i < c4; i += 32) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -249,19 +269,297 @@ roialign_bwd_kernel(const float4* __restrict__ grad_out, const float4* __restric
                 const float4 v = __ldcs(gr + (size_t)x * c4 + i);
                 acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
             }
-            scatter_corners(tl, tr, bl, br, i, acc, wy0, ly, wx0, lx);
+            scatter_corners(gimg, C, nullptr, qbase, top + tx.lo, top + tx.hi, bot + tx.lo, bot + tx.hi, i, acc, wy0, ly,
+                            wx0, lx);
         }
         return;
     }
     for (int x = 0; x < pw; ++x, gr += c4) {
         const AxisTap tx = axis_tap(g.x0, g.ws, x, g.W);
         if (!tx.valid) continue;
-        float* tl = gimg + (size_t)(top + tx.lo) * C;
-        float* tr = gimg + (size_t)(top + tx.hi) * C;
-        float* bl = gimg + (size_t)(bot + tx.lo) * C;
-        float* br = gimg + (size_t)(bot + tx.hi) * C;
+        const int ptl = top + tx.lo, ptr_ = top + tx.hi, pbl = bot + tx.lo, pbr = bot + tx.hi;
+        if (count != nullptr && !(corner_is_ours(count, qbase + ptl) || corner_is_ours(count, qbase + ptr_) ||
+                                  corner_is_ours(count, qbase + pbl) || corner_is_ours(count, qbase + pbr)))
+            continue;  // warp-uniform: no gradient row is read for bins the gather kernel owns entirely
         const float lx = tx.lerp, wx0 = __fsub_rn(1.0f, tx.lerp);
-        for (int i = lane; i < c4; i += 32) scatter_corners(tl, tr, bl, br, i, __ldcs(gr + i), wy0, ly, wx0, lx);
+        for (int i = lane; i < c4; i += 32)
+            scatter_corners(gimg, C, count, qbase, ptl, ptr_, pbl, pbr, i, __ldcs(gr + i), wy0, ly, wx0, lx);
+    }
+}
+
+// ---- deterministic gather backward -------------------------------------------------------------------------
+// One thread per output bin (f, y, x): the up-to-four gradient-map pixels its gradient lands on.
+struct BinTaps {
+    int q[4];      // global pixel ids: tl, tr, bl, br
+    bool on[4];    // weight != 0 and the forward pass did not extrapolate
+    bool constant; // zero-size ROI: every bin of the ROI samples the same pixels
+    float wy[2], wx[2];  // (1 - ly, ly), (1 - lx, lx): corner c weighs wx[c & 1] * (wy[c >> 1] * g)
+};
+
+__device__ __forceinline__ BinTaps bin_taps(const float4* __restrict__ boxes, const int32_t* __restrict__ roi_map,
+                                            const GradTable& tbl, const PixelSpace& ps, int N, int ph, int pw, int s) {
+    const int bins = ph * pw;
+    const int f = s / bins, r = s - f * bins, y = r / pw, x = r - y * pw;
+    const int m = roi_map[f];
+    const RoiGeom g = roi_geom(__ldg(boxes + f), m, tbl.H, tbl.W, ph, pw);
+    const AxisTap ty = axis_tap(g.y0, g.hs, y, g.H), tx = axis_tap(g.x0, g.ws, x, g.W);
+    const int qbase = ps.base[m] + (f / N) * g.H * g.W;
+    const float wy0 = __fsub_rn(1.0f, ty.lerp), wx0 = __fsub_rn(1.0f, tx.lerp);
+    const bool valid = ty.valid && tx.valid;
+    BinTaps t;
+    t.wy[0] = wy0; t.wy[1] = ty.lerp; t.wx[0] = wx0; t.wx[1] = tx.lerp;
+    t.constant = (g.hs == 0.0f && g.ws == 0.0f);
+    t.q[0] = qbase + ty.lo * g.W + tx.lo; t.on[0] = valid && wy0 != 0.0f && wx0 != 0.0f;
+    t.q[1] = qbase + ty.lo * g.W + tx.hi; t.on[1] = valid && wy0 != 0.0f && tx.lerp != 0.0f;
+    t.q[2] = qbase + ty.hi * g.W + tx.lo; t.on[2] = valid && ty.lerp != 0.0f && wx0 != 0.0f;
+    t.q[3] = qbase + ty.hi * g.W + tx.hi; t.on[3] = valid && ty.lerp != 0.0f && tx.lerp != 0.0f;
+    return t;
+}
+
+__global__ void __launch_bounds__(256)
+roialign_bwd_count_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ roi_map, GradTable tbl,
+                          PixelSpace ps, int N, int ph, int pw, int total_bins, uint32_t* __restrict__ count,
+                          int* __restrict__ misc) {
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= total_bins) return;
+    const BinTaps t = bin_taps(boxes, roi_map, tbl, ps, N, ph, pw, s);
+    if (t.constant) {  // one flag per ROI instead of ph*pw increments on one address
+        if (s % (ph * pw) == 0) {
+            misc[1] = 1;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (t.on[c]) atomicOr(count + t.q[c], kConstFlag);
+        }
+        return;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (t.on[c]) atomicAdd(count + t.q[c], 1u);
+}
+
+// Four pixels per thread: a segment of the key list for every pixel the gather kernel will sum (1..kMediumMax samples);
+// pixels above kLightMax are also appended to the medium list.  Segment order is whatever the atomics give; only the
+// order INSIDE a segment matters and that is sorted later.  misc: [0] key-list bump pointer, [1] "the atomic fallback
+// has work" (a constant-tap ROI, or ordinary samples on a pixel above kMediumMax), [2] length of the medium list.
+__global__ void __launch_bounds__(256)
+roialign_bwd_alloc_kernel(const uint32_t* __restrict__ count, int NP, int* __restrict__ start, int* __restrict__ misc,
+                          int* __restrict__ medium) {
+    __shared__ int warp_sums[32];
+    __shared__ int block_total, block_base;
+    const int q0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    uint32_t c[4];
+    int n[4], mine = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        c[i] = (q0 + i < NP) ? count[q0 + i] : 0u;
+        n[i] = (c[i] <= (uint32_t)kMediumMax) ? (int)c[i] : 0;
+        mine += n[i];
+        if (c[i] > (uint32_t)kMediumMax && (c[i] & ~kConstFlag) != 0u) misc[1] = 1;
+        if (n[i] > kLightMax) medium[atomicAdd(&misc[2], 1)] = q0 + i;
+    }
+    int off = block_exclusive_scan(mine, warp_sums, &block_total);
+    if (threadIdx.x == 0) block_base = (block_total > 0) ? atomicAdd(&misc[0], block_total) : 0;
+    __syncthreads();
+    off += block_base;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (q0 + i < NP) start[q0 + i] = off;
+        off += n[i];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+roialign_bwd_fill_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ roi_map, GradTable tbl,
+                         PixelSpace ps, int N, int ph, int pw, int total_bins, const uint32_t* __restrict__ count,
+                         const int* __restrict__ start, int* __restrict__ cursor, int4* __restrict__ entries) {
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= total_bins) return;
+    const BinTaps t = bin_taps(boxes, roi_map, tbl, ps, N, ph, pw, s);
+    if (t.constant) return;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (t.on[c] && count[t.q[c]] <= (uint32_t)kMediumMax)
+            entries[start[t.q[c]] + atomicAdd(cursor + t.q[c], 1)] =  // key order = TF's accumulation order
+                make_int4((s << 2) | c, __float_as_int(t.wy[c >> 1]), __float_as_int(t.wx[c & 1]), 0);
+}
+
+__device__ __forceinline__ int warp_sort_asc(int v, int lane) {  // bitonic network over the 32 lanes
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int o = __shfl_xor_sync(0xffffffffu, v, j);
+            const bool up = ((lane & k) == 0), lower = ((lane & j) == 0);
+            v = (lower == up) ? min(v, o) : max(v, o);
+        }
+    return v;
+}
+
+__device__ __forceinline__ void fma_in_order(float4& acc, const float4& v, float a, float b) {
+    acc.x = __fadd_rn(acc.x, __fmul_rn(b, __fmul_rn(a, v.x)));  // acc += wx * (wy * g): TF's two products, then the add
+    acc.y = __fadd_rn(acc.y, __fmul_rn(b, __fmul_rn(a, v.y)));
+    acc.z = __fadd_rn(acc.z, __fmul_rn(b, __fmul_rn(a, v.z)));
+    acc.w = __fadd_rn(acc.w, __fmul_rn(b, __fmul_rn(a, v.w)));
+}
+
+__device__ __forceinline__ float4* pixel_ptr(const GradTable& tbl, const PixelSpace& ps, int q, int c4) {
+    const int m = (q >= ps.base[3]) ? 3 : (q >= ps.base[2]) ? 2 : (q >= ps.base[1]) ? 1 : 0;
+    return reinterpret_cast<float4*>((m == 0) ? tbl.ptr[0] : (m == 1) ? tbl.ptr[1] : (m == 2) ? tbl.ptr[2] : tbl.ptr[3]) +
+           (size_t)(q - ps.base[m]) * c4;
+}
+
+// The gather pass.  Every pixel of every gradient map is written exactly once.  An entry is (key, wy, wx): sample
+// s = key >> 2 (= its row of grad_out), corner = key & 3; ascending key = TF's accumulation order.
+//   * CTAs [kMediumCtas, grid): persistent warps stream over the pixels -- zeros, or (<= kLightMax samples) the sum
+//     in TF's order: each lane ranks its entry among the pixel's (n shuffles), then the rows are fetched two at a
+//     time and added strictly in rank order;
+//   * CTAs [0, kMediumCtas): walk the medium list, one CTA per pixel: (key, slot) pairs sorted in shared memory, then
+//     one thread per channel adds the rows strictly in order, sixteen loads in flight.  They sit at the head of the
+//     grid so these long sums start first and overlap the streaming pass.
+template <int VPL>
+__global__ void __launch_bounds__(256, 4)
+roialign_bwd_gather_kernel(const float4* __restrict__ grad_out, GradTable tbl, PixelSpace ps, int C,
+                           const uint32_t* __restrict__ count, const int* __restrict__ start,
+                           const int4* __restrict__ entries, const int* __restrict__ misc,
+                           const int* __restrict__ medium) {
+    constexpr int V = VPL > 0 ? VPL : 1;
+    __shared__ uint64_t s_sort[kMediumMax];
+    __shared__ int s_row[kMediumMax];
+    __shared__ float s_wy[kMediumMax], s_wx[kMediumMax];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c4 = C >> 2;
+    if (blockIdx.x < kMediumCtas) {
+        const int n_medium = misc[2];
+        const float* grad_f = reinterpret_cast<const float*>(grad_out);
+        for (int mi = blockIdx.x; mi < n_medium; mi += kMediumCtas) {
+            const int q = medium[mi];
+            const int n = (int)count[q], seg = start[q];
+            const int np2 = max(64, 1 << (32 - __clz(n - 1)));
+            for (int e = threadIdx.x; e < np2; e += 256)
+                s_sort[e] = (e < n) ? (((uint64_t)(uint32_t)__ldg(&entries[seg + e].x) << 10) | (uint32_t)e) + 1u : 0ull;
+            __syncthreads();
+            block_bitonic_sort_desc(s_sort, np2);  // descending, zero padding last: ascending rank e sits at n - 1 - e
+            for (int e = threadIdx.x; e < n; e += 256) {
+                const int4 ent = __ldg(entries + seg + (int)((s_sort[n - 1 - e] - 1u) & 1023u));
+                s_row[e] = ent.x >> 2;
+                s_wy[e] = __int_as_float(ent.y);
+                s_wx[e] = __int_as_float(ent.z);
+            }
+            __syncthreads();
+            // one thread per channel (a warp covers 128 B of every gradient row), sixteen rows in flight, strict order
+            float* dst = reinterpret_cast<float*>(pixel_ptr(tbl, ps, q, c4));
+            for (int ch = threadIdx.x; ch < C; ch += 256) {
+                float acc = 0.0f;
+                int e = 0;
+                for (; e + 16 <= n; e += 16) {
+                    float val[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) val[u] = __ldg(grad_f + (size_t)s_row[e + u] * C + ch);
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) acc = __fadd_rn(acc, __fmul_rn(s_wx[e + u], __fmul_rn(s_wy[e + u], val[u])));
+                }
+                for (; e < n; ++e)
+                    acc = __fadd_rn(acc, __fmul_rn(s_wx[e], __fmul_rn(s_wy[e], __ldg(grad_f + (size_t)s_row[e] * C + ch))));
+                __stcs(dst + ch, acc);
+            }
+            __syncthreads();
+        }
+        return;
+    }
+    // persistent streaming pass: a CTA walks 32-pixel chunks (32 KB of contiguous gradient map at C = 256, 4 pixels per
+    // warp); the next chunk's headers are fetched one iteration ahead and the entry lists of a warp's four pixels are
+    // requested together, so a touched pixel costs one gradient-row latency, not three dependent ones.
+    const int NP = ps.base[4];
+    const int nctas = gridDim.x - kMediumCtas, chunks = (NP + 31) >> 5;
+    int chunk = blockIdx.x - kMediumCtas;
+    auto header = [&](int ch, uint32_t& cnt, int& st) {
+        const int q = ch * 32 + warp * 4 + lane;
+        const bool ok = (lane < 4) && (ch < chunks) && (q < NP);
+        cnt = ok ? __ldg(count + q) : 0u;
+        st = ok ? __ldg(start + q) : 0;
+    };
+    uint32_t c_next;
+    int seg_next;
+    header(chunk, c_next, seg_next);
+#pragma unroll 1
+    for (; chunk < chunks; chunk += nctas) {
+        const uint32_t my_count = c_next;
+        const int my_start = seg_next;
+        header(chunk + nctas, c_next, seg_next);
+        const int q0 = chunk * 32 + warp * 4;
+        // -1: a medium CTA writes this pixel; 0: zeros (untouched, or the atomic fallback adds to it later)
+        auto samples_of = [&](int i) {
+            const uint32_t c = __shfl_sync(0xffffffffu, my_count, i);
+            return (c <= (uint32_t)kLightMax) ? (int)c : (c <= (uint32_t)kMediumMax) ? -1 : 0;
+        };
+        auto entry_of = [&](int i, int n) {
+            const int seg = __shfl_sync(0xffffffffu, my_start, i);
+            return (lane < n) ? __ldg(entries + seg + lane) : make_int4(INT_MAX, 0, 0, 0);
+        };
+        int n_next = samples_of(0);
+        int4 ent_next = entry_of(0, n_next);
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+            const int q = q0 + i, n = n_next;
+            const int4 ent = ent_next;
+            if (i < 3) { n_next = samples_of(i + 1); ent_next = entry_of(i + 1, n_next); }  // one pixel ahead
+            if (q >= NP || n < 0) continue;
+            float4* dst = pixel_ptr(tbl, ps, q, c4);
+            if (n == 0) {
+                if (VPL > 0) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) __stcs(dst + lane + 32 * v, make_float4(0.f, 0.f, 0.f, 0.f));
+                } else {
+                    for (int v = lane; v < c4; v += 32) __stcs(dst + v, make_float4(0.f, 0.f, 0.f, 0.f));
+                }
+                continue;
+            }
+            int rank = 0;
+            for (int j = 0; j < n; ++j) rank += (__shfl_sync(0xffffffffu, ent.x, j) < ent.x);
+            if (lane >= n) rank = -1;
+            const int row = ent.x >> 2;
+            const float wy = __int_as_float(ent.y), wx = __int_as_float(ent.z);
+            auto lane_of_rank = [&](int j) { return __ffs(__ballot_sync(0xffffffffu, rank == j)) - 1; };
+            if (VPL > 0) {
+                float4 acc[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                int j = 0;
+                for (; j + 2 <= n; j += 2) {  // two gradient rows in flight, added strictly in order
+                    const int s0 = lane_of_rank(j), s1 = lane_of_rank(j + 1);
+                    const float4* g0 = grad_out + (size_t)__shfl_sync(0xffffffffu, row, s0) * c4;
+                    const float4* g1 = grad_out + (size_t)__shfl_sync(0xffffffffu, row, s1) * c4;
+                    const float a0 = __shfl_sync(0xffffffffu, wy, s0), b0 = __shfl_sync(0xffffffffu, wx, s0);
+                    const float a1 = __shfl_sync(0xffffffffu, wy, s1), b1 = __shfl_sync(0xffffffffu, wx, s1);
+                    float4 v0[V], v1[V];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) { v0[v] = __ldg(g0 + lane + 32 * v); v1[v] = __ldg(g1 + lane + 32 * v); }
+#pragma unroll
+                    for (int v = 0; v < V; ++v) { fma_in_order(acc[v], v0[v], a0, b0); fma_in_order(acc[v], v1[v], a1, b1); }
+                }
+                if (j < n) {
+                    const int s0 = lane_of_rank(j);
+                    const float4* g0 = grad_out + (size_t)__shfl_sync(0xffffffffu, row, s0) * c4;
+                    const float a0 = __shfl_sync(0xffffffffu, wy, s0), b0 = __shfl_sync(0xffffffffu, wx, s0);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) fma_in_order(acc[v], __ldg(g0 + lane + 32 * v), a0, b0);
+                }
+#pragma unroll
+                for (int v = 0; v < V; ++v) __stcs(dst + lane + 32 * v, acc[v]);
+            } else {
+                for (int v0 = 0; v0 < c4; v0 += 32) {  // warp-uniform trip count: the shuffles need every lane
+                    const int v = v0 + lane;
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int j = 0; j < n; ++j) {
+                        const int s0 = lane_of_rank(j);
+                        const size_t r = (size_t)__shfl_sync(0xffffffffu, row, s0) * c4;
+                        const float a0 = __shfl_sync(0xffffffffu, wy, s0), b0 = __shfl_sync(0xffffffffu, wx, s0);
+                        if (v < c4) fma_in_order(acc, __ldg(grad_out + r + v), a0, b0);
+                    }
+                    if (v < c4) __stcs(dst + v, acc);
+                }
+            }
+        }
     }
 }
 
@@ -323,9 +621,38 @@ MRCNN_EXPORT int mrcnn_roialign_forward(const float* boxes, const float* image_m
     return last_error();
 }
 
+static int pixel_space(const int* H, const int* W, int B, PixelSpace* ps) {
+    long long acc = 0;
+    for (int l = 0; l < 4; ++l) { ps->base[l] = (int)acc; acc += (long long)B * H[l] * W[l]; }
+    if (acc > INT_MAX / 2) return MRCNN_ERR_RANGE;
+    ps->base[4] = (int)acc;
+    return MRCNN_OK;
+}
+
+// workspace of the deterministic backward:
+// [count NP | cursor NP | misc 64] (zeroed per call) [start NP] [medium list] [entries 4*bins x 16 B]
+static size_t roialign_bwd_ws_bytes(int NP, long long bins, int /*C*/) {
+    return align_up((2 * (size_t)NP + 64) * sizeof(int), 256) + align_up((size_t)NP * sizeof(int), 256) +
+           align_up(((size_t)NP / 32 + 1 + 4 * (size_t)bins / 32) * sizeof(int), 256) +
+           align_up(4 * (size_t)bins * sizeof(int4), 256);
+}
+
+MRCNN_EXPORT int mrcnn_roialign_backward_workspace_bytes(int B, int N, int ph, int pw, const int* H, const int* W,
+                                                         int C, size_t* bytes) {
+    if (!bytes || !H || !W) return MRCNN_ERR_NULL;
+    if (B < 1 || N < 1 || ph < 1 || pw < 1 || C < 4 || (C & 3) || C > 8192) return MRCNN_ERR_RANGE;
+    for (int l = 0; l < 4; ++l)
+        if (H[l] < 1 || W[l] < 1) return MRCNN_ERR_RANGE;
+    PixelSpace ps;
+    const long long bins = (long long)B * N * ph * pw;
+    if (pixel_space(H, W, B, &ps) != MRCNN_OK || bins >= (1LL << 29)) return MRCNN_ERR_RANGE;
+    *bytes = roialign_bwd_ws_bytes(ps.base[4], bins, C);
+    return MRCNN_OK;
+}
+
 MRCNN_EXPORT int mrcnn_roialign_backward(const float* grad_out, const float* boxes, const int32_t* roi_map,
                                          float* const* grad_fmaps, const int* H, const int* W, int C, int B, int N,
-                                         int ph, int pw, void* stream) {
+                                         int ph, int pw, void* ws, size_t ws_bytes, void* stream) {
     if (!grad_out || !boxes || !roi_map) return MRCNN_ERR_NULL;
     int rc = check_maps((const void* const*)grad_fmaps, H, W, C);
     if (rc != MRCNN_OK) return rc;
@@ -333,11 +660,10 @@ MRCNN_EXPORT int mrcnn_roialign_backward(const float* grad_out, const float* box
     if (!aligned16(boxes) || !aligned16(grad_out)) return MRCNN_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     GradTable tbl;
-    for (int l = 0; l < 4; ++l) {
-        tbl.ptr[l] = grad_fmaps[l]; tbl.H[l] = H[l]; tbl.W[l] = W[l];
-        cudaError_t e = cudaMemsetAsync(grad_fmaps[l], 0, (size_t)B * H[l] * W[l] * C * sizeof(float), st);
-        if (e != cudaSuccess) return (int)e;
-    }
+    for (int l = 0; l < 4; ++l) { tbl.ptr[l] = grad_fmaps[l]; tbl.H[l] = H[l]; tbl.W[l] = W[l]; }
+    PixelSpace ps;
+    rc = pixel_space(H, W, B, &ps);
+    if (rc != MRCNN_OK) return rc;
     const int groups = (ph + kRoiThreads / 32 - 1) / (kRoiThreads / 32);
     const int rows_per_group = (ph + groups - 1) / groups;  // 7x7 -> 1 x 7 rows, 14x14 -> 2 x 7, 28x28 -> 4 x 7
     const size_t smem = (size_t)(kRoiThreads / 32) * C * sizeof(float);
@@ -345,7 +671,50 @@ MRCNN_EXPORT int mrcnn_roialign_backward(const float* grad_out, const float* box
         cudaError_t e = cudaFuncSetAttribute(roialign_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
+    if (ws == nullptr) {  // atomic mode: zero-fill, then scatter every sample with vector reductions
+        for (int l = 0; l < 4; ++l) {
+            cudaError_t e = cudaMemsetAsync(grad_fmaps[l], 0, (size_t)B * H[l] * W[l] * C * sizeof(float), st);
+            if (e != cudaSuccess) return (int)e;
+        }
+        roialign_bwd_kernel<<<B * N * groups, kRoiThreads, smem, st>>>((const float4*)grad_out, (const float4*)boxes,
+                                                                      roi_map, tbl, C, N, ph, pw, groups, rows_per_group,
+                                                                      ps, nullptr, nullptr);
+        return last_error();
+    }
+    // deterministic mode
+    const long long bins_ll = (long long)B * N * ph * pw;
+    if (bins_ll >= (1LL << 29)) return MRCNN_ERR_RANGE;
+    const int NP = ps.base[4], bins = (int)bins_ll;
+    if (!aligned16(ws)) return MRCNN_ERR_ALIGN;
+    if (ws_bytes < roialign_bwd_ws_bytes(NP, bins_ll, C)) return MRCNN_ERR_WORKSPACE;
+    const size_t zeroed = align_up((2 * (size_t)NP + 64) * sizeof(int), 256);
+    uint32_t* count = (uint32_t*)ws;
+    int* cursor = (int*)ws + NP;
+    int* misc = (int*)ws + 2 * (size_t)NP;  // [0] key-list bump pointer, [1] "ordinary samples on a fallback pixel"
+    int* start = (int*)((char*)ws + zeroed);
+    // a medium pixel holds > kLightMax of the <= 4*bins keys, and there are at most NP pixels
+    int* medium = (int*)((char*)start + align_up((size_t)NP * sizeof(int), 256));
+    int4* entries = (int4*)((char*)medium + align_up(((size_t)NP / 32 + 1 + 4 * (size_t)bins / 32) * sizeof(int), 256));
+    cudaError_t e = cudaMemsetAsync(ws, 0, zeroed, st);
+    if (e != cudaSuccess) return (int)e;
+    const int bin_grid = (bins + 255) / 256;
+    roialign_bwd_count_kernel<<<bin_grid, 256, 0, st>>>((const float4*)boxes, roi_map, tbl, ps, N, ph, pw, bins, count,
+                                                        misc);
+    roialign_bwd_alloc_kernel<<<(NP + 1023) / 1024, 256, 0, st>>>(count, NP, start, misc, medium);
+    roialign_bwd_fill_kernel<<<bin_grid, 256, 0, st>>>((const float4*)boxes, roi_map, tbl, ps, N, ph, pw, bins, count,
+                                                      start, cursor, entries);
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int gather_grid = kMediumCtas + min((NP + 31) / 32, 4 * sms);  // 4 resident CTAs per SM (__launch_bounds__)
+#define MRCNN_GATHER(V) roialign_bwd_gather_kernel<V><<<gather_grid, 256, 0, st>>>((const float4*)grad_out, tbl, ps, C, \
+        count, start, entries, misc, medium)
+    if (C == 128) MRCNN_GATHER(1);
+    else if (C == 256) MRCNN_GATHER(2);
+    else if (C == 512) MRCNN_GATHER(4);
+    else MRCNN_GATHER(0);
+#undef MRCNN_GATHER
     roialign_bwd_kernel<<<B * N * groups, kRoiThreads, smem, st>>>((const float4*)grad_out, (const float4*)boxes, roi_map,
-                                                                  tbl, C, N, ph, pw, groups, rows_per_group);
+                                                                  tbl, C, N, ph, pw, groups, rows_per_group, ps, count,
+                                                                  misc + 1);
     return last_error();
 }

@@ -4,6 +4,7 @@ Every function is asynchronous on torch's current stream and never synchronises 
 per (op, shape, device) so repeated calls (and CUDA-graph capture) do not allocate.
 """
 import ctypes
+import os
 
 import torch
 
@@ -179,8 +180,17 @@ def roialign_forward(boxes, image_meta, feature_maps, pool_shape, denominator=24
     return out, roi_map
 
 
-def roialign_backward(grad_out, boxes, roi_map, fmap_shapes):
-    """Feature-map gradients of PyramidROIAlign: list of four [B,H,W,C] tensors."""
+def deterministic_ops():
+    """TensorFlow's switch for reproducible kernels (TF_DETERMINISTIC_OPS=1), honoured by the ROIAlign gradient."""
+    return os.environ.get("TF_DETERMINISTIC_OPS", "0").strip().lower() in ("1", "true")
+
+
+def roialign_backward(grad_out, boxes, roi_map, fmap_shapes, deterministic=None):
+    """Feature-map gradients of PyramidROIAlign: list of four [B,H,W,C] tensors.  deterministic=True sums every
+    pixel's samples in TF CropAndResizeGradImage's sequential order (bit-identical to the CPU kernel, reproducible);
+    False scatters with fp32 vector atomics (order not fixed; faster at 14x14).  None -> TF_DETERMINISTIC_OPS."""
+    if deterministic is None:
+        deterministic = deterministic_ops()
     L = _lib.lib()
     grad_out = _req(grad_out, torch.float32, "grad_out", 5)
     boxes = _req(boxes, torch.float32, "boxes", 3)
@@ -190,8 +200,12 @@ def roialign_backward(grad_out, boxes, roi_map, fmap_shapes):
     ptrs = (c_void_p * 4)(*[g.data_ptr() for g in grads])
     Hs = (c_int * 4)(*[s[1] for s in fmap_shapes])
     Ws = (c_int * 4)(*[s[2] for s in fmap_shapes])
-    check(L.mrcnn_roialign_backward(ptr(grad_out), ptr(boxes), ptr(roi_map), ptrs, Hs, Ws, C, B, N, ph, pw,
-                                    _stream()), "mrcnn_roialign_backward")
+    ws, nbytes = None, 0
+    if deterministic:
+        nbytes = _query(L.mrcnn_roialign_backward_workspace_bytes, B, N, ph, pw, Hs, Ws, C)
+        ws = _workspace(("roialign_bwd", B, N, ph, pw, C, tuple(tuple(s) for s in fmap_shapes)), nbytes, grad_out.device)
+    check(L.mrcnn_roialign_backward(ptr(grad_out), ptr(boxes), ptr(roi_map), ptrs, Hs, Ws, C, B, N, ph, pw, ptr(ws),
+                                    nbytes, _stream()), "mrcnn_roialign_backward")
     return grads
 
 

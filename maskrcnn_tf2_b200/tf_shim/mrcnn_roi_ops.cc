@@ -185,9 +185,16 @@ class MrcnnPyramidRoiAlignGradOp : public tf::OpKernel {
       H[l] = g->dim_size(1);
       W[l] = g->dim_size(2);
     }
+    // deterministic mode: every gradient pixel is summed in CropAndResizeGradImage's sequential order
+    size_t ws_bytes = 0;
+    OP_REQUIRES_OK(ctx, LauncherStatus(mrcnn_roialign_backward_workspace_bytes(B, N, ph, pw, H, W, C, &ws_bytes),
+                                       "mrcnn_roialign_backward_workspace_bytes"));
+    tf::Tensor ws;
+    OP_REQUIRES_OK(ctx, Scratch(ctx, ws_bytes, &ws));
     OP_REQUIRES_OK(ctx, LauncherStatus(
         mrcnn_roialign_backward(grad.flat<float>().data(), boxes.flat<float>().data(),
-                                roi_map.flat<tf::int32>().data(), grads, H, W, C, B, N, ph, pw, StreamOf(ctx)),
+                                roi_map.flat<tf::int32>().data(), grads, H, W, C, B, N, ph, pw,
+                                ws.flat<tf::uint8>().data(), ws_bytes, StreamOf(ctx)),
         "mrcnn_roialign_backward"));
   }
 };

@@ -97,7 +97,12 @@ def test_launchers_reject_bad_arguments_without_launching(lib):
                                       fake, 1 << 20, None) == -1                                # roi_map required
     assert lib.mrcnn_roialign_forward(fake, fake, 93, maps, hw, hw, 256, 1, 10, 7, 7, 244.0, 0, fake, fake, None,
                                       fake, 16, None) == -3                                     # workspace
-    assert lib.mrcnn_roialign_backward(fake, fake, fake, maps, hw, hw, 256, 1, 10, 0, 7, None) == -2
+    assert lib.mrcnn_roialign_backward(fake, fake, fake, maps, hw, hw, 256, 1, 10, 0, 7, None, 0, None) == -2
+    assert lib.mrcnn_roialign_backward(fake, fake, fake, maps, hw, hw, 256, 1, 10, 7, 7, fake, 64, None) == -3  # workspace
+    need = ctypes.c_size_t(0)
+    assert lib.mrcnn_roialign_backward_workspace_bytes(8, 200, 7, 7, hw, hw, 256, ctypes.byref(need)) == 0
+    assert need.value >= 4 * 8 * 200 * 49 * 4 + 3 * 8 * 85 * 4
+    assert lib.mrcnn_roialign_backward_workspace_bytes(8, 200, 7, 7, hw, hw, 256, None) == -1
     assert lib.mrcnn_detection_forward(fake, fake, fake, fake, 93, 1, 1000, 81, std, 0.7, 1, 100, 0.3, 1, fake, None,
                                        fake, 1 << 30, None) == -2                               # per_class unsupported
     assert lib.mrcnn_detection_forward(fake, fake, fake, fake, 93, 1, 9000, 81, std, 0.7, 1, 100, 0.3, 0, fake, None,

@@ -294,12 +294,35 @@ def test_roialign_backward_within_tolerance(F, orc, dev, B, Nr, C, pool, sizes, 
     ref = orc.pyramid_roi_align_grad(g, boxes, 1024.0, 1024.0, shapes)
     fm = [torch.zeros(s, device=dev) for s in shapes]
     _, roi_map = F.roialign_forward(T(boxes, dev), T(_meta(B, 1024), dev), fm, pool)
-    grads = F.roialign_backward(T(g, dev), T(boxes, dev), roi_map, shapes)
+    mag = orc.pyramid_roi_align_grad(np.abs(g), boxes, 1024.0, 1024.0, shapes)
+    for deterministic in (True, False):
+        grads = F.roialign_backward(T(g, dev), T(boxes, dev), roi_map, shapes, deterministic=deterministic)
+        for l in range(4):
+            got = N(grads[l])
+            # fp32 accumulation order differs where atomics are used: tolerance relative to the accumulated magnitude
+            scale = np.maximum(np.abs(ref[l]), mag[l])
+            assert np.all(np.abs(got - ref[l]) <= ATOL + RTOL * scale)
+
+
+def test_roialign_backward_deterministic_bit_exact_at_training_shape(F, orc, dev):
+    # T=200 ROIs/image on COCO-shape maps (config 3), no zero padding: no pixel collects more than 1024 samples, so
+    # the whole gradient equals TF's sequential CPU accumulation bit for bit, run after run
+    rng = np.random.default_rng(131)
+    B, Nr, C = 2, 200, 256
+    boxes = _roi_boxes(rng, B, Nr, 0, 0)
+    shapes = [(B, s, s, C) for s in (256, 128, 64, 32)]
+    g = rng.standard_normal((B, Nr, 7, 7, C)).astype(np.float32)
+    ref = orc.pyramid_roi_align_grad(g, boxes, 1024.0, 1024.0, shapes)
+    _, roi_map = F.roialign_forward(T(boxes, dev), T(_meta(B, 1024), dev), [torch.zeros(s, device=dev) for s in shapes],
+                                    (7, 7))
+    a = F.roialign_backward(T(g, dev), T(boxes, dev), roi_map, shapes, deterministic=True)
+    b = F.roialign_backward(T(g, dev), T(boxes, dev), roi_map, shapes, deterministic=True)
     for l in range(4):
-        got = N(grads[l])
-        # fp32 accumulation order differs (atomics): tolerance relative to the accumulated magnitude
-        scale = np.maximum(np.abs(ref[l]), orc.pyramid_roi_align_grad(np.abs(g), boxes, 1024.0, 1024.0, shapes)[l])
-        assert np.all(np.abs(got - ref[l]) <= ATOL + RTOL * scale)
+        assert torch.equal(a[l], b[l])                       # run-to-run reproducible
+        assert np.array_equal(N(a[l]), ref[l])               # and equal to the sequential accumulation, bit for bit
+    # the atomic mode agrees within the north-star tolerance only
+    c = F.roialign_backward(T(g, dev), T(boxes, dev), roi_map, shapes, deterministic=False)
+    assert all(np.allclose(N(c[l]), ref[l], rtol=1e-5, atol=1e-5) for l in range(4))
 
 
 def test_roialign_adjoint_property_full_size(F, dev):
@@ -317,6 +340,23 @@ def test_roialign_adjoint_property_full_size(F, dev):
     assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), (out.double().abs() * g.double().abs()).sum().item() * 1e-2)
     out2, _ = F.roialign_forward(boxes, T(_meta(B, 1024), dev), [2.0 * f for f in fm], (7, 7))
     assert torch.equal(out2, 2.0 * out)                   # exact linearity under power-of-two scaling
+
+
+def test_roialign_backward_bit_exact_with_medium_fan_in(F, orc, dev):
+    # small maps under many ROIs: most pixels collect 33..1024 samples (the CTA-per-pixel path), 14x14 bins
+    rng = np.random.default_rng(132)
+    B, Nr, C = 2, 48, 256
+    boxes = _roi_boxes(rng, B, Nr, 0, 4)
+    shapes = [(B, s, s, C) for s in (32, 16, 8, 8)]
+    g = rng.standard_normal((B, Nr, 14, 14, C)).astype(np.float32)
+    ref = orc.pyramid_roi_align_grad(g, boxes, 1024.0, 1024.0, shapes)
+    _, roi_map = F.roialign_forward(T(boxes, dev), T(_meta(B, 1024), dev), [torch.zeros(s, device=dev) for s in shapes],
+                                    (14, 14))
+    got = F.roialign_backward(T(g, dev), T(boxes, dev), roi_map, shapes, deterministic=True)
+    exact = sum(int((N(got[l]) == ref[l]).all(-1).sum()) for l in range(4))
+    total = sum(s[0] * s[1] * s[2] for s in shapes)
+    assert all(np.allclose(N(got[l]), ref[l], rtol=1e-5, atol=1e-4) for l in range(4))
+    assert exact >= 0.9 * total                              # only > 1024-sample pixels may differ in the last bits
 
 
 def test_pyramid_roi_align_layer_autograd(orc, dev):
