@@ -16,6 +16,7 @@
 // backward (no workspace) = memset of the four gradient maps + roialign_bwd_kernel: scatter with
 //           red.global.add.v4.f32 (one 16-byte reduction per lane and corner).
 #include <limits.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -163,6 +164,147 @@ roialign_fwd_kernel(const float4* __restrict__ boxes, const int32_t* __restrict_
             for (int v = 0; v < VPL; ++v) __stcs(o + lane + 32 * v, lerp4(a[v], b[v], c[v], d[v]));
         } else {
             for (int i = lane; i < c4; i += 32) __stcs(o + i, lerp4(__ldg(tl + i), __ldg(tr + i), __ldg(bl + i), __ldg(br + i)));
+        }
+    }
+}
+
+// ---- TMA-staged forward (C == 256: one feature-map pixel = one 1 KB bulk copy) ----------------------------------
+// Persistent warps; each warp owns a ring of STAGES x 4 KB in shared memory.  For every output bin the warp's lane 0
+// arms an mbarrier with 4096 expected bytes and issues four `cp.async.bulk.shared.global` copies (the four bilinear
+// corners; SASS: UBLKCP) -- the copy engine, not the LSU, moves the pixels, the warp never holds them in registers
+// while they are in flight, and the ring runs STAGES-1 bins ahead ACROSS row boundaries (a second geometry context
+// follows the producer cursor), so there is no exposed latency per row.  Consumption: 8 x LDS.128 per lane, the same
+// individually rounded lerps as roialign_fwd_kernel, 2 x streaming STG.128.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tma_mbar_arm(uint32_t bar, uint32_t tx_bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx_bytes) : "memory");
+}
+__device__ __forceinline__ void tma_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct RowCtx {        // everything about one output row (roi f, row y) that does not depend on x
+    const float4* img; // feature map of the ROI's image
+    float x0, ws, ly;
+    int top, bot, W;   // pixel index of the two sampled map rows
+    bool yvalid;
+};
+
+__device__ __forceinline__ RowCtx make_row_ctx(int row, const float4* __restrict__ boxes,
+                                               const int32_t* __restrict__ level_ws, const int* __restrict__ first,
+                                               int map_mode, const MapTable& tbl, int N, int ph, int pw, int& m_out) {
+    const int f = row / ph, y = row - f * ph;
+    const int m = roi_map_index(level_ws[f], first, map_mode);
+    const RoiGeom g = roi_geom(__ldg(boxes + f), m, tbl.H, tbl.W, ph, pw);
+    const AxisTap ty = axis_tap(g.y0, g.hs, y, g.H);
+    RowCtx c;
+    c.img = reinterpret_cast<const float4*>(((m == 0) ? tbl.ptr[0] : (m == 1) ? tbl.ptr[1] : (m == 2) ? tbl.ptr[2]
+                                                                                              : tbl.ptr[3]) +
+                                            (size_t)(f / N) * g.H * g.W * 256);
+    c.x0 = g.x0; c.ws = g.ws; c.ly = ty.lerp; c.top = ty.lo * g.W; c.bot = ty.hi * g.W; c.W = g.W; c.yvalid = ty.valid;
+    m_out = m;
+    return c;
+}
+
+template <int WARPS, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32)
+roialign_fwd_tma_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ level_ws,
+                        const int* __restrict__ first, int map_mode, MapTable tbl, int N, int ph, int pw,
+                        int total_rows, float* __restrict__ out, int32_t* __restrict__ roi_map) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* ring = reinterpret_cast<float4*>(smem_raw) + (size_t)warp * STAGES * 256;        // [STAGES][4 corners][64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * STAGES * 4096) + warp * STAGES;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) tma_mbar_init(smem_addr(bars + s), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int nwarps = gridDim.x * WARPS;
+    const int w0 = blockIdx.x * WARPS + warp;
+    if (w0 >= total_rows) return;
+    const int my_rows = (total_rows - w0 + nwarps - 1) / nwarps;  // rows w0, w0 + nwarps, ...
+    const int my_bins = my_rows * pw;
+
+    int m_dummy;
+    RowCtx pc = make_row_ctx(w0, boxes, level_ws, first, map_mode, tbl, N, ph, pw, m_dummy);  // producer cursor
+    int p_row = 0, p_x = 0, issued = 0;
+    auto produce = [&]() {  // bin `issued` of this warp's stream -> stage issued % STAGES
+        const AxisTap tx = axis_tap(pc.x0, pc.ws, p_x, pc.W);
+        const bool valid = pc.yvalid && tx.valid;
+        if (lane == 0) {
+            const int s = issued % STAGES;
+            const uint32_t bar = smem_addr(bars + s), dst = smem_addr(ring + s * 256);
+            tma_mbar_arm(bar, valid ? 4096u : 0u);
+            if (valid && tx.hi == tx.lo + 1) {  // left and right pixels are neighbours in memory: one 2 KB copy per row
+                tma_load_1d(dst, pc.img + (size_t)(pc.top + tx.lo) * 64, 2048, bar);
+                tma_load_1d(dst + 2048, pc.img + (size_t)(pc.bot + tx.lo) * 64, 2048, bar);
+            } else if (valid) {                 // integer sample position: lo == hi
+                tma_load_1d(dst, pc.img + (size_t)(pc.top + tx.lo) * 64, 1024, bar);
+                tma_load_1d(dst + 1024, pc.img + (size_t)(pc.top + tx.hi) * 64, 1024, bar);
+                tma_load_1d(dst + 2048, pc.img + (size_t)(pc.bot + tx.lo) * 64, 1024, bar);
+                tma_load_1d(dst + 3072, pc.img + (size_t)(pc.bot + tx.hi) * 64, 1024, bar);
+            }
+        }
+        ++issued;
+        if (++p_x == pw) {
+            p_x = 0;
+            if (++p_row < my_rows)
+                pc = make_row_ctx(w0 + p_row * nwarps, boxes, level_ws, first, map_mode, tbl, N, ph, pw, m_dummy);
+        }
+    };
+    for (int k = 0; k < STAGES - 1 && issued < my_bins; ++k) produce();
+
+    int consumed = 0;
+#pragma unroll 1
+    for (int r = 0; r < my_rows; ++r) {
+        const int row = w0 + r * nwarps;
+        int m;
+        const RowCtx cc = make_row_ctx(row, boxes, level_ws, first, map_mode, tbl, N, ph, pw, m);
+        if (lane == 0 && row % ph == 0) roi_map[row / ph] = m;
+        float4* o = reinterpret_cast<float4*>(out) + (size_t)row * pw * 64;
+        const float ly = cc.ly;
+#pragma unroll 1
+        for (int x = 0; x < pw; ++x, o += 64, ++consumed) {
+            __syncwarp();                       // every lane is done reading the stage the next copy will overwrite
+            if (issued < my_bins) produce();
+            const AxisTap tx = axis_tap(cc.x0, cc.ws, x, cc.W);
+            const int s = consumed % STAGES;
+            tma_mbar_wait(smem_addr(bars + s), (uint32_t)(consumed / STAGES) & 1u);
+            if (!(cc.yvalid && tx.valid)) {     // extrapolation_value = 0
+                __stcs(o + lane, make_float4(0.f, 0.f, 0.f, 0.f));
+                __stcs(o + lane + 32, make_float4(0.f, 0.f, 0.f, 0.f));
+                continue;
+            }
+            const float4* st = ring + s * 256;
+            const float lx = tx.lerp;
+            auto lerp1 = [&](float a, float b, float c, float d) {
+                const float t = __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), lx));
+                const float u = __fadd_rn(c, __fmul_rn(__fsub_rn(d, c), lx));
+                return __fadd_rn(t, __fmul_rn(__fsub_rn(u, t), ly));
+            };
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const float4 a = st[lane + 32 * v], b = st[64 + lane + 32 * v], c = st[128 + lane + 32 * v],
+                             d = st[192 + lane + 32 * v];
+                __stcs(o + lane + 32 * v, make_float4(lerp1(a.x, b.x, c.x, d.x), lerp1(a.y, b.y, c.y, d.y),
+                                                       lerp1(a.z, b.z, c.z, d.z), lerp1(a.w, b.w, c.w, d.w)));
+            }
         }
     }
 }
@@ -576,6 +718,13 @@ MRCNN_EXPORT int mrcnn_roialign_workspace_bytes(int B, int N, size_t* bytes) {
     return MRCNN_OK;
 }
 
+// MRCNN_ROIALIGN_FWD (read once per process): 0 / unset = LDG kernel (default, the faster one);
+// 1 = TMA-staged kernel, 4 warps x 2 stages x 6 CTAs per SM; 2, 3 = other ring shapes kept for the measurement script
+static int fwd_variant() {
+    static const int v = [] { const char* e = getenv("MRCNN_ROIALIGN_FWD"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
 static int check_maps(const void* const* maps, const int* H, const int* W, int C) {
     if (!maps || !H || !W) return MRCNN_ERR_NULL;
     if (C < 4 || (C & 3)) return MRCNN_ERR_RANGE;
@@ -613,6 +762,28 @@ MRCNN_EXPORT int mrcnn_roialign_forward(const float* boxes, const float* image_m
     const int grid = (total_rows + kRoiThreads / 32 - 1) / (kRoiThreads / 32);
 #define MRCNN_FWD(V) roialign_fwd_kernel<V><<<grid, kRoiThreads, 0, st>>>((const float4*)boxes, level_ws, first, \
         map_mode, tbl, C, N, ph, pw, total_rows, out, roi_map)
+    const int variant = fwd_variant();
+    if (C == 256 && variant != 0) {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#define MRCNN_TMA(WARPS, STAGES, CTAS)                                                                             \
+        {                                                                                                          \
+            const size_t smem = (size_t)WARPS * STAGES * 4096 + (size_t)WARPS * STAGES * 8;                        \
+            cudaError_t e2 = cudaFuncSetAttribute(roialign_fwd_tma_kernel<WARPS, STAGES>,                         \
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+            if (e2 != cudaSuccess) return (int)e2;                                                                 \
+            const int g2 = min((total_rows + WARPS - 1) / WARPS, CTAS * sms);                                      \
+            roialign_fwd_tma_kernel<WARPS, STAGES><<<g2, WARPS * 32, smem, st>>>(                                  \
+                (const float4*)boxes, level_ws, first, map_mode, tbl, N, ph, pw, total_rows, out, roi_map);        \
+        }
+        // measured on B200, config 2 (profiles/r1_roialign_fwd_tma.md): 4 warps x 2 stages x 6 CTAs/SM is the best
+        // of the shapes tried and ties the LDG kernel at 7x7 (138.8 vs 140.0 us) but loses at 14x14 (103 vs 59 us)
+        if (variant == 2) MRCNN_TMA(8, 3, 2)
+        else if (variant == 3) MRCNN_TMA(4, 3, 4)
+        else MRCNN_TMA(4, 2, 6)
+#undef MRCNN_TMA
+        return last_error();
+    }
     if (C == 128) MRCNN_FWD(1);
     else if (C == 256) MRCNN_FWD(2);
     else if (C == 512) MRCNN_FWD(4);

@@ -20,6 +20,6 @@ def timed(fn, n=30):
     torch.cuda.synchronize()
     ts = sorted(a.elapsed_time(b) / 3 for a, b in e)
     return ts[len(ts) // 2] * 1e3
-print("LD mode", os.environ.get("MRCNN_ROIALIGN_LD", "0"),
+print("fwd variant", os.environ.get("MRCNN_ROIALIGN_FWD", "0"),
       "7x7: %.1f us" % timed(lambda: F.roialign_forward(rois, d["image_meta"], maps, (7, 7))),
       "14x14: %.1f us" % timed(lambda: F.roialign_forward(boxes, d["image_meta"], maps, (14, 14))))
