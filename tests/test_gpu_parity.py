@@ -496,3 +496,19 @@ def test_proposal_layer_class_api_and_errors(orc, dev):
     bad = make_config(img_size=256, pre_nms_limit=9000)
     with pytest.raises(MrcnnError):
         ProposalLayer(1000, bad)([T(probs, dev), T(bbox, dev), T(anchors, dev)])               # K > MRCNN_MAX_SORT
+
+
+@pytest.mark.gpu
+def test_tma_staged_roialign_forward_is_bit_exact_too():
+    """The cp.async.bulk (TMA engine) variant of the forward kernel is not the default (it is not faster, DESIGN.md
+    section 4) but stays verified: the forward parity tests are re-run in a child process with the knob set."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("MRCNN_ROIALIGN_FWD"):
+        pytest.skip("already inside the child run")
+    env = dict(os.environ, MRCNN_ROIALIGN_FWD="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                        "roialign_forward"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "passed" in r.stdout
