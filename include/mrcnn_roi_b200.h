@@ -116,12 +116,14 @@ int mrcnn_roialign_backward(const float* grad_out, const float* boxes, const int
  * row, normalised with image 0's h,w, L:513-515).  use_min_conf mirrors the Python truthiness test at
  * L:404.  per_class 0 = reference behaviour (one class-agnostic NMS, L:440-468); 1 is rejected
  * (MRCNN_ERR_RANGE) in this build.  detections [B,max_inst,6] = (y1,x1,y2,x2,class,score), zero padded;
- * det_count [B] optional.  Requires N <= MRCNN_MAX_SORT. */
+ * det_count [B] optional.  det_boxes [B,max_inst,4] optional: detections[..., :4], the tensor
+ * DetectedBoxesExtraction (L:535-550) feeds to the mask branch's PyramidROIAlign, written by the same kernel so the
+ * slice copy disappears.  Requires N <= MRCNN_MAX_SORT. */
 int mrcnn_detection_workspace_bytes(int B, int N, int NC, size_t* bytes);
 int mrcnn_detection_forward(const float* rois, const float* probs, const float* deltas, const float* image_meta,
                             int meta_len, int B, int N, int NC, const float* std_dev, float min_conf,
                             int use_min_conf, int max_inst, float nms_thr, int per_class, float* detections,
-                            int32_t* det_count, void* ws, size_t ws_bytes, void* stream);
+                            int32_t* det_count, float* det_boxes, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- DetectionTargetLayer.call + detection_targets_graph  (mrcnn_layers.py:313-325, 844-1007) ----------
  * proposals [B,P,4]; gt_class_ids [B,G] int32 (crowds negative); gt_boxes [B,G,4] normalised; gt_masks

@@ -42,7 +42,7 @@ PROTOTYPES = {
     "mrcnn_detection_workspace_bytes": [c_int, c_int, c_int, ctypes.POINTER(c_size_t)],
     "mrcnn_detection_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 ctypes.POINTER(c_float), c_float, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
-                                c_void_p, c_size_t, c_void_p],
+                                c_void_p, c_void_p, c_size_t, c_void_p],
     "mrcnn_detection_target_workspace_bytes": [c_int, c_int, c_int, c_int, ctypes.POINTER(c_size_t)],
     "mrcnn_detection_target_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                        c_int, c_int, c_double, ctypes.POINTER(c_float), c_int, c_int, c_int, c_void_p,

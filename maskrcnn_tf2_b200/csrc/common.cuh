@@ -348,6 +348,7 @@ struct NmsEpilogue {
     const float* scores;         // [B,N]
     const int32_t* class_ids;    // [B,N]
     float* detections;           // [B,max_out,6]
+    float4* det_boxes;           // [B,max_out] optional: detections[..., :4] (DetectedBoxesExtraction, L:535-550)
     int N;
 };
 

@@ -113,14 +113,14 @@ MRCNN_EXPORT int mrcnn_detection_workspace_bytes(int B, int N, int NC, size_t* b
 MRCNN_EXPORT int mrcnn_detection_forward(const float* rois, const float* probs, const float* deltas,
                                          const float* image_meta, int meta_len, int B, int N, int NC,
                                          const float* std_dev, float min_conf, int use_min_conf, int max_inst,
-                                         float nms_thr, int per_class, float* detections, int32_t* det_count, void* ws,
-                                         size_t ws_bytes, void* stream) {
+                                         float nms_thr, int per_class, float* detections, int32_t* det_count,
+                                         float* det_boxes, void* ws, size_t ws_bytes, void* stream) {
     if (!rois || !probs || !deltas || !image_meta || !std_dev || !detections || !ws) return MRCNN_ERR_NULL;
     if (B < 1 || N < 1 || N > kMaxSort || NC < 1 || meta_len < 11 || max_inst < 1 || per_class != 0 ||
         !(nms_thr >= 0.0f && nms_thr <= 1.0f))
         return MRCNN_ERR_RANGE;
     if (ws_bytes < det_ws_bytes(B, N)) return MRCNN_ERR_WORKSPACE;
-    if (!aligned16(rois) || !aligned16(deltas) || !aligned16(ws)) return MRCNN_ERR_ALIGN;
+    if (!aligned16(rois) || !aligned16(deltas) || !aligned16(ws) || !aligned16(det_boxes)) return MRCNN_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t bn = (size_t)B * N;
     DetWs w;
@@ -153,6 +153,7 @@ MRCNN_EXPORT int mrcnn_detection_forward(const float* rois, const float* probs, 
     epi.class_ids = w.class_ids;
     epi.detections = detections;
     epi.count = det_count;
+    epi.det_boxes = (float4*)det_boxes;
     epi.N = N;
     return launch_nms_sorted(w.boxes_sorted, w.ncand, B, N, max_inst, nms_thr, epi, st);
 }

@@ -98,8 +98,10 @@ __device__ __forceinline__ void nms_write_outputs(const NmsEpilogue& epi, const 
                 o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
                 o[4] = (float)epi.class_ids[(size_t)b * epi.N + i];
                 o[5] = epi.scores[(size_t)b * epi.N + i];
+                if (epi.det_boxes) epi.det_boxes[(size_t)b * max_out + r] = v;
             } else {
                 o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = 0.0f;
+                if (epi.det_boxes) epi.det_boxes[(size_t)b * max_out + r] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         if (tid == 0 && epi.count) epi.count[b] = total;

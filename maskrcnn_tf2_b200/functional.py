@@ -210,8 +210,9 @@ def roialign_backward(grad_out, boxes, roi_map, fmap_shapes, deterministic=None)
 
 
 def detection_forward(rois, probs, deltas, image_meta, bbox_std_dev, min_confidence, max_instances, nms_threshold,
-                      return_count=False):
-    """DetectionLayer.call -> detections [B,max_instances,6]."""
+                      return_count=False, return_boxes=False):
+    """DetectionLayer.call -> detections [B,max_instances,6] (, count [B]) (, boxes [B,max_instances,4] =
+    detections[..., :4], the DetectedBoxesExtraction output, written by the same kernel)."""
     L = _lib.lib()
     rois = _req(rois, torch.float32, "rois", 3)
     probs = _req(probs, torch.float32, "mrcnn_class", 3)
@@ -225,12 +226,14 @@ def detection_forward(rois, probs, deltas, image_meta, bbox_std_dev, min_confide
     ws = _workspace(("detection", B, N, NC), nbytes, dev)
     det = torch.empty((B, int(max_instances), 6), dtype=torch.float32, device=dev)
     cnt = torch.empty((B,), dtype=torch.int32, device=dev) if return_count else None
+    boxes = torch.empty((B, int(max_instances), 4), dtype=torch.float32, device=dev) if return_boxes else None
     use_conf = 1 if min_confidence else 0
     check(L.mrcnn_detection_forward(ptr(rois), ptr(probs), ptr(deltas), ptr(image_meta), image_meta.shape[1], B, N,
                                     NC, _lib.float4(bbox_std_dev), c_float(float(min_confidence or 0.0)), use_conf,
-                                    int(max_instances), c_float(float(nms_threshold)), 0, ptr(det), ptr(cnt), ptr(ws),
-                                    ws.numel(), _stream()), "mrcnn_detection_forward")
-    return (det, cnt) if return_count else det
+                                    int(max_instances), c_float(float(nms_threshold)), 0, ptr(det), ptr(cnt), ptr(boxes),
+                                    ptr(ws), ws.numel(), _stream()), "mrcnn_detection_forward")
+    out = (det,) + ((cnt,) if return_count else ()) + ((boxes,) if return_boxes else ())
+    return out if len(out) > 1 else det
 
 
 def detection_target_forward(proposals, gt_class_ids, gt_boxes, gt_masks, rand_keys, train_rois_per_image,

@@ -131,13 +131,33 @@ class DetectionLayer(_Layer):
         if rois.shape[1] != self.proposals:
             # the reference builds tf.range(self.proposals) indices (L:388-391) and fails on a mismatch
             raise ValueError(f"DetectionLayer built for {self.proposals} proposals, got {rois.shape[1]}")
-        det = F.detection_forward(rois, mrcnn_class, mrcnn_bbox, image_meta,
-                                  np.asarray(self.bbox_std_dev, dtype=np.float32), self.detection_min_confidence,
-                                  self.detection_max_instances, self.detection_nms_threshold)
-        return det.reshape(self.batch_size, self.detection_max_instances, 6)  # L:524
+        det, boxes = F.detection_forward(rois, mrcnn_class, mrcnn_bbox, image_meta,
+                                         np.asarray(self.bbox_std_dev, dtype=np.float32), self.detection_min_confidence,
+                                         self.detection_max_instances, self.detection_nms_threshold, return_boxes=True)
+        det = det.reshape(self.batch_size, self.detection_max_instances, 6)  # L:524
+        # detections[..., :4] came out of the same kernel: DetectedBoxesExtraction hands it on without a slice copy
+        det._mrcnn_detected_boxes = boxes.reshape(self.batch_size, self.detection_max_instances, 4)
+        return det
 
     def compute_output_shape(self, input_shape):
         return None, self.detection_max_instances, 6
+
+
+class DetectedBoxesExtraction(_Layer):
+    """mrcnn_layers.py:535-550: detections[..., :4], the boxes the mask branch's PyramidROIAlign crops
+    (model.py:566-573).  When the input is the tensor DetectionLayer just produced, the contiguous [B,D,4] copy its
+    kernel wrote alongside is returned; any other tensor is sliced."""
+
+    def __init__(self, config=None, name='detected_boxes_extraction', **kwargs):
+        super().__init__(name=name, **kwargs)
+        self.config = config
+
+    def call(self, inputs, **kwargs):
+        boxes = getattr(inputs, "_mrcnn_detected_boxes", None)
+        return boxes if boxes is not None else inputs[..., :4].contiguous()
+
+    def compute_output_shape(self, input_shape):
+        return tuple(input_shape[:-1]) + (4,)
 
 
 class DetectionTargetLayer(_Layer):

@@ -28,10 +28,16 @@ def _pyramid_roi_align_grad(op, grad_pooled, _grad_roi_map):
     return [None, None, d2, d3, d4, d5]
 
 
-# The reference back-propagates mrcnn_bbox_loss through the proposals into rpn_bbox (no stop_gradient at
-# mrcnn_layers.py:227).  This op is not differentiable: proposals are constants for the heads, as
-# in matterport/Mask_RCNN.  Listed under "what comes next" in DESIGN.md.
-tf.no_gradient("MrcnnProposal")
+@tf.RegisterGradient("MrcnnProposal")
+def _proposal_grad(op, grad_proposals, _grad_topk, _grad_keep):
+    # the reference back-propagates mrcnn_bbox_loss through the proposals into rpn_bbox (no stop_gradient at
+    # mrcnn_layers.py:227); rpn_probs (top_k / NMS indices) and the anchors receive none
+    g = _ops.mrcnn_proposal_grad(grad_proposals, op.inputs[1], op.inputs[2], op.outputs[1], op.outputs[2],
+                                 std_dev=op.get_attr("std_dev"))
+    return [None, g, None]
+
+
+tf.no_gradient("MrcnnProposalGrad")
 tf.no_gradient("MrcnnDetection")
 tf.no_gradient("MrcnnDetectionTarget")
 
@@ -45,9 +51,11 @@ class ProposalLayer(tfl.Layer):
         self.nms_threshold = self.config['rpn_nms_threshold']
 
     def call(self, inputs, **kwargs):
-        return _ops.mrcnn_proposal(inputs[0], inputs[1], inputs[2], proposal_count=self.proposal_count,
-                                   pre_nms_limit=self.config['pre_nms_limit'], nms_threshold=self.nms_threshold,
-                                   std_dev=[float(v) for v in self.config['rpn_bbox_std_dev']])
+        proposals, _, _ = _ops.mrcnn_proposal(inputs[0], inputs[1], inputs[2], proposal_count=self.proposal_count,
+                                              pre_nms_limit=self.config['pre_nms_limit'],
+                                              nms_threshold=self.nms_threshold,
+                                              std_dev=[float(v) for v in self.config['rpn_bbox_std_dev']])
+        return proposals
 
     def build(self, input_shape):
         self.built = True
@@ -102,19 +110,41 @@ class DetectionLayer(tfl.Layer):
         super(DetectionLayer, self).build(input_shape)
 
     def call(self, inputs, **kwargs):
-        det = _ops.mrcnn_detection(inputs[0], inputs[1], inputs[2], inputs[3],
-                                   min_confidence=float(self.detection_min_confidence or 0.0),
-                                   use_min_confidence=bool(self.detection_min_confidence),
-                                   max_instances=self.detection_max_instances,
-                                   nms_threshold=self.detection_nms_threshold,
-                                   std_dev=[float(v) for v in np.asarray(self.bbox_std_dev)])
-        return tf.reshape(det, [self.batch_size, self.detection_max_instances, 6])
+        det, boxes = _ops.mrcnn_detection(inputs[0], inputs[1], inputs[2], inputs[3],
+                                          min_confidence=float(self.detection_min_confidence or 0.0),
+                                          use_min_confidence=bool(self.detection_min_confidence),
+                                          max_instances=self.detection_max_instances,
+                                          nms_threshold=self.detection_nms_threshold,
+                                          std_dev=[float(v) for v in np.asarray(self.bbox_std_dev)])
+        det = tf.reshape(det, [self.batch_size, self.detection_max_instances, 6])
+        # detections[..., :4] written by the same kernel: DetectedBoxesExtraction below hands it on without a slice
+        det._mrcnn_detected_boxes = tf.reshape(boxes, [self.batch_size, self.detection_max_instances, 4])
+        return det
 
     def compute_output_shape(self, input_shape):
         return None, self.detection_max_instances, 6
 
     def get_config(self):
         return super(DetectionLayer, self).get_config()
+
+
+class DetectedBoxesExtraction(tfl.Layer):
+    """mrcnn_layers.py:535-550 (detections[..., :4] for the mask branch, model.py:566-573)."""
+
+    def __init__(self, config=None, name='detected_boxes_extraction', **kwargs):
+        super(DetectedBoxesExtraction, self).__init__(name=name, **kwargs)
+        self.config = config
+
+    def build(self, input_shape):
+        self.built = True
+        super(DetectedBoxesExtraction, self).build(input_shape)
+
+    def call(self, inputs, **kwargs):
+        boxes = getattr(inputs, "_mrcnn_detected_boxes", None)
+        return boxes if boxes is not None else inputs[..., :4]
+
+    def get_config(self):
+        return super(DetectedBoxesExtraction, self).get_config()
 
 
 @tf.keras.utils.register_keras_serializable()

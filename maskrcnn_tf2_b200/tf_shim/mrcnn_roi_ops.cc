@@ -43,6 +43,8 @@ REGISTER_OP("MrcnnProposal")
     .Input("rpn_bbox: float")    // [B,A,4]
     .Input("anchors: float")     // [B,A,4]
     .Output("proposals: float")  // [B,P,4]
+    .Output("topk_idx: int32")   // [B,K] anchors selected by tf.nn.top_k (L:246), saved for the gradient
+    .Output("keep_idx: int32")   // [B,P] NMS survivors as positions in the top-k list, -1 padded (saved too)
     .Attr("proposal_count: int")
     .Attr("pre_nms_limit: int = 6000")
     .Attr("nms_threshold: float = 0.7")
@@ -51,6 +53,8 @@ REGISTER_OP("MrcnnProposal")
       int p;
       TF_RETURN_IF_ERROR(c->GetAttr("proposal_count", &p));
       c->set_output(0, c->MakeShape({c->Dim(c->input(0), 0), p, 4}));
+      c->set_output(1, c->MakeShape({c->Dim(c->input(0), 0), c->UnknownDim()}));
+      c->set_output(2, c->MakeShape({c->Dim(c->input(0), 0), p}));
       return tf::Status();
     });
 
@@ -73,14 +77,20 @@ class MrcnnProposalOp : public tf::OpKernel {
                 tf::errors::InvalidArgument("rpn_bbox / anchors must be [B,A,4]"));
     tf::Tensor* out = nullptr;
     OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({B, p_, 4}), &out));
+    const int K = pre_ < A ? pre_ : A;  // L:245
+    tf::Tensor* topk = nullptr;
+    tf::Tensor* keep = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({B, K}), &topk));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, tf::TensorShape({B, p_}), &keep));
     size_t ws_bytes = 0;
     OP_REQUIRES_OK(ctx, LauncherStatus(mrcnn_proposal_workspace_bytes(B, A, pre_, p_, &ws_bytes), "proposal ws"));
     tf::Tensor ws;
     OP_REQUIRES_OK(ctx, Scratch(ctx, ws_bytes, &ws));
     OP_REQUIRES_OK(ctx, LauncherStatus(
         mrcnn_proposal_forward(probs.flat<float>().data(), bbox.flat<float>().data(), anchors.flat<float>().data(), B,
-                               A, pre_, p_, std_.data(), thr_, out->flat<float>().data(), nullptr, nullptr, nullptr,
-                               nullptr, ws.flat<tf::uint8>().data(), ws_bytes, StreamOf(ctx)),
+                               A, pre_, p_, std_.data(), thr_, out->flat<float>().data(),
+                               topk->flat<tf::int32>().data(), keep->flat<tf::int32>().data(), nullptr, nullptr,
+                               ws.flat<tf::uint8>().data(), ws_bytes, StreamOf(ctx)),
         "mrcnn_proposal_forward"));
   }
 
@@ -90,6 +100,51 @@ class MrcnnProposalOp : public tf::OpKernel {
   std::vector<float> std_;
 };
 REGISTER_KERNEL_BUILDER(Name("MrcnnProposal").Device(tf::DEVICE_GPU), MrcnnProposalOp);
+
+// Gradient of ProposalLayer.call w.r.t. rpn_bbox: the reference does not stop it (model.py:155-157,168 back-propagate
+// mrcnn_bbox_loss through the proposals: gather L:227 -> clip utils.py:854-869 -> decode utils.py:830-851 -> L:238).
+REGISTER_OP("MrcnnProposalGrad")
+    .Input("grad_proposals: float")  // [B,P,4]
+    .Input("rpn_bbox: float")        // [B,A,4]
+    .Input("anchors: float")         // [B,A,4]
+    .Input("topk_idx: int32")        // [B,K]
+    .Input("keep_idx: int32")        // [B,P]
+    .Output("grad_rpn_bbox: float")  // [B,A,4]
+    .Attr("std_dev: list(float) = [0.1, 0.1, 0.2, 0.2]")
+    .SetShapeFn([](InferenceContext* c) {
+      c->set_output(0, c->input(1));
+      return tf::Status();
+    });
+
+class MrcnnProposalGradOp : public tf::OpKernel {
+ public:
+  explicit MrcnnProposalGradOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("std_dev", &std_));
+    OP_REQUIRES(c, std_.size() == 4, tf::errors::InvalidArgument("std_dev needs 4 values"));
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    const tf::Tensor& grad = ctx->input(0);
+    const tf::Tensor& bbox = ctx->input(1);
+    const tf::Tensor& anchors = ctx->input(2);
+    const tf::Tensor& topk = ctx->input(3);
+    const tf::Tensor& keep = ctx->input(4);
+    OP_REQUIRES(ctx, bbox.dims() == 3 && bbox.dim_size(2) == 4 && anchors.shape() == bbox.shape(),
+                tf::errors::InvalidArgument("rpn_bbox / anchors must be [B,A,4]"));
+    const int B = bbox.dim_size(0), A = bbox.dim_size(1), K = topk.dim_size(1), P = keep.dim_size(1);
+    OP_REQUIRES(ctx, grad.shape() == tf::TensorShape({B, P, 4}), tf::errors::InvalidArgument("grad_proposals [B,P,4]"));
+    tf::Tensor* out = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, bbox.shape(), &out));
+    OP_REQUIRES_OK(ctx, LauncherStatus(
+        mrcnn_proposal_backward(grad.flat<float>().data(), bbox.flat<float>().data(), anchors.flat<float>().data(),
+                                topk.flat<tf::int32>().data(), keep.flat<tf::int32>().data(), B, A, K, P, std_.data(),
+                                out->flat<float>().data(), StreamOf(ctx)),
+        "mrcnn_proposal_backward"));
+  }
+
+ private:
+  std::vector<float> std_;
+};
+REGISTER_KERNEL_BUILDER(Name("MrcnnProposalGrad").Device(tf::DEVICE_GPU), MrcnnProposalGradOp);
 
 // ---- PyramidROIAlign.call (mrcnn_layers.py:583-664) and its feature-map gradient ------------------------
 REGISTER_OP("MrcnnPyramidRoiAlign")
@@ -204,6 +259,7 @@ REGISTER_KERNEL_BUILDER(Name("MrcnnPyramidRoiAlignGrad").Device(tf::DEVICE_GPU),
 REGISTER_OP("MrcnnDetection")
     .Input("rois: float").Input("mrcnn_class: float").Input("mrcnn_bbox: float").Input("image_meta: float")
     .Output("detections: float")  // [B,max_instances,6]
+    .Output("boxes: float")       // [B,max_instances,4] = detections[..., :4] (DetectedBoxesExtraction, L:535-550)
     .Attr("min_confidence: float = 0.7")
     .Attr("use_min_confidence: bool = true")
     .Attr("max_instances: int = 100")
@@ -213,6 +269,7 @@ REGISTER_OP("MrcnnDetection")
       int d;
       TF_RETURN_IF_ERROR(c->GetAttr("max_instances", &d));
       c->set_output(0, c->MakeShape({c->Dim(c->input(0), 0), d, 6}));
+      c->set_output(1, c->MakeShape({c->Dim(c->input(0), 0), d, 4}));
       return tf::Status();
     });
 
@@ -236,6 +293,8 @@ class MrcnnDetectionOp : public tf::OpKernel {
                 tf::errors::InvalidArgument("rois [B,N,4], mrcnn_bbox [B,N,NC,4]"));
     tf::Tensor* out = nullptr;
     OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({B, d_, 6}), &out));
+    tf::Tensor* boxes_out = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({B, d_, 4}), &boxes_out));
     size_t ws_bytes = 0;
     OP_REQUIRES_OK(ctx, LauncherStatus(mrcnn_detection_workspace_bytes(B, N, NC, &ws_bytes), "detection ws"));
     tf::Tensor ws;
@@ -244,7 +303,7 @@ class MrcnnDetectionOp : public tf::OpKernel {
         mrcnn_detection_forward(rois.flat<float>().data(), probs.flat<float>().data(), deltas.flat<float>().data(),
                                 meta.flat<float>().data(), meta.dim_size(1), B, N, NC, std_.data(), conf_,
                                 use_conf_ ? 1 : 0, d_, thr_, 0, out->flat<float>().data(), nullptr,
-                                ws.flat<tf::uint8>().data(), ws_bytes, StreamOf(ctx)),
+                                boxes_out->flat<float>().data(), ws.flat<tf::uint8>().data(), ws_bytes, StreamOf(ctx)),
         "mrcnn_detection_forward"));
   }
 

@@ -104,9 +104,11 @@ def test_launchers_reject_bad_arguments_without_launching(lib):
     assert need.value >= 4 * 8 * 200 * 49 * 4 + 3 * 8 * 85 * 4
     assert lib.mrcnn_roialign_backward_workspace_bytes(8, 200, 7, 7, hw, hw, 256, None) == -1
     assert lib.mrcnn_detection_forward(fake, fake, fake, fake, 93, 1, 1000, 81, std, 0.7, 1, 100, 0.3, 1, fake, None,
-                                       fake, 1 << 30, None) == -2                               # per_class unsupported
+                                       None, fake, 1 << 30, None) == -2                         # per_class unsupported
     assert lib.mrcnn_detection_forward(fake, fake, fake, fake, 93, 1, 9000, 81, std, 0.7, 1, 100, 0.3, 0, fake, None,
-                                       fake, 1 << 30, None) == -2
+                                       None, fake, 1 << 30, None) == -2
+    assert lib.mrcnn_detection_forward(fake, fake, fake, fake, 93, 1, 1000, 81, std, 0.7, 1, 100, 0.3, 0, fake, None,
+                                       odd, fake, 1 << 30, None) == -4                          # det_boxes alignment
     assert lib.mrcnn_detection_target_forward(fake, fake, fake, fake, fake, 1, 2000, 100, 64, 64, 200, 0.0, std, 28,
                                               28, 0, fake, fake, fake, fake, None, fake, 1 << 30, None) == -2
     assert lib.mrcnn_detection_target_forward(fake, fake, fake, fake, None, 1, 2000, 100, 64, 64, 200, 0.33, std, 28,
