@@ -303,14 +303,10 @@ def main():
         streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
         keep_alive = [None, None]
 
-        from maskrcnn_tf2_b200 import functional as _Fn
-        saved_ws = _Fn._ws_cache
-        ws_sets = [dict(), dict()]                      # launchers own no state: one workspace set per stream
-
         def run_pipelined(n):
             for i in range(n):
-                _Fn._ws_cache = ws_sets[i & 1]
-                with torch.cuda.stream(streams[i & 1]):
+                # launchers own no state: each stream gets its own workspace set
+                with F.workspace_namespace(1 + (i & 1)), torch.cuda.stream(streams[i & 1]):
                     keep_alive[i & 1] = stage(d, d_maps)
         for s_ in streams:
             s_.wait_stream(torch.cuda.current_stream())
@@ -325,7 +321,6 @@ def main():
             torch.cuda.current_stream().wait_stream(s_)
         p1.record()
         barrier()
-        _Fn._ws_cache = saved_ws
         ms_pipe = p0.elapsed_time(p1)
 
     # ---- end to end: pinned host inputs -> H2D every step, detections -> host every step ----

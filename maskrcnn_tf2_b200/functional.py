@@ -12,6 +12,25 @@ from . import _lib
 from ._lib import c_float, c_int, c_size_t, c_void_p, check, ptr
 
 _ws_cache = {}
+_ws_namespace = [0]
+
+
+class workspace_namespace:
+    """Launchers are stateless and the caller owns every workspace; this module caches them per (op, shape, device).
+    Calls that may run CONCURRENTLY (several CUDA streams in one process) must not share a workspace: wrap each
+    stream's calls in `with workspace_namespace(i):` to give them their own set."""
+
+    def __init__(self, key):
+        self.key = key
+
+    def __enter__(self):
+        self.prev = _ws_namespace[0]
+        _ws_namespace[0] = self.key
+        return self
+
+    def __exit__(self, *exc):
+        _ws_namespace[0] = self.prev
+        return False
 
 
 def _stream():
@@ -29,7 +48,7 @@ def _req(t, dtype, name, ndim=None):
 
 
 def _workspace(key, nbytes, device):
-    key = key + (device.index,)
+    key = key + (device.index, _ws_namespace[0])
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
