@@ -47,8 +47,9 @@ def inference(cfg_id, B, S, NC, regime, rows, distinct=8):
     prop = lambda: F.proposal_forward(d["rpn_probs"], d["rpn_bbox"], d["anchors"], 6000, 1000, SD, 0.7)
     rois = prop()
     a7 = lambda: F.roialign_forward(rois, d["image_meta"], maps, (7, 7))
-    det = lambda: F.detection_forward(rois, d["mrcnn_class"], d["mrcnn_bbox"], d["image_meta"], SD, 0.7, 100, 0.3)
-    boxes = det()[..., :4].contiguous()
+    det = lambda: F.detection_forward(rois, d["mrcnn_class"], d["mrcnn_bbox"], d["image_meta"], SD, 0.7, 100, 0.3,
+                                      return_boxes=True)
+    boxes = det()[1]
     a14 = lambda: F.roialign_forward(boxes, d["image_meta"], maps, (14, 14))
     tp, t7, td, t14 = timed(prop), timed(a7), timed(det), timed(a14)
     total = tp + t7 + td + t14
@@ -77,13 +78,15 @@ def training(rows, B=8, S=1024, T=200, mini=None):
         out, roi_map = F.roialign_forward(rois, d["image_meta"], maps, (ph, ph))
         gout = torch.randn_like(out)
         res[ph] = (timed(lambda: F.roialign_forward(rois, d["image_meta"], maps, (ph, ph))),
-                   timed(lambda: F.roialign_backward(gout, rois, roi_map, shapes)))
+                   timed(lambda: F.roialign_backward(gout, rois, roi_map, shapes, deterministic=False)),
+                   timed(lambda: F.roialign_backward(gout, rois, roi_map, shapes, deterministic=True)))
     tt = timed(tgt)
     mb = sum(np.prod(s) for s in shapes) * 4
     name = f"cfg3 B={B} S={S} T={T} masks={'mini32' if mini else 'full'} (pos/neg {counts.float().mean(0).tolist()})"
-    rows.append(f"| {name} | DetectionTarget {tt:.0f} | 7x7 fwd {res[7][0]:.0f} / bwd {res[7][1]:.0f} "
-                f"({(B * T * 49 * 1024 + mb) / res[7][1] / 1e3:.0f} GB/s) | 14x14 fwd {res[14][0]:.0f} / bwd {res[14][1]:.0f} "
-                f"({(B * T * 196 * 1024 + mb) / res[14][1] / 1e3:.0f} GB/s) | | | |")
+    rows.append(f"| {name} | DetectionTarget {tt:.0f} | 7x7 fwd {res[7][0]:.0f} / bwd atomic {res[7][1]:.0f} "
+                f"({(B * T * 49 * 1024 + mb) / res[7][1] / 1e3:.0f} GB/s), deterministic {res[7][2]:.0f} | 14x14 fwd "
+                f"{res[14][0]:.0f} / bwd atomic {res[14][1]:.0f} ({(B * T * 196 * 1024 + mb) / res[14][1] / 1e3:.0f} GB/s), "
+                f"deterministic {res[14][2]:.0f} | | | |")
 
 
 if __name__ == "__main__":

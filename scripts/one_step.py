@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from maskrcnn_tf2_b200 import make_config, synth
-from maskrcnn_tf2_b200.layers import DetectionLayer, ProposalLayer, PyramidROIAlign
+from maskrcnn_tf2_b200.layers import DetectedBoxesExtraction, DetectionLayer, ProposalLayer, PyramidROIAlign
 B = int(os.environ.get("B", "8"))
 regime = os.environ.get("REGIME", "clustered")
 cfg = make_config(batch_size=B)
@@ -17,6 +17,6 @@ for _ in range(2):
     rois = prop([d["rpn_probs"], d["rpn_bbox"], d["anchors"]])
     p7 = a7([rois, d["image_meta"]] + maps)
     dt = det([rois, d["mrcnn_class"], d["mrcnn_bbox"], d["image_meta"]])
-    p14 = a14([dt[..., :4].contiguous(), d["image_meta"]] + maps)
+    p14 = a14([DetectedBoxesExtraction(cfg)(dt), d["image_meta"]] + maps)
 torch.cuda.synchronize()
 print("ok", float(p7.sum()), float(p14.sum()))
