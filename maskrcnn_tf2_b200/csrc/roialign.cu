@@ -11,7 +11,7 @@
 //           gradient-map pixel, give each touched pixel a segment of a key list, fill it, then ONE pass over all
 //           pixels writes each of them exactly once -- zeros, or the sum of its samples in TF CropAndResizeGradImage's
 //           own (box, y, x, corner) order, so the result is bit-identical to the sequential CPU kernel and the
-//           713 MB zero-fill and the accumulation are the same HBM write.  Pixels that collect more than 256
+//           713 MB zero-fill and the accumulation are the same HBM write.  Pixels that collect more than 1024
 //           samples (zero-padded ROIs pile thousands on pixel (0,0), quirk Q5) fall back to vector atomics.
 // backward (no workspace) = memset of the four gradient maps + roialign_bwd_kernel: scatter with
 //           red.global.add.v4.f32 (one 16-byte reduction per lane and corner).
