@@ -334,6 +334,47 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* 
     return warp_sums[warp] + incl - v;
 }
 
+// Largest cluster size in {8,4,2,1} (bounded by max_cs) for which the driver can keep one cluster per image resident
+// at the same time (cudaOccupancyMaxActiveClusters >= B): a batch whose clusters do not all co-schedule runs in
+// waves and loses more than the wider clusters gain.  `cache` is a per-kernel table of pure query results (idempotent
+// writes, so unsynchronised access is harmless); smem_for(cs) gives the dynamic shared memory of a CTA at that size.
+template <typename Kernel, typename SmemFn>
+static int pick_cluster_size(Kernel kernel, int threads, int B, int max_cs, SmemFn smem_for, int (&cache)[4][2]) {
+    int best = 1;
+    for (int i = 3; i >= 0; --i) {
+        const int cs = 1 << i;
+        if (cs > max_cs) continue;
+        if (cs == 1) return 1;
+        const size_t smem = smem_for(cs);
+        int active = 0;
+        if (cache[i][0] == (int)smem + 1) {
+            active = cache[i][1];
+        } else {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(cs * 64));
+            cfg.blockDim = dim3((unsigned)threads);
+            cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)cs;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+                cudaOccupancyMaxActiveClusters(&active, kernel, &cfg) != cudaSuccess) {
+                (void)cudaGetLastError();
+                active = 148 / cs;  // the old estimate: one CTA per SM
+            }
+            cache[i][1] = active;
+            cache[i][0] = (int)smem + 1;
+        }
+        if (active >= B) return cs;
+        best = 1;
+    }
+    return best;
+}
+
 // ---- internal launchers shared between translation units (hidden visibility) -----------------------
 struct NmsEpilogue {
     int mode;                    // 0 = indices, 1 = proposal boxes, 2 = detection rows

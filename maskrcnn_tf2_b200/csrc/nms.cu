@@ -224,11 +224,9 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
 // portable maximum of 8 (16-CTA clusters do not co-schedule for 8 images on this part: measured); small candidate
 // sets do not amortise the exchange
 static int nms_cluster_size(int B, int M, size_t smem) {
-    (void)smem;
     if (M <= 2048) return 1;
-    int cs = 1;
-    while (cs < 8 && (long long)B * (cs * 2) <= 148) cs *= 2;
-    return cs;
+    static int cache[4][2] = {};
+    return pick_cluster_size(nms_lazy_kernel, kNmsThreads, B, 8, [smem](int) { return smem; }, cache);
 }
 
 int launch_nms_sorted(const float4* boxes_sorted, const int32_t* valid, int B, int M, int max_out, float thr,

@@ -315,10 +315,10 @@ topk_cluster_kernel(const float* __restrict__ scores, int stride, int offset, in
     cluster.sync();  // no CTA leaves while a peer may still read its exchange buffers
 }
 
-static int tk_cluster_size(int B) {
-    int cs = 1;
-    while (cs < 8 && (long long)B * (cs * 2) <= 148) cs *= 2;
-    return cs;
+static size_t tk_smem_bytes(int cs);
+template <int M> static int tk_cluster_size_for(int B) {
+    static int cache[4][2] = {};
+    return pick_cluster_size(topk_cluster_kernel<M>, kTkThreads, B, 8, [](int cs) { return tk_smem_bytes(cs); }, cache);
 }
 
 static size_t tk_smem_bytes(int cs) {
@@ -330,15 +330,15 @@ static size_t tk_smem_bytes(int cs) {
 
 int launch_topk_cluster(const float* scores, int stride, int offset, int B, int A, int K, int32_t* idx, float* vals,
                         const TopkDecode* dec, cudaStream_t stream) {
-    const int cs = tk_cluster_size(B);
-    const size_t smem = tk_smem_bytes(cs);
-    int chunk = (A + cs - 1) / cs;
-    chunk = (chunk + 3) & ~3;
     int mode = 0;
     if (aligned16(scores)) {
         if (stride == 2 && (A % 2) == 0) mode = 2;
         else if (stride == 1 && (A % 4) == 0) mode = 1;
     }
+    const int cs = (mode == 2) ? tk_cluster_size_for<2>(B) : (mode == 1) ? tk_cluster_size_for<1>(B) : tk_cluster_size_for<0>(B);
+    const size_t smem = tk_smem_bytes(cs);
+    int chunk = (A + cs - 1) / cs;
+    chunk = (chunk + 3) & ~3;
     TopkDecode d{};
     if (dec) d = *dec;
     const bool has_dec = dec != nullptr;
