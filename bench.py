@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bound on the CPU baseline sample")
     ap.add_argument("--no-pipelined", action="store_true", help="skip the extra two-stream throughput measurement")
+    ap.add_argument("--first-image", type=int, default=0, help="index of the first synthetic image (rank r adds r*batch)")
     return ap.parse_args()
 
 
@@ -151,6 +152,26 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+def bind_to_gpu_cpus(index):
+    """Pin this process to the CPU cores NVML reports as local to GPU `index` (same NUMA node / PCIe root), so the
+    pinned host buffers of the end-to-end loop are allocated next to the GPU that reads them.  Returns the previous
+    affinity (restored around the CPU baseline, which uses every core) or None."""
+    try:
+        import pynvml
+        before = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        handle = None
+        try:                                   # CUDA and NVML orderings can differ: match by UUID when torch has it
+            import torch
+            handle = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(index).uuid))
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return before
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------------------------------------
 def cpu_stage(oracle, x, cfg):
     """The reference's CPU path for one batch (oracle = restatement of the TF kernels + layer control flow)."""
@@ -235,6 +256,7 @@ def main():
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus = bind_to_gpu_cpus(local_rank)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
@@ -242,7 +264,7 @@ def main():
     B, S, NC = args.batch, args.img_size, args.num_classes
     cfg = make_config(img_size=S, num_classes=NC, batch_size=B)
     # distinct images per rank (weak scaling: every GPU processes its own B images per step)
-    x = synth.inference_batch(2, B, img_size=S, num_classes=NC, regime=args.regime, first_image=rank * B)
+    x = synth.inference_batch(2, B, img_size=S, num_classes=NC, regime=args.regime, first_image=args.first_image + rank * B)
     A = x["anchors"].shape[1]
 
     def pin(a):
@@ -392,6 +414,8 @@ def main():
         achieved = bytes7 / (ms7_avg * 1e-3) / 1e9
         cpu = None
         if not args.no_cpu_baseline:
+            if all_cpus:
+                os.sched_setaffinity(0, all_cpus)     # the CPU baseline gets every host core
             ips, sec, reps, threads = time_cpu(x, cfg, B, args.cpu_seconds)
             cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"{reps} x the full batch of {B} images (whole stage), median; oracle/ C restatement of "
