@@ -42,7 +42,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bound on the CPU baseline sample")
     ap.add_argument("--no-pipelined", action="store_true", help="skip the extra two-stream throughput measurement")
-    ap.add_argument("--first-image", type=int, default=0, help="index of the first synthetic image (rank r adds r*batch)")
+    ap.add_argument("--first-image", type=int, default=0, help="index of the first synthetic image")
+    ap.add_argument("--distinct-images", action="store_true",
+                    help="rank r processes images first+r*batch.. instead of the same batch as every other rank")
     return ap.parse_args()
 
 
@@ -263,8 +265,11 @@ def main():
 
     B, S, NC = args.batch, args.img_size, args.num_classes
     cfg = make_config(img_size=S, num_classes=NC, batch_size=B)
-    # distinct images per rank (weak scaling: every GPU processes its own B images per step)
-    x = synth.inference_batch(2, B, img_size=S, num_classes=NC, regime=args.regime, first_image=args.first_image + rank * B)
+    # weak scaling: every GPU processes B images per step.  By default every rank gets the SAME synthetic batch, so
+    # per-GPU work is exactly fixed as N grows (step time is data dependent: the 7x7 ROIAlign of other image sets of
+    # this generator takes 154-158 us against 141 us for images 0-7); --distinct-images gives rank r its own images.
+    first = args.first_image + (rank * B if args.distinct_images else 0)
+    x = synth.inference_batch(2, B, img_size=S, num_classes=NC, regime=args.regime, first_image=first)
     A = x["anchors"].shape[1]
 
     def pin(a):
@@ -425,6 +430,8 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "img_size": S, "anchors": A, "regime": args.regime,
+                       "images": ("distinct images per rank" if args.distinct_images else
+                                  "the same synthetic batch on every rank") + f", first image {args.first_image}",
                        "l2": "inputs larger than L2 (feature maps 89 MB/image, 713 MB/step per GPU vs 126 MB L2)",
                        "stage_algorithmic_bytes_per_image": stage_bytes(S, A, NC=NC),
                        "stage_hbm_gbs": world * B * stage_bytes(S, A, NC=NC) * args.steps / (ms_total * 1e-3) / 1e9},
