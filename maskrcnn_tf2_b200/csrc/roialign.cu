@@ -629,6 +629,15 @@ roialign_bwd_gather_kernel(const float4* __restrict__ grad_out, GradTable tbl, P
         const int my_start = seg_next;
         header(chunk + nctas, c_next, seg_next);
         const int q0 = chunk * 32 + warp * 4;
+        // fast path (most of the fine maps): none of the warp's four pixels has a sample and they are contiguous in
+        // one map -> eight stores
+        if (__all_sync(0xffffffffu, my_count == 0u) && q0 + 3 < NP &&
+            (q0 + 3 < ps.base[1] || (q0 >= ps.base[1] && q0 + 3 < ps.base[2]) || (q0 >= ps.base[2] && q0 + 3 < ps.base[3]) ||
+             q0 >= ps.base[3])) {
+            float4* dst = pixel_ptr(tbl, ps, q0, c4);
+            for (int v = lane; v < 4 * c4; v += 32) __stcs(dst + v, make_float4(0.f, 0.f, 0.f, 0.f));
+            continue;
+        }
         // -1: a medium CTA writes this pixel; 0: zeros (untouched, or the atomic fallback adds to it later)
         auto samples_of = [&](int i) {
             const uint32_t c = __shfl_sync(0xffffffffu, my_count, i);
