@@ -141,6 +141,26 @@ int mrcnn_detection_target_forward(const float* proposals, const int32_t* gt_cla
                                    float* deltas, float* masks, int32_t* counts, void* ws, size_t ws_bytes,
                                    void* stream);
 
+/* ---- utils.build_rpn_targets  (utils.py:154-262; compute_overlaps / compute_iou utils.py:114-151) -------------
+ * The data loader's per-image numpy routine (preprocess.py:342-348), for a padded batch in one launch sequence.
+ * anchors [A,4] float64 PIXEL boxes, as utils.generate_pyramid_anchors returns them and the loader keeps them
+ * (preprocess.py:82,297), shared by the batch; gt_class_ids [B,G] int32 (0 = padding row, negative = COCO crowd);
+ * gt_boxes [B,G,4] int32 pixel boxes (utils.extract_bboxes); rand_keys [B,A] fp32, finite and >= 0 (e.g. uniform
+ * [0,1)): the injected stand-in for np.random.choice (utils.py:219,227) -- of an oversubscribed class the anchors
+ * with the largest key are kept, ties -> lower anchor index.
+ * Arithmetic is float64 in numpy's operation order, so rpn_match [B,A] int32 (1 / -1 / 0) and the first two
+ * columns of rpn_bbox are bit-identical to the reference's; the log columns differ by the last ulp of log().
+ * rpn_bbox [B,R,4] float64 (R = rpn_train_anchors_per_image): refinements of the kept positives in ascending anchor
+ * order, divided by std_dev (host pointer to 4 doubles), zero padded.  rpn_bbox_f32 [B,R,4] optional: the same
+ * rounded to fp32 (what the model's float32 input_rpn_bbox receives, model.py:420).  counts [B,2] optional: kept
+ * positives / negatives.  An image without instances (the loader skips those, preprocess.py:336-338) yields
+ * negatives only.  Requires 2 <= R <= MRCNN_MAX_SORT, G <= MRCNN_MAX_GT, A <= 2^24, y2 >= y1 and x2 >= x1. */
+int mrcnn_rpn_targets_workspace_bytes(int B, int A, int G, int R, size_t* bytes);
+int mrcnn_rpn_targets_forward(const double* anchors, const int32_t* gt_class_ids, const int32_t* gt_boxes,
+                              const float* rand_keys, int B, int A, int G, int R, const double* std_dev, double eps,
+                              int32_t* rpn_match, double* rpn_bbox, float* rpn_bbox_f32, int32_t* counts, void* ws,
+                              size_t ws_bytes, void* stream);
+
 /* ---- helpers exported for the parity tests (device arrays of n elements) ------------------------------ */
 int mrcnn_test_expf(const float* x, float* y, int n, void* stream);
 int mrcnn_test_logf(const float* x, float* y, int n, void* stream);

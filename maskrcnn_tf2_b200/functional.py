@@ -287,3 +287,37 @@ def detection_target_forward(proposals, gt_class_ids, gt_boxes, gt_masks, rand_k
     if return_counts:
         return rois, cls, dl, masks, counts
     return rois, cls, dl, masks
+
+
+def rpn_targets_forward(anchors_px, gt_class_ids, gt_boxes, rand_keys, rpn_train_anchors_per_image, rpn_bbox_std,
+                        eps=1e-3, return_f32=False, return_counts=False):
+    """utils.build_rpn_targets (utils.py:154-262) for a padded batch -> rpn_match [B,A] int32, rpn_bbox [B,R,4] float64
+    (+ the same in fp32, + counts [B,2] of kept positives / negatives).
+
+    anchors_px [A,4] float64 pixel anchors (shared by the batch); gt_class_ids [B,G] int32 (0 = padding row, negative =
+    crowd); gt_boxes [B,G,4] int32 pixel boxes; rand_keys [B,A] fp32 >= 0 in place of np.random.choice."""
+    L = _lib.lib()
+    anchors_px = _req(anchors_px, torch.float64, "anchors_px", 2)
+    gt_class_ids = _req(gt_class_ids, torch.int32, "gt_class_ids", 2)
+    gt_boxes = _req(gt_boxes, torch.int32, "gt_boxes", 3)
+    rand_keys = _req(rand_keys, torch.float32, "rand_keys", 2)
+    A, (B, G), R = anchors_px.shape[0], gt_class_ids.shape, int(rpn_train_anchors_per_image)
+    if anchors_px.shape[1] != 4 or tuple(gt_boxes.shape) != (B, G, 4) or tuple(rand_keys.shape) != (B, A):
+        raise ValueError("expected anchors_px [A,4], gt_boxes [B,G,4], rand_keys [B,A]")
+    dev = anchors_px.device
+    nbytes = _query(L.mrcnn_rpn_targets_workspace_bytes, B, A, G, R)
+    ws = _workspace(("rpn_targets", B, A, G, R), nbytes, dev)
+    match = torch.empty((B, A), dtype=torch.int32, device=dev)
+    bbox = torch.empty((B, R, 4), dtype=torch.float64, device=dev)
+    bbox32 = torch.empty((B, R, 4), dtype=torch.float32, device=dev) if return_f32 else None
+    counts = torch.empty((B, 2), dtype=torch.int32, device=dev) if return_counts else None
+    sd = (ctypes.c_double * 4)(*[float(v) for v in rpn_bbox_std])
+    check(L.mrcnn_rpn_targets_forward(ptr(anchors_px), ptr(gt_class_ids), ptr(gt_boxes), ptr(rand_keys), B, A, G, R, sd,
+                                      ctypes.c_double(eps), ptr(match), ptr(bbox), ptr(bbox32), ptr(counts), ptr(ws),
+                                      ws.numel(), _stream()), "mrcnn_rpn_targets_forward")
+    out = [match, bbox]
+    if return_f32:
+        out.append(bbox32)
+    if return_counts:
+        out.append(counts)
+    return tuple(out)

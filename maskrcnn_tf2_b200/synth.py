@@ -14,10 +14,11 @@ def backbone_shapes(img_size, strides):
     return [(int(math.ceil(img_size / s)), int(math.ceil(img_size / s))) for s in strides]
 
 
-def pyramid_anchors(img_size, scales=(32, 64, 128, 256, 512), ratios=(0.5, 1, 2), strides=(4, 8, 16, 32, 64),
-                    anchor_stride=1):
-    """Normalised fp32 anchors [A,4]: level-major, then row-major (y, x), ratio innermost (utils.py:54-111);
-    float64 pixel boxes -> fp32 -> (a - [0,0,1,1]) / ([h,w,h,w] - 1) in fp32 (mrcnn_layers.py:34-39)."""
+def pyramid_anchors_px(img_size, scales=(32, 64, 128, 256, 512), ratios=(0.5, 1, 2), strides=(4, 8, 16, 32, 64),
+                       anchor_stride=1):
+    """float64 pixel anchors [A,4] as utils.generate_pyramid_anchors returns them (utils.py:54-111): level-major,
+    then row-major (y, x), ratio innermost.  These are what the data loader hands to build_rpn_targets
+    (preprocess.py:82,297,343)."""
     out = []
     ratios = np.asarray(ratios, dtype=np.float64)
     for scale, (fh, fw), stride in zip(scales, backbone_shapes(img_size, strides), strides):
@@ -32,7 +33,14 @@ def pyramid_anchors(img_size, scales=(32, 64, 128, 256, 512), ratios=(0.5, 1, 2)
         WW = np.broadcast_to(ws[None, None, :], CY.shape)
         boxes = np.stack([CY - 0.5 * HH, CX - 0.5 * WW, CY + 0.5 * HH, CX + 0.5 * WW], axis=-1).reshape(-1, 4)
         out.append(boxes)
-    a = np.concatenate(out, axis=0).astype(np.float32)
+    return np.concatenate(out, axis=0)
+
+
+def pyramid_anchors(img_size, scales=(32, 64, 128, 256, 512), ratios=(0.5, 1, 2), strides=(4, 8, 16, 32, 64),
+                    anchor_stride=1):
+    """Normalised fp32 anchors [A,4]: float64 pixel boxes (pyramid_anchors_px) -> fp32 ->
+    (a - [0,0,1,1]) / ([h,w,h,w] - 1) in fp32 (mrcnn_layers.py:34-39,116-132)."""
+    a = pyramid_anchors_px(img_size, scales, ratios, strides, anchor_stride).astype(np.float32)
     scale = np.array([img_size, img_size, img_size, img_size], dtype=np.float32) - np.float32(1.0)
     shift = np.array([0, 0, 1, 1], dtype=np.float32)
     return ((a - shift) / scale).astype(np.float32)

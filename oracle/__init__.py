@@ -253,3 +253,23 @@ def detection_target_layer(proposals, gt_class_ids, gt_boxes, gt_masks, rand_key
                                      mh, mw, 1 if use_mini_masks else 0, _p(rois, _f32p), _p(cls, _i32p),
                                      _p(dl, _f32p), _p(mk, _f32p), _p(cnt, _i32p))
     return dict(rois=rois, class_ids=cls, deltas=dl, masks=mk, counts=cnt)
+
+
+def build_rpn_targets(anchors_px, gt_class_ids, gt_boxes, rand_keys, rpn_train_anchors_per_image, rpn_bbox_std,
+                      eps=1e-3):
+    """utils.build_rpn_targets (utils.py:154-262) over a padded batch (class id 0 = padding row) with injected keys
+    in place of np.random.choice -> dict(rpn_match [B,A] int32, rpn_bbox [B,R,4] float64, counts [B,2])."""
+    an = np.ascontiguousarray(anchors_px, dtype=np.float64)
+    gc = np.ascontiguousarray(gt_class_ids, dtype=np.int32)
+    gb = np.ascontiguousarray(gt_boxes, dtype=np.int32)
+    rk = _f32(rand_keys)
+    B, G = gc.shape
+    A, R = an.shape[0], int(rpn_train_anchors_per_image)
+    sd = np.ascontiguousarray(rpn_bbox_std, dtype=np.float64)
+    match = np.empty((B, A), dtype=np.int32)
+    bbox = np.empty((B, R, 4), dtype=np.float64)
+    cnt = np.empty((B, 2), dtype=np.int32)
+    f64p = ctypes.POINTER(ctypes.c_double)
+    lib().orc_build_rpn_targets(_p(an, f64p), _p(gc, _i32p), _p(gb, _i32p), _p(rk, _f32p), B, A, G, R, _p(sd, f64p),
+                                ctypes.c_double(eps), _p(match, _i32p), _p(bbox, f64p), _p(cnt, _i32p))
+    return dict(rpn_match=match, rpn_bbox=bbox, counts=cnt)

@@ -859,6 +859,135 @@ ORC_API void orc_detection_target_layer(const float* proposals /*[B,P,4]*/, cons
     }
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* utils.build_rpn_targets (U:154-262) + compute_overlaps / compute_iou (U:114-151), per image  */
+/* of a padded batch.  PINNED: unlike the TF kernels above, this function's reference is plain  */
+/* numpy and runs here; tests/golden/reference_rpn_targets_golden.npz holds its own outputs.    */
+/* float64 throughout, as numpy computes it (anchors float64 pixel boxes, GT boxes int32).      */
+/* Padding rows have class id 0 (the loader passes only real instances, preprocess.py:342-348). */
+/* np.random.choice (U:219,227) is replaced by injected keys: of the candidate anchors keep the */
+/* ones with the largest key (ties -> lower anchor index).                                      */
+/* ------------------------------------------------------------------------------------------ */
+static double orc_np_iou(const double* a /*anchor*/, double area_a, const int32_t* g, double area_g) {
+    /* U:125-133: maximum/minimum, max(.,0) products, union = area_g + area_a - inter, true division */
+    const double y1 = (double)g[0] > a[0] ? (double)g[0] : a[0];
+    const double y2 = (double)g[2] < a[2] ? (double)g[2] : a[2];
+    const double x1 = (double)g[1] > a[1] ? (double)g[1] : a[1];
+    const double x2 = (double)g[3] < a[3] ? (double)g[3] : a[3];
+    const double dx = x2 - x1 > 0.0 ? x2 - x1 : 0.0, dy = y2 - y1 > 0.0 ? y2 - y1 : 0.0;
+    const double inter = dx * dy;
+    const double uni = area_g + area_a - inter;
+    return inter / uni;
+}
+
+typedef struct { float key; int32_t idx; } orc_keyed;
+static int orc_keyed_cmp(const void* pa, const void* pb) { /* key desc, idx asc */
+    const orc_keyed* a = (const orc_keyed*)pa; const orc_keyed* b = (const orc_keyed*)pb;
+    if (a->key != b->key) return a->key > b->key ? -1 : 1;
+    return a->idx < b->idx ? -1 : (a->idx > b->idx ? 1 : 0);
+}
+/* reset all but the `keep` best-keyed anchors whose match equals `label` to neutral (U:215-228) */
+static void orc_subsample(int32_t* match, int A, int32_t label, int keep, const float* keys) {
+    int n = 0;
+    for (int a = 0; a < A; ++a) n += match[a] == label;
+    if (n - keep <= 0) return;
+    orc_keyed* c = (orc_keyed*)malloc(sizeof(orc_keyed) * (size_t)n);
+    int m = 0;
+    for (int a = 0; a < A; ++a) if (match[a] == label) { c[m].key = keys[a]; c[m].idx = a; ++m; }
+    qsort(c, (size_t)n, sizeof(orc_keyed), orc_keyed_cmp);
+    for (int i = keep < 0 ? 0 : keep; i < n; ++i) match[c[i].idx] = 0;
+    free(c);
+}
+
+static void orc_build_rpn_targets_one(const double* anchors /*[A,4]*/, const int32_t* cls_in /*[G]*/,
+                                      const int32_t* box_in /*[G,4]*/, const float* keys /*[A]*/, int A, int G, int R,
+                                      const double* std_dev, double eps, int32_t* match /*[A]*/,
+                                      double* rpn_bbox /*[R,4]*/, int32_t* counts /*[2] or NULL*/) {
+    memset(match, 0, sizeof(int32_t) * (size_t)A);                       /* U:168 */
+    memset(rpn_bbox, 0, sizeof(double) * (size_t)R * 4);                 /* U:170 */
+    /* U:175-188: crowds (class < 0) are split off only when there is at least one */
+    int any_crowd = 0;
+    for (int g = 0; g < G; ++g) any_crowd |= cls_in[g] < 0;
+    int* gt = (int*)malloc(sizeof(int) * (size_t)(G > 0 ? G : 1));
+    int* crowd = (int*)malloc(sizeof(int) * (size_t)(G > 0 ? G : 1));
+    int ng = 0, ncrowd = 0;
+    for (int g = 0; g < G; ++g) {
+        if (cls_in[g] == 0) continue;                                    /* padding row */
+        if (cls_in[g] < 0) crowd[ncrowd++] = g;
+        else if (!any_crowd || cls_in[g] > 0) gt[ng++] = g;
+    }
+    double* area_g = (double*)malloc(sizeof(double) * (size_t)(G > 0 ? G : 1));
+    for (int g = 0; g < G; ++g) /* U:143: int32 products in numpy; exact in double for pixel boxes */
+        area_g[g] = (double)((box_in[4 * g + 2] - box_in[4 * g]) * (box_in[4 * g + 3] - box_in[4 * g + 1]));
+    double* ov = (double*)malloc(sizeof(double) * (size_t)A * (size_t)(ng > 0 ? ng : 1));
+    double* colmax = (double*)malloc(sizeof(double) * (size_t)(ng > 0 ? ng : 1));
+    int32_t* amax_i = (int32_t*)malloc(sizeof(int32_t) * (size_t)A);
+    for (int j = 0; j < ng; ++j) colmax[j] = -1.0;
+    for (int a = 0; a < A; ++a) {
+        const double* an = anchors + 4 * (size_t)a;
+        const double area_a = (an[2] - an[0]) * (an[3] - an[1]);         /* U:142 */
+        int no_crowd = 1;                                                /* U:184-188 */
+        if (ncrowd > 0) {
+            double cm = -1.0;
+            for (int j = 0; j < ncrowd; ++j) {
+                const double v = orc_np_iou(an, area_a, box_in + 4 * crowd[j], area_g[crowd[j]]);
+                if (v > cm) cm = v;
+            }
+            no_crowd = cm < 0.001;
+        }
+        double best = 0.0; int besti = 0;                                /* U:203-204: argmax = first maximum */
+        for (int j = 0; j < ng; ++j) {
+            const double v = orc_np_iou(an, area_a, box_in + 4 * gt[j], area_g[gt[j]]);
+            ov[(size_t)a * ng + j] = v;
+            if (j == 0 || v > best) { best = v; besti = j; }
+            if (v > colmax[j]) colmax[j] = v;
+        }
+        amax_i[a] = besti;
+        if (best < 0.3 && no_crowd) match[a] = -1;                       /* U:205 */
+    }
+    for (int a = 0; a < A; ++a) {                                        /* U:208-209: every anchor tying a column max */
+        for (int j = 0; j < ng; ++j) if (ov[(size_t)a * ng + j] == colmax[j]) { match[a] = 1; break; }
+    }
+    for (int a = 0; a < A; ++a) {                                        /* U:211 */
+        if (ng > 0 && ov[(size_t)a * ng + amax_i[a]] >= 0.7) match[a] = 1;
+    }
+    orc_subsample(match, A, 1, R / 2, keys);                             /* U:215-220 */
+    int npos = 0;
+    for (int a = 0; a < A; ++a) npos += match[a] == 1;
+    orc_subsample(match, A, -1, R - npos, keys);                         /* U:222-228 */
+    int ix = 0, nneg = 0;
+    for (int a = 0; a < A; ++a) {                                        /* U:232-260, ascending anchor index */
+        nneg += match[a] == -1;
+        if (match[a] != 1) continue;
+        const int32_t* g = box_in + 4 * gt[amax_i[a]];
+        const double* an = anchors + 4 * (size_t)a;
+        const double gt_h = (double)(g[2] - g[0]), gt_w = (double)(g[3] - g[1]);
+        const double gcy = (double)g[0] + 0.5 * gt_h, gcx = (double)g[1] + 0.5 * gt_w;
+        const double a_h = an[2] - an[0], a_w = an[3] - an[1];
+        const double acy = an[0] + 0.5 * a_h, acx = an[1] + 0.5 * a_w;
+        double* o = rpn_bbox + 4 * (size_t)ix;
+        o[0] = (gcy - acy) / a_h / std_dev[0];
+        o[1] = (gcx - acx) / a_w / std_dev[1];
+        o[2] = log(gt_h / (a_h + eps)) / std_dev[2];
+        o[3] = log(gt_w / (a_w + eps)) / std_dev[3];
+        ++ix;
+    }
+    if (counts) { counts[0] = npos; counts[1] = nneg; }
+    free(gt); free(crowd); free(area_g); free(ov); free(colmax); free(amax_i);
+}
+
+ORC_API void orc_build_rpn_targets(const double* anchors /*[A,4]*/, const int32_t* gt_class_ids /*[B,G]*/,
+                                   const int32_t* gt_boxes /*[B,G,4]*/, const float* rand_keys /*[B,A]*/, int B,
+                                   int A, int G, int R, const double* std_dev, double eps,
+                                   int32_t* rpn_match /*[B,A]*/, double* rpn_bbox /*[B,R,4]*/,
+                                   int32_t* counts /*[B,2] or NULL*/) {
+#pragma omp parallel for schedule(dynamic)
+    for (int b = 0; b < B; ++b)
+        orc_build_rpn_targets_one(anchors, gt_class_ids + (size_t)b * G, gt_boxes + (size_t)b * G * 4,
+                                  rand_keys + (size_t)b * A, A, G, R, std_dev, eps, rpn_match + (size_t)b * A,
+                                  rpn_bbox + (size_t)b * R * 4, counts ? counts + 2 * b : NULL);
+}
+
 ORC_API void orc_set_num_threads(int n) {
 #ifdef _OPENMP
     omp_set_num_threads(n > 0 ? n : 1);
