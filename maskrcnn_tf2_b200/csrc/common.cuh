@@ -274,6 +274,24 @@ __device__ __forceinline__ void iou_screen(const float4& bi, float ai, const flo
     unsure |= fabsf(d) <= __fmul_rn(t, 4.76837158203125e-07f);
 }
 
+// Cheaper screen for the NMS inner loops.  With tak = thr * area_k and tac = thr * area_c precomputed per box,
+// d = inter * (1 + thr) - (tak + tac) is the same real quantity as inter - thr * union (one FFMA).  Its roundings
+// (<= 2^-22 relative to tak + tac) plus those of the reference quotient (<= 2^-22) stay inside the band
+// m = (tak + tac) * 2^-20: d > m is a certain hit, d < -m a certain miss, anything else is re-run through the exact
+// iou_gt.  For an OR over many kept boxes only the running maximum of d is needed: max d > m_max is a certain hit,
+// max d < -m_max a certain miss (m_max from the largest tak).  One clamp is enough: a negative width makes inter <= 0.
+constexpr float kScreenBand = 9.5367431640625e-07f;  // 2^-20
+__device__ __forceinline__ float iou_screen_d(const float4& bk, float tak, const float4& bc, float tac, float c1) {
+    const float dh = fmaxf(__fsub_rn(fminf(bk.z, bc.z), fmaxf(bk.x, bc.x)), 0.0f);
+    const float dw = __fsub_rn(fminf(bk.w, bc.w), fmaxf(bk.y, bc.y));
+    return __fmaf_rn(__fmul_rn(dh, dw), c1, -__fadd_rn(tak, tac));
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {  // FMNMX3 (sm_100)
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 // TF IOU(): corners normalised with min/max; returns area in `area`
 __device__ __forceinline__ float4 normalise_box(float4 b, float& area) {
     float4 n;

@@ -1,40 +1,54 @@
 // nms.cu -- batched greedy hard NMS with TF NonMaxSuppressionV3 (CPU kernel) semantics.
 // Replaces tf.image.non_max_suppression at mrcnn_layers.py:225 (RPN, thr 0.7) and :455 (detections, thr 0.3).
 //
-// nms_lazy_kernel: a thread-block CLUSTER of 1..16 CTAs (1024 threads each) per image; every CTA stages the image's
-// candidate boxes (already in candidate order) in its own shared memory and walks the candidates in 64-box tiles.
-// Only the IoU tests that can matter are evaluated, and neither the cluster nor the CTA blocks on a full barrier
-// inside the loop.  Each CTA is warp-specialised:
-//   worker warps (16..31), up to two tiles ahead of the resolvers:
-//     far(u)  = tile u's candidates suppressed by boxes kept in tiles <= u-2: the kept list is dealt round-robin to
-//               the worker warps of every CTA of the cluster; each CTA sends its 64-bit partial to every peer with
-//               st.async (a distributed-shared-memory store that completes a transaction on the receiver's mbarrier);
-//     diag(u) = the tile's own symmetric 64x64 block: row i is computed by CTA i % CTAs and sent the same way;
-//   resolver warps (0..15), every CTA for itself, identically:
-//     near(u) = suppressed by the boxes kept in tile u-1 (<= 64 x 64 tests);
-//     resolve = warp 0 waits for the tile's mbarrier phase and decides the tile with ballots (fixed point over diag:
-//               a candidate is kept once every earlier overlapping candidate is decided-removed, removed once one is
-//               decided-kept), appends the kept ones to the CTA's copy of the kept list and releases the workers
-//               for tile u+2 through a named barrier.
-// Work is sum_t kept(t) * 64 + M * 64 pair tests instead of the M^2/2 of a full bit matrix, nothing is written to
-// global memory but the result, and the loop stops as soon as max_out boxes are kept.
+// nms_lazy_kernel: a thread-block CLUSTER of 1..16 CTAs per image; every CTA stages the image's candidate boxes
+// (already in candidate order) in its own shared memory and walks the candidates in 64-box tiles.  Only the IoU tests
+// that can matter are evaluated, and neither the cluster nor the CTA blocks on a full barrier inside the loop.  Each CTA
+// is warp-specialised (the other warps only help with the staging and exit):
+//   far warps, up to kDepth tiles ahead of the resolver: far(u) = tile u's candidates suppressed by boxes kept in tiles
+//     <= u-kDepth.  The kept list is dealt round-robin to the far warps of the whole cluster; each streams its boxes
+//     from dense shared-memory copies (box, thr * area) four at a time through a multiplicative IoU screen (one FFMA
+//     per pair; the exact division only inside a 2^-20 band) and sends its 64-bit partial straight to every CTA;
+//   row warps, one more tile ahead: diag(u) = the tile's own symmetric 64x64 block and cross_d(u) = tile u-d (rows) x
+//     tile u (columns), d < kDepth -- independent of what is kept.  The rows are dealt over the cluster in contiguous
+//     blocks, staged locally and shipped as ONE bulk copy per peer;
+//     everything travels through distributed shared memory (st.async / cp.async.bulk) and completes transactions on
+//     the receiver's mbarrier;
+//   resolver warp (0), every CTA for itself, identically, alone on its scheduler: waits for the tile's mbarrier phase,
+//     ORs the far partials and the cross rows of the boxes kept in the previous kDepth-1 tiles (one warp-wide redux, no
+//     IoU test on the critical path), then decides the tile with ballots (fixed point over diag: a candidate is kept
+//     once every earlier overlapping candidate is decided-removed, removed once one is decided-kept), appends the kept
+//     ones to the CTA's copy of the kept list and releases the workers for tile u+kDepth through a named barrier.
+// Work is sum_t kept(t) * 64 + kDepth * M * 64 pair tests instead of the M^2/2 of a full bit matrix, nothing is written
+// to global memory but the result, and the loop stops as soon as max_out boxes are kept.  What bounds it (measured,
+// DESIGN.md): the per-tile instruction count of the far and row warps on the SM's four schedulers and the resolver's
+// serial chain of ~300 dependent instructions per tile.
+#include <cstdlib>
+
 #include "nms_dev.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace mrcnn {
 
+// COMPACT: the kept boxes are also appended, by the resolver, to dense arrays (box, thr * area) so that the far loop
+// streams them with plain strided shared-memory loads; false (shared memory too small for the copies): the far loop
+// goes through the kept index list.
+template <bool COMPACT>
 __global__ void __launch_bounds__(kNmsThreads, 1)
 nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ valid, int M, int max_out, float thr,
-                NmsEpilogue epi) {
+                int nfar, int nrow, NmsEpilogue epi) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
+    const int cap = min(max_out, M);
     float4* sb = reinterpret_cast<float4*>(nms_smem);          // [M] min/max-normalised corners
-    float* sa = reinterpret_cast<float*>(sb + M);               // [M] areas
-    int32_t* sel = reinterpret_cast<int32_t*>(sa + M);          // [min(max_out, M)] kept candidate positions
-    __shared__ unsigned long long s_diag[4][kTile];             // [tile & 3][row]: symmetric in-tile block, from the peers
-    __shared__ unsigned long long s_far[4][16];                 // [tile & 3][source CTA], written by the peers
-    __shared__ unsigned long long s_near[2];                    // [tile parity]
-    __shared__ unsigned long long s_farpart[2];                 // [tile parity] this CTA's partial of far(u)
+    float4* kb = sb + M;                                        // [cap] kept boxes in selection order (COMPACT)
+    float* sa = reinterpret_cast<float*>(kb + (COMPACT ? cap : 0));  // [M] areas
+    float* kt = sa + M;                                         // [cap] thr * area of the kept boxes (COMPACT)
+    int32_t* sel = reinterpret_cast<int32_t*>(kt + (COMPACT ? cap : 0));  // [cap] kept candidate positions
+    __shared__ __align__(16) unsigned long long s_rows[4][kRows];   // [tile & 3][0..63 diag rows, 64 d + i: cross_d rows]
+    __shared__ __align__(16) unsigned long long s_stage[8][kRows];  // [tile & 7] this CTA's rows on their way out: a slot is
+                                                                    // reused 8 tiles later, long after its copy was read
+    __shared__ unsigned long long s_far[4][kMaxFarSrc];         // [tile & 3][source CTA * nfar + far warp], written by the peers
     __shared__ __align__(8) uint64_t s_bar[4];                  // mbarriers, [tile & 3]: a peer can run at most two
                                                                 // tiles ahead, so four phases never alias
     __shared__ int s_nk[4];                                     // [tile & 3] kept count after that tile's resolve
@@ -45,7 +59,7 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
     const int n = valid ? min(max(valid[b], 0), M) : M;
     const int tiles = (n + kTile - 1) / kTile;
     const float4* bx = boxes + (size_t)b * M;
-    const float4 kNone = make_float4(3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f);  // overlaps nothing, never ambiguous
+    const float4 kNone = make_float4(1.0e18f, 1.0e18f, -1.0e18f, -1.0e18f);  // overlaps nothing, never ambiguous, no inf
     for (int i = tid; i < n; i += kNmsThreads) {
         float a;
         float4 t = normalise_box(__ldg(bx + i), a);
@@ -54,10 +68,12 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
         sa[i] = a;
     }
     const uint32_t bar_base = smem_u32(&s_bar[0]);
-    // per tile every CTA receives one 64-bit far partial from each CTA and the 64 rows of the tile's diag block
-    const uint32_t far_bytes = (uint32_t)csize * 8u + (uint32_t)kTile * 8u;
+    const int rel_threads = 32 * (1 + nfar + nrow);  // the release barrier: resolver (arrives) + far and row warps (wait)
+    const int nsrc = csize * nfar;                   // far partials per tile: one per far warp of the cluster
+    // per tile every CTA receives one 64-bit far partial from each far warp of the cluster and, as one bulk copy per
+    // CTA, the rows of the tile's diag + cross blocks
+    const uint32_t far_bytes = (uint32_t)nsrc * 8u + (uint32_t)kRows * 8u;
     if (tid == 0) {
-        s_near[0] = 0ull; s_near[1] = 0ull; s_farpart[0] = 0ull; s_farpart[1] = 0ull;
         for (int j = 0; j < 4; ++j) { mbar_init(bar_base + 8u * j, 1); s_nk[j] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int j = 1; j < 4; ++j) mbar_arm(bar_base + 8u * j, far_bytes);  // tiles 1..3; tile 4 is armed in tile 0
@@ -73,168 +89,251 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
             const float4 bi = (i < n) ? sb[i] : kNone;
             const float ai = (i < n) ? sa[i] : 1.0f;
             const uint64_t row = ballot64(iou_gt(bi, ai, b0, a0, thr), iou_gt(bi, ai, b1, a1, thr)) & ~(1ull << i);
-            if (lane == 0) s_diag[0][i] = row;
+            if (lane == 0) s_rows[0][i] = row;
         }
     }
     cluster.sync();  // every CTA of the cluster is resident and its mbarriers are initialised before any st.async
+    // Roles.  Warp 0 resolves; it keeps its scheduler (warps 4, 8, ... share it) to itself, because its per-tile chain
+    // is the serial part of the kernel.  The other 24 warps are numbered 0..23 in order: the first nfar are far warps,
+    // the next nrow row warps; the rest only helped with the staging and exit (exited threads count as arrived at the
+    // barriers below).
+    const int ri = (warp & 3) ? (warp >> 2) * 3 + (warp & 3) - 1 : -1;
+    if (warp != 0 && (ri < 0 || ri >= nfar + nrow)) return;
+    const int eidx = (warp == 0) ? lane : (1 + ri) * 32 + lane;  // dense index of the surviving threads (epilogue)
     int nkept = 0, t = 0;
     PROF_DECL;
-    if (warp < kResolvers) {
-        // ================= resolver warps: near(t) + resolve(t), tile by tile =================
+    if (warp == 0) {
+        // ================= resolver warp: tile by tile =================
+        uint64_t kept_hist[kDepth - 1];  // kept masks of tiles t-1 .. t-(kDepth-1)
+#pragma unroll
+        for (int d = 0; d < kDepth - 1; ++d) kept_hist[d] = 0ull;
         for (; t < tiles && nkept < max_out; ++t) {
             PROF_TILE;
-            const int p = t & 1;
             const int base = t * kTile;
-            const int nkept_before = nkept;  // boxes kept in tiles <= t-1
-            if (warp == 0) {
-                uint64_t removed = (uint64_t)s_near[p];
-                const uint32_t bar_t = bar_base + 8u * (uint32_t)(t & 3);
-                if (t >= 1) {  // barrier (t & 3) serves tiles t&3, t&3 + 4, ...; tile 0 has no far set
-                    mbar_wait(bar_t, (uint32_t)(((t >> 2) - ((t & 3) == 0 ? 1 : 0)) & 1));
-                    for (int r = 0; r < csize; ++r) removed |= (uint64_t)s_far[t & 3][r];
-                }
+            const uint32_t bar_t = bar_base + 8u * (uint32_t)(t & 3);
+            // this lane's two candidates, for the compact kept arrays (loaded while the far set is still in flight)
+            const int c0 = base + lane, c1 = c0 + 32;
+            float4 mb0 = kNone, mb1 = kNone;
+            float mt0 = thr, mt1 = thr;
+            if (COMPACT) {
+                if (c0 < n) { mb0 = sb[c0]; mt0 = __fmul_rn(thr, sa[c0]); }
+                if (c1 < n) { mb1 = sb[c1]; mt1 = __fmul_rn(thr, sa[c1]); }
+            }
+            uint64_t removed = 0;
+            if (t >= 1) {  // barrier (t & 3) serves tiles t&3, t&3 + 4, ...; tile 0 has no far / cross set
+                mbar_wait(bar_t, (uint32_t)(((t >> 2) - ((t & 3) == 0 ? 1 : 0)) & 1));
                 PROF_MARK(0);
-                const int rem = n - base;
-                const uint64_t validbits = (rem >= kTile) ? ~0ull : ((1ull << rem) - 1ull);
-                uint64_t und = ~removed & validbits, kept = 0;
-                const uint64_t blk0 = (uint64_t)s_diag[t & 3][lane] & ((1ull << lane) - 1ull);  // earlier overlapping candidates
-                const uint64_t blk1 = (uint64_t)s_diag[t & 3][lane + 32] & ((1ull << (lane + 32)) - 1ull);
-                while (und) {
-                    const bool u0 = (und >> lane) & 1ull, u1 = (und >> (lane + 32)) & 1ull;
-                    const bool d0 = u0 && (blk0 & kept), d1 = u1 && (blk1 & kept);              // removed
-                    const bool k0 = u0 && !d0 && !(blk0 & und), k1 = u1 && !d1 && !(blk1 & und);  // kept
-                    const uint64_t nk = ballot64(k0, k1), nd = ballot64(d0, d1);
-                    kept |= nk;
-                    und &= ~(nk | nd);
+                uint64_t v = 0ull;
+                for (int i = lane; i < nsrc; i += 32) v |= (uint64_t)s_far[t & 3][i];        // far(t)
+#pragma unroll
+                for (int d = 1; d < kDepth; ++d) {  // near(t) = cross_d rows of the boxes kept in tile t-d
+                    if ((kept_hist[d - 1] >> lane) & 1ull) v |= (uint64_t)s_rows[t & 3][d * kTile + lane];
+                    if ((kept_hist[d - 1] >> (lane + 32)) & 1ull) v |= (uint64_t)s_rows[t & 3][d * kTile + lane + 32];
                 }
-                const int room = max_out - nkept;
-                while (__popcll(kept) > room) kept &= ~(1ull << (63 - __clzll(kept)));
-                if ((kept >> lane) & 1ull) sel[nkept + __popcll(kept & ((1ull << lane) - 1ull))] = base + lane;
-                if ((kept >> (lane + 32)) & 1ull)
-                    sel[nkept + __popcll(kept & ((1ull << (lane + 32)) - 1ull))] = base + lane + 32;
-                __syncwarp();
-                if (lane == 0) {
-                    s_nk[t & 3] = nkept + __popcll(kept);
-                    s_near[p] = 0ull;            // next accumulated for tile t+2, two resolver barriers later
-                    mbar_arm(bar_t, far_bytes);  // phase of tile t+4
-                }
-                __threadfence_block();
-                // release the workers for tile t+2 (they need the kept list through tile t)
-                if (t + 2 < tiles) asm volatile("bar.arrive %0, %1;" ::"r"(3 + p), "r"(32 + kWorkers * 32) : "memory");
-                PROF_MARK(1);
+                removed = (uint64_t)__reduce_or_sync(0xffffffffu, (unsigned)v) |
+                          ((uint64_t)__reduce_or_sync(0xffffffffu, (unsigned)(v >> 32)) << 32);
             }
-            named_barrier(1, kResolvers * 32);
-            nkept = s_nk[t & 3];
-            PROF_MARK(2);
-            // near(t+1): boxes kept in tile t x tile t+1
-            if (t + 1 < tiles && nkept < max_out && nkept_before + warp < nkept) {
-                const int c0 = base + kTile + lane, c1 = c0 + 32;
-                const float4 b0 = (c0 < n) ? sb[c0] : kNone, b1 = (c1 < n) ? sb[c1] : kNone;
-                const float a0 = (c0 < n) ? sa[c0] : 1.0f, a1 = (c1 < n) ? sa[c1] : 1.0f;
-                bool r0 = false, r1 = false, u0 = false, u1 = false;
-                for (int k = nkept_before + warp; k < nkept; k += kResolvers) {
-                    const int ki = sel[k];
-                    const float4 bk = sb[ki];
-                    const float ak = sa[ki];
-                    iou_screen(bk, ak, b0, a0, thr, r0, u0);
-                    iou_screen(bk, ak, b1, a1, thr, r1, u1);
-                }
-                if (__any_sync(0xffffffffu, u0 || u1)) {  // a pair within 2^-21 of the threshold: exact division
-                    r0 = false; r1 = false;
-                    for (int k = nkept_before + warp; k < nkept; k += kResolvers) {
-                        const int ki = sel[k];
-                        r0 |= iou_gt(sb[ki], sa[ki], b0, a0, thr);
-                        r1 |= iou_gt(sb[ki], sa[ki], b1, a1, thr);
-                    }
-                }
-                const uint64_t hit = ballot64(r0, r1);
-                if (lane == 0 && hit) or_into(&s_near[p ^ 1], hit);
+            const int rem = n - base;
+            const uint64_t validbits = (rem >= kTile) ? ~0ull : ((1ull << rem) - 1ull);
+            uint64_t und = ~removed & validbits, kept = 0;
+            const uint64_t blk0 = (uint64_t)s_rows[t & 3][lane] & ((1ull << lane) - 1ull);  // earlier overlapping candidates
+            const uint64_t blk1 = (uint64_t)s_rows[t & 3][lane + 32] & ((1ull << (lane + 32)) - 1ull);
+            while (und) {
+                const bool u0 = (und >> lane) & 1ull, u1 = (und >> (lane + 32)) & 1ull;
+                const bool d0 = u0 && (blk0 & kept), d1 = u1 && (blk1 & kept);              // removed
+                const bool k0 = u0 && !d0 && !(blk0 & und), k1 = u1 && !d1 && !(blk1 & und);  // kept
+                const uint64_t nk = ballot64(k0, k1), nd = ballot64(d0, d1);
+                kept |= nk;
+                und &= ~(nk | nd);
             }
-            named_barrier(1, kResolvers * 32);
-            PROF_MARK(3);
+            const int room = max_out - nkept;
+            while (__popcll(kept) > room) kept &= ~(1ull << (63 - __clzll(kept)));
+            if ((kept >> lane) & 1ull) {
+                const int pos = nkept + __popcll(kept & ((1ull << lane) - 1ull));
+                sel[pos] = c0;
+                if (COMPACT) { kb[pos] = mb0; kt[pos] = mt0; }
+            }
+            if ((kept >> (lane + 32)) & 1ull) {
+                const int pos = nkept + __popcll(kept & ((1ull << (lane + 32)) - 1ull));
+                sel[pos] = c1;
+                if (COMPACT) { kb[pos] = mb1; kt[pos] = mt1; }
+            }
+            nkept += __popcll(kept);
+#pragma unroll
+            for (int d = kDepth - 2; d > 0; --d) kept_hist[d] = kept_hist[d - 1];
+            kept_hist[0] = kept;
+            __syncwarp();
+            if (lane == 0) {
+                s_nk[t & 3] = nkept;
+                mbar_arm(bar_t, far_bytes);  // phase of tile t+4
+            }
+            __threadfence_block();
+            // release the workers for tile t+kDepth (they need the kept list through tile t)
+            if (t + kDepth < tiles) asm volatile("bar.arrive %0, %1;" ::"r"(3 + (t % kDepth)), "r"(rel_threads) : "memory");
+            PROF_MARK(1);
         }
-    } else {
-        // ================= worker warps: far(u) share + diag(u) rows, u = 1 .. tiles-1 =================
-        const int wk = warp - kResolvers;  // 0..15
+    } else if (ri < nfar) {
+        // ================= far warps: far(u) share, u = 1 .. tiles-1 =================
+        // Kept box k of the list belongs to far warp (k mod nsrc) of the cluster.  Every far warp sends its own 64-bit
+        // partial straight to every CTA (no reduction inside the CTA on the critical path).
+        const int fw = ri;  // 0..nfar-1
+        const int k0 = crank * nfar + fw;
+        const float inv_src = __frcp_rn((float)nsrc), cthr = __fadd_rn(1.0f, thr);
+        PROFW_DECL;
         for (int u = 1; u < tiles; ++u) {
-            int nk = 0;  // boxes kept in tiles <= u-2
-            if (u >= 2) {
-                asm volatile("bar.sync %0, %1;" ::"r"(3 + (u & 1)), "r"(32 + kWorkers * 32) : "memory");
-                nk = s_nk[(u - 2) & 3];
-                if (nk >= max_out) break;  // the resolvers stop after tile u-2
-            }
             const int ubase = u * kTile;
             const int c0 = ubase + lane, c1 = c0 + 32;
             const float4 b0 = (c0 < n) ? sb[c0] : kNone, b1 = (c1 < n) ? sb[c1] : kNone;
             const float a0 = (c0 < n) ? sa[c0] : 1.0f, a1 = (c1 < n) ? sa[c1] : 1.0f;
-            bool r0 = false, r1 = false, u0 = false, u1 = false;
-#pragma unroll 4
-            for (int k = crank * kWorkers + wk; k < nk; k += csize * kWorkers) {
-                const int ki = sel[k];
-                const float4 bk = sb[ki];
-                const float ak = sa[ki];
-                iou_screen(bk, ak, b0, a0, thr, r0, u0);
-                iou_screen(bk, ak, b1, a1, thr, r1, u1);
+            const float tc0 = __fmul_rn(thr, a0), tc1 = __fmul_rn(thr, a1);
+            const uint32_t bar_u = bar_base + 8u * (uint32_t)(u & 3);
+            const uint32_t my_far = smem_u32(&s_far[u & 3][k0]);
+            PROFW_MARK(0);
+            int nk = 0;  // boxes kept in tiles <= u-kDepth
+            if (u >= kDepth) {
+                asm volatile("bar.sync %0, %1;" ::"r"(3 + (u % kDepth)), "r"(rel_threads) : "memory");
+                nk = s_nk[(u - kDepth) & 3];
+                if (nk >= max_out) {
+                    // the resolver stops before tile u-kDepth+1.  The row warps have already sent rows(u): complete the tile's
+                    // transaction set with empty partials so that the final drain can wait for it
+                    if (lane < csize) st_async_u64(mapa_u32(my_far, (uint32_t)lane), 0ull, mapa_u32(bar_u, (uint32_t)lane));
+                    break;
+                }
             }
-            if (__any_sync(0xffffffffu, u0 || u1)) {  // a pair within 2^-21 of the threshold: exact division
+            PROFW_MARK(1);
+            // cnt = ceil((nk - k0) / nsrc) without the integer-division sequence (operands < 2^14: exact in fp32)
+            int cnt = 0;
+            if (nk > k0) {
+                const int x = nk - k0 + nsrc - 1;
+                cnt = (int)__fmul_rn((float)x, inv_src);
+                cnt += ((cnt + 1) * nsrc <= x) - (cnt * nsrc > x);
+            }
+            float dmax0 = -3.0e38f, dmax1 = -3.0e38f, tkmax = 0.0f;
+            for (int j = 0; j < cnt; j += 4) {  // four kept boxes per round: independent IoU chains; a round that runs
+                float d0[4], d1[4];             // past the list repeats its last box (harmless)
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    const int k = min(k0 + (j + qq) * nsrc, nk - 1);
+                    float4 bk;
+                    float tk;
+                    if (COMPACT) { bk = kb[k]; tk = kt[k]; }
+                    else { const int ki = sel[k]; bk = sb[ki]; tk = __fmul_rn(thr, sa[ki]); }
+                    tkmax = fmaxf(tkmax, tk);
+                    d0[qq] = iou_screen_d(bk, tk, b0, tc0, cthr);
+                    d1[qq] = iou_screen_d(bk, tk, b1, tc1, cthr);
+                }
+                dmax0 = fmax3(fmax3(dmax0, d0[0], d0[1]), d0[2], d0[3]);
+                dmax1 = fmax3(fmax3(dmax1, d1[0], d1[1]), d1[2], d1[3]);
+            }
+            const float m0 = __fmul_rn(__fadd_rn(tkmax, tc0), kScreenBand), m1 = __fmul_rn(__fadd_rn(tkmax, tc1), kScreenBand);
+            bool r0 = dmax0 > m0, r1 = dmax1 > m1;
+            const bool unsure = (!r0 && dmax0 >= -m0) || (!r1 && dmax1 >= -m1);
+            if (__any_sync(0xffffffffu, unsure)) {  // a pair within 2^-20 of the threshold: exact division
+                PROFW_COUNT;
                 r0 = false; r1 = false;
-                for (int k = crank * kWorkers + wk; k < nk; k += csize * kWorkers) {
+                for (int k = k0; k < nk; k += nsrc) {
                     const int ki = sel[k];
                     r0 |= iou_gt(sb[ki], sa[ki], b0, a0, thr);
                     r1 |= iou_gt(sb[ki], sa[ki], b1, a1, thr);
                 }
             }
             const uint64_t hit = ballot64(r0, r1);
-            if (lane == 0 && hit) or_into(&s_farpart[u & 1], hit);
-            const uint32_t bar_u = bar_base + 8u * (uint32_t)(u & 3);
-            for (int i = crank + csize * wk; i < kTile; i += csize * kWorkers) {  // this CTA's rows of diag(u)
-                const int ci = ubase + i;
-                const float4 bi = (ci < n) ? sb[ci] : kNone;
-                const float ai = (ci < n) ? sa[ci] : 1.0f;
-                const uint64_t row = ballot64(iou_gt(bi, ai, b0, a0, thr), iou_gt(bi, ai, b1, a1, thr)) & ~(1ull << i);
-                if (lane < csize)
-                    st_async_u64(mapa_u32(smem_u32(&s_diag[u & 3][i]), (uint32_t)lane), row, mapa_u32(bar_u, (uint32_t)lane));
+            PROFW_MARK(2);
+            if (lane < csize) st_async_u64(mapa_u32(my_far, (uint32_t)lane), hit, mapa_u32(bar_u, (uint32_t)lane));
+            PROFW_MARK(3);
+        }
+        PROFW_DUMP;
+    } else {
+        // ================= row warps: diag(v) + cross(v), one tile ahead of the far warps =================
+        // Rows do not depend on the kept list; the release barrier only provides flow control: rows(u+1) goes into ring
+        // slot (u+1) & 3 of every CTA, last read by resolve(u-3), and is sent once resolve(u-kDepth) has released tile u.
+        const int rw = ri - nfar;  // 0..nrow-1
+        const float cthr = __fadd_rn(1.0f, thr);
+        auto send_rows = [&](int v) {
+            const int vbase = v * kTile;
+            const int c0 = vbase + lane, c1 = c0 + 32;
+            const float4 b0 = (c0 < n) ? sb[c0] : kNone, b1 = (c1 < n) ? sb[c1] : kNone;
+            const float a0 = (c0 < n) ? sa[c0] : 1.0f, a1 = (c1 < n) ? sa[c1] : 1.0f;
+            const uint32_t bar_v = bar_base + 8u * (uint32_t)(v & 3);
+            const float tc0 = __fmul_rn(thr, a0), tc1 = __fmul_rn(thr, a1);
+            // this CTA owns the contiguous rows [crank * rpc, (crank + 1) * rpc) of the tile (0..63 diag, 64 d + i:
+            // candidate i of tile v-d against tile v); they are staged locally and travel as ONE bulk copy per peer:
+            // the receivers' mbarriers see csize transactions per tile instead of one per row
+            const int rpc = kRows / csize;
+            unsigned long long* stage = &s_stage[v & 7][0];
+            for (int j = rw; j < rpc; j += nrow) {
+                const int r = crank * rpc + j;
+                const int i = r & (kTile - 1);
+                const int ci = vbase - (r / kTile) * kTile + i;  // negative: that earlier tile does not exist
+                const float4 bi = (ci >= 0 && ci < n) ? sb[ci] : kNone;
+                const float ai = (ci >= 0 && ci < n) ? sa[ci] : 1.0f;
+                const float ti = __fmul_rn(thr, ai);  // screen first; the exact division only inside the 2^-20 band
+                const float e0 = iou_screen_d(bi, ti, b0, tc0, cthr), e1 = iou_screen_d(bi, ti, b1, tc1, cthr);
+                const float m0 = __fmul_rn(__fadd_rn(ti, tc0), kScreenBand), m1 = __fmul_rn(__fadd_rn(ti, tc1), kScreenBand);
+                bool h0 = e0 > m0, h1 = e1 > m1;
+                if (__any_sync(0xffffffffu, fabsf(e0) <= m0 || fabsf(e1) <= m1)) {
+                    h0 = iou_gt(bi, ai, b0, a0, thr);
+                    h1 = iou_gt(bi, ai, b1, a1, thr);
+                }
+                uint64_t row = ballot64(h0, h1);
+                if (r < kTile) row &= ~(1ull << i);
+                if (lane == 0) stage[j] = row;
             }
-            named_barrier(2, kWorkers * 32);  // all partials of this CTA are in s_farpart[u & 1]
-            if (wk == 0) {
-                const unsigned long long part = s_farpart[u & 1];
-                __syncwarp();
-                if (lane < csize)
-                    st_async_u64(mapa_u32(smem_u32(&s_far[u & 3][crank]), (uint32_t)lane), part, mapa_u32(bar_u, (uint32_t)lane));
-                if (lane == 0) s_farpart[u & 1] = 0ull;  // next used for tile u+2, one worker barrier later
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async-proxy reads
+            named_barrier(1, nrow * 32);
+            if (rw == 0 && lane < csize)
+                bulk_copy_to_peer(mapa_u32(smem_u32(&s_rows[v & 3][crank * rpc]), (uint32_t)lane), smem_u32(stage),
+                                  (uint32_t)rpc * 8u, mapa_u32(bar_v, (uint32_t)lane));
+        };
+        if (tiles > 1) send_rows(1);
+        for (int u = 1; u < tiles; ++u) {
+            if (u >= kDepth) {
+                asm volatile("bar.sync %0, %1;" ::"r"(3 + (u % kDepth)), "r"(rel_threads) : "memory");
+                if (s_nk[(u - kDepth) & 3] >= max_out) break;  // same test as the far warps: both leave at the same tile
             }
+            if (u + 1 < tiles) send_rows(u + 1);
         }
     }
-    if (tid == 0) { s_final[0] = t; s_final[1] = nkept; }  // the resolvers' loop state, for everybody
+    if (tid == 0) { s_final[0] = t; s_final[1] = nkept; }  // the resolver's loop state, for everybody
     __syncthreads();
     t = s_final[0];
     nkept = s_final[1];
     PROF_DUMP;
-    // far(t) was sent during the last iteration but never consumed: drain it, so that no st.async is in flight
-    // towards this CTA when it exits; the cluster barrier then keeps every CTA alive until its peers have drained
-    if (warp == 0 && t >= 1 && t < tiles)
-        mbar_wait(bar_base + 8u * (uint32_t)(t & 3), (uint32_t)(((t >> 2) - ((t & 3) == 0 ? 1 : 0)) & 1));
+    // The sets of tiles t .. t+kDepth-1 (far or empty far partials + rows) were sent but never consumed: drain
+    // them, so that no st.async is in flight towards this CTA when it exits; the cluster barrier then keeps every CTA
+    // alive until its peers have drained
+    if (warp == 0) {
+        for (int d = t; d < t + kDepth; ++d)
+            if (d >= 1 && d < tiles)
+                mbar_wait(bar_base + 8u * (uint32_t)(d & 3), (uint32_t)(((d >> 2) - ((d & 3) == 0 ? 1 : 0)) & 1));
+    }
     cluster.sync();
     if (crank != 0) return;
     const int total = nkept;
-    nms_write_outputs(epi, bx, b, M, max_out, total, sel);
+    nms_write_outputs(epi, bx, b, M, max_out, total, sel, eidx, rel_threads);
 }
 
 // cluster size: spread one image over as many SMs as the batch leaves free (148 SMs, 1 CTA per SM), up to the
 // portable maximum of 8 (16-CTA clusters do not co-schedule for 8 images on this part: measured); small candidate
 // sets do not amortise the exchange
-static int nms_cluster_size(int B, int M, size_t smem) {
+static int nms_cluster_size(int B, int M, size_t smem, bool compact) {
     if (M <= 2048) return 1;
-    static int cache[4][2] = {};
-    return pick_cluster_size(nms_lazy_kernel, kNmsThreads, B, 8, [smem](int) { return smem; }, cache);
+    static int cache[2][4][2] = {};
+    if (compact)
+        return pick_cluster_size(nms_lazy_kernel<true>, kNmsThreads, B, 8, [smem](int) { return smem; }, cache[1]);
+    return pick_cluster_size(nms_lazy_kernel<false>, kNmsThreads, B, 8, [smem](int) { return smem; }, cache[0]);
 }
 
 int launch_nms_sorted(const float4* boxes_sorted, const int32_t* valid, int B, int M, int max_out, float thr,
                       const NmsEpilogue& epi, cudaStream_t stream) {
-    const size_t smem = nms_smem_bytes(M, max_out);
-    cudaError_t e = cudaFuncSetAttribute(nms_lazy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // dense copies of the kept boxes (24 more bytes per output slot) whenever they fit beside the candidates
+    static const bool env_indirect = getenv("MRCNN_NMS_INDIRECT") != nullptr;  // test knob: force the index-list path
+    const bool compact = !env_indirect && nms_smem_bytes(M, max_out, true) <= kNmsMaxDynSmem;
+    const size_t smem = nms_smem_bytes(M, max_out, compact);
+    cudaError_t e = compact ? cudaFuncSetAttribute(nms_lazy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(nms_lazy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    const int cs = nms_cluster_size(B, M, smem);
+    const int cs = nms_cluster_size(B, M, smem, compact);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * cs));
     cfg.blockDim = dim3(kNmsThreads);
@@ -247,7 +346,16 @@ int launch_nms_sorted(const float4* boxes_sorted, const int32_t* valid, int B, i
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, nms_lazy_kernel, boxes_sorted, valid, M, max_out, thr, epi);
+    // warp roles: 1 resolver, nfar far warps (the kept list x tile tests), nrow row warps (diag + cross blocks: 128 rows
+    // per tile dealt over the cluster); the remaining warps only help with the staging and exit.  Few, fat workers:
+    // the per-tile work of a warp is a latency-bound chain (~5 cycles per instruction), so fixed overhead per warp
+    // costs more than it buys.
+    static const int env_far = getenv("MRCNN_NMS_NFAR") ? atoi(getenv("MRCNN_NMS_NFAR")) : 0;
+    static const int env_row = getenv("MRCNN_NMS_NROW") ? atoi(getenv("MRCNN_NMS_NROW")) : 0;
+    int nfar = cs >= 4 ? 8 : 12, nrow = cs >= 4 ? 4 : (cs == 2 ? 8 : 12);
+    if (env_far > 0 && env_row > 0 && env_far + env_row <= 24) { nfar = env_far; nrow = env_row; }  // tuning knob
+    if (compact) e = cudaLaunchKernelEx(&cfg, nms_lazy_kernel<true>, boxes_sorted, valid, M, max_out, thr, nfar, nrow, epi);
+    else e = cudaLaunchKernelEx(&cfg, nms_lazy_kernel<false>, boxes_sorted, valid, M, max_out, thr, nfar, nrow, epi);
     if (e != cudaSuccess) return (int)e;
     return last_error();
 }
@@ -302,7 +410,10 @@ using namespace mrcnn;
 
 #ifdef MRCNN_NMS_PROFILE
 MRCNN_EXPORT int mrcnn_debug_nms_profile(long long* host_out8) {
-    return (int)cudaMemcpyFromSymbol(host_out8, g_nms_prof, sizeof(long long) * 8);
+    cudaError_t e = cudaMemcpyFromSymbol(host_out8, g_nms_prof, sizeof(long long) * 8);
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(host_out8 + 8, g_nms_profw, sizeof(long long) * 8);
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(host_out8 + 16, g_nms_tl, sizeof(long long) * 16);
+    return (int)e;
 }
 #endif
 

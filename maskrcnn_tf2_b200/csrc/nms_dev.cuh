@@ -14,21 +14,39 @@ static __device__ long long g_nms_prof[8];  // one copy per translation unit
 #define PROF_TILE ++p_tiles
 #define PROF_DUMP do { if (blockIdx.x == 0 && threadIdx.x == 0) { for (int q = 0; q < 4; ++q) g_nms_prof[q] = p_acc[q]; \
                        g_nms_prof[4] = p_tiles; g_nms_prof[5] = nkept; } } while (0)
+static __device__ long long g_nms_profw[8];  // far warp 1 of CTA 0: prologue, wait release, far, barrier, send far
+#define PROFW_DECL long long w_t0 = clock64(), w_acc[7] = {0, 0, 0, 0, 0, 0, 0}
+#define PROFW_COUNT ++w_acc[6]
+#define PROFW_MARK(i) do { const long long w_now = clock64(); w_acc[i] += w_now - w_t0; w_t0 = w_now; } while (0)
+static __device__ long long g_nms_tl[16];    // spare slots for ad-hoc clock64 stamps
+#define PROFW_DUMP do { if (blockIdx.x == 0 && threadIdx.x == 32) { for (int q = 0; q < 7; ++q) g_nms_profw[q] = w_acc[q]; } } while (0)
 #else
 #define PROF_DECL
 #define PROF_MARK(i)
 #define PROF_TILE
 #define PROF_DUMP
+#define PROFW_DECL
+#define PROFW_MARK(i)
+#define PROFW_DUMP
+#define PROFW_COUNT
 #endif
 
 constexpr int kTile = 64;
+// Pipeline depth: far(u) covers the boxes kept in tiles <= u - kDepth, so the far warps run kDepth tiles ahead of the
+// resolver; the tiles in between are covered by kDepth - 1 precomputed cross blocks.  The ring of 4 slots per tile
+// (rows, far partials, mbarriers, kept counts) requires kDepth <= 3.
+constexpr int kDepth = 2;
+constexpr int kRows = kDepth * kTile;              // rows per tile: diag + (kDepth - 1) cross blocks
 constexpr int kNmsThreads = 1024;
 constexpr int kNmsWarps = kNmsThreads / 32;
-constexpr int kResolvers = 16;                     // warps 0..15: near + resolve
-constexpr int kWorkers = kNmsWarps - kResolvers;   // warps 16..31: far + diag, ahead of the resolvers
 
-static size_t nms_smem_bytes(int M, int max_out) {
-    return (size_t)M * (sizeof(float4) + sizeof(float)) + (size_t)(max_out < M ? max_out : M) * sizeof(int32_t);
+constexpr int kMaxFarSrc = 16 * 12;                // far partials per tile: cluster size x far warps per CTA
+constexpr size_t kNmsMaxDynSmem = 212 * 1024;      // 227 KB per CTA minus the kernel's static shared memory (~15 KB)
+
+static size_t nms_smem_bytes(int M, int max_out, bool compact) {
+    const size_t cap = (size_t)(max_out < M ? max_out : M);
+    return (size_t)M * (sizeof(float4) + sizeof(float)) + cap * sizeof(int32_t) +
+           (compact ? cap * (sizeof(float4) + sizeof(float)) : 0);
 }
 
 __device__ __forceinline__ uint64_t ballot64(bool lo, bool hi) {
@@ -48,12 +66,15 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arm(uint32_t bar, uint32_t tx_bytes) {  // one arrival + expected bytes
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(tx_bytes) : "memory");
 }
+// CTA-scope acquire (the default) on purpose: the awaited data is written into THIS CTA's shared memory by the peers'
+// st.async / bulk copies, whose complete_tx makes it visible; a cluster-scope acquire makes ptxas add CCTL.IVALL (an
+// L1 invalidate, ~700 cycles of long-scoreboard stall per wait -- half of the resolver's time when it was measured)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);
@@ -62,6 +83,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void st_async_u64(uint32_t peer_addr, uint64_t v, uint32_t peer_bar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
                  ::"r"(peer_addr), "l"(v), "r"(peer_bar) : "memory");
+}
+// bulk copy of `bytes` (multiple of 16) from this CTA's shared memory into a peer's, completing `bytes` transaction
+// bytes on the peer's mbarrier (SASS UBLKCP); both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t peer_dst, uint32_t local_src, uint32_t bytes, uint32_t peer_bar) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(peer_dst), "r"(local_src), "r"(bytes), "r"(peer_bar) : "memory");
 }
 __device__ __forceinline__ void named_barrier(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -74,23 +101,22 @@ __device__ __forceinline__ void or_into(unsigned long long* word, uint64_t bits)
 
 // fixed-size padded outputs, no host round trip; `sel` = kept candidate positions (shared memory), `total` of them
 __device__ __forceinline__ void nms_write_outputs(const NmsEpilogue& epi, const float4* __restrict__ bx, int b, int M,
-                                                  int max_out, int total, const int32_t* sel) {
-    const int tid = threadIdx.x;
+                                                  int max_out, int total, const int32_t* sel, int tid, int nthreads) {
     if (epi.mode == 0) {
-        for (int r = tid; r < max_out; r += kNmsThreads) {
+        for (int r = tid; r < max_out; r += nthreads) {
             int32_t v = -1;
             if (r < total) v = epi.orig_idx ? epi.orig_idx[(size_t)b * M + sel[r]] : sel[r];
             epi.keep[(size_t)b * max_out + r] = v;
         }
         if (tid == 0 && epi.count) epi.count[b] = total;
     } else if (epi.mode == 1) {  // ProposalLayer.nms L:227-230: gather + zero pad
-        for (int r = tid; r < max_out; r += kNmsThreads) {
+        for (int r = tid; r < max_out; r += nthreads) {
             epi.proposals[(size_t)b * max_out + r] = (r < total) ? __ldg(bx + sel[r]) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (epi.keep) epi.keep[(size_t)b * max_out + r] = (r < total) ? sel[r] : -1;
         }
         if (tid == 0 && epi.count) epi.count[b] = total;
     } else {  // refine_detections L:494-500: [y1,x1,y2,x2,class,score] rows + zero pad
-        for (int r = tid; r < max_out; r += kNmsThreads) {
+        for (int r = tid; r < max_out; r += nthreads) {
             float* o = epi.detections + ((size_t)b * max_out + r) * 6;
             if (r < total) {
                 const int i = epi.orig_idx[(size_t)b * M + sel[r]];

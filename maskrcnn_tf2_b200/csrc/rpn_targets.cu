@@ -41,7 +41,8 @@ __device__ __forceinline__ double np_iou(const double a0, const double a1, const
     const double dx = fmax(__dsub_rn(x2, x1), 0.0), dy = fmax(__dsub_rn(y2, y1), 0.0);
     const double inter = __dmul_rn(dx, dy);
     const double uni = __dsub_rn(__dadd_rn(g.area, area_a), inter);
-    return __ddiv_rn(inter, uni);
+    // most (anchor, instance) pairs are disjoint: 0 / uni is +0 for every positive union, without the fp64 division
+    return (inter == 0.0 && uni > 0.0) ? 0.0 : __ddiv_rn(inter, uni);
 }
 
 // stage the image's GT rows; U:175-182: crowds (class < 0) are split off from the instances (class > 0); class 0

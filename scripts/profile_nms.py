@@ -16,9 +16,12 @@ probs, bbox, anch = t(np.stack(pr)), t(np.stack(bb)), t(np.broadcast_to(a, (B,) 
 for _ in range(3):
     out = F.proposal_forward(probs, bbox, anch, 6000, 1000, [0.1, 0.1, 0.2, 0.2], 0.7, debug=True)
 torch.cuda.synchronize()
-buf = (ctypes.c_longlong * 8)()
+buf = (ctypes.c_longlong * 32)()
 L.mrcnn_debug_nms_profile(buf)
 v = list(buf)
 tiles = max(v[4], 1)
 print(f"B={B} {regime}: tiles {v[4]} kept {v[5]}  cycles/tile: wait far {v[0]/tiles:.0f}  resolve {v[1]/tiles:.0f}  "
-      f"barrier {v[2]/tiles:.0f}  near+barrier {v[3]/tiles:.0f}  total {sum(v[:4])/tiles:.0f}")
+      f"total {sum(v[:4])/tiles:.0f}")
+w = v[8:12]
+print("  far warp 1 of CTA 0, cycles/tile: prologue %.0f  wait release %.0f  far loop %.0f  send %.0f  total %.0f; exact-division fallbacks: %d"
+      % tuple([x / tiles for x in w] + [sum(w) / tiles, v[14]]))
