@@ -174,3 +174,17 @@ class DetectionTargetLayer(tfl.Layer):
 
     def get_config(self):
         return super(DetectionTargetLayer, self).get_config()
+
+
+def build_rpn_targets(anchors, gt_class_ids, gt_boxes, rpn_train_anchors_per_image, rpn_bbox_std, eps=1e-3):
+    """Device twin of utils.build_rpn_targets (utils.py:154-262) for a padded batch: anchors [A,4] float64 pixel
+    boxes, gt_class_ids [B,G] (0 = padding row, negative = crowd), gt_boxes [B,G,4] pixel boxes ->
+    (rpn_match [B,A,1] int32, rpn_bbox [B,R,4] float32), the shapes and dtypes model.py:419-420 declares for
+    input_rpn_match / input_rpn_bbox.  np.random.choice (utils.py:219,227) becomes one uniform key per anchor."""
+    a = tf.shape(anchors)[0]
+    keys = tf.random.uniform(tf.stack([tf.shape(gt_class_ids)[0], a]), dtype=tf.float32)
+    match, _, bbox32 = _ops.mrcnn_rpn_targets(
+        tf.cast(anchors, tf.float64), tf.cast(gt_class_ids, tf.int32), tf.cast(gt_boxes, tf.int32), keys,
+        rpn_train_anchors_per_image=int(rpn_train_anchors_per_image),
+        rpn_bbox_std_dev=[float(v) for v in rpn_bbox_std], eps=float(eps))
+    return match, bbox32

@@ -387,3 +387,65 @@ class MrcnnDetectionTargetOp : public tf::OpKernel {
   std::vector<float> std_;
 };
 REGISTER_KERNEL_BUILDER(Name("MrcnnDetectionTarget").Device(tf::DEVICE_GPU), MrcnnDetectionTargetOp);
+
+// ---- utils.build_rpn_targets (utils.py:154-262), batched; called from the input pipeline instead of per image in
+// SegmentationDataGenerator (preprocess.py:342-348).  anchors: [A,4] float64 pixel boxes (preprocess.py:82,297).
+REGISTER_OP("MrcnnRpnTargets")
+    .Input("anchors: double").Input("gt_class_ids: int32").Input("gt_boxes: int32")
+    .Input("rand_keys: float")    // [B,A] uniform [0,1): stands in for np.random.choice (utils.py:219,227)
+    .Output("rpn_match: int32").Output("rpn_bbox: double").Output("rpn_bbox_f32: float")
+    .Attr("rpn_train_anchors_per_image: int = 256")
+    .Attr("rpn_bbox_std_dev: list(float) = [0.1, 0.1, 0.2, 0.2]")
+    .Attr("eps: float = 0.001")
+    .SetShapeFn([](InferenceContext* c) {
+      int r;
+      TF_RETURN_IF_ERROR(c->GetAttr("rpn_train_anchors_per_image", &r));
+      auto b = c->Dim(c->input(1), 0);
+      c->set_output(0, c->MakeShape({b, c->Dim(c->input(0), 0), 1}));  // [B,A,1] as the loader stacks it (preprocess.py:369-370)
+      c->set_output(1, c->MakeShape({b, r, 4}));
+      c->set_output(2, c->MakeShape({b, r, 4}));
+      return tf::Status();
+    });
+
+class MrcnnRpnTargetsOp : public tf::OpKernel {
+ public:
+  explicit MrcnnRpnTargetsOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("rpn_train_anchors_per_image", &r_));
+    OP_REQUIRES_OK(c, c->GetAttr("rpn_bbox_std_dev", &std_));
+    OP_REQUIRES_OK(c, c->GetAttr("eps", &eps_));
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    const tf::Tensor& anchors = ctx->input(0);
+    const tf::Tensor& cls = ctx->input(1);
+    const tf::Tensor& boxes = ctx->input(2);
+    const tf::Tensor& keys = ctx->input(3);
+    OP_REQUIRES(ctx, anchors.dims() == 2 && anchors.dim_size(1) == 4 && cls.dims() == 2 && boxes.dims() == 3,
+                tf::errors::InvalidArgument("expected anchors [A,4], gt_class_ids [B,G], gt_boxes [B,G,4]"));
+    const int A = anchors.dim_size(0), B = cls.dim_size(0), G = cls.dim_size(1);
+    tf::Tensor *match, *bbox, *bbox32;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({B, A, 1}), &match));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({B, r_, 4}), &bbox));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(2, tf::TensorShape({B, r_, 4}), &bbox32));
+    size_t ws_bytes = 0;
+    OP_REQUIRES_OK(ctx, LauncherStatus(mrcnn_rpn_targets_workspace_bytes(B, A, G, r_, &ws_bytes), "rpn targets ws"));
+    tf::Tensor ws;
+    OP_REQUIRES_OK(ctx, Scratch(ctx, ws_bytes, &ws));
+    // the attr list is float; the reference divides by the float64 array np.array([0.1, 0.1, 0.2, 0.2]) (config.py:90):
+    // round-trip through the shortest decimal so 0.1f means 0.1
+    double sd[4];
+    for (int i = 0; i < 4; ++i) sd[i] = std::stod(std::to_string(std_[i]));
+    OP_REQUIRES_OK(ctx, LauncherStatus(
+        mrcnn_rpn_targets_forward(anchors.flat<double>().data(), cls.flat<tf::int32>().data(),
+                                  boxes.flat<tf::int32>().data(), keys.flat<float>().data(), B, A, G, r_, sd,
+                                  std::stod(std::to_string(eps_)), match->flat<tf::int32>().data(),
+                                  bbox->flat<double>().data(), bbox32->flat<float>().data(), nullptr,
+                                  ws.flat<tf::uint8>().data(), ws_bytes, StreamOf(ctx)),
+        "mrcnn_rpn_targets_forward"));
+  }
+
+ private:
+  int r_;
+  float eps_;
+  std::vector<float> std_;
+};
+REGISTER_KERNEL_BUILDER(Name("MrcnnRpnTargets").Device(tf::DEVICE_GPU), MrcnnRpnTargetsOp);
