@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--regime", default="clustered", choices=["clustered", "sparse", "iid"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-full-copy", action="store_true",
+                    help="e2e leg: bulk-copy the feature maps to HBM every step instead of demand-fetching the sampled pixels")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bound on the CPU baseline sample")
     ap.add_argument("--no-pipelined", action="store_true", help="skip the extra two-stream throughput measurement")
     ap.add_argument("--first-image", type=int, default=0, help="index of the first synthetic image")
@@ -291,15 +293,15 @@ def main():
     KERNELS_PER_STEP = 2 + 2 + 3 + 2
     ev7 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
 
-    def stage(t, maps, step=None):
+    def stage(t, maps, step=None, host_stage=None):
         rois = proposal([t["rpn_probs"], t["rpn_bbox"], anchors])
         if step is not None:
             ev7[step][0].record()
-        pooled = align7([rois, t["image_meta"]] + maps)
+        pooled = align7([rois, t["image_meta"]] + maps, host_stage=host_stage, new_maps=True)
         if step is not None:
             ev7[step][1].record()
         det = detect([rois, t["mrcnn_class"], t["mrcnn_bbox"], t["image_meta"]])
-        mask_pooled = align14([boxes_of(det), t["image_meta"]] + maps)
+        mask_pooled = align14([boxes_of(det), t["image_meta"]] + maps, host_stage=host_stage, new_maps=False)
         return rois, pooled, det, mask_pooled
 
     def barrier():
@@ -354,14 +356,28 @@ def main():
     # ---- end to end: pinned host inputs -> H2D every step, detections -> host every step ----
     e2e = None
     if not args.no_e2e:
-        # two device buffer sets: the H2D copy of step i+1 (copy stream) overlaps the kernels of step i (compute stream);
-        # every step still copies all of its inputs from pinned host memory and the host reads its detections back
-        sets = [({k: torch.empty_like(v, device=dev) for k, v in host.items() if k != "anchors"},
-                 [torch.empty_like(f, device=dev) for f in host_maps]) for _ in range(2)]
+        # Host buffers in, detections out, every step.  The small inputs (RPN outputs, head outputs, image_meta: 63 MB)
+        # are copied on a copy stream, the copy of step i+1 overlapping the kernels of step i.  The feature maps
+        # (713 MB per step) stay in pinned host memory: each PyramidROIAlign call first fetches exactly the map pixels
+        # its ROIs sample, once each, straight out of the host maps (F.HostMapStage / mrcnn_roialign_fetch_hostmaps),
+        # so the PCIe traffic of a step is the sampled pixels, not the maps.  --e2e-full-copy restores the bulk copy.
+        full_copy = args.e2e_full_copy
+        # rpn_bbox [B,A,4] and mrcnn_bbox [B,N,NC,4] are read sparsely by index (the K top-k winners' rows; one class
+        # row per ROI): they too stay in pinned host memory and only those rows cross the bus
+        sparse = () if full_copy else ("rpn_bbox", "mrcnn_bbox")
+        small = {k: v for k, v in host.items() if k != "anchors" and k not in sparse}
+        sets = [{k: torch.empty_like(v, device=dev) for k, v in small.items()} for _ in range(2)]
+        for s_ in sets:
+            for k in sparse:
+                s_[k] = host[k]
+        sparse_bytes = 0 if full_copy else B * (min(cfg["pre_nms_limit"], A) + cfg["post_nms_rois_inference"]) * 16
+        map_sets = [[torch.empty_like(f, device=dev) for f in host_maps] for _ in range(2)] if full_copy else None
+        stages = None if full_copy else [F.HostMapStage(host_maps, dev) for _ in range(2)]
         det_host = [torch.empty((B, cfg["detection_max_instances"], 6), dtype=torch.float32).pin_memory()
                     for _ in range(2)]
-        h2d = sum(v.numel() * v.element_size() for k, v in host.items() if k != "anchors") + \
-            sum(f.numel() * f.element_size() for f in host_maps)
+        small_bytes = sum(v.numel() * v.element_size() for v in small.values())
+        map_bytes = sum(f.numel() * f.element_size() for f in host_maps)
+        pixel_bytes = host_maps[0].shape[3] * 4
         d2h = det_host[0].numel() * det_host[0].element_size()
         copy_stream, compute_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         copied = [torch.cuda.Event(), torch.cuda.Event()]
@@ -370,20 +386,24 @@ def main():
         alive = [None, None]
 
         def issue_copy(i):
-            dd, dm = sets[i & 1]
+            dd = sets[i & 1]
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(consumed[i & 1])          # the buffers' previous step has been computed
-                for k in dd:
-                    dd[k].copy_(host[k], non_blocking=True)
-                for a_, b_ in zip(dm, host_maps):
-                    a_.copy_(b_, non_blocking=True)
+                for k in small:
+                    dd[k].copy_(small[k], non_blocking=True)
+                if full_copy:
+                    for a_, b_ in zip(map_sets[i & 1], host_maps):
+                        a_.copy_(b_, non_blocking=True)
                 copied[i & 1].record(copy_stream)
 
         def issue_compute(i):
-            dd, dm = sets[i & 1]
+            dd = sets[i & 1]
             with torch.cuda.stream(compute_stream), F.workspace_namespace(3):
                 compute_stream.wait_event(copied[i & 1])
-                o = stage(dd, dm)
+                if full_copy:
+                    o = stage(dd, map_sets[i & 1])
+                else:
+                    o = stage(dd, host_maps, host_stage=stages[i & 1])
                 alive[i & 1] = o
                 consumed[i & 1].record(compute_stream)
                 det_host[i & 1].copy_(o[2], non_blocking=True)
@@ -404,10 +424,16 @@ def main():
         e2e_steps = max(3, min(args.steps, 10))
         run_e2e(3)
         barrier()
+        fetched0 = 0 if full_copy else sum(s_.fetched_pixels() for s_ in stages)
         t0 = time.perf_counter()
         run_e2e(e2e_steps)
         barrier()
         t_e2e = time.perf_counter() - t0
+        if full_copy:
+            h2d = small_bytes + map_bytes
+        else:   # bytes that actually crossed the bus: counted on the device by the fetch kernel
+            h2d = small_bytes + sparse_bytes + \
+                (sum(s_.fetched_pixels() for s_ in stages) - fetched0) * pixel_bytes / e2e_steps
 
     # ---- max over ranks ----
     if world > 1:
@@ -423,8 +449,17 @@ def main():
     if not args.no_e2e:
         e2e = {"value": world * B * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-               "note": "pinned host inputs copied to HBM and detections read back every step (copy of step i+1 "
-                       "overlaps the kernels of step i on a second stream); anchors stay resident"}
+               "maps": "full copy" if args.e2e_full_copy else "demand-fetched",
+               "note": ("pinned host inputs copied to HBM and detections read back every step (copy of step i+1 "
+                        "overlaps the kernels of step i on a second stream); anchors stay resident"
+                        if args.e2e_full_copy else
+                        "pinned host inputs in, detections read back every step; RPN/head outputs copied to HBM (copy "
+                        "of step i+1 overlaps step i), feature maps left in pinned host memory and only the pixels "
+                        "the ROIs sample fetched over the bus (h2d_bytes_per_step counts them on the device; a full "
+                        "copy of all inputs would be %d bytes); rpn_bbox / mrcnn_bbox are read in place, only the rows "
+                        "used; anchors stay resident" % sum(v.numel() * v.element_size() for k, v in
+                                                            list(host.items()) + list(enumerate(host_maps))
+                                                            if k != "anchors"))}
 
     if not args.no_pipelined:
         pipelined = {"value": world * B * args.steps / (ms_pipe * 1e-3), "unit": UNIT, "streams": 2,

@@ -96,6 +96,25 @@ int mrcnn_roialign_forward(const float* boxes, const float* image_meta, int meta
                            int map_mode, float* out, int32_t* roi_map, int32_t* roi_level, void* ws,
                            size_t ws_bytes, void* stream);
 
+/* ---- PyramidROIAlign with the feature maps in PINNED HOST memory: demand-driven staging ---------------------------
+ * For callers whose P2..P5 start in host memory (this repository's end-to-end benchmark; a TF input pipeline that
+ * keeps maps on the host).  Instead of copying all four maps (89 MB per image at 1024^2) before
+ * mrcnn_roialign_forward, mrcnn_roialign_fetch_hostmaps marks the map pixels the given ROIs sample (the forward
+ * kernel's own taps) and copies exactly those, once each, from host_fmaps (host array of 4 pointers to page-locked,
+ * device-accessible host maps: cudaHostAlloc / cudaHostRegister under UVA) into dev_fmaps (host array of 4 device
+ * staging maps of the same shapes).  mrcnn_roialign_forward on dev_fmaps then returns bit-identical results.
+ * resident: device bitmap of mrcnn_roialign_resident_words() 32-bit words (one bit per map pixel of the batch): a set
+ * bit = the staging pixel already holds the host pixel; pass reset != 0 when the host maps hold new contents (first
+ * call of a step), 0 to fetch only what is still missing (the mask branch's call on the detections).
+ * fetched: optional device counter, incremented by the number of pixels copied (each C * 4 bytes). */
+int mrcnn_roialign_resident_words(int B, const int* H, const int* W, size_t* words);
+int mrcnn_roialign_fetch_workspace_bytes(int B, int N, const int* H, const int* W, size_t* bytes);
+int mrcnn_roialign_fetch_hostmaps(const float* boxes, const float* image_meta, int meta_len,
+                                  const float* const* host_fmaps, float* const* dev_fmaps, const int* H, const int* W,
+                                  int C, int B, int N, int ph, int pw, float denominator, int map_mode,
+                                  uint32_t* resident, int reset, unsigned long long* fetched, void* ws,
+                                  size_t ws_bytes, void* stream);
+
 /* ---- gradient of PyramidROIAlign w.r.t. the four feature maps (TF CropAndResizeGradImage through the
  * reference's gather/concat, M:142,168; boxes get no gradient, L:628-629).  grad_fmaps: host array of 4
  * device pointers; every element is written by the launcher (no pre-clearing needed).

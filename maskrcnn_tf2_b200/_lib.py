@@ -35,6 +35,12 @@ PROTOTYPES = {
     "mrcnn_roialign_forward": [c_void_p, c_void_p, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_int),
                                ctypes.POINTER(c_int), c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
+    "mrcnn_roialign_resident_words": [c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_size_t)],
+    "mrcnn_roialign_fetch_workspace_bytes": [c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int),
+                                             ctypes.POINTER(c_size_t)],
+    "mrcnn_roialign_fetch_hostmaps": [c_void_p, c_void_p, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
+                                      ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int, c_int, c_int, c_int, c_int,
+                                      c_float, c_int, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
     "mrcnn_roialign_backward_workspace_bytes": [c_int, c_int, c_int, c_int, ctypes.POINTER(c_int),
                                                 ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_size_t)],
     "mrcnn_roialign_backward": [c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_int),

@@ -898,3 +898,166 @@ MRCNN_EXPORT int mrcnn_roialign_backward(const float* grad_out, const float* box
                                                                   misc + 1);
     return last_error();
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Demand-driven host -> device staging of the feature maps (maps resident in PINNED HOST memory).
+// PyramidROIAlign touches only the pixels its ROIs sample (about half of the 89 MB per image at 1024^2 for 1000
+// proposals); when the maps start in host memory, copying all of them is the whole cost of the stage (PCIe).  Instead:
+//   roialign_mark_kernel   thread per output bin: the same taps as the forward kernel -> one bit per sampled map pixel
+//                          (skipping pixels that are already resident);
+//   roialign_fetch_kernel  warp per 32-pixel bitmap word: every marked pixel (C floats, 1 KB at C = 256) is read ONCE
+//                          straight out of the pinned host map (zero-copy loads over PCIe / C2C, 128-bit per lane,
+//                          several pixels in flight per warp) and written to the device staging map; the word is then
+//                          merged into the `resident` bitmap, so a later call (the mask branch's ROIAlign on the
+//                          detections) only fetches what is still missing.
+// The ordinary forward kernel then runs on the staging maps, bit-identical to a full copy.
+// ---------------------------------------------------------------------------------------------------------------
+namespace mrcnn {
+
+__global__ void __launch_bounds__(256)
+roialign_mark_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ level_ws,
+                     const int* __restrict__ first, int map_mode, MapTable tbl, PixelSpace ps, int N, int ph, int pw,
+                     int total_bins, const uint32_t* __restrict__ resident, uint32_t* __restrict__ need) {
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= total_bins) return;
+    const int f = s / (ph * pw), r = s - f * (ph * pw), y = r / pw, x = r - y * pw;
+    const int m = roi_map_index(level_ws[f], first, map_mode);
+    const RoiGeom g = roi_geom(__ldg(boxes + f), m, tbl.H, tbl.W, ph, pw);
+    const AxisTap ty = axis_tap(g.y0, g.hs, y, g.H), tx = axis_tap(g.x0, g.ws, x, g.W);
+    if (!(ty.valid && tx.valid)) return;  // the forward kernel writes zeros without reading
+    const int base = ((m == 0) ? ps.base[0] : (m == 1) ? ps.base[1] : (m == 2) ? ps.base[2] : ps.base[3]) +
+                     (f / N) * g.H * g.W;
+    const int q[4] = {base + ty.lo * g.W + tx.lo, base + ty.lo * g.W + tx.hi, base + ty.hi * g.W + tx.lo,
+                      base + ty.hi * g.W + tx.hi};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (c == 1 && q[1] == q[0]) continue;
+        if (c == 2 && q[2] == q[0]) continue;
+        if (c == 3 && (q[3] == q[1] || q[3] == q[2])) continue;
+        const uint32_t bit = 1u << (q[c] & 31);
+        const int w = q[c] >> 5;
+        if ((__ldg(resident + w) | need[w]) & bit) continue;  // racy pre-check: saves most of the atomics
+        atomicOr(need + w, bit);
+    }
+}
+
+// pixel q of the concatenated pixel space -> map index and offset (in pixels) inside that map
+__device__ __forceinline__ int pixel_map_of(const PixelSpace& ps, int q) {
+    return (q >= ps.base[3]) ? 3 : (q >= ps.base[2]) ? 2 : (q >= ps.base[1]) ? 1 : 0;
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256)
+roialign_fetch_kernel(MapTable host, GradTable dev, PixelSpace ps, int C, int words, uint32_t* __restrict__ need,
+                      uint32_t* __restrict__ resident, unsigned long long* __restrict__ fetched) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, nwarps = (gridDim.x * 256) >> 5;
+    const int c4 = C >> 2;
+    unsigned long long mine = 0;
+    for (int w = warp; w < words; w += nwarps) {
+        uint32_t bits = need[w] & ~resident[w];
+        if (bits == 0u) continue;
+        mine += __popc(bits);
+        const uint32_t all = bits;
+        while (bits) {  // two pixels per round: 2 * VPL independent 16-byte host loads per lane in flight
+            const int i0 = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int i1 = bits ? __ffs(bits) - 1 : -1;
+            if (bits) bits &= bits - 1;
+            const int q0 = w * 32 + i0, q1 = w * 32 + (i1 < 0 ? i0 : i1);
+            const int m0 = pixel_map_of(ps, q0), m1 = pixel_map_of(ps, q1);
+            const size_t o0 = (size_t)(q0 - ps.base[m0]) * c4, o1 = (size_t)(q1 - ps.base[m1]) * c4;
+            const float4* h0 = reinterpret_cast<const float4*>(host.ptr[m0]) + o0;
+            const float4* h1 = reinterpret_cast<const float4*>(host.ptr[m1]) + o1;
+            float4* d0 = reinterpret_cast<float4*>(dev.ptr[m0]) + o0;
+            float4* d1 = reinterpret_cast<float4*>(dev.ptr[m1]) + o1;
+            if (VPL > 0) {
+                float4 a[VPL > 0 ? VPL : 1], b[VPL > 0 ? VPL : 1];
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) { a[v] = __ldcs(h0 + lane + 32 * v); b[v] = __ldcs(h1 + lane + 32 * v); }
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) { d0[lane + 32 * v] = a[v]; if (i1 >= 0) d1[lane + 32 * v] = b[v]; }
+            } else {
+                for (int i = lane; i < c4; i += 32) { d0[i] = __ldcs(h0 + i); if (i1 >= 0) d1[i] = __ldcs(h1 + i); }
+            }
+        }
+        if (lane == 0) { resident[w] |= all; need[w] = 0u; }  // one warp owns a word: no atomics needed
+    }
+    if (fetched && lane == 0 && mine) atomicAdd(fetched, mine);
+}
+
+static size_t fetch_ws_bytes(int B, int N, int NP) {
+    return roialign_ws_bytes(B, N) + align_up((size_t)((NP + 31) / 32) * sizeof(uint32_t), 256);
+}
+
+}  // namespace mrcnn
+
+MRCNN_EXPORT int mrcnn_roialign_resident_words(int B, const int* H, const int* W, size_t* words) {
+    if (!H || !W || !words) return MRCNN_ERR_NULL;
+    PixelSpace ps;
+    if (B < 1) return MRCNN_ERR_RANGE;
+    const int rc = pixel_space(H, W, B, &ps);
+    if (rc != MRCNN_OK) return rc;
+    *words = (size_t)((ps.base[4] + 31) / 32);
+    return MRCNN_OK;
+}
+
+MRCNN_EXPORT int mrcnn_roialign_fetch_workspace_bytes(int B, int N, const int* H, const int* W, size_t* bytes) {
+    if (!H || !W || !bytes) return MRCNN_ERR_NULL;
+    if (B < 1 || N < 1) return MRCNN_ERR_RANGE;
+    PixelSpace ps;
+    const int rc = pixel_space(H, W, B, &ps);
+    if (rc != MRCNN_OK) return rc;
+    *bytes = fetch_ws_bytes(B, N, ps.base[4]);
+    return MRCNN_OK;
+}
+
+MRCNN_EXPORT int mrcnn_roialign_fetch_hostmaps(const float* boxes, const float* image_meta, int meta_len,
+                                               const float* const* host_fmaps, float* const* dev_fmaps, const int* H,
+                                               const int* W, int C, int B, int N, int ph, int pw, float denominator,
+                                               int map_mode, uint32_t* resident, int reset,
+                                               unsigned long long* fetched, void* ws, size_t ws_bytes, void* stream) {
+    if (!boxes || !image_meta || !resident || !ws) return MRCNN_ERR_NULL;
+    int rc = check_maps((const void* const*)host_fmaps, H, W, C);
+    if (rc == MRCNN_OK) rc = check_maps((const void* const*)dev_fmaps, H, W, C);
+    if (rc != MRCNN_OK) return rc;
+    if (B < 1 || N < 1 || ph < 1 || pw < 1 || meta_len < 6 || (map_mode != 0 && map_mode != 1) ||
+        (long long)B * N * ph * pw > INT_MAX / 2 || !(denominator > 0.0f))
+        return MRCNN_ERR_RANGE;
+    PixelSpace ps;
+    rc = pixel_space(H, W, B, &ps);
+    if (rc != MRCNN_OK) return rc;
+    if (ws_bytes < fetch_ws_bytes(B, N, ps.base[4])) return MRCNN_ERR_WORKSPACE;
+    if (!aligned16(boxes) || !aligned16(ws)) return MRCNN_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    MapTable host;
+    GradTable dev;
+    for (int l = 0; l < 4; ++l) {
+        host.ptr[l] = host_fmaps[l]; host.H[l] = H[l]; host.W[l] = W[l];
+        dev.ptr[l] = dev_fmaps[l]; dev.H[l] = H[l]; dev.W[l] = W[l];
+    }
+    const int BN = B * N, words = (ps.base[4] + 31) / 32;
+    int* first = (int*)ws;
+    int32_t* level_ws = (int32_t*)((char*)ws + 256);
+    uint32_t* need = (uint32_t*)((char*)ws + roialign_ws_bytes(B, N));
+    cudaError_t e = cudaMemsetAsync(first, 0x7f, 4 * sizeof(int), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(need, 0, (size_t)words * sizeof(uint32_t), st);
+    if (e == cudaSuccess && reset) e = cudaMemsetAsync(resident, 0, (size_t)words * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return (int)e;
+    roialign_prep_kernel<<<(BN + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, st>>>(
+        (const float4*)boxes, image_meta, BN, denominator, level_ws, first, nullptr);
+    const int bins = BN * ph * pw;
+    roialign_mark_kernel<<<(bins + 255) / 256, 256, 0, st>>>((const float4*)boxes, level_ws, first, map_mode, host, ps, N,
+                                                            ph, pw, bins, resident, need);
+    int devid = 0, sms = 148;
+    if (cudaGetDevice(&devid) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devid);
+    const int grid = min((words + 7) / 8, 8 * sms);
+#define MRCNN_FETCH(V) roialign_fetch_kernel<V><<<grid, 256, 0, st>>>(host, dev, ps, C, words, need, resident, fetched)
+    if (C == 128) MRCNN_FETCH(1);
+    else if (C == 256) MRCNN_FETCH(2);
+    else if (C == 512) MRCNN_FETCH(4);
+    else MRCNN_FETCH(0);
+#undef MRCNN_FETCH
+    return last_error();
+}

@@ -37,8 +37,10 @@ def _stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _req(t, dtype, name, ndim=None):
-    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+def _req(t, dtype, name, ndim=None, pinned_ok=False):
+    """pinned_ok: the launcher reads this tensor sparsely by index (a few rows out of many), so a page-locked host
+    tensor -- device-accessible under unified addressing -- may be passed as is: only the rows used cross the bus."""
+    if not isinstance(t, torch.Tensor) or not (t.is_cuda or (pinned_ok and t.is_pinned())):
         raise TypeError(f"{name}: expected a CUDA tensor (the ROI-stage kernels have no CPU path)")
     if t.dtype != dtype:
         raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
@@ -120,7 +122,7 @@ def proposal_forward(rpn_probs, rpn_bbox, anchors, pre_nms_limit, proposal_count
     """ProposalLayer.call.  Returns proposals [B,P,4]; with debug=True a dict with the intermediate indices too."""
     L = _lib.lib()
     rpn_probs = _req(rpn_probs, torch.float32, "rpn_probs", 3)
-    rpn_bbox = _req(rpn_bbox, torch.float32, "rpn_bbox", 3)
+    rpn_bbox = _req(rpn_bbox, torch.float32, "rpn_bbox", 3, pinned_ok=True)   # only the K winners' rows are read
     anchors = _req(anchors, torch.float32, "anchors", 3)
     B, A, two = rpn_probs.shape
     if two != 2 or tuple(rpn_bbox.shape) != (B, A, 4) or tuple(anchors.shape) != (B, A, 4):
@@ -235,7 +237,7 @@ def detection_forward(rois, probs, deltas, image_meta, bbox_std_dev, min_confide
     L = _lib.lib()
     rois = _req(rois, torch.float32, "rois", 3)
     probs = _req(probs, torch.float32, "mrcnn_class", 3)
-    deltas = _req(deltas, torch.float32, "mrcnn_bbox", 4)
+    deltas = _req(deltas, torch.float32, "mrcnn_bbox", 4, pinned_ok=True)   # only the argmax class's row per ROI
     image_meta = _req(image_meta, torch.float32, "image_meta", 2)
     B, N, NC = probs.shape
     if tuple(rois.shape) != (B, N, 4) or tuple(deltas.shape) != (B, N, NC, 4):
@@ -321,3 +323,51 @@ def rpn_targets_forward(anchors_px, gt_class_ids, gt_boxes, rand_keys, rpn_train
     if return_counts:
         out.append(counts)
     return tuple(out)
+
+
+class HostMapStage:
+    """Device-side staging of feature maps that live in PINNED HOST memory (demand-driven H2D, csrc/roialign.cu).
+
+    `stage.fetch(boxes, image_meta, pool_shape, reset=...)` copies exactly the map pixels those ROIs sample, once
+    each, straight out of the pinned host tensors; `stage.maps` are then valid inputs for roialign_forward /
+    PyramidROIAlign with the same boxes.  reset=True declares new host contents (first call of a step); later calls of
+    the step (the mask branch) fetch only pixels that are not resident yet.  `fetched_pixels()` synchronises and
+    returns the running count of pixels copied (each C * 4 bytes)."""
+
+    def __init__(self, host_maps, device):
+        if len(host_maps) != 4:
+            raise ValueError("PyramidROIAlign needs exactly four feature maps (P2..P5)")
+        for i, m in enumerate(host_maps):
+            if not isinstance(m, torch.Tensor) or m.is_cuda or not m.is_pinned() or m.dtype != torch.float32 or \
+                    m.dim() != 4 or not m.is_contiguous():
+                raise TypeError(f"host_maps[{i}]: expected a contiguous pinned (page-locked) fp32 CPU tensor [B,H,W,C]")
+        self.host_maps = list(host_maps)
+        self.device = device
+        self.maps = [torch.empty(m.shape, dtype=torch.float32, device=device) for m in host_maps]
+        self.B, self.C = host_maps[0].shape[0], host_maps[0].shape[3]
+        self._Hs = (c_int * 4)(*[m.shape[1] for m in host_maps])
+        self._Ws = (c_int * 4)(*[m.shape[2] for m in host_maps])
+        self._host_ptrs = (c_void_p * 4)(*[m.data_ptr() for m in host_maps])   # device-accessible under UVA
+        self._dev_ptrs = (c_void_p * 4)(*[m.data_ptr() for m in self.maps])
+        words = _query(_lib.lib().mrcnn_roialign_resident_words, self.B, self._Hs, self._Ws)
+        self.resident = torch.zeros(int(words), dtype=torch.int32, device=device)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def fetch(self, boxes, image_meta, pool_shape, reset, denominator=244.0, map_mode=0):
+        L = _lib.lib()
+        boxes = _req(boxes, torch.float32, "boxes", 3)
+        image_meta = _req(image_meta, torch.float32, "image_meta", 2)
+        B, N, _ = boxes.shape
+        if B != self.B:
+            raise ValueError("boxes and host maps disagree on the batch size")
+        nbytes = _query(L.mrcnn_roialign_fetch_workspace_bytes, B, N, self._Hs, self._Ws)
+        ws = _workspace(("roialign_fetch", B, N, id(self)), nbytes, self.device)
+        check(L.mrcnn_roialign_fetch_hostmaps(ptr(boxes), ptr(image_meta), image_meta.shape[1], self._host_ptrs,
+                                              self._dev_ptrs, self._Hs, self._Ws, self.C, B, N, int(pool_shape[0]),
+                                              int(pool_shape[1]), c_float(float(denominator)), int(map_mode),
+                                              ptr(self.resident), 1 if reset else 0, ptr(self.counter), ptr(ws),
+                                              ws.numel(), _stream()), "mrcnn_roialign_fetch_hostmaps")
+        return self.maps
+
+    def fetched_pixels(self):
+        return int(self.counter.item())

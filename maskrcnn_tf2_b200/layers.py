@@ -101,9 +101,15 @@ class PyramidROIAlign(_Layer):
         self.denominator = denominator
         self.map_mode = map_mode
 
-    def call(self, inputs, **kwargs):
+    def call(self, inputs, host_stage=None, new_maps=True, **kwargs):
+        """host_stage (functional.HostMapStage): the feature maps live in pinned host memory; only the pixels these
+        boxes sample are staged on the device before pooling (inference only; inputs[2:] are then ignored).
+        new_maps=False: same host contents as the previous call with this stage (fetch only what is missing)."""
         boxes, image_meta = inputs[0], inputs[1]
         feature_maps = list(inputs[2:])
+        if host_stage is not None:
+            feature_maps = host_stage.fetch(boxes, image_meta, self.pool_shape, reset=new_maps,
+                                            denominator=self.denominator, map_mode=self.map_mode)
         return _PyramidROIAlignFn.apply(boxes, image_meta, self.pool_shape, self.denominator, self.map_mode,
                                         *feature_maps)
 

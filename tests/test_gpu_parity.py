@@ -512,3 +512,89 @@ def test_tma_staged_roialign_forward_is_bit_exact_too():
                         "roialign_forward"], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "passed" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("map_mode", [0, 1])
+def test_roialign_from_pinned_host_maps_fetches_exactly_the_sampled_pixels(orc, dev, map_mode):
+    """Demand-driven staging (mrcnn_roialign_fetch_hostmaps): pooled values bit-identical to the full-copy path, the
+    number of pixels copied equals the number of distinct map pixels the forward kernel's taps touch, and a second call
+    on other boxes only fetches what is missing."""
+    import torch
+    from maskrcnn_tf2_b200 import functional as F
+    from maskrcnn_tf2_b200.layers import PyramidROIAlign
+    rng = np.random.default_rng(77)
+    B, S, C, N = 3, 256, 256, 150
+    maps = [rng.standard_normal((B, S // s, S // s, C), dtype=np.float32) for s in (4, 8, 16, 32)]
+    boxes = random_boxes(rng, B * N, 0.02, 0.6).reshape(B, N, 4)
+    boxes[0, 5] = 0.0                                            # zero-padded ROI
+    boxes[1, 7] = [0.9, 0.9, 1.3, 1.2]                           # partly outside: extrapolated bins read nothing
+    boxes2 = random_boxes(rng, B * 40, 0.05, 0.3).reshape(B, 40, 4)
+    meta = np.zeros((B, 12 + 5), np.float32)
+    meta[:, 4:6] = S
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    host = [torch.from_numpy(m).pin_memory() for m in maps]
+    stage = F.HostMapStage(host, dev)
+    for m in stage.maps:
+        m.fill_(float("nan"))                                    # anything not fetched would poison the output
+    layer7 = PyramidROIAlign([7, 7], map_mode=map_mode)
+    layer14 = PyramidROIAlign([14, 14], map_mode=map_mode)
+    full = [t(m) for m in maps]
+    want7 = layer7([t(boxes), t(meta)] + full)
+    got7 = layer7([t(boxes), t(meta)] + host, host_stage=stage, new_maps=True)
+    assert torch.equal(got7, want7)
+    n1 = stage.fetched_pixels()
+
+    def touched(bx, pool, seen):
+        r = orc.pyramid_roi_align(bx, float(S), float(S), maps, pool, map_mode=map_mode)
+        for b in range(B):
+            for i in range(bx.shape[1]):
+                m = int(r["roi_map"][b, i])
+                H = W = maps[m].shape[1]
+                y1, x1, y2, x2 = [np.float32(v) for v in bx[b, i]]
+                for axis, (c1, c2, n) in enumerate(((y1, y2, pool[0]), (x1, x2, pool[1]))):
+                    sc = np.float32(np.float32((c2 - c1) * np.float32(H - 1)) / np.float32(n - 1))
+                    pos = np.float32(c1 * np.float32(H - 1)) + np.arange(n, dtype=np.float32) * sc
+                    ok = (pos >= 0) & (pos <= H - 1)
+                    lo, hi = np.floor(pos[ok]).astype(int), np.ceil(pos[ok]).astype(int)
+                    if axis == 0:
+                        ys = np.unique(np.concatenate([lo, hi]))
+                    else:
+                        xs = np.unique(np.concatenate([lo, hi]))
+                for y in ys:
+                    for x in xs:
+                        seen.add((m, b, int(y), int(x)))
+        return seen
+    seen = touched(boxes, (7, 7), set())
+    assert n1 == len(seen)
+    want14 = layer14([t(boxes2), t(meta)] + full)
+    got14 = layer14([t(boxes2), t(meta)] + host, host_stage=stage, new_maps=False)
+    assert torch.equal(got14, want14)
+    seen2 = touched(boxes2, (14, 14), set(seen))
+    assert stage.fetched_pixels() == len(seen2)                  # only the pixels that were still missing
+    got7b = layer7([t(boxes), t(meta)] + host, host_stage=stage, new_maps=True)   # reset: everything fetched again
+    assert torch.equal(got7b, want7) and stage.fetched_pixels() == len(seen2) + len(seen)
+
+
+@pytest.mark.gpu
+def test_sparsely_read_inputs_may_stay_in_pinned_host_memory(dev):
+    """rpn_bbox (ProposalLayer) and mrcnn_bbox (DetectionLayer) are read by index only: page-locked host tensors give
+    the same outputs as device copies."""
+    import torch
+    from maskrcnn_tf2_b200 import make_config, synth
+    from maskrcnn_tf2_b200.layers import DetectionLayer, ProposalLayer
+    B, S, NC = 2, 256, 7
+    cfg = make_config(img_size=S, num_classes=NC, batch_size=B)
+    x = synth.inference_batch(31, B, img_size=S, num_classes=NC, regime="clustered", n_rois=1000, channels=8)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    prop = ProposalLayer(1000, cfg)
+    r_dev = prop([t(x["rpn_probs"]), t(x["rpn_bbox"]), t(x["anchors"])])
+    r_pin = prop([t(x["rpn_probs"]), pin(x["rpn_bbox"]), t(x["anchors"])])
+    assert torch.equal(r_dev, r_pin)
+    det = DetectionLayer(1000, 0.7, 100, 0.3, cfg["bbox_std_dev"], B, B)
+    d_dev = det([r_dev, t(x["mrcnn_class"]), t(x["mrcnn_bbox"]), t(x["image_meta"])])
+    d_pin = det([r_dev, t(x["mrcnn_class"]), pin(x["mrcnn_bbox"]), t(x["image_meta"])])
+    assert torch.equal(d_dev, d_pin)
+    with pytest.raises(TypeError):
+        prop([t(x["rpn_probs"]), torch.from_numpy(x["rpn_bbox"]), t(x["anchors"])])   # pageable host memory: rejected
