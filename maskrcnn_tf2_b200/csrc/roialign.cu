@@ -117,23 +117,26 @@ template <int VPL>
 __global__ void __launch_bounds__(kRoiThreads, 5)
 roialign_fwd_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ level_ws,
                     const int* __restrict__ first, int map_mode, MapTable tbl, int C, int N, int ph, int pw,
-                    int total_rows, float* __restrict__ out, int32_t* __restrict__ roi_map) {
+                    int total_rows, int xsplit, float* __restrict__ out, int32_t* __restrict__ roi_map) {
     const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (kRoiThreads / 32) + (threadIdx.x >> 5);
-    if (row >= total_rows) return;
+    // a warp owns one output row, or 1/xsplit of it (wide crops: more, shorter warps fill the last wave better)
+    const int unit = blockIdx.x * (kRoiThreads / 32) + (threadIdx.x >> 5);
+    if (unit >= total_rows * xsplit) return;
+    const int row = unit / xsplit, part = unit - row * xsplit;
+    const int x_begin = part * pw / xsplit, x_end = (part + 1) * pw / xsplit;
     const int f = row / ph, y = row - f * ph;
     const int m = roi_map_index(level_ws[f], first, map_mode);
     const RoiGeom g = roi_geom(__ldg(boxes + f), m, tbl.H, tbl.W, ph, pw);
-    if (y == 0 && lane == 0) roi_map[f] = m;
+    if (y == 0 && part == 0 && lane == 0) roi_map[f] = m;
     const int c4 = C >> 2;
     const float4* img = reinterpret_cast<const float4*>(
         ((m == 0) ? tbl.ptr[0] : (m == 1) ? tbl.ptr[1] : (m == 2) ? tbl.ptr[2] : tbl.ptr[3]) +
         (size_t)(f / N) * g.H * g.W * C);
-    float4* o = reinterpret_cast<float4*>(out) + (size_t)row * pw * c4;
+    float4* o = reinterpret_cast<float4*>(out) + ((size_t)row * pw + x_begin) * c4;
     const AxisTap ty = axis_tap(g.y0, g.hs, y, g.H);
     const int top = ty.lo * g.W, bot = ty.hi * g.W;  // pixel index of the two sampled rows
     const float ly = ty.lerp;
-    for (int x = 0; x < pw; ++x, o += c4) {
+    for (int x = x_begin; x < x_end; ++x, o += c4) {
         const AxisTap tx = axis_tap(g.x0, g.ws, x, g.W);
         if (!(ty.valid && tx.valid)) {  // extrapolation_value = 0
             for (int v = lane; v < c4; v += 32) __stcs(o + v, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -768,9 +771,11 @@ MRCNN_EXPORT int mrcnn_roialign_forward(const float* boxes, const float* image_m
     roialign_prep_kernel<<<(BN + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, st>>>(
         (const float4*)boxes, image_meta, BN, denominator, level_ws, first, roi_level);
     const int total_rows = BN * ph;
-    const int grid = (total_rows + kRoiThreads / 32 - 1) / (kRoiThreads / 32);
+    static const int env_xsplit = getenv("MRCNN_ROIALIGN_XSPLIT") ? atoi(getenv("MRCNN_ROIALIGN_XSPLIT")) : 0;
+    const int xsplit = env_xsplit > 0 ? (env_xsplit < pw ? env_xsplit : pw) : (pw >= 12 ? 2 : 1);
+    const int grid = (total_rows * xsplit + kRoiThreads / 32 - 1) / (kRoiThreads / 32);
 #define MRCNN_FWD(V) roialign_fwd_kernel<V><<<grid, kRoiThreads, 0, st>>>((const float4*)boxes, level_ws, first, \
-        map_mode, tbl, C, N, ph, pw, total_rows, out, roi_map)
+        map_mode, tbl, C, N, ph, pw, total_rows, xsplit, out, roi_map)
     const int variant = fwd_variant();
     if (C == 256 && variant != 0) {
         int dev = 0, sms = 148;
