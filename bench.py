@@ -503,7 +503,7 @@ def main():
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": KERNELS_PER_STEP * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "roialign_fwd_kernel<2> (7x7, N=1000, +prep)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "roialign_fwd_kernel<2, 1> (7x7, N=1000, +prep)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at the default config, from
                          # the ncu --set full capture summarised in profiles/r1_ncu_full_summary.md
