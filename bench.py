@@ -234,12 +234,31 @@ def run_reference(args, rank):
                          "sample": f"{reps} x the full batch of {args.batch} images, median"},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly one JSON line.  Libraries loaded later (NCCL prints its version banner with printf)
+    write to file descriptor 1 behind Python's back, so keep a private duplicate of the real stdout for the JSON line
+    and point descriptor 1 at stderr for everybody else."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -514,7 +533,7 @@ def main():
             "cpu_baseline": cpu,
             "pipelined": pipelined,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -160,6 +160,19 @@ int mrcnn_detection_target_forward(const float* proposals, const int32_t* gt_cla
                                    float* deltas, float* masks, int32_t* counts, void* ws, size_t ws_bytes,
                                    void* stream);
 
+/* ---- utils.generate_pyramid_anchors (utils.py:54-111) + AnchorsLayer.get_anchors / NormBoxesLayer.call
+ * (mrcnn_layers.py:34-39,116-132): the anchor constant, built on the device -----------------------------------------
+ * scales / strides / feat_h / feat_w: host arrays of `levels` entries (rpn_anchor_scales, backbone_strides,
+ * utils.compute_backbone_shapes); ratios: host array of `nratios` doubles.  Order: level-major, row-major (y, x),
+ * ratio innermost.  anchors_px [A,4] float64 (optional): generate_pyramid_anchors' output bit for bit (what the data
+ * loader hands to build_rpn_targets); anchors_norm [B,A,4] fp32 (optional): the AnchorsLayer output (fp32 cast, then
+ * (a - [0,0,1,1]) / ([h,w,h,w] - 1) in fp32, broadcast to the batch) that ProposalLayer consumes.
+ * mrcnn_anchors_count gives A.  Requires levels <= 8, nratios <= 8, A <= 2^24. */
+int mrcnn_anchors_count(const int* feat_h, const int* feat_w, int levels, int nratios, int anchor_stride, int* count);
+int mrcnn_anchors_forward(const double* scales, const double* ratios, const int* feat_h, const int* feat_w,
+                          const int* strides, int levels, int nratios, int anchor_stride, int img_h, int img_w, int B,
+                          double* anchors_px, float* anchors_norm, void* stream);
+
 /* ---- utils.build_rpn_targets  (utils.py:154-262; compute_overlaps / compute_iou utils.py:114-151) -------------
  * The data loader's per-image numpy routine (preprocess.py:342-348), for a padded batch in one launch sequence.
  * anchors [A,4] float64 PIXEL boxes, as utils.generate_pyramid_anchors returns them and the loader keeps them

@@ -53,6 +53,10 @@ PROTOTYPES = {
     "mrcnn_detection_target_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                        c_int, c_int, c_double, ctypes.POINTER(c_float), c_int, c_int, c_int, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
+    "mrcnn_anchors_count": [ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int, c_int, c_int, ctypes.POINTER(c_int)],
+    "mrcnn_anchors_forward": [ctypes.POINTER(c_double), ctypes.POINTER(c_double), ctypes.POINTER(c_int),
+                              ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int, c_int, c_int, c_int, c_int, c_int,
+                              c_void_p, c_void_p, c_void_p],
     "mrcnn_rpn_targets_workspace_bytes": [c_int, c_int, c_int, c_int, ctypes.POINTER(c_size_t)],
     "mrcnn_rpn_targets_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                   ctypes.POINTER(c_double), c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

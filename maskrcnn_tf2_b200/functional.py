@@ -371,3 +371,24 @@ class HostMapStage:
 
     def fetched_pixels(self):
         return int(self.counter.item())
+
+
+def anchors_forward(scales, ratios, feature_shapes, strides, anchor_stride, image_hw, batch, device,
+                    return_px=False):
+    """utils.generate_pyramid_anchors + AnchorsLayer.get_anchors on the device -> anchors [batch,A,4] fp32 normalised
+    (and, with return_px, the float64 pixel anchors [A,4] the data loader / build_rpn_targets use)."""
+    L = _lib.lib()
+    n = len(scales)
+    fh = (c_int * n)(*[int(s[0]) for s in feature_shapes])
+    fw = (c_int * n)(*[int(s[1]) for s in feature_shapes])
+    st = (c_int * n)(*[int(s) for s in strides])
+    sc = (ctypes.c_double * n)(*[float(s) for s in scales])
+    ra = (ctypes.c_double * len(ratios))(*[float(r) for r in ratios])
+    count = c_int(0)
+    check(L.mrcnn_anchors_count(fh, fw, n, len(ratios), int(anchor_stride), ctypes.byref(count)), "mrcnn_anchors_count")
+    A = count.value
+    norm = torch.empty((int(batch), A, 4), dtype=torch.float32, device=device)
+    px = torch.empty((A, 4), dtype=torch.float64, device=device) if return_px else None
+    check(L.mrcnn_anchors_forward(sc, ra, fh, fw, st, n, len(ratios), int(anchor_stride), int(image_hw[0]),
+                                  int(image_hw[1]), int(batch), ptr(px), ptr(norm), _stream()), "mrcnn_anchors_forward")
+    return (norm, px) if return_px else norm

@@ -32,6 +32,27 @@ class _Layer:
         return {"name": self.name}
 
 
+class AnchorsLayer(_Layer):
+    """mrcnn_layers.py:104-145: the anchor pyramid of the configured image size, normalised and broadcast to the
+    batch, as a constant of the model -- built by one kernel on `device` (csrc/anchors.cu) instead of numpy.
+    `call` returns it whatever the input (the reference ignores `inputs` too, L:138-139); `anchors_px` holds the
+    float64 pixel anchors the data loader passes to build_rpn_targets (preprocess.py:82,297)."""
+
+    def __init__(self, config, training=False, name="anchors", device=None, **kwargs):
+        super().__init__(name=name, **kwargs)
+        self.config = config
+        self.training = training
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        S = config['img_size']
+        shapes = [(-(-S // s), -(-S // s)) for s in config['backbone_strides']]      # utils.compute_backbone_shapes
+        self.anchors, self.anchors_px = F.anchors_forward(
+            config['rpn_anchor_scales'], config['rpn_anchor_ratios'], shapes, config['backbone_strides'],
+            config['rpn_anchor_stride'], config['image_shape'][:2], config['batch_size'], dev, return_px=True)
+
+    def call(self, inputs=None, **kwargs):
+        return self.anchors
+
+
 class _ProposalFn(torch.autograd.Function):
     """rpn_bbox receives the reference's gradient (no stop_gradient on proposals, model.py:155-157,168 through
     mrcnn_layers.py:227); rpn_probs and anchors receive none (top_k / NMS indices are not differentiable)."""

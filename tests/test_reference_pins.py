@@ -105,3 +105,24 @@ def test_cuda_detection_targets_against_reference_overlaps_and_refinement(R, dev
     n = len(pos_ref)
     assert np.array_equal(rois[0, :n], props[pos_ref]) and np.array_equal(class_ids[0, :n], cls[arg_ref[pos_ref]])
     assert np.allclose(deltas[0, :n], R["refinement"][pos_ref] / SD, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_device_anchor_producer_bit_exact_against_the_reference(R, dev):
+    """csrc/anchors.cu: float64 pixel anchors identical to generate_pyramid_anchors' output (full vector at 128,
+    SHA-256 at 128 / 256 / 1024), AnchorsLayer output identical to the fp32 NormBoxesLayer arithmetic."""
+    from maskrcnn_tf2_b200 import make_config
+    from maskrcnn_tf2_b200.layers import AnchorsLayer
+    for S in (128, 256, 1024):
+        cfg = make_config(img_size=S, batch_size=3)
+        layer = AnchorsLayer(cfg, training=False, device=dev)
+        px = layer.anchors_px.cpu().numpy()
+        assert px.dtype == np.float64 and px.shape[0] == int(R[f"anchors_count_{S}"])
+        digest = np.frombuffer(hashlib.sha256(np.ascontiguousarray(px).tobytes()).digest(), np.uint8)
+        assert np.array_equal(digest, R[f"anchors_px_sha256_{S}"])
+        if S == 128:
+            assert np.array_equal(px, R["anchors_px_128"])
+        norm = layer(None).cpu().numpy()
+        assert norm.shape == (3, px.shape[0], 4)
+        assert np.array_equal(norm[0], _norm_fp32(px, S)) and np.array_equal(norm[2], norm[0])
+        assert np.array_equal(norm[1], synth.pyramid_anchors(S))
