@@ -41,7 +41,6 @@ constexpr int kNmsThreads = 1024;
 constexpr int kNmsWarps = kNmsThreads / 32;
 
 constexpr int kMaxFarSrc = 16 * 12;                // far partials per tile: cluster size x far warps per CTA
-constexpr size_t kNmsMaxDynSmem = 212 * 1024;      // 227 KB per CTA minus the kernel's static shared memory (~15 KB)
 
 static size_t nms_smem_bytes(int M, int max_out, bool compact) {
     const size_t cap = (size_t)(max_out < M ? max_out : M);

@@ -598,3 +598,20 @@ def test_sparsely_read_inputs_may_stay_in_pinned_host_memory(dev):
     assert torch.equal(d_dev, d_pin)
     with pytest.raises(TypeError):
         prop([t(x["rpn_probs"]), torch.from_numpy(x["rpn_bbox"]), t(x["anchors"])])   # pageable host memory: rejected
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,max_out", [(8192, 2000), (8192, 2100), (8192, 8192), (6000, 2000), (2049, 2049)])
+def test_nms_shared_memory_boundaries(orc, dev, M, max_out):
+    """Candidate counts / output sizes on both sides of the point where the dense kept-box copies stop fitting in shared
+    memory (the kernel then walks the kept index list instead): same keep list as the oracle either way."""
+    import torch
+    from maskrcnn_tf2_b200 import functional as F
+    rng = np.random.default_rng(M + max_out)
+    boxes = random_boxes(rng, M, 0.01, 0.2, clusters=60)
+    scores = rng.random(M, dtype=np.float32)
+    keep, count = F.nms(torch.from_numpy(boxes[None]).to(dev), torch.from_numpy(scores[None]).to(dev), max_out, 0.5)
+    want = orc.nms(boxes, scores, max_out, 0.5)
+    n = int(count[0])
+    assert n == want.size and np.array_equal(keep[0, :n].cpu().numpy(), want)
+    assert (keep[0, n:] == -1).all()
