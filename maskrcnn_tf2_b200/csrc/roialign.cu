@@ -773,7 +773,10 @@ MRCNN_EXPORT int mrcnn_roialign_forward(const float* boxes, const float* image_m
     roialign_prep_kernel<<<(BN + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, st>>>(
         (const float4*)boxes, image_meta, BN, denominator, level_ws, first, roi_level);
     const int total_rows = BN * ph;
-    const int xsplit = (pw >= 12) ? 2 : 1;  // measured at config 2: 14x14 62 -> 58 us with two warps per row; 7x7 slower
+    // two warps per output row for wide crops on large maps (memory-latency-bound: 14x14 at S=1024 62 -> 58 us at B=8,
+    // 236 -> 232 at B=32); 7x7 and the small, cache-resident maps of config 4 (S=512 / 256: 189 -> 195, 150 -> 162 us)
+    // are issue-bound and lose with the split
+    const int xsplit = (pw >= 12 && (long long)H[0] * W[0] >= 192LL * 192LL) ? 2 : 1;
     const int grid = (total_rows * xsplit + kRoiThreads / 32 - 1) / (kRoiThreads / 32);
 #define MRCNN_FWD(V)                                                                                              \
     do {                                                                                                          \
