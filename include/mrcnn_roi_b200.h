@@ -74,6 +74,21 @@ int mrcnn_proposal_forward(const float* rpn_probs, const float* rpn_bbox, const 
                            int32_t* topk_idx, int32_t* keep_idx, int32_t* keep_count, float* pre_nms_boxes,
                            void* ws, size_t ws_bytes, void* stream);
 
+/* ---- ProposalLayer fed by the RPN head's per-level outputs (rpn_graph mrcnn_layers.py:1052-1093 called per pyramid
+ * level and concatenated at model.py:465-478) ---------------------------------------------------------------------
+ * rpn_class_logits / rpn_bbox: host arrays of `levels` device pointers; level l holds [B,A_l,2] raw logits (the
+ * reshaped rpn_class_raw output) and [B,A_l,4] raw deltas (rpn_bbox_pred), level_anchors[l] = A_l; the concatenated
+ * anchor order is level-major, which is the order of `anchors` [B,A,4], A = sum A_l.  The foreground probability is
+ * Keras' softmax over the two logits (TF SoftmaxEigenImpl: exp(l - max) * (1 / sum)); no concatenated tensor and no
+ * [B,A,2] softmax pass is materialised unless rpn_probs [B,A,2] (optional: the model's `rpn_class` output) is given.
+ * Everything after the scores is mrcnn_proposal_forward: same proposals, same optional index outputs. */
+int mrcnn_proposal_levels_workspace_bytes(int B, int A, int pre_nms_limit, int P, size_t* bytes);
+int mrcnn_proposal_forward_levels(const float* const* rpn_class_logits, const float* const* rpn_bbox,
+                                  const int* level_anchors, int levels, const float* anchors, int B, int pre_nms_limit,
+                                  int P, const float* std_dev, float nms_thr, float* proposals, float* rpn_probs,
+                                  int32_t* topk_idx, int32_t* keep_idx, int32_t* keep_count, void* ws, size_t ws_bytes,
+                                  void* stream);
+
 /* ---- gradient of ProposalLayer.call w.r.t. rpn_bbox (TF autodiff through L:227 gather, utils.py:854-869 clip,
  * utils.py:830-851 decode, L:238 scale; the reference has no stop_gradient on the proposals: model.py:155-157,168).
  * topk_idx [B,K] and keep_idx [B,P] are the tensors mrcnn_proposal_forward returned for the same inputs.

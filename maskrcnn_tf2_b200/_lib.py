@@ -29,6 +29,10 @@ PROTOTYPES = {
     "mrcnn_proposal_forward": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.POINTER(c_float),
                                c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                c_void_p],
+    "mrcnn_proposal_levels_workspace_bytes": [c_int, c_int, c_int, c_int, ctypes.POINTER(c_size_t)],
+    "mrcnn_proposal_forward_levels": [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_int), c_int,
+                                      c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_float), c_float, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     "mrcnn_proposal_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 ctypes.POINTER(c_float), c_void_p, c_void_p],
     "mrcnn_roialign_workspace_bytes": [c_int, c_int, ctypes.POINTER(c_size_t)],

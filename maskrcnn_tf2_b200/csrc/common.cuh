@@ -416,13 +416,25 @@ __attribute__((visibility("hidden"))) int launch_nms_sorted(const float4* boxes_
                                                             int M, int max_out, float thr, const NmsEpilogue& epi,
                                                             cudaStream_t stream);
 
+constexpr int kMaxRpnLevels = 8;
 struct TopkDecode {              // optional fused epilogue of the top-k final kernel (ProposalLayer)
     const float4* anchors;       // [B,A]
-    const float4* deltas;        // [B,A] raw
+    const float4* deltas;        // [B,A] raw; NULL when the deltas come per pyramid level:
+    const float4* level_deltas[kMaxRpnLevels];  // level l: [B, level_start[l+1] - level_start[l]] (rpn_bbox_pred outputs)
+    int level_start[kMaxRpnLevels + 1];         // first anchor of each level in the concatenated order (L:1074-1091)
+    int levels;
     float4 std_dev;
     float4* boxes_sorted;        // [B,K]
     float4* pre_nms_boxes;       // [B,K] optional copy
 };
+// raw deltas of anchor a of image b: from the concatenated [B,A,4] tensor, or straight from the level that owns it
+__device__ __forceinline__ float4 topk_load_delta(const TopkDecode& dec, int b, int A, int a) {
+    if (dec.deltas) return __ldg(dec.deltas + (size_t)b * A + a);
+    int l = 0;
+    while (l + 1 < dec.levels && a >= dec.level_start[l + 1]) ++l;
+    const int n = dec.level_start[l + 1] - dec.level_start[l];
+    return __ldg(dec.level_deltas[l] + (size_t)b * n + (a - dec.level_start[l]));
+}
 __attribute__((visibility("hidden"))) size_t topk_ws_bytes(int B);
 __attribute__((visibility("hidden"))) int launch_topk_cluster(const float* scores, int stride, int offset, int B, int A,
                                                               int K, int32_t* idx, float* vals, const TopkDecode* dec,

@@ -98,7 +98,7 @@ MRCNN_EXPORT int mrcnn_proposal_forward(const float* rpn_probs, const float* rpn
     w.topk = p;                  p += align_up(topk_ws_bytes(B), 256);
     w.boxes_sorted = (float4*)p;
 
-    TopkDecode dec;
+    TopkDecode dec{};
     dec.anchors = (const float4*)anchors;
     dec.deltas = (const float4*)rpn_bbox;
     dec.std_dev = make_float4(std_dev[0], std_dev[1], std_dev[2], std_dev[3]);
@@ -113,4 +113,93 @@ MRCNN_EXPORT int mrcnn_proposal_forward(const float* rpn_probs, const float* rpn
     epi.keep = keep_idx;
     epi.count = keep_count;
     return launch_nms_sorted(w.boxes_sorted, nullptr, B, K, P, nms_thr, epi, st);
+}
+
+
+// ---- ProposalLayer fed by the RPN head's per-level outputs ---------------------------
+// The reference concatenates the five levels' rpn_class_logits / rpn_class / rpn_bbox (model.py:465-478) after a Keras
+// softmax over [B,A_l,2] per level (mrcnn_layers.py:1081) and hands the concatenated tensors to ProposalLayer.  Here one
+// kernel reads the level logits where they lie and writes the dense foreground-probability row [B,A] the top-k needs
+// (TF SoftmaxEigenImpl: exp(l - max) * (1 / sum), exp = the shared deterministic sequence), and the decode epilogue of
+// the top-k fetches the winners' deltas straight from the level tensors: no concatenated copy, no [B,A,2] softmax pass.
+namespace {
+struct RpnLevels {
+    const float2* logits[kMaxRpnLevels];
+    int start[kMaxRpnLevels + 1];
+    int levels;
+};
+
+__global__ void __launch_bounds__(256)
+rpn_fg_score_kernel(RpnLevels lv, int A, float* __restrict__ fg /*[B,A]*/, float2* __restrict__ probs /*[B,A] or null*/) {
+    const int a = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
+    if (a >= A) return;
+    int l = 0;
+    while (l + 1 < lv.levels && a >= lv.start[l + 1]) ++l;
+    const int n = lv.start[l + 1] - lv.start[l];
+    const float2 x = __ldg(lv.logits[l] + (size_t)b * n + (a - lv.start[l]));
+    const float m = fmaxf(x.x, x.y);
+    const float e0 = det_expf(__fsub_rn(x.x, m)), e1 = det_expf(__fsub_rn(x.y, m));
+    const float inv = __fdiv_rn(1.0f, __fadd_rn(e0, e1));
+    const float p1 = __fmul_rn(e1, inv);
+    fg[(size_t)b * A + a] = p1;
+    if (probs) probs[(size_t)b * A + a] = make_float2(__fmul_rn(e0, inv), p1);
+}
+}  // namespace
+
+MRCNN_EXPORT int mrcnn_proposal_levels_workspace_bytes(int B, int A, int pre_nms_limit, int P, size_t* bytes) {
+    if (!bytes) return MRCNN_ERR_NULL;
+    const int K = pre_nms_limit < A ? pre_nms_limit : A;
+    if (B < 1 || A < 1 || K < 1 || K > kMaxSort || P < 1) return MRCNN_ERR_RANGE;
+    *bytes = proposal_ws_bytes(B, K) + align_up((size_t)B * A * sizeof(float), 256);
+    return MRCNN_OK;
+}
+
+MRCNN_EXPORT int mrcnn_proposal_forward_levels(const float* const* rpn_class_logits, const float* const* rpn_bbox,
+                                               const int* level_anchors, int levels, const float* anchors, int B,
+                                               int pre_nms_limit, int P, const float* std_dev, float nms_thr,
+                                               float* proposals, float* rpn_probs, int32_t* topk_idx, int32_t* keep_idx,
+                                               int32_t* keep_count, void* ws, size_t ws_bytes, void* stream) {
+    if (!rpn_class_logits || !rpn_bbox || !level_anchors || !anchors || !std_dev || !proposals || !ws)
+        return MRCNN_ERR_NULL;
+    if (levels < 1 || levels > kMaxRpnLevels) return MRCNN_ERR_RANGE;
+    RpnLevels lv{};
+    TopkDecode dec{};
+    long long acc = 0;
+    for (int l = 0; l < levels; ++l) {
+        if (!rpn_class_logits[l] || !rpn_bbox[l]) return MRCNN_ERR_NULL;
+        if (level_anchors[l] < 1) return MRCNN_ERR_RANGE;
+        if ((reinterpret_cast<uintptr_t>(rpn_class_logits[l]) & 7u) || !aligned16(rpn_bbox[l])) return MRCNN_ERR_ALIGN;
+        lv.logits[l] = (const float2*)rpn_class_logits[l];
+        dec.level_deltas[l] = (const float4*)rpn_bbox[l];
+        lv.start[l] = dec.level_start[l] = (int)acc;
+        acc += level_anchors[l];
+        if (acc > (1 << 24)) return MRCNN_ERR_RANGE;
+    }
+    const int A = (int)acc;
+    lv.start[levels] = dec.level_start[levels] = A;
+    lv.levels = dec.levels = levels;
+    const int K = pre_nms_limit < A ? pre_nms_limit : A;  // L:245
+    if (B < 1 || K < 1 || K > kMaxSort || P < 1 || !(nms_thr >= 0.0f && nms_thr <= 1.0f)) return MRCNN_ERR_RANGE;
+    if (ws_bytes < proposal_ws_bytes(B, K) + align_up((size_t)B * A * sizeof(float), 256)) return MRCNN_ERR_WORKSPACE;
+    if (!aligned16(anchors) || !aligned16(proposals) || !aligned16(ws) || (reinterpret_cast<uintptr_t>(rpn_probs) & 7u))
+        return MRCNN_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* p = (char*)ws;
+    void* topk_ws = p;            p += align_up(topk_ws_bytes(B), 256);
+    float4* boxes_sorted = (float4*)p; p += align_up((size_t)B * K * sizeof(float4), 256);
+    float* fg = (float*)p;
+    rpn_fg_score_kernel<<<dim3((A + 255) / 256, B), 256, 0, st>>>(lv, A, fg, (float2*)rpn_probs);
+    dec.anchors = (const float4*)anchors;
+    dec.deltas = nullptr;
+    dec.std_dev = make_float4(std_dev[0], std_dev[1], std_dev[2], std_dev[3]);
+    dec.boxes_sorted = boxes_sorted;
+    dec.pre_nms_boxes = nullptr;
+    int rc = launch_topk(fg, 1, 0, B, A, K, topk_idx, nullptr, &dec, topk_ws, st);
+    if (rc != 0) return rc;
+    NmsEpilogue epi{};
+    epi.mode = 1;
+    epi.proposals = (float4*)proposals;
+    epi.keep = keep_idx;
+    epi.count = keep_count;
+    return launch_nms_sorted(boxes_sorted, nullptr, B, K, P, nms_thr, epi, st);
 }

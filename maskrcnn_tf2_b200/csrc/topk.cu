@@ -257,7 +257,7 @@ __device__ __forceinline__ void topk_sort_emit(uint64_t* s, int n, bool in_smem,
         if (has_dec) {
             // L:247-261: gather anchors / deltas by index, scale by std_dev (L:238), decode, clip to [0,1]
             const float4 an = __ldg(dec.anchors + (size_t)b * A + a);
-            const float4 dl = scale_deltas(__ldg(dec.deltas + (size_t)b * A + a), dec.std_dev);
+            const float4 dl = scale_deltas(topk_load_delta(dec, b, A, a), dec.std_dev);
             const float4 bx = clip_box(apply_box_deltas(an, dl), make_float4(0.f, 0.f, 1.f, 1.f));
             dec.boxes_sorted[(size_t)b * K + r] = bx;
             if (dec.pre_nms_boxes) dec.pre_nms_boxes[(size_t)b * K + r] = bx;

@@ -392,3 +392,44 @@ def anchors_forward(scales, ratios, feature_shapes, strides, anchor_stride, imag
     check(L.mrcnn_anchors_forward(sc, ra, fh, fw, st, n, len(ratios), int(anchor_stride), int(image_hw[0]),
                                   int(image_hw[1]), int(batch), ptr(px), ptr(norm), _stream()), "mrcnn_anchors_forward")
     return (norm, px) if return_px else norm
+
+
+def proposal_forward_levels(rpn_class_logits, rpn_bbox, anchors, pre_nms_limit, proposal_count, std_dev, nms_threshold,
+                            return_probs=False, debug=False):
+    """ProposalLayer fed by the RPN head's per-level outputs: rpn_class_logits = list of [B,A_l,2] raw logits,
+    rpn_bbox = list of [B,A_l,4] raw deltas (level-major = the order of `anchors` [B,A,4]).  The softmax and the three
+    Concatenate layers of model.py:465-478 are fused away.  Returns proposals [B,P,4] (, rpn_probs [B,A,2])."""
+    L = _lib.lib()
+    n = len(rpn_class_logits)
+    if n != len(rpn_bbox) or n < 1:
+        raise ValueError("rpn_class_logits and rpn_bbox must be lists with one tensor per pyramid level")
+    lg = [_req(t, torch.float32, f"rpn_class_logits[{i}]", 3) for i, t in enumerate(rpn_class_logits)]
+    bb = [_req(t, torch.float32, f"rpn_bbox[{i}]", 3) for i, t in enumerate(rpn_bbox)]
+    anchors = _req(anchors, torch.float32, "anchors", 3)
+    B, A = anchors.shape[0], anchors.shape[1]
+    counts = [t.shape[1] for t in lg]
+    for a_, b_ in zip(lg, bb):
+        if a_.shape[0] != B or a_.shape[2] != 2 or tuple(b_.shape) != (B, a_.shape[1], 4):
+            raise ValueError("expected per-level rpn_class_logits [B,A_l,2] and rpn_bbox [B,A_l,4]")
+    if sum(counts) != A:
+        raise ValueError("the levels' anchor counts must add up to anchors.shape[1]")
+    P, K = int(proposal_count), min(int(pre_nms_limit), A)
+    dev = anchors.device
+    nbytes = _query(L.mrcnn_proposal_levels_workspace_bytes, B, A, int(pre_nms_limit), P)
+    ws = _workspace(("proposal_levels", B, A, K, P), nbytes, dev)
+    proposals = torch.empty((B, P, 4), dtype=torch.float32, device=dev)
+    probs = torch.empty((B, A, 2), dtype=torch.float32, device=dev) if return_probs else None
+    tk = ki = kc = None
+    if debug:
+        tk = torch.empty((B, K), dtype=torch.int32, device=dev)
+        ki = torch.empty((B, P), dtype=torch.int32, device=dev)
+        kc = torch.empty((B,), dtype=torch.int32, device=dev)
+    lp = (c_void_p * n)(*[t.data_ptr() for t in lg])
+    bp = (c_void_p * n)(*[t.data_ptr() for t in bb])
+    cn = (c_int * n)(*counts)
+    check(L.mrcnn_proposal_forward_levels(lp, bp, cn, n, ptr(anchors), B, int(pre_nms_limit), P, _lib.float4(std_dev),
+                                          c_float(float(nms_threshold)), ptr(proposals), ptr(probs), ptr(tk), ptr(ki),
+                                          ptr(kc), ptr(ws), ws.numel(), _stream()), "mrcnn_proposal_forward_levels")
+    if debug:
+        return dict(proposals=proposals, rpn_probs=probs, topk_idx=tk, keep_idx=ki, keep_count=kc)
+    return (proposals, probs) if return_probs else proposals

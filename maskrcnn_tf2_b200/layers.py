@@ -90,6 +90,15 @@ class ProposalLayer(_Layer):
         return _ProposalFn.apply(rpn_probs, rpn_bbox, anchors, self.config['pre_nms_limit'], self.proposal_count,
                                  np.asarray(self.config['rpn_bbox_std_dev'], dtype=np.float32), self.nms_threshold)
 
+    def call_levels(self, rpn_class_logits, rpn_bbox, anchors, return_probs=False):
+        """The same layer fed by the RPN head's per-level outputs (lists of [B,A_l,2] logits and [B,A_l,4] deltas, one
+        entry per pyramid level): the per-level softmax and the Concatenate layers of model.py:465-478 are fused into
+        the launch (inference path: no gradient)."""
+        return F.proposal_forward_levels(rpn_class_logits, rpn_bbox, anchors, self.config['pre_nms_limit'],
+                                         self.proposal_count,
+                                         np.asarray(self.config['rpn_bbox_std_dev'], dtype=np.float32),
+                                         self.nms_threshold, return_probs=return_probs)
+
     def compute_output_shape(self, input_shape):
         return None, self.proposal_count, 4
 

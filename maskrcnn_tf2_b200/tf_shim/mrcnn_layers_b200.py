@@ -57,6 +57,14 @@ class ProposalLayer(tfl.Layer):
                                               std_dev=[float(v) for v in self.config['rpn_bbox_std_dev']])
         return proposals
 
+    def call_levels(self, rpn_class_logits, rpn_bbox, anchors):
+        """Inference path fed by the per-level RPN outputs (lists, one [B,A_l,2] / [B,A_l,4] tensor per pyramid
+        level, before model.py:465-478 concatenates them): returns (proposals, rpn_class [B,A,2])."""
+        return _ops.mrcnn_proposal_levels(list(rpn_class_logits), list(rpn_bbox), anchors,
+                                          proposal_count=self.proposal_count,
+                                          pre_nms_limit=self.config['pre_nms_limit'], nms_threshold=self.nms_threshold,
+                                          std_dev=[float(v) for v in self.config['rpn_bbox_std_dev']])
+
     def build(self, input_shape):
         self.built = True
         super(ProposalLayer, self).build(input_shape)

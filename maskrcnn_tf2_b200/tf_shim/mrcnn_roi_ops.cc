@@ -449,3 +449,77 @@ class MrcnnRpnTargetsOp : public tf::OpKernel {
   std::vector<float> std_;
 };
 REGISTER_KERNEL_BUILDER(Name("MrcnnRpnTargets").Device(tf::DEVICE_GPU), MrcnnRpnTargetsOp);
+
+// ---- ProposalLayer fed by the per-level RPN head outputs (rpn_graph per pyramid level, model.py:465-478): the Keras
+// softmax and the three Concatenate layers are fused into the launch.  Inference path (no gradient registered).
+REGISTER_OP("MrcnnProposalLevels")
+    .Input("rpn_class_logits: N * float")   // level l: [B,A_l,2] raw logits (reshaped rpn_class_raw)
+    .Input("rpn_bbox: N * float")           // level l: [B,A_l,4] raw deltas (reshaped rpn_bbox_pred)
+    .Input("anchors: float")                // [B,A,4], A = sum A_l, level-major
+    .Output("proposals: float")             // [B,P,4]
+    .Output("rpn_probs: float")             // [B,A,2]: the model's `rpn_class` output (concat_rpn_class)
+    .Attr("N: int >= 1")
+    .Attr("proposal_count: int")
+    .Attr("pre_nms_limit: int = 6000")
+    .Attr("nms_threshold: float = 0.7")
+    .Attr("std_dev: list(float) = [0.1, 0.1, 0.2, 0.2]")
+    .SetShapeFn([](InferenceContext* c) {
+      int p, n;
+      TF_RETURN_IF_ERROR(c->GetAttr("proposal_count", &p));
+      TF_RETURN_IF_ERROR(c->GetAttr("N", &n));
+      auto anchors = c->input(2 * n);
+      c->set_output(0, c->MakeShape({c->Dim(anchors, 0), p, 4}));
+      c->set_output(1, c->MakeShape({c->Dim(anchors, 0), c->Dim(anchors, 1), 2}));
+      return tf::Status();
+    });
+
+class MrcnnProposalLevelsOp : public tf::OpKernel {
+ public:
+  explicit MrcnnProposalLevelsOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("N", &n_));
+    OP_REQUIRES_OK(c, c->GetAttr("proposal_count", &p_));
+    OP_REQUIRES_OK(c, c->GetAttr("pre_nms_limit", &pre_));
+    OP_REQUIRES_OK(c, c->GetAttr("nms_threshold", &thr_));
+    OP_REQUIRES_OK(c, c->GetAttr("std_dev", &std_));
+    OP_REQUIRES(c, std_.size() == 4 && n_ <= 8, tf::errors::InvalidArgument("std_dev needs 4 values, N <= 8"));
+  }
+  void Compute(tf::OpKernelContext* ctx) override {
+    const tf::Tensor& anchors = ctx->input(2 * n_);
+    OP_REQUIRES(ctx, anchors.dims() == 3 && anchors.dim_size(2) == 4, tf::errors::InvalidArgument("anchors [B,A,4]"));
+    const int B = anchors.dim_size(0), A = anchors.dim_size(1);
+    std::vector<const float*> logits(n_), bbox(n_);
+    std::vector<int> counts(n_);
+    int total = 0;
+    for (int l = 0; l < n_; ++l) {
+      const tf::Tensor& lg = ctx->input(l);
+      const tf::Tensor& bb = ctx->input(n_ + l);
+      OP_REQUIRES(ctx, lg.dims() == 3 && lg.dim_size(0) == B && lg.dim_size(2) == 2 &&
+                           bb.shape() == tf::TensorShape({B, lg.dim_size(1), 4}),
+                  tf::errors::InvalidArgument("level tensors must be [B,A_l,2] and [B,A_l,4]"));
+      logits[l] = lg.flat<float>().data();
+      bbox[l] = bb.flat<float>().data();
+      counts[l] = lg.dim_size(1);
+      total += counts[l];
+    }
+    OP_REQUIRES(ctx, total == A, tf::errors::InvalidArgument("level anchor counts must add up to anchors.shape[1]"));
+    tf::Tensor *out = nullptr, *probs = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({B, p_, 4}), &out));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({B, A, 2}), &probs));
+    size_t ws_bytes = 0;
+    OP_REQUIRES_OK(ctx, LauncherStatus(mrcnn_proposal_levels_workspace_bytes(B, A, pre_, p_, &ws_bytes), "proposal ws"));
+    tf::Tensor ws;
+    OP_REQUIRES_OK(ctx, Scratch(ctx, ws_bytes, &ws));
+    OP_REQUIRES_OK(ctx, LauncherStatus(
+        mrcnn_proposal_forward_levels(logits.data(), bbox.data(), counts.data(), n_, anchors.flat<float>().data(), B,
+                                      pre_, p_, std_.data(), thr_, out->flat<float>().data(),
+                                      probs->flat<float>().data(), nullptr, nullptr, nullptr,
+                                      ws.flat<tf::uint8>().data(), ws_bytes, StreamOf(ctx)),
+        "mrcnn_proposal_forward_levels"));
+  }
+
+ private:
+  int n_, p_, pre_;
+  float thr_;
+  std::vector<float> std_;
+};
+REGISTER_KERNEL_BUILDER(Name("MrcnnProposalLevels").Device(tf::DEVICE_GPU), MrcnnProposalLevelsOp);

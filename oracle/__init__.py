@@ -273,3 +273,11 @@ def build_rpn_targets(anchors_px, gt_class_ids, gt_boxes, rand_keys, rpn_train_a
     lib().orc_build_rpn_targets(_p(an, f64p), _p(gc, _i32p), _p(gb, _i32p), _p(rk, _f32p), B, A, G, R, _p(sd, f64p),
                                 ctypes.c_double(eps), _p(match, _i32p), _p(bbox, f64p), _p(cnt, _i32p))
     return dict(rpn_match=match, rpn_bbox=bbox, counts=cnt)
+
+
+def rpn_softmax(logits):
+    """Keras softmax over the last axis of [..., 2] RPN logits (TF SoftmaxEigenImpl order) -> probs, same shape."""
+    x = _f32(logits)
+    out = np.empty_like(x)
+    lib().orc_softmax2(_p(x, _f32p), ctypes.c_int(x.size // 2), _p(out, _f32p))
+    return out

@@ -988,6 +988,21 @@ ORC_API void orc_build_rpn_targets(const double* anchors /*[A,4]*/, const int32_
                                   rpn_bbox + (size_t)b * R * 4, counts ? counts + 2 * b : NULL);
 }
 
+/* Keras Activation("softmax") over the two RPN logits (mrcnn_layers.py:1081) = tf.nn.softmax = TF SoftmaxEigenImpl
+ * (tensorflow/core/kernels/softmax_op_functor.h): shifted = logits - max; e = exp(shifted); p = e * (1 / sum(e)).
+ * PARITY UNPINNED like the other TF kernels; exp is the shared deterministic sequence. */
+ORC_API void orc_softmax2(const float* logits /*[n,2]*/, int n, float* probs /*[n,2]*/) {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; ++i) {
+        const float a = logits[2 * i], b = logits[2 * i + 1];
+        const float m = orc_maxf(a, b);
+        const float e0 = orc_expf(a - m), e1 = orc_expf(b - m);
+        const float inv = 1.0f / (e0 + e1);
+        probs[2 * i] = e0 * inv;
+        probs[2 * i + 1] = e1 * inv;
+    }
+}
+
 ORC_API void orc_set_num_threads(int n) {
 #ifdef _OPENMP
     omp_set_num_threads(n > 0 ? n : 1);

@@ -615,3 +615,41 @@ def test_nms_shared_memory_boundaries(orc, dev, M, max_out):
     n = int(count[0])
     assert n == want.size and np.array_equal(keep[0, :n].cpu().numpy(), want)
     assert (keep[0, n:] == -1).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("S,B", [(256, 3), (1024, 2)])
+def test_proposal_from_per_level_rpn_outputs(orc, dev, S, B):
+    """mrcnn_proposal_forward_levels: raw per-level logits / deltas in, no concatenation, fused softmax -- the same
+    proposals, bit for bit, as the oracle's softmax + ProposalLayer on the concatenated tensors, and the same as the
+    concatenated CUDA entry fed with the probabilities it returns."""
+    import torch
+    from maskrcnn_tf2_b200 import make_config, synth
+    from maskrcnn_tf2_b200.layers import ProposalLayer
+    rng = np.random.default_rng(S * 10 + B)
+    cfg = make_config(img_size=S, batch_size=B)
+    anchors = synth.pyramid_anchors(S)
+    A = anchors.shape[0]
+    counts = [3 * h * w for h, w in synth.backbone_shapes(S, cfg["backbone_strides"])]
+    assert sum(counts) == A
+    probs0, deltas = zip(*[synth.rpn_outputs(np.random.default_rng(500 + b), anchors, "clustered", S) for b in range(B)])
+    p1 = np.clip(np.stack(probs0)[..., 1].astype(np.float64), 1e-6, 1 - 1e-6)
+    logits = np.stack([rng.normal(0, 1, p1.shape), np.zeros_like(p1)], -1)
+    logits[..., 1] = logits[..., 0] + np.log(p1 / (1 - p1))              # realistic objectness, arbitrary offset
+    logits = logits.astype(np.float32)
+    logits[0, :64] = logits[0, 64:128]                                     # exact score ties across anchors
+    deltas = np.stack(deltas).astype(np.float32)
+    an = np.ascontiguousarray(np.broadcast_to(anchors, (B,) + anchors.shape))
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    lv_logits = [t(logits[:, s:e]) for s, e in zip(starts[:-1], starts[1:])]
+    lv_deltas = [t(deltas[:, s:e]) for s, e in zip(starts[:-1], starts[1:])]
+    layer = ProposalLayer(1000, cfg)
+    rois, probs = layer.call_levels(lv_logits, lv_deltas, t(an), return_probs=True)
+    want_probs = orc.rpn_softmax(logits)
+    assert np.array_equal(probs.cpu().numpy(), want_probs)
+    want = orc.proposal_layer(want_probs, deltas, an, 6000, 1000, cfg["rpn_bbox_std_dev"], 0.7)["proposals"]
+    assert np.array_equal(rois.cpu().numpy(), want)
+    same = layer([probs, t(deltas), t(an)])
+    assert torch.equal(same, rois)
+    assert torch.equal(layer.call_levels(lv_logits, lv_deltas, t(an)), rois)   # without the optional rpn_probs output

@@ -192,3 +192,17 @@ def test_detection_target_hand_case(orc):
     assert np.allclose(r["deltas"][0, 1, :2], 0.0) and r["deltas"][0, 1, 2] < 0   # log(h/(h+1e-3)) slightly < 0
     assert np.allclose(r["deltas"][0, 0, 1], (0.4 - 0.35) / 0.3 / 0.1, rtol=1e-5)
     assert np.array_equal(r["masks"][0, 0], np.ones((4, 4))) and np.array_equal(r["masks"][0, 2], np.zeros((4, 4)))
+
+
+def test_rpn_softmax_known_answers(orc):
+    """Keras softmax over two logits in TF's order exp(l - max) * (1 / sum): exact halves, saturation, invariance to a
+    common offset, and agreement with float64 softmax to fp32 rounding."""
+    x = np.array([[0, 0], [3, 3], [100, -100], [-100, 100], [1, 2], [1001, 1002]], np.float32)
+    p = orc.rpn_softmax(x)
+    assert np.array_equal(p[0], [0.5, 0.5]) and np.array_equal(p[1], [0.5, 0.5])
+    assert np.array_equal(p[2], [1.0, 0.0]) and np.array_equal(p[3], [0.0, 1.0])
+    assert np.array_equal(p[4], p[5])                                       # only the difference matters
+    rng = np.random.default_rng(3)
+    y = rng.normal(0, 4, (4096, 2)).astype(np.float32)
+    e = np.exp(y.astype(np.float64) - y.max(1, keepdims=True))
+    assert np.abs(orc.rpn_softmax(y) - e / e.sum(1, keepdims=True)).max() < 3e-7
