@@ -99,3 +99,15 @@ def test_shard_ranges_cover_the_batch_once():
         assert max(shard_sizes(total, world)) - min(shard_sizes(total, world)) <= 1
     with pytest.raises(ValueError):
         shard_range(8, 2, 2)
+
+
+def test_host_resident_inputs_must_be_page_locked():
+    """The demand-driven paths dereference host pointers on the device: pageable memory is refused up front (before
+    any CUDA call), there is no silent copy and no CPU path."""
+    import torch
+    from maskrcnn_tf2_b200 import functional as F
+    maps = [torch.zeros((1, 8 // s, 8 // s, 4)) for s in (1, 2, 4, 8)]
+    with pytest.raises(TypeError):
+        F.HostMapStage(maps, torch.device("cpu"))
+    with pytest.raises(TypeError):
+        F._req(torch.zeros(4), torch.float32, "rpn_bbox", pinned_ok=True)
