@@ -526,7 +526,7 @@ def main():
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at the default config, from
                          # the ncu --set full capture summarised in profiles/r1_ncu_full_summary.md
-                         "traffic": (712815616 if (B, S, args.regime) == (8, 1024, "clustered") else None),
+                         "traffic": (351996160 + 359010560 if (B, S, args.regime) == (8, 1024, "clustered") else None),
                          "peak_source": peak_src, "ms_per_launch": ms7_avg,
                          "algorithmic_bytes_per_launch": bytes7, "survey_closed_form_bytes_per_launch": bytes7_upper,
                          "real_rois_per_image": float((np.abs(rois_np).sum(-1) > 0).sum(1).mean())},
