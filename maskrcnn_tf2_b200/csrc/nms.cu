@@ -124,7 +124,9 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
                 mbar_wait(bar_t, (uint32_t)(((t >> 2) - ((t & 3) == 0 ? 1 : 0)) & 1));
                 PROF_MARK(0);
                 uint64_t v = 0ull;
-                for (int i = lane; i < nsrc; i += 32) v |= (uint64_t)s_far[t & 3][i];        // far(t)
+#pragma unroll
+                for (int q = 0; q < kMaxFarSrc / 32; ++q)  // far(t): fixed trip count, predicated loads (a generic
+                    if (lane + 32 * q < nsrc) v |= (uint64_t)s_far[t & 3][lane + 32 * q];  // loop costs ~60 instructions)
 #pragma unroll
                 for (int d = 1; d < kDepth; ++d) {  // near(t) = cross_d rows of the boxes kept in tile t-d
                     if ((kept_hist[d - 1] >> lane) & 1ull) v |= (uint64_t)s_rows[t & 3][d * kTile + lane];
