@@ -370,7 +370,10 @@ int launch_nms_sorted(const float4* boxes_sorted, const int32_t* valid, int B, i
     // measured at config 2 (ProposalLayer, B=8 / B=16): (8,4) 134.5 / 200 us, (6,8) 129.2 / 194, (6,12) 130.4 / 192,
     // (8,12) 132.4 / 198, (10,14) 136.6 / 202; the single-CTA detection NMS does not react to the split (13.1-13.6 us)
     int nfar = cs >= 4 ? 6 : 12, nrow = cs >= 4 ? 8 : (cs == 2 ? 8 : 12);
-    if (env_far > 0 && env_row > 0 && env_far + env_row <= 24) { nfar = env_far; nrow = env_row; }  // tuning knob
+    if (env_far > 0 && env_row > 0 && env_far + env_row <= 24 && env_far * cs <= kMaxFarSrc) {  // tuning knob
+        nfar = env_far;
+        nrow = env_row;
+    }
     if (compact) e = cudaLaunchKernelEx(&cfg, nms_lazy_kernel<true>, boxes_sorted, valid, M, max_out, thr, nfar, nrow, epi);
     else e = cudaLaunchKernelEx(&cfg, nms_lazy_kernel<false>, boxes_sorted, valid, M, max_out, thr, nfar, nrow, epi);
     if (e != cudaSuccess) return (int)e;

@@ -111,3 +111,42 @@ def test_host_resident_inputs_must_be_page_locked():
         F.HostMapStage(maps, torch.device("cpu"))
     with pytest.raises(TypeError):
         F._req(torch.zeros(4), torch.float32, "rpn_bbox", pinned_ok=True)
+
+
+def test_onnx_export_table_matches_the_op_registrations():
+    """tf_shim/onnx_export.py (tf2onnx kwargs for maskrcnn_to_onnx, inference_optimize.py:12-20) must name op types,
+    result-output counts and attributes exactly as tf_shim/mrcnn_roi_ops.cc registers them."""
+    import importlib.util
+    import os
+    import re
+    shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "maskrcnn_tf2_b200", "tf_shim")
+    spec = importlib.util.spec_from_file_location("onnx_export", os.path.join(shim, "onnx_export.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)  # imports neither tensorflow nor tf2onnx
+    src = open(os.path.join(shim, "mrcnn_roi_ops.cc")).read()
+    regs = {}
+    for m in re.finditer(r'REGISTER_OP\("(\w+)"\)(.*?)\.SetShapeFn', src, re.S):
+        body = re.sub(r'//[^\n]*', '', m.group(2))
+        regs[m.group(1)] = (re.findall(r'\.Output\("(\w+):', body), re.findall(r'\.Attr\("(\w+):', body))
+    for op, (n_out, attrs) in mod.EXPORTED_OPS.items():
+        outs, reg_attrs = regs[op]
+        assert 1 <= n_out <= len(outs), op
+        assert set(attrs) == set(reg_attrs), (op, attrs, reg_attrs)
+    kw = mod.tf2onnx_kwargs({"opset": 11, "custom_ops": {"Foo": "bar"}})
+    assert kw["opset"] == 11 and kw["custom_ops"]["Foo"] == "bar"
+    assert set(mod.EXPORTED_OPS) <= set(kw["custom_ops"]) and set(mod.EXPORTED_OPS) == set(kw["custom_op_handlers"])
+
+    class _Node:  # the handler keeps the node and moves it into the custom domain; gradient-only outputs unconsumed
+        type, output, domain = "MrcnnProposal", ["p:0", "p:1", "p:2"], ""
+
+    class _Ctx:
+        def __init__(self, used):
+            self.used = used
+
+        def find_output_consumers(self, out):
+            return [1] if out in self.used else []
+
+    fn, extra = kw["custom_op_handlers"]["MrcnnProposal"]
+    assert fn(_Ctx({"p:0"}), _Node(), "n", extra).domain == mod.DOMAIN
+    with pytest.raises(ValueError):
+        fn(_Ctx({"p:1"}), _Node(), "n", extra)
