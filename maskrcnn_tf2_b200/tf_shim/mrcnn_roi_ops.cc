@@ -3,10 +3,13 @@
 // NOT BUILT IN THIS REPOSITORY'S CI: TensorFlow is not installable in the build image (no network; the
 // reference pins tensorflow==2.2-2.5, whose wheels cannot drive sm_100 anyway).  Build it where a CUDA-12
 // TensorFlow exists:
-//   g++ -std=c++17 -shared -fPIC mrcnn_roi_ops.cc -o libmrcnn_roi_ops.so \
-//       $(python -c "import tensorflow as tf; print(' '.join(tf.sysconfig.get_compile_flags()))") \
-//       $(python -c "import tensorflow as tf; print(' '.join(tf.sysconfig.get_link_flags()))") \
-//       -I../../include -L.. -lmrcnn_roi_b200 -DGOOGLE_CUDA=1
+//   g++ -std=c++17 -shared -fPIC mrcnn_roi_ops.cc -o libmrcnn_roi_ops.so
+//       $(python -c "import tensorflow as tf; print(' '.join(tf.sysconfig.get_compile_flags()))")
+//       $(python -c "import tensorflow as tf; print(' '.join(tf.sysconfig.get_link_flags()))")
+//       -I../../include -L.. -lmrcnn_roi_b200 -DGOOGLE_CUDA=1        (one command line)
+// What IS checked here: the file is compiled against tests/tf_stub/ (a functional stand-in for the TF op API), which
+// type-checks every launcher call against include/mrcnn_roi_b200.h, and each OpKernel::Compute below is executed on
+// the B200 through a fake OpKernelContext and compared with the ctypes path (tests/test_tf_shim_stub.py).
 //
 // Each kernel only validates shapes, allocates outputs + one scratch buffer through TF's allocator, fetches
 // TF's CUDA stream and calls the launcher; there is deliberately no CPU kernel registration.
@@ -14,6 +17,11 @@
 #include "tensorflow/core/framework/op.h"
 #include "tensorflow/core/framework/op_kernel.h"
 #include "tensorflow/core/framework/shape_inference.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
 
 #include "mrcnn_roi_b200.h"
 
@@ -30,6 +38,18 @@ tf::Status LauncherStatus(int rc, const char* what) {
 }
 
 void* StreamOf(tf::OpKernelContext* ctx) { return ctx->eigen_device<GPUDevice>().stream(); }
+
+// Attributes are fp32, but the reference computes with the Python floats the user wrote (0.1, 0.33, 1e-3 as float64:
+// config.py:90, mrcnn_layers.py:904, utils.py:794).  Recover them: the shortest decimal that reads back as the same
+// fp32 is what the user typed (0.1f -> 0.1, not 0.100000001490116).
+double AttrAsDouble(float v) {
+  char buf[32];
+  for (int prec = 1; prec <= 9; ++prec) {
+    std::snprintf(buf, sizeof(buf), "%.*g", prec, static_cast<double>(v));
+    if (std::strtof(buf, nullptr) == v) break;
+  }
+  return std::strtod(buf, nullptr);
+}
 
 tf::Status Scratch(tf::OpKernelContext* ctx, size_t bytes, tf::Tensor* t) {
   return ctx->allocate_temp(tf::DT_UINT8, tf::TensorShape({static_cast<tf::int64>(bytes)}), t);
@@ -281,6 +301,7 @@ class MrcnnDetectionOp : public tf::OpKernel {
     OP_REQUIRES_OK(c, c->GetAttr("max_instances", &d_));
     OP_REQUIRES_OK(c, c->GetAttr("nms_threshold", &thr_));
     OP_REQUIRES_OK(c, c->GetAttr("std_dev", &std_));
+    OP_REQUIRES(c, std_.size() == 4, tf::errors::InvalidArgument("std_dev needs 4 values"));
   }
   void Compute(tf::OpKernelContext* ctx) override {
     const tf::Tensor& rois = ctx->input(0);
@@ -347,6 +368,7 @@ class MrcnnDetectionTargetOp : public tf::OpKernel {
     OP_REQUIRES_OK(c, c->GetAttr("mask_width", &mw_));
     OP_REQUIRES_OK(c, c->GetAttr("use_mini_masks", &mini_));
     OP_REQUIRES_OK(c, c->GetAttr("std_dev", &std_));
+    OP_REQUIRES(c, std_.size() == 4, tf::errors::InvalidArgument("std_dev needs 4 values"));
   }
   void Compute(tf::OpKernelContext* ctx) override {
     const tf::Tensor& props = ctx->input(0);
@@ -374,7 +396,7 @@ class MrcnnDetectionTargetOp : public tf::OpKernel {
             reinterpret_cast<const uint32_t*>(keys.flat<tf::int32>().data()), B, P, G, MH, MW, t_,
             // the attr is a float; the reference evaluates int(T * ratio) in Python doubles (L:904): round-trip
             // through the shortest decimal so 0.33f means 0.33
-            std::stod(std::to_string(ratio_)), std_.data(), mh_, mw_, mini_ ? 1 : 0, rois->flat<float>().data(),
+            AttrAsDouble(ratio_), std_.data(), mh_, mw_, mini_ ? 1 : 0, rois->flat<float>().data(),
             ids->flat<tf::int32>().data(), deltas->flat<float>().data(), out_masks->flat<float>().data(), nullptr,
             ws.flat<tf::uint8>().data(), ws_bytes, StreamOf(ctx)),
         "mrcnn_detection_target_forward"));
@@ -412,6 +434,7 @@ class MrcnnRpnTargetsOp : public tf::OpKernel {
   explicit MrcnnRpnTargetsOp(tf::OpKernelConstruction* c) : tf::OpKernel(c) {
     OP_REQUIRES_OK(c, c->GetAttr("rpn_train_anchors_per_image", &r_));
     OP_REQUIRES_OK(c, c->GetAttr("rpn_bbox_std_dev", &std_));
+    OP_REQUIRES(c, std_.size() == 4, tf::errors::InvalidArgument("rpn_bbox_std_dev needs 4 values"));
     OP_REQUIRES_OK(c, c->GetAttr("eps", &eps_));
   }
   void Compute(tf::OpKernelContext* ctx) override {
@@ -430,14 +453,13 @@ class MrcnnRpnTargetsOp : public tf::OpKernel {
     OP_REQUIRES_OK(ctx, LauncherStatus(mrcnn_rpn_targets_workspace_bytes(B, A, G, r_, &ws_bytes), "rpn targets ws"));
     tf::Tensor ws;
     OP_REQUIRES_OK(ctx, Scratch(ctx, ws_bytes, &ws));
-    // the attr list is float; the reference divides by the float64 array np.array([0.1, 0.1, 0.2, 0.2]) (config.py:90):
-    // round-trip through the shortest decimal so 0.1f means 0.1
+    // the attr list is float; the reference divides by the float64 array np.array([0.1, 0.1, 0.2, 0.2]) (config.py:90)
     double sd[4];
-    for (int i = 0; i < 4; ++i) sd[i] = std::stod(std::to_string(std_[i]));
+    for (int i = 0; i < 4; ++i) sd[i] = AttrAsDouble(std_[i]);
     OP_REQUIRES_OK(ctx, LauncherStatus(
         mrcnn_rpn_targets_forward(anchors.flat<double>().data(), cls.flat<tf::int32>().data(),
                                   boxes.flat<tf::int32>().data(), keys.flat<float>().data(), B, A, G, r_, sd,
-                                  std::stod(std::to_string(eps_)), match->flat<tf::int32>().data(),
+                                  AttrAsDouble(eps_), match->flat<tf::int32>().data(),
                                   bbox->flat<double>().data(), bbox32->flat<float>().data(), nullptr,
                                   ws.flat<tf::uint8>().data(), ws_bytes, StreamOf(ctx)),
         "mrcnn_rpn_targets_forward"));

@@ -1,0 +1,259 @@
+"""The TensorFlow custom-op shim (maskrcnn_tf2_b200/tf_shim/mrcnn_roi_ops.cc) cannot be built against TensorFlow in
+this image, so it is compiled against tests/tf_stub/ -- a functional stand-in for the TF op API -- instead:
+
+* CPU (`-m "not gpu"`): the file compiles with -Wall -Wextra -Werror (every launcher call is type-checked against
+  include/mrcnn_roi_b200.h), registers the eight ops with GPU kernels only, its shape functions return the reference
+  layers' output shapes, the kernels reject bad attributes, and the Python side of the shim
+  (tf_shim/mrcnn_layers_b200.py, parsed, not imported) passes exactly the inputs / attributes the ops declare.
+* GPU (`-m gpu`): every OpKernel::Compute runs on the B200 through a fake OpKernelContext and returns, bit for bit,
+  what the ctypes path (maskrcnn_tf2_b200.functional) returns for the same inputs.
+"""
+import ast
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import tf_stub
+from conftest import random_boxes
+
+SD = [0.1, 0.1, 0.2, 0.2]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PY_SHIM = os.path.join(ROOT, "maskrcnn_tf2_b200", "tf_shim", "mrcnn_layers_b200.py")
+OPS = ["MrcnnProposal", "MrcnnProposalGrad", "MrcnnPyramidRoiAlign", "MrcnnPyramidRoiAlignGrad", "MrcnnDetection",
+       "MrcnnDetectionTarget", "MrcnnRpnTargets", "MrcnnProposalLevels"]
+
+
+# --------------------------------------------------------------------------------------------------- CPU
+def test_shim_compiles_against_the_stub_and_registers_gpu_only_kernels():
+    tf_stub.build(force=True)        # g++ -Wall -Wextra -Werror
+    sig = tf_stub.signatures()
+    assert sorted(sig) == sorted(OPS)
+    for op, s in sig.items():
+        assert s["devices"] == ["GPU"], f"{op}: no CPU kernel may be registered (north star: no CPU fallback)"
+    assert [o for o, _ in sig["MrcnnProposal"]["outputs"]] == ["proposals", "topk_idx", "keep_idx"]
+    assert sig["MrcnnProposal"]["attrs"]["pre_nms_limit"] == ("int", "6000")          # config.py defaults
+    assert sig["MrcnnProposal"]["attrs"]["nms_threshold"] == ("float", "0.7")
+    assert sig["MrcnnPyramidRoiAlign"]["attrs"]["denominator"] == ("float", "244.0")  # quirk Q1
+    assert sig["MrcnnDetection"]["attrs"]["nms_threshold"] == ("float", "0.3")
+    assert sig["MrcnnDetectionTarget"]["attrs"]["roi_positive_ratio"] == ("float", "0.33")
+    assert sig["MrcnnProposalLevels"]["inputs"][0] == ("rpn_class_logits", "float", "N")
+
+
+def test_shape_functions_return_the_reference_layers_output_shapes():
+    B, A = 8, 261888
+    assert tf_stub.infer_shapes("MrcnnProposal", [(B, A, 2), (B, A, 4), (B, A, 4)], proposal_count=1000) == \
+        [(B, 1000, 4), (B, -1), (B, 1000)]                       # compute_output_shape, mrcnn_layers.py:275-276
+    maps = [(B, 256 >> l, 256 >> l, 256) for l in range(4)]
+    assert tf_stub.infer_shapes("MrcnnPyramidRoiAlign", [(B, 1000, 4), (B, 93)] + maps, pool_height=7,
+                                pool_width=7) == [(B, 1000, 7, 7, 256), (B, 1000)]          # L:666-667
+    assert tf_stub.infer_shapes("MrcnnPyramidRoiAlignGrad", [(B, 200, 14, 14, 256), (B, 200, 4), (B, 200)] + maps) == maps
+    assert tf_stub.infer_shapes("MrcnnDetection", [(B, 1000, 4), (B, 1000, 81), (B, 1000, 81, 4), (B, 93)]) == \
+        [(B, 100, 6), (B, 100, 4)]                               # L:526-527
+    assert tf_stub.infer_shapes("MrcnnDetectionTarget",
+                                [(B, 2000, 4), (B, 100), (B, 100, 4), (B, 1024, 1024, 100), (B, 2000)]) == \
+        [(B, 200, 4), (B, 200), (B, 200, 4), (B, 200, 28, 28)]   # L:327-333
+    assert tf_stub.infer_shapes("MrcnnRpnTargets", [(A, 4), (B, 100), (B, 100, 4), (B, A)]) == \
+        [(B, A, 1), (B, 256, 4), (B, 256, 4)]
+    lv = [(B, n, 2) for n in (196608, 49152, 12288, 3072, 768)]
+    lb = [(B, n, 4) for n in (196608, 49152, 12288, 3072, 768)]
+    assert tf_stub.infer_shapes("MrcnnProposalLevels", lv + lb + [(B, A, 4)], N=5, proposal_count=1000) == \
+        [(B, 1000, 4), (B, A, 2)]
+    assert tf_stub.infer_shapes("MrcnnProposalGrad", [(B, 1000, 4), (B, A, 4), (B, A, 4), (B, 6000), (B, 1000)]) == \
+        [(B, A, 4)]
+    with pytest.raises(ValueError):
+        tf_stub.infer_shapes("MrcnnProposal", [(B, A, 2), (B, A, 4), (B, A, 4)])      # required attr missing
+
+
+def test_kernel_construction_validates_attributes():
+    for op, bad in [("MrcnnProposal", dict(proposal_count=10, std_dev=[0.1, 0.2])),
+                    ("MrcnnProposalGrad", dict(std_dev=[0.1])),
+                    ("MrcnnDetection", dict(std_dev=[0.1, 0.1, 0.2])),
+                    ("MrcnnDetectionTarget", dict(std_dev=[1.0] * 5)),
+                    ("MrcnnRpnTargets", dict(rpn_bbox_std_dev=[0.1, 0.1])),
+                    ("MrcnnProposalLevels", dict(N=9, proposal_count=10)),
+                    ("MrcnnProposal", dict()),                                       # proposal_count is required
+                    ("MrcnnPyramidRoiAlign", dict(pool_height=7))]:                  # pool_width is required
+        with pytest.raises(ValueError):
+            tf_stub.StubOp(op, **bad)
+    for op, good in [("MrcnnProposal", dict(proposal_count=1000)), ("MrcnnPyramidRoiAlign", dict(pool_height=7, pool_width=7)),
+                     ("MrcnnDetection", dict()), ("MrcnnDetectionTarget", dict()), ("MrcnnRpnTargets", dict()),
+                     ("MrcnnPyramidRoiAlignGrad", dict()), ("MrcnnProposalGrad", dict()),
+                     ("MrcnnProposalLevels", dict(N=5, proposal_count=1000))]:
+        assert tf_stub.StubOp(op, **good).h
+
+
+def _camel(snake):
+    return "".join(p.capitalize() for p in snake.split("_"))
+
+
+def test_python_side_of_the_shim_passes_what_the_ops_declare():
+    """mrcnn_layers_b200.py is parsed (TensorFlow is not importable): every `_ops.<op>(...)` call must pass one
+    positional argument per declared input, only declared attributes, every required attribute, and unpack as many
+    results as the op has outputs; every @tf.RegisterGradient / tf.no_gradient names a registered op."""
+    sig = tf_stub.signatures()
+    tree = ast.parse(open(PY_SHIM).read())
+    seen = set()
+    for node in ast.walk(tree):
+        calls = []
+        if isinstance(node, ast.Assign) and isinstance(node.value, ast.Call):
+            calls.append((node.value, node.targets[0]))
+        elif isinstance(node, ast.Call):
+            calls.append((node, None))
+        for call, target in calls:
+            f = call.func
+            if not (isinstance(f, ast.Attribute) and isinstance(f.value, ast.Name) and f.value.id == "_ops"):
+                continue
+            op = _camel(f.attr)
+            assert op in sig, f"_ops.{f.attr}: no op {op} registered"
+            seen.add(op)
+            n_pos = 0
+            for a in call.args:
+                if isinstance(a, ast.Starred):      # *inputs[2:6]
+                    sl = a.value.slice
+                    n_pos += sl.upper.value - sl.lower.value
+                else:
+                    n_pos += 1
+            assert n_pos == len(sig[op]["inputs"]), (op, n_pos)
+            kws = {k.arg for k in call.keywords}
+            assert kws <= set(sig[op]["attrs"]), (op, kws - set(sig[op]["attrs"]))
+            required = {a for a, (_, d) in sig[op]["attrs"].items() if d is None} - {"N"}   # N: inferred from the list
+            assert required <= kws, (op, required - kws)
+            if isinstance(target, ast.Tuple):
+                assert len(target.elts) == len(sig[op]["outputs"]), op
+    assert seen == set(OPS)
+    src = open(PY_SHIM).read()
+    for name in re.findall(r'(?:RegisterGradient|no_gradient)\("(\w+)"\)', src):
+        assert name in sig, name
+    # the reference's class names / layer names survive in the Python shim
+    for cls, lname in [("ProposalLayer", "roi"), ("DetectionLayer", "mrcnn_detection"),
+                       ("DetectionTargetLayer", "proposal_targets"), ("PyramidROIAlign", "roi_align")]:
+        assert re.search(rf"class {cls}\(", src) and f"name='{lname}'" in src, cls
+
+
+# --------------------------------------------------------------------------------------------------- GPU
+def T(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+@pytest.fixture(scope="module")
+def F():
+    from maskrcnn_tf2_b200 import functional
+    return functional
+
+
+@pytest.mark.gpu
+def test_proposal_ops_run_through_the_shim(F, dev):
+    from maskrcnn_tf2_b200 import synth
+    B, S = 2, 256
+    anchors = synth.pyramid_anchors(S)
+    probs, bbox = zip(*[synth.rpn_outputs(np.random.default_rng(40 + b), anchors, "clustered", S) for b in range(B)])
+    tp, tb = T(np.stack(probs), dev), T(np.stack(bbox), dev)
+    ta = T(np.broadcast_to(anchors, (B,) + anchors.shape), dev)
+    ref = F.proposal_forward(tp, tb, ta, 6000, 1000, SD, 0.7, debug=True)
+    out, topk, keep = tf_stub.StubOp("MrcnnProposal", proposal_count=1000, pre_nms_limit=6000, nms_threshold=0.7,
+                                     std_dev=SD)(tp, tb, ta)
+    assert torch.equal(out, ref["proposals"]) and torch.equal(topk, ref["topk_idx"])
+    assert torch.equal(keep, ref["keep_idx"])
+    g = torch.randn_like(out)
+    (grad,) = tf_stub.StubOp("MrcnnProposalGrad", std_dev=SD)(g, tb, ta, topk, keep)
+    assert torch.equal(grad, F.proposal_backward(g, tb, ta, topk, keep, SD))
+    # per-level entry: logits whose softmax is `probs`, split at the level boundaries
+    counts = [3 * h * w for h, w in synth.backbone_shapes(S, [4, 8, 16, 32, 64])]
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    logits = torch.log(tp.clamp_min(1e-30))
+    lv = [logits[:, s:e].contiguous() for s, e in zip(starts[:-1], starts[1:])]
+    lb = [tb[:, s:e].contiguous() for s, e in zip(starts[:-1], starts[1:])]
+    want, want_probs = F.proposal_forward_levels(lv, lb, ta, 6000, 1000, SD, 0.7, return_probs=True)
+    got, got_probs = tf_stub.StubOp("MrcnnProposalLevels", N=5, proposal_count=1000)(*lv, *lb, ta)
+    assert torch.equal(got, want) and torch.equal(got_probs, want_probs)
+    with pytest.raises(RuntimeError, match="rpn_bbox / anchors"):
+        tf_stub.StubOp("MrcnnProposal", proposal_count=10)(tp, tb[:, :-1], ta)
+    with pytest.raises(RuntimeError, match="add up"):
+        tf_stub.StubOp("MrcnnProposalLevels", N=5, proposal_count=10)(*lv, *lb, ta[:, :-3])
+
+
+@pytest.mark.gpu
+def test_roialign_ops_run_through_the_shim(F, dev):
+    from maskrcnn_tf2_b200 import synth
+    rng = np.random.default_rng(41)
+    B, Nr, C = 2, 120, 64
+    boxes = np.stack([random_boxes(rng, Nr, min_size=0.02, max_size=0.8) for _ in range(B)])
+    boxes[:, -10:] = 0
+    fm = [T(rng.standard_normal((B, s, s, C)).astype(np.float32), dev) for s in (64, 32, 16, 8)]
+    tb, meta = T(boxes, dev), T(synth.image_meta(B, 256, 81), dev)
+    for pool in ((7, 7), (14, 14)):
+        want, want_map = F.roialign_forward(tb, meta, fm, pool)
+        got, got_map = tf_stub.StubOp("MrcnnPyramidRoiAlign", pool_height=pool[0], pool_width=pool[1])(tb, meta, *fm)
+        assert torch.equal(got, want) and torch.equal(got_map, want_map)
+        g = torch.randn_like(want)
+        grads = tf_stub.StubOp("MrcnnPyramidRoiAlignGrad")(g, tb, got_map, *fm)
+        ref = F.roialign_backward(g, tb, want_map, [tuple(f.shape) for f in fm], deterministic=True)
+        for l, (a, b) in enumerate(zip(grads, ref)):
+            # the shim always passes a workspace: the sequential-order (reproducible) gradient.  Pixel (0,0) collects
+            # every bin of the zero-padded ROIs and is the one place that still accumulates atomically
+            a0, b0 = a[:, 0, 0, :].clone(), b[:, 0, 0, :].clone()
+            a[:, 0, 0, :] = 0
+            b[:, 0, 0, :] = 0
+            assert torch.equal(a, b), (pool, l, float((a - b).abs().max()))
+            assert torch.allclose(a0, b0, rtol=1e-4, atol=1e-3), (pool, l, float((a0 - b0).abs().max()))
+    with pytest.raises(RuntimeError, match="feature maps"):
+        tf_stub.StubOp("MrcnnPyramidRoiAlign", pool_height=7, pool_width=7)(tb, meta, fm[0], fm[1], fm[2], fm[3][:1])
+
+
+@pytest.mark.gpu
+def test_detection_op_runs_through_the_shim(F, dev):
+    from maskrcnn_tf2_b200 import synth
+    rng = np.random.default_rng(42)
+    B, Nr, NC = 3, 1000, 81
+    rois = T(np.stack([random_boxes(rng, Nr, clusters=6) for _ in range(B)]), dev)
+    probs, deltas = synth.head_outputs(rng, B, Nr, NC)
+    tp, td, meta = T(probs, dev), T(deltas, dev), T(synth.image_meta(B, 1024, NC), dev)
+    for conf in (0.7, 0.0):
+        want, want_boxes = F.detection_forward(rois, tp, td, meta, SD, conf, 100, 0.3, return_boxes=True)
+        got, got_boxes = tf_stub.StubOp("MrcnnDetection", min_confidence=conf, use_min_confidence=bool(conf),
+                                        max_instances=100, nms_threshold=0.3, std_dev=SD)(rois, tp, td, meta)
+        assert torch.equal(got, want) and torch.equal(got_boxes, want_boxes)
+        assert torch.equal(got[..., :4], got_boxes)
+    with pytest.raises(RuntimeError, match="mrcnn_bbox"):
+        tf_stub.StubOp("MrcnnDetection")(rois, tp, td[:, :, :5], meta)
+
+
+@pytest.mark.gpu
+def test_training_side_ops_run_through_the_shim(F, dev):
+    rng = np.random.default_rng(43)
+    B, P, G, MH = 2, 600, 20, 56
+    props = np.stack([random_boxes(rng, P, min_size=0.04, max_size=0.5, clusters=8) for _ in range(B)])
+    props[:, -60:] = 0
+    gtb = np.zeros((B, G, 4), np.float32)
+    gtc = np.zeros((B, G), np.int32)
+    for b in range(B):
+        pick = rng.choice(P - 60, 6, replace=False)
+        gtb[b, :6] = props[b, pick] + rng.normal(0, 0.004, (6, 4)).astype(np.float32)
+        gtc[b, :6] = rng.integers(1, 81, 6)
+    gtc[0, 5] *= -1
+    masks = rng.uniform(0, 1, (B, MH, MH, G)) < 0.5
+    keys = rng.integers(0, 2 ** 32, (B, P), dtype=np.uint64).astype(np.uint32).view(np.int32)
+    tp, tc, tb, tk = T(props, dev), T(gtc, dev), T(gtb, dev), T(keys, dev)
+    want = F.detection_target_forward(tp, tc, tb, T(masks.astype(np.uint8), dev), tk, 100, 0.33, SD, (28, 28))
+    got = tf_stub.StubOp("MrcnnDetectionTarget", train_rois_per_image=100, roi_positive_ratio=0.33, mask_height=28,
+                         mask_width=28, use_mini_masks=False, std_dev=SD)(tp, tc, tb, T(masks, dev), tk)   # tf.bool masks
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    assert int((want[1] > 0).sum()) > 0
+    # RPN targets (data-loader side, float64)
+    from maskrcnn_tf2_b200 import make_config
+    from maskrcnn_tf2_b200.layers import AnchorsLayer
+    anchors_px = AnchorsLayer(make_config(img_size=256, batch_size=B), device=dev).anchors_px
+    A = anchors_px.shape[0]
+    gcls = T(np.array([[3, 1, 0, -2], [7, 0, 0, 0]], np.int32), dev)
+    gbox = T(np.array([[[20, 30, 120, 140], [100, 60, 220, 250], [0, 0, 0, 0], [10, 10, 200, 90]],
+                       [[64, 64, 192, 192], [0, 0, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0]]], np.int32), dev)
+    rk = T(rng.random((B, A), dtype=np.float32), dev)
+    w_match, w_bbox, w_bbox32 = F.rpn_targets_forward(anchors_px, gcls, gbox, rk, 64, SD, return_f32=True)
+    match, bbox, bbox32 = tf_stub.StubOp("MrcnnRpnTargets", rpn_train_anchors_per_image=64, rpn_bbox_std_dev=SD,
+                                         eps=1e-3)(anchors_px, gcls, gbox, rk)
+    assert tuple(match.shape) == (B, A, 1) and torch.equal(match[..., 0], w_match)
+    assert torch.equal(bbox, w_bbox) and torch.equal(bbox32, w_bbox32)   # 0.1f attr -> the double 0.1 (AttrAsDouble)
