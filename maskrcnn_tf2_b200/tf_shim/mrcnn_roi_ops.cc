@@ -453,9 +453,10 @@ class MrcnnRpnTargetsOp : public tf::OpKernel {
     OP_REQUIRES_OK(ctx, LauncherStatus(mrcnn_rpn_targets_workspace_bytes(B, A, G, r_, &ws_bytes), "rpn targets ws"));
     tf::Tensor ws;
     OP_REQUIRES_OK(ctx, Scratch(ctx, ws_bytes, &ws));
-    // the attr list is float; the reference divides by the float64 array np.array([0.1, 0.1, 0.2, 0.2]) (config.py:90)
+    // the loader passes config['rpn_bbox_std_dev'], a FLOAT32 array (config.py:90, preprocess.py:347), and numpy widens
+    // it for `rpn_bbox[ix] /= rpn_bbox_std` (utils.py:259): the divisor is (double)0.1f, not 0.1 -- plain widening here
     double sd[4];
-    for (int i = 0; i < 4; ++i) sd[i] = AttrAsDouble(std_[i]);
+    for (int i = 0; i < 4; ++i) sd[i] = static_cast<double>(std_[i]);
     OP_REQUIRES_OK(ctx, LauncherStatus(
         mrcnn_rpn_targets_forward(anchors.flat<double>().data(), cls.flat<tf::int32>().data(),
                                   boxes.flat<tf::int32>().data(), keys.flat<float>().data(), B, A, G, r_, sd,

@@ -252,8 +252,143 @@ def test_training_side_ops_run_through_the_shim(F, dev):
     gbox = T(np.array([[[20, 30, 120, 140], [100, 60, 220, 250], [0, 0, 0, 0], [10, 10, 200, 90]],
                        [[64, 64, 192, 192], [0, 0, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0]]], np.int32), dev)
     rk = T(rng.random((B, A), dtype=np.float32), dev)
-    w_match, w_bbox, w_bbox32 = F.rpn_targets_forward(anchors_px, gcls, gbox, rk, 64, SD, return_f32=True)
+    # the reference's loader hands over the float32 config array (config.py:90): the divisor is (double)0.1f
+    w_match, w_bbox, w_bbox32 = F.rpn_targets_forward(anchors_px, gcls, gbox, rk, 64, np.array(SD, np.float32),
+                                                      return_f32=True)
     match, bbox, bbox32 = tf_stub.StubOp("MrcnnRpnTargets", rpn_train_anchors_per_image=64, rpn_bbox_std_dev=SD,
                                          eps=1e-3)(anchors_px, gcls, gbox, rk)
     assert tuple(match.shape) == (B, A, 1) and torch.equal(match[..., 0], w_match)
-    assert torch.equal(bbox, w_bbox) and torch.equal(bbox32, w_bbox32)   # 0.1f attr -> the double 0.1 (AttrAsDouble)
+    assert torch.equal(bbox, w_bbox) and torch.equal(bbox32, w_bbox32)
+
+
+# ------------------------------------------------------------------------ the Python side, executed (fake `tensorflow`)
+def test_python_shim_executes_under_the_fake_tensorflow_and_keeps_the_reference_surface():
+    """tf_shim/mrcnn_layers_b200.py is run as it is against tests/tf_stub/fake_tf.py: the module body (op library,
+    gradient registrations), the constructors, names, shapes and configs of SURVEY.md 8(b)."""
+    import inspect
+    from tf_stub import fake_tf
+    from maskrcnn_tf2_b200 import layers as torch_layers, make_config
+    with fake_tf.installed() as tf:
+        shim = fake_tf.import_shim()
+        assert set(tf.gradients) == {"MrcnnPyramidRoiAlign", "MrcnnProposal"}
+        assert tf.no_gradients == {"MrcnnProposalGrad", "MrcnnDetection", "MrcnnDetectionTarget"}
+        assert set(tf.serializable) >= {"ProposalLayer", "PyramidROIAlign", "DetectionLayer", "DetectionTargetLayer"}
+        cfg = make_config()
+        want = {   # constructor parameters of the reference classes (mrcnn_layers.py:218, 574, 353-355, 309)
+            "ProposalLayer": ["proposal_count", "config", "name", "kwargs"],
+            "PyramidROIAlign": ["pool_shape", "denominator", "name", "kwargs"],
+            "DetectionLayer": ["proposals", "detection_min_confidence", "detection_max_instances",
+                               "detection_nms_threshold", "bbox_std_dev", "images_per_gpu", "batch_size", "name",
+                               "kwargs"],
+            "DetectionTargetLayer": ["config", "name", "kwargs"],
+        }
+        for cls, params in want.items():
+            got = list(inspect.signature(getattr(shim, cls).__init__).parameters)[1:]
+            assert got == params, (cls, got)
+            # the torch mirror takes the same arguments in the same order (plus keyword-only-in-practice extensions)
+            got = list(inspect.signature(getattr(torch_layers, cls).__init__).parameters)[1:]
+            assert got[:len(params) - 1] == params[:-1] and got[-1] == "kwargs", (cls, got)
+        p = shim.ProposalLayer(proposal_count=1000, config=cfg)
+        assert p.name == "roi" and p.compute_output_shape(None) == (None, 1000, 4) and p.nms_threshold == 0.7
+        r = shim.PyramidROIAlign([7, 7], name="roi_align_classifier")
+        assert r.name == "roi_align_classifier" and r.denominator == 244.0
+        assert r.compute_output_shape([(None, 1000, 4), (None, 93), (None, 256, 256, 256)]) == (None, 1000, 7, 7, 256)
+        assert shim.PyramidROIAlign([14, 14]).name == "roi_align"
+        d = shim.DetectionLayer(1000, 0.7, 100, 0.3, cfg["bbox_std_dev"], 8, 8)
+        assert d.name == "mrcnn_detection" and d.compute_output_shape(None) == (None, 100, 6)
+        t = shim.DetectionTargetLayer(cfg)
+        assert t.name == "proposal_targets" and t.compute_mask(None) == [None] * 4
+        assert t.compute_output_shape(None) == [(None, 200, 4), (None, 200), (None, 200, 4), (None, 200, 28, 28)]
+        for layer in (p, r, d, t):
+            assert layer.get_config()["name"] == layer.name
+            layer.build(None)
+            assert layer.built
+    assert "tensorflow" not in __import__("sys").modules or not getattr(__import__("sys").modules["tensorflow"],
+                                                                        "__fake__", False)
+
+
+@pytest.mark.gpu
+def test_python_shim_layers_run_the_roi_stage_through_the_cpp_shim(F, dev):
+    """Inference wiring of model.py:556-573 with the shim's own Keras classes (ProposalLayer -> PyramidROIAlign ->
+    DetectionLayer -> DetectedBoxesExtraction -> PyramidROIAlign), every op going Python shim -> C++ OpKernel ->
+    launcher, against the torch mirror of the same classes; then the training layer and both registered gradients."""
+    from tf_stub import fake_tf
+    from maskrcnn_tf2_b200 import layers as TL, make_config, synth
+    B, S, NC = 2, 256, 5
+    cfg = make_config(img_size=S, num_classes=NC, batch_size=B)
+    x = synth.inference_batch(77, B, img_size=S, num_classes=NC, regime="clustered", n_rois=1000, channels=64)
+    t = lambda a: T(a, dev)
+    probs, bbox, anchors, meta = t(x["rpn_probs"]), t(x["rpn_bbox"]), t(x["anchors"]), t(x["image_meta"])
+    fm = [t(f) for f in x["feature_maps"]]
+    cls, dl = t(x["mrcnn_class"]), t(x["mrcnn_bbox"])
+    det_args = (1000, cfg["detection_min_confidence"], cfg["detection_max_instances"],
+                cfg["detection_nms_threshold"], cfg["bbox_std_dev"], B, B)
+    with fake_tf.installed() as tf:
+        shim = fake_tf.import_shim()
+        rois = shim.ProposalLayer(1000, cfg)([probs, bbox, anchors])
+        pooled = shim.PyramidROIAlign([7, 7], name="roi_align_classifier")([rois, meta] + fm)
+        det = shim.DetectionLayer(*det_args)([rois, cls, dl, meta])
+        boxes = shim.DetectedBoxesExtraction(cfg)(det)
+        mask_pooled = shim.PyramidROIAlign([14, 14], name="roi_align_mask")([boxes, meta] + fm)
+        assert [c[0] for c in tf.library.calls] == ["MrcnnProposal", "MrcnnPyramidRoiAlign", "MrcnnDetection",
+                                                    "MrcnnPyramidRoiAlign"]
+        # the same through the torch mirror of the classes
+        w_rois = TL.ProposalLayer(1000, cfg)([probs, bbox, anchors])
+        w_pooled = TL.PyramidROIAlign([7, 7], name="roi_align_classifier")([w_rois, meta] + fm)
+        w_det = TL.DetectionLayer(*det_args)([w_rois, cls, dl, meta])
+        w_mask = TL.PyramidROIAlign([14, 14], name="roi_align_mask")([w_det[..., :4].contiguous(), meta] + fm)
+        assert torch.equal(rois, w_rois) and torch.equal(pooled, w_pooled) and torch.equal(det, w_det)
+        assert torch.equal(boxes, w_det[..., :4]) and torch.equal(mask_pooled, w_mask)
+        assert int((w_det[..., 4] > 0).sum()) > 0
+
+        # registered gradients: ROIAlign (feature maps only) and Proposal (rpn_bbox only)
+        g = torch.randn_like(pooled)
+        roi_map = F.roialign_forward(rois, meta, fm, (7, 7))[1]
+        grads = tf.gradients["MrcnnPyramidRoiAlign"](fake_tf.FakeOp([rois, meta] + fm, [pooled, roi_map], {}), g, None)
+        assert grads[0] is None and grads[1] is None and len(grads) == 6
+        ref = F.roialign_backward(g, rois, roi_map, [tuple(f.shape) for f in fm], deterministic=True)
+        for a, b in zip(grads[2:], ref):
+            # a wiring check: pixels with > 1024 samples and pixel (0,0) (zero-padded ROIs) accumulate atomically
+            assert torch.allclose(a, b, rtol=1e-3, atol=1e-2)
+        dbg = F.proposal_forward(probs, bbox, anchors, 6000, 1000, cfg["rpn_bbox_std_dev"], 0.7, debug=True)
+        gp = torch.randn_like(rois)
+        sd = [float(v) for v in cfg["rpn_bbox_std_dev"]]
+        out = tf.gradients["MrcnnProposal"](fake_tf.FakeOp([probs, bbox, anchors],
+                                                           [rois, dbg["topk_idx"], dbg["keep_idx"]], {"std_dev": sd}),
+                                            gp, None, None)
+        assert out[0] is None and out[2] is None
+        assert torch.equal(out[1], F.proposal_backward(gp, bbox, anchors, dbg["topk_idx"], dbg["keep_idx"], sd))
+
+        # training layer: the keys the shim draws are captured and replayed through the ctypes path
+        rng = np.random.default_rng(78)
+        P, G = 500, 20
+        props = np.stack([random_boxes(rng, P, min_size=0.04, max_size=0.5, clusters=8) for _ in range(B)])
+        gtb = np.zeros((B, G, 4), np.float32)
+        gtc = np.zeros((B, G), np.int32)
+        for b in range(B):
+            pick = rng.choice(P, 6, replace=False)
+            gtb[b, :6] = props[b, pick] + rng.normal(0, 0.004, (6, 4)).astype(np.float32)
+            gtc[b, :6] = rng.integers(1, NC, 6)
+        masks = rng.uniform(0, 1, (B, 56, 56, G)) < 0.5
+        drawn = []
+        uniform = tf.random.uniform
+        tf.random.uniform = lambda *a, **k: drawn.append(uniform(*a, **k)) or drawn[-1]
+        tcfg = make_config(img_size=S, num_classes=NC, batch_size=B, train_rois_per_image=64)
+        got = shim.DetectionTargetLayer(tcfg)([t(props), t(gtc.astype(np.int64)), t(gtb), t(masks.astype(np.uint8))])
+        assert len(got) == 4 and len(drawn) == 1 and drawn[0].dtype == torch.int32
+        want = F.detection_target_forward(t(props), t(gtc), t(gtb), t(masks.astype(np.uint8)), drawn[0], 64,
+                                          tcfg["roi_positive_ratio"], tcfg["bbox_std_dev"], tcfg["mask_shape"],
+                                          use_mini_masks=bool(tcfg["use_mini_masks"]))
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+        assert int((want[1] > 0).sum()) > 0
+        # loader-side helper of the shim
+        anchors_px = TL.AnchorsLayer(cfg, device=dev).anchors_px
+        gcls = t(np.array([[3, 1, 0, -2], [2, 0, 0, 0]], np.int64))
+        gbox = t(np.array([[[20, 30, 120, 140], [100, 60, 220, 250], [0, 0, 0, 0], [10, 10, 200, 90]],
+                           [[64, 64, 192, 192], [0, 0, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0]]], np.float32))
+        drawn.clear()
+        match, bbox32 = shim.build_rpn_targets(anchors_px, gcls, gbox, 64, cfg["rpn_bbox_std_dev"])
+        w_match, _, w_bbox32 = F.rpn_targets_forward(anchors_px, gcls.to(torch.int32), gbox.to(torch.int32), drawn[0],
+                                                     64, cfg["rpn_bbox_std_dev"], return_f32=True)
+        assert torch.equal(match[..., 0], w_match) and torch.equal(bbox32, w_bbox32)
