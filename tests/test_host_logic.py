@@ -150,3 +150,30 @@ def test_onnx_export_table_matches_the_op_registrations():
     assert fn(_Ctx({"p:0"}), _Node(), "n", extra).domain == mod.DOMAIN
     with pytest.raises(ValueError):
         fn(_Ctx({"p:1"}), _Node(), "n", extra)
+
+
+def test_bench_reference_arm_prints_one_contract_line_and_only_on_rank_zero():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): exactly one JSON line on stdout with the
+    contract's keys; under torchrun every rank but 0 exits 0 without work or output."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+           "--batch", "2", "--img-size", "256", "--num-classes", "5"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "roi_stage_images_per_sec" and line["unit"] == "images/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"]
+    other = subprocess.run(cmd + ["--gpus", "2"], env=dict(env, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2"),
+                           capture_output=True, text=True, timeout=300)
+    assert other.returncode == 0 and other.stdout.strip() == ""
