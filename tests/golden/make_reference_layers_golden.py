@@ -1,0 +1,357 @@
+"""Generates tests/golden/reference_layers_golden.npz by EXECUTING THE REFERENCE'S OWN LAYER CODE in this container
+(`python tests/golden/make_reference_layers_golden.py`; needs /root/reference, so it cannot run on the GPU box -- the
+vectors it writes are committed).
+
+`src/layers/mrcnn_layers.py` is loaded from where it lies and its `ProposalLayer.call`, `PyramidROIAlign.call` and
+`DetectionLayer.call` / `refine_detections` (L:233-269, 583-664, 369-524) -- with `utils.batch_slice`,
+`apply_box_deltas_graph`, `clip_boxes_graph`, `parse_image_meta_graph`, `log2_graph` and `NormBoxesLayer` underneath --
+run UNMODIFIED on top of `numpy_tf` below: a numpy stand-in for the ~55 `tf.*` functions those lines call
+(TensorFlow itself cannot be installed here).  What this pins, and what it does not:
+
+  * pinned by the reference's own Python: everything the layers DO with the ops -- operation order of the fp32
+    arithmetic, the std-dev scaling, per-image slicing, the level formula with its 244 denominator (Q1), the
+    first-appearance map table and the `batch*100000+box` re-sort (Q2), the single class-agnostic NMS over the kept
+    set (Q3), the broadcast intersections, padding, the window normalised with image 0's shape, the final reshape;
+  * NOT pinned (restated here from the TF kernels' documented behaviour): the bodies of
+    `tf.nn.top_k`, `tf.image.non_max_suppression`, `tf.image.crop_and_resize` -- written below in plain numpy,
+    independently of oracle/; and `tf.exp` / `tf.math.log`, which call the oracle's correctly-rounded-to-<1ulp
+    routines so that the stored boxes are bit-comparable (numpy's own expf/logf differ from them in the last bit on
+    some inputs, as TF's Eigen versions differ from each other).
+
+Nothing is copied from the reference: only its outputs are stored.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference/src"
+sys.path.insert(0, ROOT)
+
+f32 = np.float32
+
+
+# ------------------------------------------------------------------------------------------------ numpy_tf
+class T(np.ndarray):
+    """ndarray with the two Tensor methods the reference calls."""
+
+    def set_shape(self, shape):
+        pass
+
+    def numpy(self):
+        return np.asarray(self)
+
+
+def _t(x, dtype=None):
+    return np.asarray(x, dtype=dtype).view(T)
+
+
+def _np_dtype(d):
+    if isinstance(d, str):
+        return np.dtype(d)
+    return d
+
+
+def make_numpy_tf():
+    import oracle
+    tf = types.ModuleType("tensorflow")
+    tf.float32, tf.float64, tf.int32, tf.int64, tf.bool = np.float32, np.float64, np.int32, np.int64, np.bool_
+    tf.newaxis = None
+
+    def _elem(fn):
+        def run(x, *a, **k):
+            x = np.asarray(x)
+            if x.dtype.kind != "f":
+                x = x.astype(f32)                       # python floats become float32 tensors, as in TF
+            return _t(fn(x.astype(f32)).reshape(x.shape))
+        return run
+
+    tf.exp = _elem(oracle.expf)                         # see the module docstring
+    math = types.SimpleNamespace(
+        log=_elem(oracle.logf), maximum=lambda a, b, **k: _t(np.maximum(a, b)),
+        minimum=lambda a, b, **k: _t(np.minimum(a, b)), multiply=lambda a, b, **k: _t(np.multiply(a, b)),
+        divide=lambda a, b, **k: _t(np.divide(a, b)),
+        reduce_max=lambda x, axis=None, **k: _t(np.max(x, axis=axis)),
+        reduce_sum=lambda x, axis=None, **k: _t(np.sum(x, axis=axis, dtype=np.asarray(x).dtype)))
+    tf.math = math
+    tf.maximum, tf.minimum, tf.reduce_sum = math.maximum, math.minimum, math.reduce_sum
+    tf.sqrt = lambda x, **k: _t(np.sqrt(np.asarray(x, f32)))         # IEEE correctly rounded everywhere
+    tf.abs = lambda x, **k: _t(np.abs(x))
+    tf.round = lambda x, **k: _t(np.round(x))                         # half to even, like tf.round
+    tf.equal = lambda a, b, **k: _t(np.equal(a, b))
+    tf.greater = lambda a, b, **k: _t(np.greater(a, b))
+    tf.logical_and = lambda a, b, **k: _t(np.logical_and(a, b))
+    tf.identity = lambda x, **k: _t(x)
+    tf.stop_gradient = lambda x, **k: _t(x)
+    tf.constant = lambda v, dtype=None, **k: _t(v, _np_dtype(dtype) if dtype is not None else
+                                                 (f32 if np.asarray(v).dtype.kind == "f" else None))
+
+    def cast(x, dtype, **k):
+        with np.errstate(invalid="ignore"):             # -inf / NaN -> INT_MIN, what the x86 TF kernel yields too
+            return _t(np.asarray(x).astype(_np_dtype(dtype)))
+    tf.cast = cast
+    tf.shape = lambda x, **k: _t(np.asarray(np.shape(x), np.int32))
+    tf.reshape = lambda x, shape, **k: _t(np.reshape(x, tuple(int(s) for s in np.asarray(shape).reshape(-1))))
+    tf.squeeze = lambda x, axis=None, **k: _t(np.squeeze(x, axis=axis))
+    tf.expand_dims = lambda x, axis, **k: _t(np.expand_dims(x, axis))
+    tf.transpose = lambda x, perm=None, **k: _t(np.transpose(x, perm))
+    tf.tile = lambda x, m, **k: _t(np.tile(x, tuple(int(v) for v in m)))
+    tf.stack = lambda xs, axis=0, **k: _t(np.stack([np.asarray(x) for x in xs], axis=axis))
+    tf.concat = lambda xs, axis=0, **k: _t(np.concatenate([np.asarray(x) for x in xs], axis=axis))
+    tf.range = lambda *a, **k: _t(np.arange(*[int(v) for v in a], dtype=np.int32))
+    tf.argmax = lambda x, axis=None, output_type=np.int64, **k: _t(np.argmax(x, axis=axis).astype(output_type))
+
+    def split(x, n, axis=0, **k):
+        x = np.asarray(x)
+        if isinstance(n, (int, np.integer)):
+            return [_t(p) for p in np.split(x, int(n), axis=axis)]
+        return [_t(p) for p in np.split(x, np.cumsum([int(v) for v in n])[:-1], axis=axis)]
+    tf.split = split
+
+    def pad(x, paddings, mode="CONSTANT", constant_values=0, **k):
+        assert mode == "CONSTANT"
+        p = [(int(a), int(b)) for a, b in np.asarray(paddings).reshape(-1, 2)]
+        return _t(np.pad(np.asarray(x), p, mode="constant", constant_values=constant_values))
+    tf.pad = pad
+
+    def gather(params, indices, axis=0, **k):
+        return _t(np.take(np.asarray(params), np.asarray(indices).astype(np.int64), axis=axis))
+    tf.gather = gather
+
+    def gather_nd(params, indices, **k):
+        idx = np.asarray(indices).astype(np.int64)
+        return _t(np.asarray(params)[tuple(idx[..., d] for d in range(idx.shape[-1]))])
+    tf.gather_nd = gather_nd
+
+    def where(cond, x=None, y=None, **k):
+        if x is None:
+            return _t(np.argwhere(np.asarray(cond)).astype(np.int64))     # row-major coordinates, int64
+        return _t(np.where(cond, x, y))
+    tf.where = where
+
+    def boolean_mask(x, mask, axis=None, **k):
+        return _t(np.asarray(x)[np.asarray(mask).astype(bool)])
+    tf.boolean_mask = boolean_mask
+
+    def unique(x, **k):                                                   # values in first-occurrence order
+        x = np.asarray(x)
+        vals, first, inv = np.unique(x, return_index=True, return_inverse=True)
+        order = np.argsort(first, kind="stable")
+        rank = np.empty_like(order)
+        rank[order] = np.arange(order.size)
+        return _t(vals[order]), _t(rank[inv].astype(np.int32))
+    tf.unique = unique
+
+    class TopK(tuple):
+        values = property(lambda s: s[0])
+        indices = property(lambda s: s[1])
+
+    def top_k(x, k=1, sorted=True, **kw):
+        """TopKV2: descending, equal values -> lower index first; int32 indices."""
+        x = np.asarray(x)
+        k = int(k)
+        idx = np.argsort(-x.astype(np.float64) if x.dtype.kind == "f" else -x.astype(np.int64), axis=-1,
+                         kind="stable")[..., :k].astype(np.int32)
+        return TopK((_t(np.take_along_axis(x, idx.astype(np.int64), axis=-1)), _t(idx)))
+    tf.nn = types.SimpleNamespace(top_k=top_k)
+
+    def iou(boxes, i, j):
+        """NonMaxSuppressionV3's IOU(): corners min/max-normalised, non-positive areas -> 0; fp32 throughout."""
+        a, b = boxes[i], boxes[j]
+        ymin_i, xmin_i, ymax_i, xmax_i = min(a[0], a[2]), min(a[1], a[3]), max(a[0], a[2]), max(a[1], a[3])
+        ymin_j, xmin_j, ymax_j, xmax_j = min(b[0], b[2]), min(b[1], b[3]), max(b[0], b[2]), max(b[1], b[3])
+        area_i = (ymax_i - ymin_i) * (xmax_i - xmin_i)
+        area_j = (ymax_j - ymin_j) * (xmax_j - xmin_j)
+        if area_i <= 0 or area_j <= 0:
+            return f32(0)
+        ih = max(min(ymax_i, ymax_j) - max(ymin_i, ymin_j), f32(0))
+        iw = max(min(xmax_i, xmax_j) - max(xmin_i, xmin_j), f32(0))
+        inter = ih * iw
+        return inter / (area_i + area_j - inter)
+
+    def non_max_suppression(boxes, scores, max_output_size, iou_threshold=0.5, score_threshold=float("-inf"), **k):
+        """Greedy hard NMS: candidates by (score desc, index asc); kept iff IoU with every kept box is not > thr."""
+        boxes, scores = np.asarray(boxes, f32), np.asarray(scores, f32)
+        thr = f32(iou_threshold)
+        order = [int(i) for i in np.argsort(-scores.astype(np.float64), kind="stable") if scores[i] > score_threshold]
+        keep = []
+        for i in order:
+            if len(keep) >= int(max_output_size):
+                break
+            if all(not (iou(boxes, i, j) > thr) for j in reversed(keep)):
+                keep.append(i)
+        return _t(np.asarray(keep, np.int32))
+
+    def crop_and_resize(image, boxes, box_indices, crop_size, method="bilinear", extrapolation_value=0.0, **k):
+        """CropAndResize, bilinear: one sample per output bin at y1*(H-1) + y*(y2-y1)*(H-1)/(ph-1)."""
+        assert method == "bilinear"
+        image, boxes = np.asarray(image, f32), np.asarray(boxes, f32)
+        ph, pw = int(crop_size[0]), int(crop_size[1])
+        _, H, W, C = image.shape
+        out = np.zeros((boxes.shape[0], ph, pw, C), f32)
+
+        def taps(c1, c2, size, crop):
+            if crop > 1:
+                scale = (c2 - c1) * f32(size - 1) / f32(crop - 1)
+                pos = c1 * f32(size - 1) + np.arange(crop, dtype=f32) * scale
+            else:
+                pos = np.asarray([f32(0.5) * (c1 + c2) * f32(size - 1)], f32)
+            ok = (pos >= 0) & (pos <= f32(size - 1))
+            safe = np.where(ok, pos, f32(0))
+            lo, hi = np.floor(safe).astype(np.int64), np.ceil(safe).astype(np.int64)
+            return ok, lo, hi, (safe - lo.astype(f32)).astype(f32)
+
+        for n in range(boxes.shape[0]):
+            img = image[int(box_indices[n])]
+            y1, x1, y2, x2 = boxes[n]
+            oky, ylo, yhi, ly = taps(y1, y2, H, ph)
+            okx, xlo, xhi, lx = taps(x1, x2, W, pw)
+            tl, tr = img[ylo][:, xlo], img[ylo][:, xhi]
+            bl, br = img[yhi][:, xlo], img[yhi][:, xhi]
+            lxb, lyb = lx[None, :, None], ly[:, None, None]
+            top = tl + (tr - tl) * lxb
+            bot = bl + (br - bl) * lxb
+            val = top + (bot - top) * lyb
+            out[n] = np.where((oky[:, None] & okx[None, :])[..., None], val, f32(extrapolation_value))
+        return _t(out)
+
+    tf.image = types.SimpleNamespace(non_max_suppression=non_max_suppression, crop_and_resize=crop_and_resize)
+    tf.function = lambda fn=None, **k: fn if fn is not None else (lambda f: f)
+    tf.map_fn = lambda fn, elems, **k: _t(np.stack([np.asarray(fn(e)) for e in elems]))
+    tf.cond = lambda pred, true_fn, false_fn, **k: true_fn() if bool(pred) else false_fn()
+
+    class Layer:
+        def __init__(self, name=None, **kwargs):
+            self.name, self.built = name, False
+
+        def build(self, input_shape):
+            self.built = True
+
+        def __call__(self, inputs, **kwargs):
+            return self.call(inputs, **kwargs)
+
+        def get_config(self):
+            return {"name": self.name}
+
+    class _Any(types.ModuleType):
+        def __getattr__(self, name):                    # Conv2D, BatchNormalization ...: only ever subclassed / built
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return type(name, (Layer,), {})
+
+    keras = types.ModuleType("tensorflow.keras")
+    keras.layers = _Any("tensorflow.keras.layers")
+    keras.layers.Layer = Layer
+    keras.utils = types.SimpleNamespace(register_keras_serializable=lambda *a, **k: (lambda cls: cls))
+    keras.backend = _Any("tensorflow.keras.backend")
+    tf.keras = keras
+    return tf
+
+
+def load_reference_layers():
+    """Loads /root/reference/src/{common/utils.py, layers/mrcnn_layers.py} on top of numpy_tf."""
+    tf = make_numpy_tf()
+    stubs = {"tensorflow": tf, "tensorflow.keras": tf.keras, "tensorflow.keras.layers": tf.keras.layers,
+             "tensorflow.keras.backend": tf.keras.backend}
+    for name in ("skimage", "skimage.transform", "efficientnet", "efficientnet.keras", "layers", "layers.backbones",
+                 "layers.backbones.models_factory", "common"):
+        stubs[name] = types.ModuleType(name)
+    stubs["layers.backbones.models_factory"].Classifiers = object
+    stubs["efficientnet"].keras = stubs["efficientnet.keras"]
+    try:
+        import distutils.version  # noqa: F401
+    except Exception:
+        d, dv = types.ModuleType("distutils"), types.ModuleType("distutils.version")
+        dv.LooseVersion = str
+        stubs["distutils"], stubs["distutils.version"] = d, dv
+    saved = {n: sys.modules.get(n) for n in stubs}
+    sys.modules.update(stubs)
+    try:
+        def load(name, path):
+            spec = importlib.util.spec_from_file_location(name, path)
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[name] = mod
+            spec.loader.exec_module(mod)
+            return mod
+        utils = load("common.utils", os.path.join(REF, "common", "utils.py"))
+        stubs["common"].utils = utils
+        layers = load("reference_mrcnn_layers", os.path.join(REF, "layers", "mrcnn_layers.py"))
+    finally:
+        for n, m in saved.items():
+            if m is None:
+                sys.modules.pop(n, None)
+            else:
+                sys.modules[n] = m
+        sys.modules.pop("common.utils", None)
+        sys.modules.pop("reference_mrcnn_layers", None)
+    return layers
+
+
+def build():
+    from maskrcnn_tf2_b200 import synth
+    L = load_reference_layers()
+    S, B, NC, C = 128, 3, 5, 8
+    K, P, D = 600, 100, 20
+    cfg = {"rpn_nms_threshold": 0.7, "pre_nms_limit": K, "images_per_gpu": B,
+           "rpn_bbox_std_dev": np.array([0.1, 0.1, 0.2, 0.2], dtype="float32"),      # config.py:90-91
+           "bbox_std_dev": np.array([0.1, 0.1, 0.2, 0.2], dtype="float32")}
+    anchors1 = synth.pyramid_anchors(S)
+    A = anchors1.shape[0]
+    rng = np.random.default_rng(20261018)
+    probs, bbox = zip(*[synth.rpn_outputs(np.random.default_rng(900 + b), anchors1, "clustered", S) for b in range(B)])
+    probs, bbox = np.stack(probs).astype(f32), np.stack(bbox).astype(f32)
+    probs[1, :, 1] = np.round(probs[1, :, 1] * 64) / 64                   # image 1: heavy score ties
+    probs[1, :, 0] = 1 - probs[1, :, 1]
+    bbox[2] *= 0.05                                                        # image 2: near-duplicate boxes, < P survivors
+    anchors = np.ascontiguousarray(np.broadcast_to(anchors1, (B, A, 4))).astype(f32)
+    meta = synth.image_meta(B, S, NC).astype(f32)
+    meta[1, 7:11] = [10, 6, 120, 100]                                     # a padded image: window inside the canvas
+    fmaps = [rng.standard_normal((B, S // s, S // s, C)).astype(f32) for s in (4, 8, 16, 32)]
+    mrcnn_class, mrcnn_bbox = synth.head_outputs(rng, B, P, NC)
+    mrcnn_class[2, :, 1:] *= 0.01                                          # image 2: (almost) background only
+    mrcnn_class[2, :, 0] = 1 - mrcnn_class[2, :, 1:].sum(-1)
+
+    t = lambda a: np.asarray(a).view(T)
+    rois = np.asarray(L.ProposalLayer(proposal_count=P, config=cfg)([t(probs), t(bbox), t(anchors)]))
+    assert rois.shape == (B, P, 4) and rois.dtype == f32
+    # more slots than survivors: the zero padding of L:229-230
+    rois_p400 = np.asarray(L.ProposalLayer(proposal_count=400, config=cfg)([t(probs), t(bbox), t(anchors)]))
+    pooled = np.asarray(L.PyramidROIAlign([7, 7], name="roi_align_classifier")([t(rois), t(meta)] + [t(f) for f in fmaps]))
+    det = np.asarray(L.DetectionLayer(proposals=P, detection_min_confidence=0.7, detection_max_instances=D,
+                                      detection_nms_threshold=0.3, bbox_std_dev=cfg["bbox_std_dev"], images_per_gpu=B,
+                                      batch_size=B)([t(rois), t(mrcnn_class), t(mrcnn_bbox), t(meta)]))
+    assert det.shape == (B, D, 6) and det.dtype == f32
+    det_boxes = np.ascontiguousarray(det[..., :4])
+    mask_pooled = np.asarray(L.PyramidROIAlign([14, 14], name="roi_align_mask")([t(det_boxes), t(meta)] + [t(f) for f in fmaps]))
+    # quirk Q2 case: the batch's first ROI is a large one, so its (coarser) level appears first and takes feature map 0
+    # (P2), and level 2 -- met second -- samples P3
+    q2_boxes = np.array([[[0.05, 0.05, 0.95, 0.95], [0.4, 0.4, 0.45, 0.46], [0.1, 0.2, 0.5, 0.7], [0, 0, 0, 0]],
+                         [[0.3, 0.3, 0.33, 0.34], [0.0, 0.0, 1.0, 1.0], [0.2, 0.1, 0.35, 0.3], [0.6, 0.6, 1.2, 1.3]],
+                         [[0, 0, 0, 0], [0, 0, 0, 0], [0.5, 0.5, 0.75, 0.8], [0.1, 0.1, 0.2, 0.2]]], f32)
+    q2_pooled = np.asarray(L.PyramidROIAlign([3, 5], name="roi_align_q2")([t(q2_boxes), t(meta)] + [t(f) for f in fmaps]))
+    # DetectionLayer without a confidence filter (detection_min_confidence = 0 skips L:404-414)
+    det0 = np.asarray(L.DetectionLayer(proposals=P, detection_min_confidence=0, detection_max_instances=D,
+                                       detection_nms_threshold=0.3, bbox_std_dev=cfg["bbox_std_dev"], images_per_gpu=B,
+                                       batch_size=B)([t(rois), t(mrcnn_class), t(mrcnn_bbox), t(meta)]))
+    kept = [int((rois[b].any(-1)).sum()) for b in range(B)]
+    dets = [int((det[b, :, 4] > 0).sum()) for b in range(B)]
+    print(f"P=400: kept {[int((rois_p400[b].any(-1)).sum()) for b in range(B)]}")
+    print(f"proposals kept per image {kept} of {P}; detections per image {dets} of {D}; "
+          f"no-confidence detections {[int((det0[b, :, 4] > 0).sum()) for b in range(B)]}")
+    out = dict(img_size=S, pre_nms_limit=K, proposal_count=P, max_instances=D, num_classes=NC,
+               rpn_probs=probs, rpn_bbox=bbox, anchors=anchors, image_meta=meta, mrcnn_class=mrcnn_class.astype(f32),
+               mrcnn_bbox=mrcnn_bbox.astype(f32), rois=rois, pooled=pooled, detections=det, mask_pooled=mask_pooled,
+               q2_boxes=q2_boxes, q2_pooled=q2_pooled, detections_noconf=det0, rois_p400=rois_p400)
+    for i, f in enumerate(fmaps):
+        out[f"fmap{i}"] = f
+    path = os.path.join(HERE, "reference_layers_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    build()

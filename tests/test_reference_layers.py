@@ -1,0 +1,81 @@
+"""The oracle and the CUDA path against outputs of the REFERENCE'S OWN LAYER CODE.
+
+tests/golden/reference_layers_golden.npz was written by tests/golden/make_reference_layers_golden.py, which loads
+/root/reference/src/layers/mrcnn_layers.py and runs its ProposalLayer / PyramidROIAlign / DetectionLayer `call` methods
+unmodified on a numpy stand-in for the `tf.*` functions they use (TensorFlow is not installable here).  That pins
+everything the layers do with the ops -- arithmetic order, per-image slicing, the level formula (Q1), the
+first-appearance map table and re-sort (Q2), the single class-agnostic NMS (Q3), intersections, padding, window
+normalisation -- to the reference's own Python; the bodies of top_k / non_max_suppression / crop_and_resize in that
+stand-in are an independent numpy restatement of the TF kernels (still not TensorFlow itself).  Bit-exact, all of it.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+SD = np.array([0.1, 0.1, 0.2, 0.2], np.float32)
+
+
+@pytest.fixture(scope="module")
+def G():
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_layers_golden.npz"))
+    return {k: g[k] for k in g.files}
+
+
+def _maps(G):
+    return [G[f"fmap{i}"] for i in range(4)]
+
+
+def test_golden_exercises_the_interesting_paths(G):
+    kept400 = (G["rois_p400"] != 0).any(-1).sum(-1)
+    assert np.all(kept400 < 400) and np.all(kept400 > 100)                  # zero padding of L:229-230 is exercised
+    dets = (G["detections"][..., 4] > 0).sum(-1)
+    assert dets[0] > 0 and dets[-1] == 0                                    # one image ends with no detection at all
+    assert (G["detections_noconf"][..., 4] > 0).sum() > dets.sum()          # the confidence filter removed something
+    assert len(np.unique(np.round(G["rpn_probs"][1, :, 1] * 64))) <= 65     # image 1: heavy score ties
+
+
+def test_oracle_reproduces_the_reference_layers(orc, G):
+    S, K, P, D = float(G["img_size"]), int(G["pre_nms_limit"]), int(G["proposal_count"]), int(G["max_instances"])
+    r = orc.proposal_layer(G["rpn_probs"], G["rpn_bbox"], G["anchors"], K, P, SD, 0.7)
+    assert np.array_equal(r["proposals"], G["rois"])
+    r4 = orc.proposal_layer(G["rpn_probs"], G["rpn_bbox"], G["anchors"], K, 400, SD, 0.7)
+    assert np.array_equal(r4["proposals"], G["rois_p400"])
+    assert np.array_equal(orc.pyramid_roi_align(G["rois"], S, S, _maps(G), (7, 7))["out"], G["pooled"])
+    d = orc.detection_layer(G["rois"], G["mrcnn_class"], G["mrcnn_bbox"], G["image_meta"], SD, 0.7, D, 0.3)
+    assert np.array_equal(d["detections"], G["detections"])
+    d0 = orc.detection_layer(G["rois"], G["mrcnn_class"], G["mrcnn_bbox"], G["image_meta"], SD, 0, D, 0.3)
+    assert np.array_equal(d0["detections"], G["detections_noconf"])
+    boxes = np.ascontiguousarray(G["detections"][..., :4])
+    assert np.array_equal(orc.pyramid_roi_align(boxes, S, S, _maps(G), (14, 14))["out"], G["mask_pooled"])
+    q = orc.pyramid_roi_align(G["q2_boxes"], S, S, _maps(G), (3, 5))
+    assert np.array_equal(q["out"], G["q2_pooled"])
+    assert q["roi_map"][0, 0] == 0 and q["roi_map"][0, 1] == 1              # Q2: first-seen level takes map 0
+
+
+@pytest.mark.gpu
+def test_cuda_layers_reproduce_the_reference_layers(G, dev):
+    from maskrcnn_tf2_b200 import make_config
+    from maskrcnn_tf2_b200.layers import DetectionLayer, ProposalLayer, PyramidROIAlign
+    S, NC, B = int(G["img_size"]), int(G["num_classes"]), G["rois"].shape[0]
+    K, P, D = int(G["pre_nms_limit"]), int(G["proposal_count"]), int(G["max_instances"])
+    cfg = make_config(img_size=S, num_classes=NC, batch_size=B, pre_nms_limit=K)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    fm = [t(f) for f in _maps(G)]
+    meta = t(G["image_meta"])
+    inputs = [t(G["rpn_probs"]), t(G["rpn_bbox"]), t(G["anchors"])]
+    rois = ProposalLayer(P, cfg)(inputs)
+    assert np.array_equal(rois.cpu().numpy(), G["rois"])
+    assert np.array_equal(ProposalLayer(400, cfg)(inputs).cpu().numpy(), G["rois_p400"])
+    pooled = PyramidROIAlign([7, 7], name="roi_align_classifier")([rois, meta] + fm)
+    assert np.array_equal(pooled.cpu().numpy(), G["pooled"])
+    for conf, key in ((0.7, "detections"), (0, "detections_noconf")):
+        det = DetectionLayer(P, conf, D, 0.3, cfg["bbox_std_dev"], B, B)([rois, t(G["mrcnn_class"]),
+                                                                          t(G["mrcnn_bbox"]), meta])
+        assert np.array_equal(det.cpu().numpy(), G[key]), key
+    boxes = t(G["detections"][..., :4])
+    mask_pooled = PyramidROIAlign([14, 14], name="roi_align_mask")([boxes, meta] + fm)
+    assert np.array_equal(mask_pooled.cpu().numpy(), G["mask_pooled"])
+    q2 = PyramidROIAlign([3, 5])([t(G["q2_boxes"]), meta] + fm)
+    assert np.array_equal(q2.cpu().numpy(), G["q2_pooled"])
