@@ -20,6 +20,7 @@ run UNMODIFIED on top of `numpy_tf` below: a numpy stand-in for the ~55 `tf.*` f
 
 Nothing is copied from the reference: only its outputs are stored.
 """
+import contextlib
 import importlib.util
 import os
 import sys
@@ -33,6 +34,7 @@ REF = "/root/reference/src"
 sys.path.insert(0, ROOT)
 
 f32 = np.float32
+SHUFFLE = {"calls": 0, "per_image": []}      # [(uint32 keys [P], original row of every non-zero proposal)] per image
 
 
 # ------------------------------------------------------------------------------------------------ numpy_tf
@@ -75,7 +77,9 @@ def make_numpy_tf():
         log=_elem(oracle.logf), maximum=lambda a, b, **k: _t(np.maximum(a, b)),
         minimum=lambda a, b, **k: _t(np.minimum(a, b)), multiply=lambda a, b, **k: _t(np.multiply(a, b)),
         divide=lambda a, b, **k: _t(np.divide(a, b)),
-        reduce_max=lambda x, axis=None, **k: _t(np.max(x, axis=axis)),
+        # Eigen's MaxReducer starts from lowest(): that is what a reduction over an empty axis returns
+        reduce_max=lambda x, axis=None, **k: _t(np.max(x, axis=axis, initial=np.finfo(f32).min)
+                                                if np.asarray(x).size == 0 else np.max(x, axis=axis)),
         reduce_sum=lambda x, axis=None, **k: _t(np.sum(x, axis=axis, dtype=np.asarray(x).dtype)))
     tf.math = math
     tf.maximum, tf.minimum, tf.reduce_sum = math.maximum, math.minimum, math.reduce_sum
@@ -220,6 +224,19 @@ def make_numpy_tf():
         return _t(out)
 
     tf.image = types.SimpleNamespace(non_max_suppression=non_max_suppression, crop_and_resize=crop_and_resize)
+    tf.Assert = lambda *a, **k: None
+    tf.control_dependencies = lambda deps: contextlib.nullcontext()
+
+    def shuffle(x, **k):
+        """tf.random.shuffle is unseeded in the reference (any permutation is reference behaviour).  The
+        stand-in draws THE permutation the B200 layer draws from the same per-proposal random keys: ascending
+        (key of the proposal's original row, index) -- see SHUFFLE below."""
+        keys, rows = SHUFFLE["per_image"][SHUFFLE["calls"] // 2]      # two calls per image: positives, negatives
+        SHUFFLE["calls"] += 1
+        x = np.asarray(x)
+        order = sorted(range(x.size), key=lambda i: (int(keys[rows[int(x[i])]]), int(x[i])))
+        return _t(x[order])
+    tf.random = types.SimpleNamespace(shuffle=shuffle)
     tf.function = lambda fn=None, **k: fn if fn is not None else (lambda f: f)
     tf.map_fn = lambda fn, elems, **k: _t(np.stack([np.asarray(fn(e)) for e in elems]))
     tf.cond = lambda pred, true_fn, false_fn, **k: true_fn() if bool(pred) else false_fn()
@@ -353,5 +370,65 @@ def build():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def build_targets():
+    """DetectionTargetLayer.call -> detection_targets_graph (+ trim_zeros_graph, overlaps_graph,
+    utils.box_refinement_graph; mrcnn_layers.py:313-325, 844-1007, utils.py:775-798), full-size and mini masks."""
+    L = load_reference_layers()
+    rng = np.random.default_rng(20261019)
+    B, P, G, T_, MH = 3, 300, 12, 32, 40
+    out = dict(train_rois_per_image=T_, roi_positive_ratio=0.33, mask_shape=np.array([14, 14]))
+
+    def boxes(n, lo, hi):
+        c = rng.uniform(0.2, 0.8, (n, 2))
+        s = rng.uniform(lo, hi, (n, 2))
+        return np.clip(np.concatenate([c - s / 2, c + s / 2], 1), 0, 1).astype(f32)
+
+    gtb = np.zeros((B, G, 4), f32)
+    gtc = np.zeros((B, G), np.int32)
+    props = np.zeros((B, P, 4), f32)
+    for b in range(B):
+        n_real = 6 - b
+        gtb[b, :n_real] = boxes(n_real, 0.15, 0.5)
+        gtc[b, :n_real] = rng.integers(1, 81, n_real)
+        jit = np.repeat(gtb[b, :n_real], 30, 0) + rng.normal(0, 0.02, (30 * n_real, 4)).astype(f32)
+        n_prop = P - 40 - 10 * b                                   # the rest stays zero padding (trimmed, L:871)
+        props[b, :jit.shape[0]] = np.clip(jit, 0, 1)
+        props[b, jit.shape[0]:n_prop] = boxes(n_prop - jit.shape[0], 0.05, 0.4)
+        perm = rng.permutation(n_prop)
+        props[b, :n_prop] = props[b, :n_prop][perm]
+    gtc[0, 2] *= -1                                                # a crowd box (negative class id, L:879-884)
+    gtb[1, 3], gtb[1, 5] = gtb[1, 5].copy(), gtb[1, 3].copy()      # a zero GT row in the middle of the list (image 1)
+    gtc[1, 3], gtc[1, 5] = gtc[1, 5], gtc[1, 3]
+    props[2, 5] = 0                                                # a zero proposal in the middle of the list
+    keys = rng.integers(0, 2 ** 32, (B, P), dtype=np.uint64).astype(np.uint32)
+    keys[0, ::3] = keys[0, 1::3]                                   # tied keys: the index decides
+    t = lambda a: np.asarray(a).view(T)
+    for mini in (False, True):
+        mh = 16 if mini else MH
+        yy, xx = np.mgrid[0:mh, 0:mh]
+        masks = np.zeros((B, mh, mh, G), bool)
+        for b in range(B):
+            for g in range(G):
+                cy, cx, ry, rx = rng.uniform(0.3, 0.7) * mh, rng.uniform(0.3, 0.7) * mh, rng.uniform(0.15, 0.45) * mh, \
+                    rng.uniform(0.15, 0.45) * mh
+                masks[b, :, :, g] = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1
+        cfg = {"train_rois_per_image": T_, "roi_positive_ratio": 0.33, "use_mini_masks": mini, "mask_shape": (14, 14),
+               "bbox_std_dev": np.array([0.1, 0.1, 0.2, 0.2], dtype="float32"), "images_per_gpu": B}
+        SHUFFLE["calls"] = 0
+        SHUFFLE["per_image"] = [(keys[b], np.flatnonzero(np.abs(props[b]).sum(1) != 0)) for b in range(B)]
+        rois, cls, deltas, tm = L.DetectionTargetLayer(cfg)([t(props), t(gtc), t(gtb), t(masks)])
+        assert SHUFFLE["calls"] == 2 * B
+        tag = "mini" if mini else "full"
+        out.update({f"gt_masks_{tag}": masks, f"rois_{tag}": np.asarray(rois, f32), f"class_ids_{tag}": np.asarray(cls),
+                    f"deltas_{tag}": np.asarray(deltas, f32), f"masks_{tag}": np.asarray(tm, f32)})
+        print(tag, "positives per image", [(np.asarray(cls)[b] != 0).sum() for b in range(B)], "rois per image",
+              [int(np.asarray(rois)[b].any(-1).sum()) for b in range(B)], "mask mean", float(np.asarray(tm).mean()))
+    out.update(proposals=props, gt_class_ids=gtc, gt_boxes=gtb, rand_keys=keys)
+    path = os.path.join(HERE, "reference_target_layer_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     build()
+    build_targets()

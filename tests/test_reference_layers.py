@@ -79,3 +79,41 @@ def test_cuda_layers_reproduce_the_reference_layers(G, dev):
     assert np.array_equal(mask_pooled.cpu().numpy(), G["mask_pooled"])
     q2 = PyramidROIAlign([3, 5])([t(G["q2_boxes"]), meta] + fm)
     assert np.array_equal(q2.cpu().numpy(), G["q2_pooled"])
+
+
+# ---- the training layer: DetectionTargetLayer.call -> detection_targets_graph, executed from the reference too -------
+@pytest.fixture(scope="module")
+def GT():
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_target_layer_golden.npz"))
+    return {k: g[k] for k in g.files}
+
+
+def _target_args(GT, tag):
+    return (GT["proposals"], GT["gt_class_ids"], GT["gt_boxes"], GT[f"gt_masks_{tag}"].astype(np.uint8), GT["rand_keys"],
+            int(GT["train_rois_per_image"]), float(GT["roi_positive_ratio"]), SD, tuple(int(v) for v in GT["mask_shape"]))
+
+
+@pytest.mark.parametrize("tag,mini", [("full", False), ("mini", True)])
+def test_oracle_reproduces_the_reference_detection_target_layer(orc, GT, tag, mini):
+    """tf.random.shuffle is unseeded in the reference (any permutation is its behaviour); the generator's stand-in draws
+    the permutation the B200 layer derives from the injected keys, so the whole of L:844-967 is compared: zero trimming
+    in the middle of the lists, the crowd box, `>= 0.5` / `< 0.5` / `< 0.001`, int(T*0.33) = 10 positives and
+    int32(fp32(1/0.33)*10) - 10 = 20 negatives, first-max GT assignment, deltas / std, the 14x14 mask targets
+    (full-size and mini-mask coordinates), padding."""
+    r = orc.detection_target_layer(*_target_args(GT, tag), use_mini_masks=mini)
+    for k in ("rois", "class_ids", "deltas", "masks"):
+        assert np.array_equal(r[k], GT[f"{k}_{tag}"]), k
+    assert np.array_equal(r["counts"], np.array([[10, 20]] * 3))
+    assert set(np.unique(GT[f"masks_{tag}"])) == {0.0, 1.0}              # tf.round of the bilinear samples, L:954
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,mini", [("full", False), ("mini", True)])
+def test_cuda_reproduces_the_reference_detection_target_layer(GT, dev, tag, mini):
+    from maskrcnn_tf2_b200 import functional as F
+    props, gtc, gtb, masks, keys, T_, ratio, sd, mshape = _target_args(GT, tag)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out = F.detection_target_forward(t(props), t(gtc), t(gtb), t(masks), t(keys.view(np.int32)), T_, ratio, sd, mshape,
+                                     use_mini_masks=mini)
+    for got, k in zip(out, ("rois", "class_ids", "deltas", "masks")):
+        assert np.array_equal(got.cpu().numpy(), GT[f"{k}_{tag}"]), k
