@@ -6,15 +6,21 @@
  * __graft_entry__.smoke(), and bench.py's cpu_baseline / --impl reference legs, and there only as
  * the checker or the timed CPU baseline.
  *
- * PARITY UNPINNED: the reference ships no golden vectors, known-answer tests or fixtures for this
- * path (its tests/ only pin library versions), and its arithmetic lives in the un-vendored PyPI
- * dependency tensorflow==2.2.0/2.3.4/2.4.3/2.5.1 (requirements/requirements_tf2.*.txt:2), which is
- * not installable here.  This file restates (a) the reference's own Python control flow
- * (src/layers/mrcnn_layers.py, src/common/utils.py -- cited per function as L:/U:) and (b) the
- * published algorithms of the TF CPU kernels it calls (TopKV2, NonMaxSuppressionV3, CropAndResize,
- * CropAndResizeGradImage).  It is pinned instead by hand-derived known-answer tests and by
- * independent implementations available offline (torchvision.ops.nms, torch.topk/sort,
- * torch.nn.functional.grid_sample + autograd) -- see tests/test_oracle_*.py.
+ * PARITY: the reference ships no golden vectors, known-answer tests or fixtures for this path (its
+ * tests/ only pin library versions), and its arithmetic lives in the un-vendored PyPI dependency
+ * tensorflow==2.2.0/2.3.4/2.4.3/2.5.1 (requirements/requirements_tf2.*.txt:2), not installable
+ * here.  This file restates (a) the reference's own Python control flow (src/layers/mrcnn_layers.py,
+ * src/common/utils.py -- cited per function as L:/U:) and (b) the published algorithms of the TF
+ * CPU kernels it calls (TopKV2, NonMaxSuppressionV3, CropAndResize, CropAndResizeGradImage).
+ *   (a) is PINNED: tests/golden/make_reference_layers_golden.py executes the reference's own
+ *       ProposalLayer / PyramidROIAlign / DetectionLayer / DetectionTargetLayer code, unmodified, on
+ *       a numpy stand-in for tf.*, and this file reproduces the committed outputs bit for bit
+ *       (tests/test_reference_layers.py); so are the numpy twins (anchors, build_rpn_targets, ...:
+ *       tests/test_reference_pins.py, tests/test_rpn_targets.py).
+ *   (b) stays PARITY UNPINNED by TensorFlow itself: pinned instead by hand-derived known answers,
+ *       property tests, a second independent numpy restatement (the stand-in above) and independent
+ *       implementations available offline (torchvision.ops.nms, torch.topk/sort, grid_sample +
+ *       autograd) -- tests/test_oracle_*.py.
  *
  * Numerics: every float operation below is IEEE binary32 in the written order (compile with
  * -ffp-contract=off, no -ffast-math).  exp/log are NOT libm: TF uses Eigen's Cephes-derived packet
