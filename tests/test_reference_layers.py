@@ -117,3 +117,43 @@ def test_cuda_reproduces_the_reference_detection_target_layer(GT, dev, tag, mini
                                      use_mini_masks=mini)
     for got, k in zip(out, ("rois", "class_ids", "deltas", "masks")):
         assert np.array_equal(got.cpu().numpy(), GT[f"{k}_{tag}"]), k
+
+
+# ---- the stand-in's own kernel restatements against the oracle's (two independent restatements of the TF kernels) ----
+@pytest.fixture(scope="module")
+def numpy_tf():
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_reference_layers_golden.py")
+    spec = importlib.util.spec_from_file_location("make_reference_layers_golden", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)            # defines the stand-in; touches /root/reference only when build() is called
+    return mod.make_numpy_tf()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_stand_in_kernels_agree_with_the_oracle_bit_for_bit(orc, numpy_tf, seed):
+    from conftest import random_boxes
+    tf = numpy_tf
+    rng = np.random.default_rng(8800 + seed)
+    m = int(rng.integers(5, 400))
+    boxes = random_boxes(rng, m, clusters=int(rng.choice([0, 3])))
+    boxes[1] = boxes[0]
+    boxes[2, 2] = boxes[2, 0]                                             # zero area
+    boxes[3] = boxes[3][[2, 3, 0, 1]]                                     # flipped corners
+    scores = (np.round(rng.uniform(0, 1, m) * 32) / 32).astype(np.float32)
+    scores[4] = -np.inf
+    for thr in (0.0, 0.3, 0.7, 1.0):
+        mo = int(rng.integers(1, m + 5))
+        assert np.array_equal(np.asarray(tf.image.non_max_suppression(boxes, scores, mo, thr)),
+                              orc.nms(boxes, scores, mo, thr)), (m, mo, thr)
+    k = int(rng.integers(1, m + 1))
+    assert np.array_equal(np.asarray(tf.nn.top_k(scores, k).indices), orc.topk(scores, k))
+    H, W, C, n = int(rng.integers(1, 20)), int(rng.integers(1, 20)), 3, 9
+    img = rng.standard_normal((2, H, W, C)).astype(np.float32)
+    cb = rng.uniform(-0.3, 1.3, (n, 4)).astype(np.float32)
+    cb[0] = [0, 0, 1, 1]
+    cb[1] = 0
+    ind = rng.integers(0, 2, n).astype(np.int32)
+    for crop in ((7, 7), (1, 1), (2, 5), (14, 3)):
+        assert np.array_equal(np.asarray(tf.image.crop_and_resize(img, cb, ind, crop)),
+                              orc.crop_and_resize(img, cb, ind, crop)), (H, W, crop)
