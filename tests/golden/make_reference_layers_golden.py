@@ -83,7 +83,10 @@ def make_numpy_tf():
         reduce_sum=lambda x, axis=None, **k: _t(np.sum(x, axis=axis, dtype=np.asarray(x).dtype)))
     tf.math = math
     tf.maximum, tf.minimum, tf.reduce_sum = math.maximum, math.minimum, math.reduce_sum
-    tf.sqrt = lambda x, **k: _t(np.sqrt(np.asarray(x, f32)))         # IEEE correctly rounded everywhere
+    def sqrt(x, **k):                                                # IEEE correctly rounded everywhere
+        with np.errstate(invalid="ignore"):                          # h*w < 0 (flipped ROI) -> NaN -> level 2, as in TF
+            return _t(np.sqrt(np.asarray(x, f32)))
+    tf.sqrt = sqrt
     tf.abs = lambda x, **k: _t(np.abs(x))
     tf.round = lambda x, **k: _t(np.round(x))                         # half to even, like tf.round
     tf.equal = lambda a, b, **k: _t(np.equal(a, b))
