@@ -272,11 +272,12 @@ def make_numpy_tf():
     return tf
 
 
-def load_reference_layers():
-    """Loads /root/reference/src/{common/utils.py, layers/mrcnn_layers.py} on top of numpy_tf."""
-    tf = make_numpy_tf()
+def load_reference_layers(tf=None):
+    """Loads /root/reference/src/{common/utils.py, layers/mrcnn_layers.py} on top of numpy_tf (or of another stand-in
+    module with the same surface: tests/test_reference_gradients.py passes a torch-backed one for autograd)."""
+    tf = tf or make_numpy_tf()
     stubs = {"tensorflow": tf, "tensorflow.keras": tf.keras, "tensorflow.keras.layers": tf.keras.layers,
-             "tensorflow.keras.backend": tf.keras.backend}
+             "tensorflow.keras.backend": getattr(tf.keras, "backend", types.ModuleType("tensorflow.keras.backend"))}
     for name in ("skimage", "skimage.transform", "efficientnet", "efficientnet.keras", "layers", "layers.backbones",
                  "layers.backbones.models_factory", "common"):
         stubs[name] = types.ModuleType(name)
