@@ -228,6 +228,7 @@ def make_numpy_tf():
 
     tf.image = types.SimpleNamespace(non_max_suppression=non_max_suppression, crop_and_resize=crop_and_resize)
     tf.Assert = lambda *a, **k: None
+    tf.Variable = lambda v, **k: _t(v)
     tf.control_dependencies = lambda deps: contextlib.nullcontext()
 
     def shuffle(x, **k):
@@ -252,7 +253,15 @@ def make_numpy_tf():
             self.built = True
 
         def __call__(self, inputs, **kwargs):
-            return self.call(inputs, **kwargs)
+            # Keras autocasts floating inputs to the layer's dtype (float32): AnchorsLayer hands float64 numpy anchors
+            # to NormBoxesLayer this way (mrcnn_layers.py:116-132)
+            def autocast(v):
+                if isinstance(v, (list, tuple)):
+                    return type(v)(autocast(e) for e in v)
+                if isinstance(v, np.ndarray) and v.dtype == np.float64:
+                    return _t(v.astype(f32))
+                return v
+            return self.call(autocast(inputs), **kwargs)
 
         def get_config(self):
             return {"name": self.name}

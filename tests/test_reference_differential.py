@@ -112,3 +112,19 @@ def test_detection_target_layer_live_against_the_reference(orc, ref, seed):
     assert np.array_equal(r["rois"], np.asarray(rois)) and np.array_equal(r["class_ids"], np.asarray(cls))
     assert np.array_equal(r["deltas"], np.asarray(deltas), equal_nan=True)
     assert np.array_equal(r["masks"], np.asarray(tm))
+
+
+@pytest.mark.parametrize("S", [64, 128, 256])
+def test_anchors_layer_live_against_the_reference(ref, S):
+    """AnchorsLayer (L:104-145): numpy float64 pyramid -> Keras autocast to float32 -> NormBoxesLayer, broadcast to the
+    batch.  The host-side synth.pyramid_anchors (what the benchmarks feed) must be the same bits; the device producer
+    is compared with the same vectors in tests/test_reference_pins.py."""
+    from maskrcnn_tf2_b200 import synth
+    gen, L = ref
+    cfg = {"image_shape": (S, S, 3), "img_size": S, "batch_size": 2, "backbone_strides": [4, 8, 16, 32, 64],
+           "rpn_anchor_scales": (32, 64, 128, 256, 512), "rpn_anchor_ratios": [0.5, 1, 2], "rpn_anchor_stride": 1,
+           "backbone": "resnet50"}
+    got = np.asarray(L.AnchorsLayer(cfg, training=False).call())
+    want = synth.pyramid_anchors(S)
+    assert got.dtype == np.float32 and got.shape == (2,) + want.shape
+    assert np.array_equal(got[0], want) and np.array_equal(got[1], want)
