@@ -21,6 +21,7 @@ run UNMODIFIED on top of `numpy_tf` below: a numpy stand-in for the ~55 `tf.*` f
 Nothing is copied from the reference: only its outputs are stored.
 """
 import contextlib
+import hashlib
 import importlib.util
 import os
 import sys
@@ -166,19 +167,21 @@ def make_numpy_tf():
         return TopK((_t(np.take_along_axis(x, idx.astype(np.int64), axis=-1)), _t(idx)))
     tf.nn = types.SimpleNamespace(top_k=top_k)
 
-    def iou(boxes, i, j):
-        """NonMaxSuppressionV3's IOU(): corners min/max-normalised, non-positive areas -> 0; fp32 throughout."""
-        a, b = boxes[i], boxes[j]
+    def iou_many(boxes, i, js):
+        """NonMaxSuppressionV3's IOU() of box i against boxes js: corners min/max-normalised, non-positive areas -> 0;
+        every operation an individually rounded fp32 numpy operation, in the kernel's order."""
+        a, b = boxes[i], boxes[js]
         ymin_i, xmin_i, ymax_i, xmax_i = min(a[0], a[2]), min(a[1], a[3]), max(a[0], a[2]), max(a[1], a[3])
-        ymin_j, xmin_j, ymax_j, xmax_j = min(b[0], b[2]), min(b[1], b[3]), max(b[0], b[2]), max(b[1], b[3])
+        ymin_j, xmin_j = np.minimum(b[:, 0], b[:, 2]), np.minimum(b[:, 1], b[:, 3])
+        ymax_j, xmax_j = np.maximum(b[:, 0], b[:, 2]), np.maximum(b[:, 1], b[:, 3])
         area_i = (ymax_i - ymin_i) * (xmax_i - xmin_i)
         area_j = (ymax_j - ymin_j) * (xmax_j - xmin_j)
-        if area_i <= 0 or area_j <= 0:
-            return f32(0)
-        ih = max(min(ymax_i, ymax_j) - max(ymin_i, ymin_j), f32(0))
-        iw = max(min(xmax_i, xmax_j) - max(xmin_i, xmin_j), f32(0))
+        ih = np.maximum(np.minimum(ymax_i, ymax_j) - np.maximum(ymin_i, ymin_j), f32(0))
+        iw = np.maximum(np.minimum(xmax_i, xmax_j) - np.maximum(xmin_i, xmin_j), f32(0))
         inter = ih * iw
-        return inter / (area_i + area_j - inter)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            v = inter / (area_i + area_j - inter)
+        return np.where((area_i <= 0) | (area_j <= 0), f32(0), v)
 
     def non_max_suppression(boxes, scores, max_output_size, iou_threshold=0.5, score_threshold=float("-inf"), **k):
         """Greedy hard NMS: candidates by (score desc, index asc); kept iff IoU with every kept box is not > thr."""
@@ -189,7 +192,7 @@ def make_numpy_tf():
         for i in order:
             if len(keep) >= int(max_output_size):
                 break
-            if all(not (iou(boxes, i, j) > thr) for j in reversed(keep)):
+            if not keep or not np.any(iou_many(boxes, i, np.asarray(keep)) > thr):
                 keep.append(i)
         return _t(np.asarray(keep, np.int32))
 
@@ -217,8 +220,8 @@ def make_numpy_tf():
             y1, x1, y2, x2 = boxes[n]
             oky, ylo, yhi, ly = taps(y1, y2, H, ph)
             okx, xlo, xhi, lx = taps(x1, x2, W, pw)
-            tl, tr = img[ylo][:, xlo], img[ylo][:, xhi]
-            bl, br = img[yhi][:, xlo], img[yhi][:, xhi]
+            tl, tr = img[ylo[:, None], xlo[None, :]], img[ylo[:, None], xhi[None, :]]
+            bl, br = img[yhi[:, None], xlo[None, :]], img[yhi[:, None], xhi[None, :]]
             lxb, lyb = lx[None, :, None], ly[:, None, None]
             top = tl + (tr - tl) * lxb
             bot = bl + (br - bl) * lxb
@@ -442,6 +445,63 @@ def build_targets():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def digest(a):
+    a = np.ascontiguousarray(a)
+    return hashlib.sha256(a.tobytes()).hexdigest()
+
+
+def full_size_inputs(batch=2):
+    """Config 2 of BASELINE.json at full size (1024^2, A = 261 888, 81 classes, C = 256), `batch` images: regenerated
+    from seeds wherever needed (the GPU test rebuilds the same arrays), never stored."""
+    from maskrcnn_tf2_b200 import synth
+    return synth.inference_batch(2, batch, img_size=1024, num_classes=81, regime="clustered", n_rois=1000, channels=256)
+
+
+def run_full_size(L, x):
+    """The inference ROI stage of model.py:556-573 through the reference's own layers at COCO shape."""
+    B = x["rpn_probs"].shape[0]
+    sd = np.array([0.1, 0.1, 0.2, 0.2], dtype="float32")
+    cfg = {"rpn_nms_threshold": 0.7, "pre_nms_limit": 6000, "images_per_gpu": B, "rpn_bbox_std_dev": sd,
+           "bbox_std_dev": sd}
+    t = lambda a: np.asarray(a).view(T)
+    fm = [t(f) for f in x["feature_maps"]]
+    meta = t(x["image_meta"].astype(f32))
+    rois = np.asarray(L.ProposalLayer(proposal_count=1000, config=cfg)([t(x["rpn_probs"]), t(x["rpn_bbox"]),
+                                                                       t(x["anchors"])]))
+    pooled = np.asarray(L.PyramidROIAlign([7, 7], name="roi_align_classifier")([t(rois), meta] + fm))
+    det = np.asarray(L.DetectionLayer(proposals=1000, detection_min_confidence=0.7, detection_max_instances=100,
+                                      detection_nms_threshold=0.3, bbox_std_dev=sd, images_per_gpu=B, batch_size=B)(
+        [t(rois), t(x["mrcnn_class"]), t(x["mrcnn_bbox"]), meta]))
+    mask_pooled = np.asarray(L.PyramidROIAlign([14, 14], name="roi_align_mask")(
+        [t(np.ascontiguousarray(det[..., :4])), meta] + fm))
+    return dict(rois=rois, pooled=pooled, detections=det, mask_pooled=mask_pooled)
+
+
+def build_full_size():
+    """SHA-256 of the reference layers' outputs at BASELINE.json's full sizes (the arrays themselves are 120 MB)."""
+    import json
+    import time
+    L = load_reference_layers()
+    x = full_size_inputs()
+    t0 = time.time()
+    out = run_full_size(L, x)
+    kept = [int(out["rois"][b].any(-1).sum()) for b in range(out["rois"].shape[0])]
+    dets = [int((out["detections"][b, :, 4] > 0).sum()) for b in range(out["rois"].shape[0])]
+    rec = {"inputs": "synth.inference_batch(2, 2, img_size=1024, num_classes=81, regime='clustered', n_rois=1000, "
+                     "channels=256)",
+           "input_sha256": {k: digest(x[k]) for k in ("rpn_probs", "rpn_bbox", "anchors", "mrcnn_class", "mrcnn_bbox",
+                                                      "image_meta")},
+           "fmap_sha256": [digest(f) for f in x["feature_maps"]],
+           "proposals_kept": kept, "detections": dets,
+           "shape": {k: list(v.shape) for k, v in out.items()},
+           "sha256": {k: digest(v.astype(f32)) for k, v in out.items()}}
+    path = os.path.join(HERE, "reference_layers_full_size_sha256.json")
+    with open(path, "w") as f:
+        json.dump(rec, f, indent=1)
+    print(f"full size: reference layers took {time.time() - t0:.1f} s; kept {kept}, detections {dets}; wrote {path}")
+
+
 if __name__ == "__main__":
     build()
     build_targets()
+    build_full_size()

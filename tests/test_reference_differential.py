@@ -128,3 +128,14 @@ def test_anchors_layer_live_against_the_reference(ref, S):
     want = synth.pyramid_anchors(S)
     assert got.dtype == np.float32 and got.shape == (2,) + want.shape
     assert np.array_equal(got[0], want) and np.array_equal(got[1], want)
+
+
+def test_full_size_digests_are_what_the_reference_layers_produce_now(ref):
+    """Regenerates the COCO-shape run of the reference's layers live and compares with the committed digests (guards the
+    committed JSON against drift of the generator or of numpy)."""
+    import json
+    gen, L = ref
+    rec = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                      "reference_layers_full_size_sha256.json")))
+    out = gen.run_full_size(L, gen.full_size_inputs())
+    assert {k: gen.digest(v.astype(np.float32)) for k, v in out.items()} == rec["sha256"]

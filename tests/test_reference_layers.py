@@ -157,3 +157,58 @@ def test_stand_in_kernels_agree_with_the_oracle_bit_for_bit(orc, numpy_tf, seed)
     for crop in ((7, 7), (1, 1), (2, 5), (14, 3)):
         assert np.array_equal(np.asarray(tf.image.crop_and_resize(img, cb, ind, crop)),
                               orc.crop_and_resize(img, cb, ind, crop)), (H, W, crop)
+
+
+# ---- BASELINE.json's full sizes: SHA-256 of the reference layers' outputs at COCO shape ---------------------------
+def _sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def full_size():
+    import json
+    from maskrcnn_tf2_b200 import synth
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_layers_full_size_sha256.json")
+    rec = json.load(open(path))
+    x = synth.inference_batch(2, 2, img_size=1024, num_classes=81, regime="clustered", n_rois=1000, channels=256)
+    for k, want in rec["input_sha256"].items():          # the inputs are regenerated from seeds, not stored
+        assert _sha(x[k]) == want, f"synthetic input {k} is not the array the digests were made from"
+    assert [_sha(f) for f in x["feature_maps"]] == rec["fmap_sha256"]
+    return rec, x
+
+
+def test_oracle_reproduces_the_reference_layers_at_coco_shape(orc, full_size):
+    """1024^2, A = 261 888 -> top-6000 -> NMS 0.7 -> 1000 proposals -> ROIAlign 7x7 over 256-channel maps -> 81-class
+    DetectionLayer -> ROIAlign 14x14: digests of the reference's own layer code (make_reference_layers_golden.py)."""
+    rec, x = full_size
+    r = orc.proposal_layer(x["rpn_probs"], x["rpn_bbox"], x["anchors"], 6000, 1000, SD, 0.7)
+    assert _sha(r["proposals"]) == rec["sha256"]["rois"]
+    pooled = orc.pyramid_roi_align(r["proposals"], 1024.0, 1024.0, x["feature_maps"], (7, 7))["out"]
+    assert _sha(pooled) == rec["sha256"]["pooled"]
+    det = orc.detection_layer(r["proposals"], x["mrcnn_class"], x["mrcnn_bbox"], x["image_meta"], SD, 0.7, 100, 0.3)
+    assert _sha(det["detections"]) == rec["sha256"]["detections"] and list(det["count"]) == rec["detections"]
+    mask = orc.pyramid_roi_align(np.ascontiguousarray(det["detections"][..., :4]), 1024.0, 1024.0, x["feature_maps"],
+                                 (14, 14))["out"]
+    assert _sha(mask) == rec["sha256"]["mask_pooled"]
+
+
+@pytest.mark.gpu
+def test_cuda_layers_reproduce_the_reference_layers_at_coco_shape(full_size, dev):
+    from maskrcnn_tf2_b200 import make_config
+    from maskrcnn_tf2_b200.layers import DetectionLayer, ProposalLayer, PyramidROIAlign
+    rec, x = full_size
+    B = 2
+    cfg = make_config(img_size=1024, num_classes=81, batch_size=B)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    fm = [t(f) for f in x["feature_maps"]]
+    meta = t(x["image_meta"])
+    rois = ProposalLayer(1000, cfg)([t(x["rpn_probs"]), t(x["rpn_bbox"]), t(x["anchors"])])
+    assert _sha(rois.cpu().numpy()) == rec["sha256"]["rois"]
+    pooled = PyramidROIAlign([7, 7], name="roi_align_classifier")([rois, meta] + fm)
+    assert _sha(pooled.cpu().numpy()) == rec["sha256"]["pooled"]
+    det = DetectionLayer(1000, 0.7, 100, 0.3, cfg["bbox_std_dev"], B, B)([rois, t(x["mrcnn_class"]), t(x["mrcnn_bbox"]),
+                                                                          meta])
+    assert _sha(det.cpu().numpy()) == rec["sha256"]["detections"]
+    mask = PyramidROIAlign([14, 14], name="roi_align_mask")([det[..., :4].contiguous(), meta] + fm)
+    assert _sha(mask.cpu().numpy()) == rec["sha256"]["mask_pooled"]
