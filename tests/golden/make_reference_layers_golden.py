@@ -501,7 +501,56 @@ def build_full_size():
     print(f"full size: reference layers took {time.time() - t0:.1f} s; kept {kept}, detections {dets}; wrote {path}")
 
 
+def training_inputs():
+    """The training-step case of tests/test_gpu_configs.py (config 3 of BASELINE.json at 512^2, two images): 2000
+    proposals per image, 100 GT slots with 20 real instances and full-size masks, 200 target ROIs."""
+    from maskrcnn_tf2_b200 import synth
+    x = synth.inference_batch(3, 2, img_size=512, regime="clustered")
+    g = synth.training_targets_batch(3, 2, img_size=512)
+    keys = np.random.default_rng(7).integers(0, 2 ** 32, (2, 2000), dtype=np.uint64).astype(np.uint32)
+    return x, g, keys
+
+
+def run_training(L, x, g, keys):
+    B = 2
+    sd = np.array([0.1, 0.1, 0.2, 0.2], dtype="float32")
+    cfg = {"rpn_nms_threshold": 0.7, "pre_nms_limit": 6000, "images_per_gpu": B, "rpn_bbox_std_dev": sd,
+           "bbox_std_dev": sd, "train_rois_per_image": 200, "roi_positive_ratio": 0.33, "use_mini_masks": False,
+           "mask_shape": (28, 28)}
+    t = lambda a: np.asarray(a).view(T)
+    props = np.asarray(L.ProposalLayer(proposal_count=2000, config=cfg)([t(x["rpn_probs"]), t(x["rpn_bbox"]),
+                                                                        t(x["anchors"])]))
+    SHUFFLE["calls"] = 0
+    SHUFFLE["per_image"] = [(keys[b], np.flatnonzero(np.abs(props[b]).sum(1) != 0)) for b in range(B)]
+    rois, cls, deltas, masks = L.DetectionTargetLayer(cfg)([t(props), t(g["gt_class_ids"]), t(g["gt_boxes"]),
+                                                            t(g["gt_masks"].astype(bool))])
+    return dict(proposals=props, rois=np.asarray(rois, f32), class_ids=np.asarray(cls).astype(np.int32),
+                deltas=np.asarray(deltas, f32), masks=np.asarray(masks, f32))
+
+
+def build_full_size_training():
+    import json
+    L = load_reference_layers()
+    x, g, keys = training_inputs()
+    out = run_training(L, x, g, keys)
+    path = os.path.join(HERE, "reference_layers_full_size_sha256.json")
+    rec = json.load(open(path))
+    rec["training"] = {
+        "inputs": "synth.inference_batch(3, 2, img_size=512, regime='clustered'); synth.training_targets_batch(3, 2, "
+                  "img_size=512); keys = default_rng(7).integers(0, 2**32, (2, 2000), uint64).astype(uint32)",
+        "input_sha256": {"rpn_probs": digest(x["rpn_probs"]), "rpn_bbox": digest(x["rpn_bbox"]),
+                         "gt_class_ids": digest(g["gt_class_ids"]), "gt_boxes": digest(g["gt_boxes"]),
+                         "gt_masks": digest(g["gt_masks"]), "keys": digest(keys)},
+        "positives": [int((out["class_ids"][b] != 0).sum()) for b in range(2)],
+        "rois_per_image": [int(out["rois"][b].any(-1).sum()) for b in range(2)],
+        "sha256": {k: digest(v) for k, v in out.items()}}
+    with open(path, "w") as f:
+        json.dump(rec, f, indent=1)
+    print("training case:", rec["training"]["positives"], rec["training"]["rois_per_image"], "-> added to", path)
+
+
 if __name__ == "__main__":
     build()
     build_targets()
     build_full_size()
+    build_full_size_training()

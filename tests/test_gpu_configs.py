@@ -89,6 +89,17 @@ def test_config2_training_step_targets_then_roialign_forward_backward(orc, dev):
                                                    (28, 28))
     for got, name in [(rois, "rois"), (cls, "class_ids"), (dl, "deltas"), (mk, "masks")]:
         assert np.array_equal(N(got), ref_t[name])
+    # ... and these are the outputs of the reference's OWN ProposalLayer / DetectionTargetLayer code on these inputs
+    # (digests written by tests/golden/make_reference_layers_golden.py; the oracle side of this is also a CPU test)
+    import hashlib
+    import json
+    import os
+    rec = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                      "reference_layers_full_size_sha256.json")))["training"]["sha256"]
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    assert sha(N(prop)) == rec["proposals"]
+    for got, name in [(rois, "rois"), (cls, "class_ids"), (dl, "deltas"), (mk, "masks")]:
+        assert sha(N(got)) == rec[name], name
     fm = [T(f, dev) for f in x["feature_maps"]]
     shapes = [tuple(f.shape) for f in x["feature_maps"]]
     meta = T(x["image_meta"], dev)

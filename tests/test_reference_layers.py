@@ -212,3 +212,31 @@ def test_cuda_layers_reproduce_the_reference_layers_at_coco_shape(full_size, dev
     assert _sha(det.cpu().numpy()) == rec["sha256"]["detections"]
     mask = PyramidROIAlign([14, 14], name="roi_align_mask")([det[..., :4].contiguous(), meta] + fm)
     assert _sha(mask.cpu().numpy()) == rec["sha256"]["mask_pooled"]
+
+
+def _training_case():
+    import json
+    from maskrcnn_tf2_b200 import synth
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_layers_full_size_sha256.json")
+    rec = json.load(open(path))["training"]
+    x = synth.inference_batch(3, 2, img_size=512, regime="clustered")
+    g = synth.training_targets_batch(3, 2, img_size=512)
+    keys = np.random.default_rng(7).integers(0, 2 ** 32, (2, 2000), dtype=np.uint64).astype(np.uint32)
+    have = {"rpn_probs": x["rpn_probs"], "rpn_bbox": x["rpn_bbox"], "gt_class_ids": g["gt_class_ids"],
+            "gt_boxes": g["gt_boxes"], "gt_masks": g["gt_masks"], "keys": keys}
+    for k, want in rec["input_sha256"].items():
+        assert _sha(have[k]) == want, f"synthetic input {k} is not the array the digests were made from"
+    return rec, x, g, keys
+
+
+def test_oracle_reproduces_the_reference_training_step_at_config3_shape(orc):
+    """ProposalLayer(2000) -> DetectionTargetLayer(T=200, full-size 512^2 masks, 100 GT slots) of the reference's own code
+    on the inputs of tests/test_gpu_configs.py::test_config2_training_step_*: that GPU test holds the CUDA path equal
+    to the oracle on exactly these arrays, so CUDA == oracle == reference code."""
+    rec, x, g, keys = _training_case()
+    props = orc.proposal_layer(x["rpn_probs"], x["rpn_bbox"], x["anchors"], 6000, 2000, SD, 0.7)["proposals"]
+    assert _sha(props) == rec["sha256"]["proposals"]
+    r = orc.detection_target_layer(props, g["gt_class_ids"], g["gt_boxes"], g["gt_masks"], keys, 200, 0.33, SD, (28, 28))
+    for k in ("rois", "class_ids", "deltas", "masks"):
+        assert _sha(r[k]) == rec["sha256"][k], k
+    assert [int(c) for c in r["counts"][:, 0]] == rec["positives"] == [66, 66]
