@@ -10,7 +10,6 @@ tf_shim/mrcnn_roi_ops.cc through tests/tf_stub (tf_stub.StubOp).  TEST INFRASTRU
 import contextlib
 import importlib.util
 import os
-import re
 import sys
 import types
 
@@ -170,7 +169,3 @@ class FakeOp:
 
     def get_attr(self, name):
         return self._attrs[name]
-
-
-def camel_ops(source=None):
-    return set(re.findall(r"_ops\.(mrcnn_\w+)\(", source or open(PY_SHIM).read()))
