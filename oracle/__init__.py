@@ -1,8 +1,11 @@
 """numpy-facing wrapper around the C oracle (oracle/mrcnn_oracle.c).
 
 TEST INFRASTRUCTURE ONLY -- see the header of mrcnn_oracle.c.  Only tests/, __graft_entry__.smoke() and
-bench.py's cpu_baseline / --impl reference legs may import this package.  PARITY UNPINNED: the reference
-holds no golden vectors for this path; the oracle is pinned by tests/test_oracle_*.py instead.
+bench.py's cpu_baseline / --impl reference legs may import this package.  PARITY: the reference holds no golden
+vectors for this path.  The layer-level restatement is pinned by outputs of the reference's own layer code executed on a
+numpy stand-in for tf.* (tests/test_reference_layers.py, test_reference_differential.py, test_reference_gradients.py);
+the bodies of the TensorFlow kernels (top_k, non_max_suppression, crop_and_resize) remain PARITY UNPINNED by TensorFlow
+itself and are pinned by known answers, properties and independent implementations (tests/test_oracle_*.py).
 """
 import ctypes
 import os
