@@ -56,6 +56,8 @@ def test_inference_layers_live_against_the_reference(orc, ref, seed):
     meta = synth.image_meta(B, S, NC).astype(np.float32)
     if seed % 3 == 0:
         meta[:, 7:11] = [3, 5, S - 9, S - 2]
+    if seed % 2 and B > 1:                                  # Q6: only image 0's shape is used (L:514-515, L:600)
+        meta[1:, 4:6] = [S // 2, 2 * S]
     fm = [rng.standard_normal((B, max(S // s, 1), max(S // s, 1), C)).astype(np.float32) for s in (4, 8, 16, 32)]
     boxes = rois.copy()
     boxes[:, ::5] = np.stack([random_boxes(rng, boxes[:, ::5].shape[1], min_size=0.02, max_size=0.9) for _ in range(B)])
