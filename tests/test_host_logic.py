@@ -177,3 +177,23 @@ def test_bench_reference_arm_prints_one_contract_line_and_only_on_rank_zero():
     other = subprocess.run(cmd + ["--gpus", "2"], env=dict(env, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2"),
                            capture_output=True, text=True, timeout=300)
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_bench_algorithmic_bytes_match_the_survey_figures():
+    """ROIAlign forward = output written once + min(4 x output, all map pixels) + boxes, per image."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert round(bench.algorithmic_bytes(1024, 1000, 7, 7) / 1e6, 2) == 139.32      # 7x7, N=1000
+    assert round(bench.algorithmic_bytes(1024, 100, 14, 14) / 1e6, 2) == 100.35     # 14x14, N=100
+    assert round(bench.algorithmic_bytes(512, 1000, 7, 7) / 1e6, 2) == 72.47
+    assert round(bench.algorithmic_bytes(256, 100, 14, 14) / 1e6, 2) == 25.64
+    # the tight count the roofline uses never exceeds the closed form
+    import numpy as np
+    boxes = np.array([[[0.1, 0.1, 0.2, 0.2], [0.0, 0.0, 1.0, 1.0]]], np.float32)
+    roi_map = np.array([[0, 3]], np.int32)
+    touched = bench.touched_map_bytes(boxes, roi_map, 1024, 7, 7)
+    assert 0 < touched <= 2 * 4 * 7 * 7 * 256 * 4
