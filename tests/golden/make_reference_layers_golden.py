@@ -549,8 +549,107 @@ def build_full_size_training():
     print("training case:", rec["training"]["positives"], rec["training"]["rois_per_image"], "-> added to", path)
 
 
+def training_full_inputs(mini):
+    """Config 3 of BASELINE.json at FULL size: 1024^2, 8 images, 2000 proposals per image into DetectionTargetLayer
+    (T = 200, 100 GT slots with 20 real instances; full-size 1024^2 masks, or 32x32 mini-masks)."""
+    from maskrcnn_tf2_b200 import synth
+    B = 8
+    x = synth.inference_batch(3, B, img_size=1024, regime="clustered")
+    g = synth.training_targets_batch(3, B, img_size=1024, mini_mask=(32, 32) if mini else None)
+    keys = np.random.default_rng(9).integers(0, 2 ** 32, (B, 2000), dtype=np.uint64).astype(np.uint32)
+    return x, g, keys
+
+
+def run_training_full(L, x, g, keys, mini, props=None):
+    """ProposalLayer(2000) -> DetectionTargetLayer -> PyramidROIAlign 7x7 and 14x14 on the target ROIs (model.py:502-504,
+    mrcnn_layers.py:1145,1215), all through the reference's own layer code."""
+    B = x["rpn_probs"].shape[0]
+    sd = np.array([0.1, 0.1, 0.2, 0.2], dtype="float32")
+    cfg = {"rpn_nms_threshold": 0.7, "pre_nms_limit": 6000, "images_per_gpu": B, "rpn_bbox_std_dev": sd,
+           "bbox_std_dev": sd, "train_rois_per_image": 200, "roi_positive_ratio": 0.33, "use_mini_masks": bool(mini),
+           "mask_shape": (28, 28)}
+    t = lambda a: np.asarray(a).view(T)
+    if props is None:
+        props = np.asarray(L.ProposalLayer(proposal_count=2000, config=cfg)([t(x["rpn_probs"]), t(x["rpn_bbox"]),
+                                                                            t(x["anchors"])]))
+    SHUFFLE["calls"] = 0
+    SHUFFLE["per_image"] = [(keys[b], np.flatnonzero(np.abs(props[b]).sum(1) != 0)) for b in range(B)]
+    rois, cls, deltas, masks = L.DetectionTargetLayer(cfg)([t(props), t(g["gt_class_ids"]), t(g["gt_boxes"]),
+                                                            t(g["gt_masks"].astype(bool))])
+    out = dict(proposals=props, rois=np.asarray(rois, f32), class_ids=np.asarray(cls).astype(np.int32),
+               deltas=np.asarray(deltas, f32), masks=np.asarray(masks, f32))
+    if not mini:
+        fm = [t(f) for f in x["feature_maps"]]
+        meta = t(x["image_meta"].astype(f32))
+        out["pooled7"] = np.asarray(L.PyramidROIAlign([7, 7], name="roi_align_classifier")([t(out["rois"]), meta] + fm), f32)
+        out["pooled14"] = np.asarray(L.PyramidROIAlign([14, 14], name="roi_align_mask")([t(out["rois"]), meta] + fm), f32)
+    return out
+
+
+def build_full_size_training_config3():
+    """SHA-256 of the reference layers' outputs for config 3 at full size (and its mini-mask variant)."""
+    import json
+    import time
+    L = load_reference_layers()
+    path = os.path.join(HERE, "reference_layers_full_size_sha256.json")
+    rec = json.load(open(path))
+    props = None
+    for mini in (False, True):
+        t0 = time.time()
+        x, g, keys = training_full_inputs(mini)
+        out = run_training_full(L, x, g, keys, mini, props)
+        props = out["proposals"]
+        B = props.shape[0]
+        rec["training_full_mini" if mini else "training_full"] = {
+            "inputs": "synth.inference_batch(3, 8, img_size=1024, regime='clustered'); synth.training_targets_batch(3, 8, "
+                      "img_size=1024, mini_mask=%s); keys = default_rng(9).integers(0, 2**32, (8, 2000), uint64)"
+                      ".astype(uint32)" % ("(32, 32)" if mini else "None"),
+            "input_sha256": {"rpn_probs": digest(x["rpn_probs"]), "rpn_bbox": digest(x["rpn_bbox"]),
+                             "gt_class_ids": digest(g["gt_class_ids"]), "gt_boxes": digest(g["gt_boxes"]),
+                             "gt_masks": digest(g["gt_masks"]), "keys": digest(keys)},
+            "positives": [int((out["class_ids"][b] != 0).sum()) for b in range(B)],
+            "rois_per_image": [int(out["rois"][b].any(-1).sum()) for b in range(B)],
+            "proposals_kept": [int(props[b].any(-1).sum()) for b in range(B)],
+            "sha256": {k: digest(v) for k, v in out.items()}}
+        print("config 3 full size, mini =", mini, rec["training_full_mini" if mini else "training_full"]["positives"],
+              f"{time.time() - t0:.1f} s")
+    with open(path, "w") as f:
+        json.dump(rec, f, indent=1)
+
+
+def build_full_size_config5():
+    """Config 5 of BASELINE.json: the batch-64 COCO-shape inference stage in the reference's own first-appearance mode
+    (Q2) -- digests for the whole batch on one replica AND for each 32 / 16 / 8-image shard run as its own batch (what
+    a 2 / 4 / 8-GPU split computes; the Q2 table is local to a replica).  Feature maps of 64 images are
+    5.7 GB, so ROIAlign outputs are hashed image by image from per-shard runs."""
+    import json
+    import time
+    from maskrcnn_tf2_b200 import synth
+    L = load_reference_layers()
+    path = os.path.join(HERE, "reference_layers_full_size_sha256.json")
+    rec = json.load(open(path))
+    out = {"inputs": "synth.inference_batch(5, n, img_size=1024, num_classes=81, regime='clustered', first_image=lo) "
+                     "for every shard [lo, lo+n) of 64 images, n in (64, 32, 16, 8)", "shards": {}}
+    t0 = time.time()
+    for n in (64, 32, 16, 8):
+        for lo in range(0, 64, n):
+            if n < 64 and lo >= 2 * n:          # two shards per split size pin the property; all of them take minutes
+                continue
+            x = synth.inference_batch(5, n, img_size=1024, num_classes=81, regime="clustered", first_image=lo)
+            o = run_full_size(L, x)
+            out["shards"][f"{lo}+{n}"] = {k: digest(v.astype(f32)) for k, v in o.items()}
+            print("config 5 shard", lo, n, f"{time.time() - t0:.0f} s", flush=True)
+            del x, o
+    rec["config5"] = out
+    with open(path, "w") as f:
+        json.dump(rec, f, indent=1)
+
+
+
 if __name__ == "__main__":
     build()
     build_targets()
     build_full_size()
     build_full_size_training()
+    build_full_size_training_config3()
+    build_full_size_config5()

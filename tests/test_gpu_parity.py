@@ -193,7 +193,13 @@ def test_proposal_layer_backward_bit_exact_and_autograd(F, orc, dev):
     ref_grad = orc.proposal_layer_grad(g, bbox, anchors, ref["topk_idx"], ref["keep_idx"], SD)
     got = F.proposal_backward(T(g, dev), T(bbox, dev), T(anchors, dev), T(ref["topk_idx"], dev), T(ref["keep_idx"], dev), SD)
     assert np.array_equal(N(got), ref_grad)                       # same fp32 operation order: bit-exact
-    assert (np.abs(ref_grad).sum(-1) > 0).sum() == ref["keep_count"].sum() or True
+    # gradient lands only on the anchors behind the kept proposals (Q7), one row each (a row can still be all zero:
+    # the clip passes no gradient where a decoded coordinate left [0, 1])
+    touched = np.zeros(ref_grad.shape[:2], bool)
+    for b in range(ref_grad.shape[0]):
+        k = ref["keep_idx"][b][ref["keep_idx"][b] >= 0]
+        touched[b, ref["topk_idx"][b][k]] = True
+    assert not np.abs(ref_grad[~touched]).any() and touched.sum() == ref["keep_count"].sum()
     # through the layer API (torch autograd): gradient reaches rpn_bbox only
     tb = T(bbox, dev).requires_grad_(True)
     tp = T(probs, dev).requires_grad_(True)
@@ -320,9 +326,11 @@ def test_roialign_backward_deterministic_bit_exact_at_training_shape(F, orc, dev
     for l in range(4):
         assert torch.equal(a[l], b[l])                       # run-to-run reproducible
         assert np.array_equal(N(a[l]), ref[l])               # and equal to the sequential accumulation, bit for bit
-    # the atomic mode agrees within the north-star tolerance only
+    # the atomic mode (unordered fp32 sums) agrees within the north-star tolerance, 1e-5 relative / 1e-6 absolute, the
+    # relative part taken against the accumulated magnitude sum |w g| -- the error bound of an unordered sum
     c = F.roialign_backward(T(g, dev), T(boxes, dev), roi_map, shapes, deterministic=False)
-    assert all(np.allclose(N(c[l]), ref[l], rtol=1e-5, atol=1e-5) for l in range(4))
+    mag = orc.pyramid_roi_align_grad(np.abs(g), boxes, 1024.0, 1024.0, shapes)
+    assert all(np.all(np.abs(N(c[l]) - ref[l]) <= ATOL + RTOL * np.maximum(np.abs(ref[l]), mag[l])) for l in range(4))
 
 
 def test_roialign_adjoint_property_full_size(F, dev):
