@@ -240,3 +240,50 @@ def test_oracle_reproduces_the_reference_training_step_at_config3_shape(orc):
     for k in ("rois", "class_ids", "deltas", "masks"):
         assert _sha(r[k]) == rec["sha256"][k], k
     assert [int(c) for c in r["counts"][:, 0]] == rec["positives"] == [66, 66]
+
+
+@pytest.mark.parametrize("mini", [False, True])
+def test_oracle_reproduces_the_reference_training_step_at_full_config3_size(orc, mini):
+    """BASELINE.json configs[2] at FULL size (1024^2, 8 images, 2000 proposals, T = 200, full 1024^2 masks / 32x32
+    mini-masks) + PyramidROIAlign 7x7 and 14x14 on the target ROIs: digests of the reference's own layer code.  The GPU
+    twin is tests/test_gpu_full_size.py::test_config3_full_size_training_step."""
+    import json
+    from maskrcnn_tf2_b200 import synth
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_layers_full_size_sha256.json")
+    rec = json.load(open(path))["training_full_mini" if mini else "training_full"]
+    B = 8
+    x = synth.inference_batch(3, B, img_size=1024, regime="clustered")
+    g = synth.training_targets_batch(3, B, img_size=1024, mini_mask=(32, 32) if mini else None)
+    keys = np.random.default_rng(9).integers(0, 2 ** 32, (B, 2000), dtype=np.uint64).astype(np.uint32)
+    have = {"rpn_probs": x["rpn_probs"], "rpn_bbox": x["rpn_bbox"], "gt_class_ids": g["gt_class_ids"],
+            "gt_boxes": g["gt_boxes"], "gt_masks": g["gt_masks"], "keys": keys}
+    for k, want in rec["input_sha256"].items():
+        assert _sha(have[k]) == want, k
+    props = orc.proposal_layer(x["rpn_probs"], x["rpn_bbox"], x["anchors"], 6000, 2000, SD, 0.7)["proposals"]
+    assert _sha(props) == rec["sha256"]["proposals"]
+    r = orc.detection_target_layer(props, g["gt_class_ids"], g["gt_boxes"], g["gt_masks"], keys, 200, 0.33, SD, (28, 28),
+                                   use_mini_masks=mini)
+    for k in ("rois", "class_ids", "deltas", "masks"):
+        assert _sha(r[k]) == rec["sha256"][k], k
+    if not mini:
+        for pool, name in (((7, 7), "pooled7"), ((14, 14), "pooled14")):
+            out = orc.pyramid_roi_align(r["rois"], 1024.0, 1024.0, x["feature_maps"], pool)["out"]
+            assert _sha(out) == rec["sha256"][name], name
+
+
+def test_oracle_reproduces_the_reference_layers_on_a_config5_shard(orc):
+    """BASELINE.json configs[4]: the 8-image shard an 8-GPU split of the batch of 64 gives rank 1 (images 8..15), in the
+    reference's first-appearance map mode; digests of the reference's own layer code.  All shard sizes run on the GPU
+    (tests/test_gpu_full_size.py::test_config5_*)."""
+    import json
+    from maskrcnn_tf2_b200 import synth
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_layers_full_size_sha256.json")
+    rec = json.load(open(path))["config5"]["shards"]["8+8"]
+    x = synth.inference_batch(5, 8, img_size=1024, num_classes=81, regime="clustered", first_image=8)
+    r = orc.proposal_layer(x["rpn_probs"], x["rpn_bbox"], x["anchors"], 6000, 1000, SD, 0.7)["proposals"]
+    assert _sha(r) == rec["rois"]
+    assert _sha(orc.pyramid_roi_align(r, 1024.0, 1024.0, x["feature_maps"], (7, 7))["out"]) == rec["pooled"]
+    d = orc.detection_layer(r, x["mrcnn_class"], x["mrcnn_bbox"], x["image_meta"], SD, 0.7, 100, 0.3)["detections"]
+    assert _sha(d) == rec["detections"]
+    m = orc.pyramid_roi_align(np.ascontiguousarray(d[..., :4]), 1024.0, 1024.0, x["feature_maps"], (14, 14))["out"]
+    assert _sha(m) == rec["mask_pooled"]
