@@ -23,6 +23,44 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 // ---------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the hot path is launched with the programmatic-stream-
+// serialization attribute and (a) calls pdl_launch_dependents() first -- the next kernel of the stream may start
+// being scheduled as soon as every CTA of this grid is resident -- and (b) calls pdl_wait() before its first access
+// to global memory: that blocks until the preceding grid has completed and its writes are visible.  Because every
+// kernel waits on ALL paths, completion is transitive along the stream (kernel N done => N-1 done), so a kernel
+// may also safely overwrite buffers an earlier kernel read.  What overlaps is launch latency, CTA scheduling and
+// the shared-memory / barrier set-up of kernel N+1 with the tail of kernel N.  MRCNN_PDL=0 disables the attribute
+// (the device-side calls are then no-ops); a launch behind a memset or a foreign kernel degrades to a plain launch.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__attribute__((visibility("hidden"))) bool pdl_enabled();   // api.cu: getenv("MRCNN_PDL") != "0", read once
+
+// fills `attr[0]` with the PDL attribute when enabled; returns the number of attributes written
+static inline int pdl_attr(cudaLaunchAttribute* attr) {
+    if (!pdl_enabled()) return 0;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    return 1;
+}
+
+// kernel<<<grid, block, smem, stream>>>(args...) with the PDL attribute
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    cfg.numAttrs = (unsigned)pdl_attr(attr);
+    cfg.attrs = attr;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // deterministic exp / log (<= 1 ulp); same operation sequence on every IEEE-754 machine
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float pow2i(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }
@@ -352,45 +390,33 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* 
     return warp_sums[warp] + incl - v;
 }
 
+// Per-device facts and occupancy queries.  The launchers keep no state that changes their results: the only
+// process-wide data are these caches of pure device queries, keyed by device ordinal (and kernel / cluster size /
+// shared-memory size) and filled under a mutex (api.cu), so concurrent first calls from several threads and several
+// GPUs per process are safe.
+struct DeviceProps {
+    int sms;          // cudaDevAttrMultiProcessorCount
+    int smem_optin;   // cudaDevAttrMaxSharedMemoryPerBlockOptin
+};
+__attribute__((visibility("hidden"))) DeviceProps device_props();   // of the current device
+// cudaOccupancyMaxActiveClusters for `kernel` at cluster size cs (threads per CTA, dynamic shared memory `smem`);
+// also raises the kernel's dynamic shared memory limit to `smem`.  Negative: the query failed.
+__attribute__((visibility("hidden"))) int max_active_clusters(const void* kernel, int threads, int cs, size_t smem);
+// static shared memory of a kernel (cudaFuncGetAttributes), cached
+__attribute__((visibility("hidden"))) size_t static_smem_bytes(const void* kernel);
+
 // Largest cluster size in {8,4,2,1} (bounded by max_cs) for which the driver can keep one cluster per image resident
-// at the same time (cudaOccupancyMaxActiveClusters >= B): a batch whose clusters do not all co-schedule runs in
-// waves and loses more than the wider clusters gain.  `cache` is a per-kernel table of pure query results (idempotent
-// writes, so unsynchronised access is harmless); smem_for(cs) gives the dynamic shared memory of a CTA at that size.
-template <typename Kernel, typename SmemFn>
-static int pick_cluster_size(Kernel kernel, int threads, int B, int max_cs, SmemFn smem_for, int (&cache)[4][2]) {
-    int best = 1;
-    for (int i = 3; i >= 0; --i) {
-        const int cs = 1 << i;
+// at the same time (max active clusters >= B): a batch whose clusters do not all co-schedule runs in waves and loses
+// more than the wider clusters gain.  smem_for(cs) gives the dynamic shared memory of a CTA at that size.
+template <typename SmemFn>
+static int pick_cluster_size(const void* kernel, int threads, int B, int max_cs, SmemFn smem_for) {
+    for (int cs = 8; cs > 1; cs >>= 1) {
         if (cs > max_cs) continue;
-        if (cs == 1) return 1;
-        const size_t smem = smem_for(cs);
-        int active = 0;
-        if (cache[i][0] == (int)smem + 1) {
-            active = cache[i][1];
-        } else {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)(cs * 64));
-            cfg.blockDim = dim3((unsigned)threads);
-            cfg.dynamicSmemBytes = smem;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = (unsigned)cs;
-            attr[0].val.clusterDim.y = 1;
-            attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-                cudaOccupancyMaxActiveClusters(&active, kernel, &cfg) != cudaSuccess) {
-                (void)cudaGetLastError();
-                active = 148 / cs;  // the old estimate: one CTA per SM
-            }
-            cache[i][1] = active;
-            cache[i][0] = (int)smem + 1;
-        }
+        int active = max_active_clusters(kernel, threads, cs, smem_for(cs));
+        if (active < 0) active = device_props().sms / cs;  // the query failed: assume one CTA per SM
         if (active >= B) return cs;
-        best = 1;
     }
-    return best;
+    return 1;
 }
 
 // ---- internal launchers shared between translation units (hidden visibility) -----------------------
@@ -416,6 +442,14 @@ __attribute__((visibility("hidden"))) int launch_nms_sorted(const float4* boxes_
                                                             int M, int max_out, float thr, const NmsEpilogue& epi,
                                                             cudaStream_t stream);
 
+// candidates in input order: the kernel orders them itself by `keys` ([B,M] order-preserving score keys, 0 = not a
+// candidate) or else by `scores` ([B,M]); only where nms_fused_applies(M, max_out) (single-CTA problems)
+__attribute__((visibility("hidden"))) bool nms_fused_applies(int M, int max_out);
+__attribute__((visibility("hidden"))) int launch_nms_unsorted(const float4* boxes, const float* scores,
+                                                              const uint32_t* keys, const int32_t* valid, int B, int M,
+                                                              int max_out, float thr, const NmsEpilogue& epi,
+                                                              cudaStream_t stream);
+
 constexpr int kMaxRpnLevels = 8;
 struct TopkDecode {              // optional fused epilogue of the top-k final kernel (ProposalLayer)
     const float4* anchors;       // [B,A]
@@ -436,9 +470,6 @@ __device__ __forceinline__ float4 topk_load_delta(const TopkDecode& dec, int b, 
     return __ldg(dec.level_deltas[l] + (size_t)b * n + (a - dec.level_start[l]));
 }
 __attribute__((visibility("hidden"))) size_t topk_ws_bytes(int B);
-__attribute__((visibility("hidden"))) int launch_topk_cluster(const float* scores, int stride, int offset, int B, int A,
-                                                              int K, int32_t* idx, float* vals, const TopkDecode* dec,
-                                                              cudaStream_t stream);
 __attribute__((visibility("hidden"))) int launch_topk(const float* scores, int stride, int offset, int B, int A, int K,
                                                       int32_t* idx, float* vals, const TopkDecode* dec, void* ws,
                                                       cudaStream_t stream);

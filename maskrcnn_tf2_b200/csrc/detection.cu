@@ -2,10 +2,12 @@
 //   detection_refine_kernel : warp per ROI -- argmax over classes (first maximum, L:385), class-specific delta
 //                             gather (L:388-393), std-dev scale + decode + clip to the image window (L:396-398,
 //                             window normalised with image 0's shape, L:513-515), keep flag (L:402-414)
-//   detection_sort_kernel   : CTA per image -- kept ROIs ordered by (score desc, ROI index asc), i.e. the
-//                             candidate order of the NMS at L:455
-//   nms.cu nms_lazy_kernel  : ONE class-agnostic NMS (quirk Q3, L:440-468) with the detection epilogue that
-//                             packs [y1,x1,y2,x2,class,score] and zero-pads (L:494-500).  The two O(n^2)
+//   nms.cu nms_lazy_kernel  : ONE class-agnostic NMS (quirk Q3, L:440-468): the kernel first orders the kept ROIs by
+//                             (score desc, ROI index asc), the candidate order of the NMS at L:455 -- only the ~15 % of
+//                             the ROIs that are candidates are sorted, in shared memory --, and ends with the detection
+//                             epilogue that packs [y1,x1,y2,x2,class,score] and zero-pads (L:494-500).
+//   detection_sort_kernel   : (N > 2048 only: the ordering as a kernel of its own in front of a cluster NMS)
+//                             The two O(n^2)
 //                             broadcast intersections (L:411-414, 475-478) and the final top_k (L:486-490) are
 //                             identities on this ordering and have no kernel.
 #include "common.cuh"
@@ -20,6 +22,8 @@ detection_refine_kernel(const float4* __restrict__ rois, const float* __restrict
     const int b = blockIdx.y;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    pdl_wait();
     if (i >= N) return;
     const float* p = probs + ((size_t)b * N + i) * NC;
     float best = __ldg(p);  // class 0 (every lane)
@@ -62,6 +66,8 @@ detection_sort_kernel(const float4* __restrict__ refined, const uint32_t* __rest
     __shared__ int s_n;
     const int b = blockIdx.x, tid = threadIdx.x;
     const int sort_n = max(32, 1 << (32 - __clz(max(N, 1) - 1)));
+    pdl_launch_dependents();
+    pdl_wait();
     if (tid == 0) s_n = 0;
     __syncthreads();
     int local = 0;
@@ -134,20 +140,12 @@ MRCNN_EXPORT int mrcnn_detection_forward(const float* rois, const float* probs, 
     w.ncand = (int32_t*)p;
 
     const float4 sd = make_float4(std_dev[0], std_dev[1], std_dev[2], std_dev[3]);
-    detection_refine_kernel<<<dim3((N + 7) / 8, B), 256, 0, st>>>((const float4*)rois, probs, (const float4*)deltas,
-                                                                  image_meta, meta_len, N, NC, sd, min_conf,
-                                                                  use_min_conf, w.refined, w.scores, w.class_ids,
-                                                                  w.keep_key);
-    const int sort_n = next_pow2(N < 32 ? 32 : N);
-    const size_t smem = (size_t)sort_n * sizeof(uint64_t) + (sort_n >= 1024 ? block_sort_xch_bytes(sort_n / 1024) : 0);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(detection_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
-    detection_sort_kernel<<<B, 1024, smem, st>>>(w.refined, w.keep_key, N, w.boxes_sorted, w.orig_idx, w.ncand);
+    cudaError_t e = launch_pdl(detection_refine_kernel, dim3((N + 7) / 8, B), dim3(256), 0, st, (const float4*)rois, probs,
+                               (const float4*)deltas, image_meta, meta_len, N, NC, sd, min_conf, use_min_conf, w.refined,
+                               w.scores, w.class_ids, w.keep_key);
+    if (e != cudaSuccess) return (int)e;
     NmsEpilogue epi{};
     epi.mode = 2;
-    epi.orig_idx = w.orig_idx;
     epi.refined = w.refined;
     epi.scores = w.scores;
     epi.class_ids = w.class_ids;
@@ -155,5 +153,17 @@ MRCNN_EXPORT int mrcnn_detection_forward(const float* rois, const float* probs, 
     epi.count = det_count;
     epi.det_boxes = (float4*)det_boxes;
     epi.N = N;
+    if (nms_fused_applies(N, max_inst))   // N <= 2048: ordering + NMS + packing in one single-CTA-per-image kernel
+        return launch_nms_unsorted(w.refined, nullptr, w.keep_key, nullptr, B, N, max_inst, nms_thr, epi, st);
+    const int sort_n = next_pow2(N < 32 ? 32 : N);
+    const size_t smem = (size_t)sort_n * sizeof(uint64_t) + (sort_n >= 1024 ? block_sort_xch_bytes(sort_n / 1024) : 0);
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(detection_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    e = launch_pdl(detection_sort_kernel, dim3(B), dim3(1024), smem, st, (const float4*)w.refined,
+                   (const uint32_t*)w.keep_key, N, w.boxes_sorted, w.orig_idx, w.ncand);
+    if (e != cudaSuccess) return (int)e;
+    epi.orig_idx = w.orig_idx;
     return launch_nms_sorted(w.boxes_sorted, w.ncand, B, N, max_inst, nms_thr, epi, st);
 }

@@ -31,53 +31,108 @@ namespace cg = cooperative_groups;
 
 namespace mrcnn {
 
+// Where the candidates come from.  Ordered input: `boxes` [B,M] is already in candidate order (ProposalLayer: the
+// top-k output) and `valid` [B] (or NULL = M) says how many rows count.  Unordered input (FUSED kernels, single-CTA
+// problems): `boxes` is in input order and the kernel orders the candidates itself, by `keys` [B,M] (order-preserving
+// score keys, 0 = not a candidate: DetectionLayer's keep set, L:402-414) or else by `scores` [B,M] (candidates:
+// score > -inf and not NaN, as NonMaxSuppressionV3).
+struct NmsInput {
+    const float4* boxes;
+    const int32_t* valid;
+    const float* scores;
+    const uint32_t* keys;
+};
+
 // COMPACT: the kept boxes are also appended, by the resolver, to dense arrays (box, thr * area) so that the far loop
 // streams them with plain strided shared-memory loads; false (shared memory too small for the copies): the far loop
 // goes through the kept index list.
-template <bool COMPACT>
+// FUSED: order the candidates in the kernel (cluster size 1 only).
+template <bool COMPACT, bool FUSED>
 __global__ void __launch_bounds__(kNmsThreads, 1)
-nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ valid, int M, int max_out, float thr,
-                int nfar, int nrow, NmsEpilogue epi) {
+nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, NmsEpilogue epi) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
     const int cap = min(max_out, M);
-    float4* sb = reinterpret_cast<float4*>(nms_smem);          // [M] min/max-normalised corners
+    // fused ordering: composites and the candidate -> row map sit in front of the NMS arrays
+    uint64_t* s_comp = reinterpret_cast<uint64_t*>(nms_smem);
+    const int sort_n_max = FUSED ? max(32, 1 << (32 - __clz(max(M, 1) - 1))) : 0;
+    int32_t* s_orig = reinterpret_cast<int32_t*>(nms_smem + (size_t)sort_n_max * 8);
+    unsigned char* body = nms_smem + (FUSED ? (size_t)sort_n_max * 8 + (((size_t)M * 4 + 15) & ~(size_t)15) : 0);
+    float4* sb = reinterpret_cast<float4*>(body);              // [M] min/max-normalised corners
     float4* kb = sb + M;                                        // [cap] kept boxes in selection order (COMPACT)
     float* sa = reinterpret_cast<float*>(kb + (COMPACT ? cap : 0));  // [M] areas
     float* kt = sa + M;                                         // [cap] thr * area of the kept boxes (COMPACT)
     int32_t* sel = reinterpret_cast<int32_t*>(kt + (COMPACT ? cap : 0));  // [cap] kept candidate positions
-    __shared__ __align__(16) unsigned long long s_rows[4][kRows];   // [tile & 3][0..63 diag rows, 64 d + i: cross_d rows]
-    __shared__ __align__(16) unsigned long long s_stage[8][kRows];  // [tile & 7] this CTA's rows on their way out: a slot is
-                                                                    // reused 8 tiles later, long after its copy was read
-    __shared__ unsigned long long s_far[4][kMaxFarSrc];         // [tile & 3][source CTA * nfar + far warp], written by the peers
-    __shared__ __align__(8) uint64_t s_bar[4];                  // mbarriers, [tile & 3]: a peer can run at most two
-                                                                // tiles ahead, so four phases never alias
-    __shared__ int s_nk[4];                                     // [tile & 3] kept count after that tile's resolve
+    __shared__ __align__(16) unsigned long long s_rows[kRing][kRows];   // [tile % kRing][0..63 diag rows, 64 d + i: cross_d rows]
+    __shared__ __align__(16) unsigned long long s_stage[kRing][kRows];  // this CTA's rows on their way out
+    __shared__ unsigned long long s_far[kRing][kMaxFarSrc];     // [tile % kRing][source CTA * nfar + far warp], written by the peers
+    __shared__ __align__(8) uint64_t s_bar[kRing];              // mbarriers, [tile % kRing] (ring depth: nms_dev.cuh)
+    __shared__ int s_nk[kRing];                                 // [tile % kRing] kept count after that tile's resolve
     __shared__ int s_final[2];
+    __shared__ int s_ncand;
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
     const int b = blockIdx.x / csize, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = valid ? min(max(valid[b], 0), M) : M;
-    const int tiles = (n + kTile - 1) / kTile;
-    const float4* bx = boxes + (size_t)b * M;
-    const float4 kNone = make_float4(1.0e18f, 1.0e18f, -1.0e18f, -1.0e18f);  // overlaps nothing, never ambiguous, no inf
-    for (int i = tid; i < n; i += kNmsThreads) {
-        float a;
-        float4 t = normalise_box(__ldg(bx + i), a);
-        if (!(a > 0.0f)) { t = kNone; a = 1.0f; }  // TF: area <= 0 -> IoU 0 with everything
-        sb[i] = t;
-        sa[i] = a;
-    }
     const uint32_t bar_base = smem_u32(&s_bar[0]);
     const int rel_threads = 32 * (1 + nfar + nrow);  // the release barrier: resolver (arrives) + far and row warps (wait)
     const int nsrc = csize * nfar;                   // far partials per tile: one per far warp of the cluster
     // per tile every CTA receives one 64-bit far partial from each far warp of the cluster and, as one bulk copy per
     // CTA, the rows of the tile's diag + cross blocks
     const uint32_t far_bytes = (uint32_t)nsrc * 8u + (uint32_t)kRows * 8u;
+    pdl_launch_dependents();
     if (tid == 0) {
-        for (int j = 0; j < 4; ++j) { mbar_init(bar_base + 8u * j, 1); s_nk[j] = 0; }
+        for (int j = 0; j < kRing; ++j) { mbar_init(bar_base + 8u * j, 1); s_nk[j] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int j = 1; j < 4; ++j) mbar_arm(bar_base + 8u * j, far_bytes);  // tiles 1..3; tile 4 is armed in tile 0
+        for (int j = 1; j < kRing; ++j) mbar_arm(bar_base + 8u * j, far_bytes);  // tiles 1..7; tile 8 is armed in tile 0
+        s_ncand = 0;
     }
+    pdl_wait();  // everything above overlaps the tail of the producing kernel; global memory is touched from here on
+    int n = in.valid ? min(max(in.valid[b], 0), M) : M;
+    const float4* bx = in.boxes + (size_t)b * M;
+    const float4 kNone = make_float4(1.0e18f, 1.0e18f, -1.0e18f, -1.0e18f);  // overlaps nothing, never ambiguous, no inf
+    if (FUSED) {
+        // candidate order = (score desc, input row asc): TF's NonMaxSuppressionV3 priority queue (L:455; L:225 via
+        // mrcnn_nms_forward).  Only the candidates are sorted (DetectionLayer: ~15 % of the ROIs).
+        __syncthreads();
+        for (int i0 = 0; i0 < n; i0 += kNmsThreads) {
+            const int i = i0 + tid;
+            uint32_t key = 0u;
+            if (i < n) {
+                if (in.keys) key = in.keys[(size_t)b * M + i];
+                else { key = score_key(__ldg(in.scores + (size_t)b * M + i)); if (key <= kKeyNegInf) key = 0u; }
+            }
+            const unsigned vote = __ballot_sync(0xffffffffu, key != 0u);
+            int base = 0;
+            if (lane == 0 && vote) base = atomicAdd(&s_ncand, __popc(vote));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (key) s_comp[base + __popc(vote & ((1u << lane) - 1u))] = make_composite(key, (uint32_t)i);
+        }
+        __syncthreads();
+        const int nc = s_ncand;
+        const int sort_n = max(32, 1 << (32 - __clz(max(nc, 1) - 1)));
+        for (int i = nc + tid; i < sort_n; i += kNmsThreads) s_comp[i] = 0ull;
+        __syncthreads();
+        block_sort_desc_any(s_comp, sort_n, reinterpret_cast<uint64_t*>(body));  // exchange buffers alias the NMS arrays
+        __syncthreads();
+        n = nc;
+        for (int r = tid; r < n; r += kNmsThreads) {
+            const int i = (int)composite_idx(s_comp[r]);
+            s_orig[r] = i;
+            float a;
+            float4 t = normalise_box(__ldg(bx + i), a);
+            if (!(a > 0.0f)) { t = kNone; a = 1.0f; }
+            sb[r] = t;
+            sa[r] = a;
+        }
+    } else {
+        for (int i = tid; i < n; i += kNmsThreads) {
+            float a;
+            float4 t = normalise_box(__ldg(bx + i), a);
+            if (!(a > 0.0f)) { t = kNone; a = 1.0f; }  // TF: area <= 0 -> IoU 0 with everything
+            sb[i] = t;
+            sa[i] = a;
+        }
+    }
+    const int tiles = (n + kTile - 1) / kTile;
     __syncthreads();
     // diag(0): rows 2*warp, 2*warp+1 of tile 0, every CTA for itself
     {
@@ -110,7 +165,8 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
         for (; t < tiles && nkept < max_out; ++t) {
             PROF_TILE;
             const int base = t * kTile;
-            const uint32_t bar_t = bar_base + 8u * (uint32_t)(t & 3);
+            const int slot = t & (kRing - 1);
+            const uint32_t bar_t = bar_base + 8u * (uint32_t)slot;
             // this lane's two candidates, for the compact kept arrays (loaded while the far set is still in flight)
             const int c0 = base + lane, c1 = c0 + 32;
             float4 mb0 = kNone, mb1 = kNone;
@@ -120,17 +176,17 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
                 if (c1 < n) { mb1 = sb[c1]; mt1 = __fmul_rn(thr, sa[c1]); }
             }
             uint64_t removed = 0;
-            if (t >= 1) {  // barrier (t & 3) serves tiles t&3, t&3 + 4, ...; tile 0 has no far / cross set
-                mbar_wait(bar_t, (uint32_t)(((t >> 2) - ((t & 3) == 0 ? 1 : 0)) & 1));
+            if (t >= 1) {  // slot j serves tiles j, j + 8, ...; tile 0 has no far / cross set
+                mbar_wait(bar_t, (uint32_t)(((t >> 3) - (slot == 0 ? 1 : 0)) & 1));
                 PROF_MARK(0);
                 uint64_t v = 0ull;
 #pragma unroll
                 for (int q = 0; q < kMaxFarSrc / 32; ++q)  // far(t): fixed trip count, predicated loads (a generic
-                    if (lane + 32 * q < nsrc) v |= (uint64_t)s_far[t & 3][lane + 32 * q];  // loop costs ~60 instructions)
+                    if (lane + 32 * q < nsrc) v |= (uint64_t)s_far[slot][lane + 32 * q];  // loop costs ~60 instructions)
 #pragma unroll
                 for (int d = 1; d < kDepth; ++d) {  // near(t) = cross_d rows of the boxes kept in tile t-d
-                    if ((kept_hist[d - 1] >> lane) & 1ull) v |= (uint64_t)s_rows[t & 3][d * kTile + lane];
-                    if ((kept_hist[d - 1] >> (lane + 32)) & 1ull) v |= (uint64_t)s_rows[t & 3][d * kTile + lane + 32];
+                    if ((kept_hist[d - 1] >> lane) & 1ull) v |= (uint64_t)s_rows[slot][d * kTile + lane];
+                    if ((kept_hist[d - 1] >> (lane + 32)) & 1ull) v |= (uint64_t)s_rows[slot][d * kTile + lane + 32];
                 }
                 removed = (uint64_t)__reduce_or_sync(0xffffffffu, (unsigned)v) |
                           ((uint64_t)__reduce_or_sync(0xffffffffu, (unsigned)(v >> 32)) << 32);
@@ -138,12 +194,12 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
             const int rem = n - base;
             const uint64_t validbits = (rem >= kTile) ? ~0ull : ((1ull << rem) - 1ull);
             uint64_t und = ~removed & validbits, kept = 0;
-            const uint64_t blk0 = (uint64_t)s_rows[t & 3][lane] & ((1ull << lane) - 1ull);  // earlier overlapping candidates
-            const uint64_t blk1 = (uint64_t)s_rows[t & 3][lane + 32] & ((1ull << (lane + 32)) - 1ull);
+            const uint64_t blk0r = (uint64_t)s_rows[slot][lane] & ((1ull << lane) - 1ull);  // earlier overlapping candidates
+            const uint64_t blk1 = (uint64_t)s_rows[slot][lane + 32] & ((1ull << (lane + 32)) - 1ull);
             while (und) {
                 const bool u0 = (und >> lane) & 1ull, u1 = (und >> (lane + 32)) & 1ull;
-                const bool d0 = u0 && (blk0 & kept), d1 = u1 && (blk1 & kept);              // removed
-                const bool k0 = u0 && !d0 && !(blk0 & und), k1 = u1 && !d1 && !(blk1 & und);  // kept
+                const bool d0 = u0 && (blk0r & kept), d1 = u1 && (blk1 & kept);              // removed
+                const bool k0 = u0 && !d0 && !(blk0r & und), k1 = u1 && !d1 && !(blk1 & und);  // kept
                 const uint64_t nk = ballot64(k0, k1), nd = ballot64(d0, d1);
                 kept |= nk;
                 und &= ~(nk | nd);
@@ -166,8 +222,8 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
             kept_hist[0] = kept;
             __syncwarp();
             if (lane == 0) {
-                s_nk[t & 3] = nkept;
-                mbar_arm(bar_t, far_bytes);  // phase of tile t+4
+                s_nk[slot] = nkept;
+                mbar_arm(bar_t, far_bytes);  // phase of tile t + kRing
             }
             __threadfence_block();
             // release the workers for tile t+kDepth (they need the kept list through tile t)
@@ -177,24 +233,58 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
     } else if (ri < nfar) {
         // ================= far warps: far(u) share, u = 1 .. tiles-1 =================
         // Kept box k of the list belongs to far warp (k mod nsrc) of the cluster.  Every far warp sends its own 64-bit
-        // partial straight to every CTA (no reduction inside the CTA on the critical path).
+        // partial straight to every CTA (no reduction inside the CTA on the critical path).  Per tile the share is
+        // tested in two instalments: the boxes this warp already knew of after the previous release (kept in tiles
+        // <= u-3) BEFORE waiting for the release of tile u, so that only the boxes kept in tile u-2 -- at most 64 for
+        // the whole cluster, one or two per far warp -- are left between the release and the send.
         const int fw = ri;  // 0..nfar-1
         const int k0 = crank * nfar + fw;
         const float inv_src = __frcp_rn((float)nsrc), cthr = __fadd_rn(1.0f, thr);
+        auto share = [&](int nk) {  // ceil((nk - k0) / nsrc), >= 0, without the integer-division sequence (operands < 2^14)
+            int cnt = 0;
+            if (nk > k0) {
+                const int x = nk - k0 + nsrc - 1;
+                cnt = (int)__fmul_rn((float)x, inv_src);
+                cnt += ((cnt + 1) * nsrc <= x) - (cnt * nsrc > x);
+            }
+            return cnt;
+        };
         PROFW_DECL;
+        int nk_known = 0;  // kept count after tile u-3 (read at the previous release)
         for (int u = 1; u < tiles; ++u) {
             const int ubase = u * kTile;
             const int c0 = ubase + lane, c1 = c0 + 32;
             const float4 b0 = (c0 < n) ? sb[c0] : kNone, b1 = (c1 < n) ? sb[c1] : kNone;
             const float a0 = (c0 < n) ? sa[c0] : 1.0f, a1 = (c1 < n) ? sa[c1] : 1.0f;
             const float tc0 = __fmul_rn(thr, a0), tc1 = __fmul_rn(thr, a1);
-            const uint32_t bar_u = bar_base + 8u * (uint32_t)(u & 3);
-            const uint32_t my_far = smem_u32(&s_far[u & 3][k0]);
+            const uint32_t bar_u = bar_base + 8u * (uint32_t)(u & (kRing - 1));
+            const uint32_t my_far = smem_u32(&s_far[u & (kRing - 1)][k0]);
+            float dmax0 = -3.0e38f, dmax1 = -3.0e38f, tkmax = 0.0f;
+            auto screen = [&](int j_begin, int j_end, int nk_lim) {  // this warp's boxes j_begin <= j < j_end of kept[0, nk_lim)
+                for (int j = j_begin; j < j_end; j += 4) {  // four kept boxes per round: independent IoU chains; a round
+                    float d0[4], d1[4];                      // that runs past the list repeats its last box (harmless)
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const int k = min(k0 + (j + qq) * nsrc, nk_lim - 1);
+                        float4 bk;
+                        float tk;
+                        if (COMPACT) { bk = kb[k]; tk = kt[k]; }
+                        else { const int ki = sel[k]; bk = sb[ki]; tk = __fmul_rn(thr, sa[ki]); }
+                        tkmax = fmaxf(tkmax, tk);
+                        d0[qq] = iou_screen_d(bk, tk, b0, tc0, cthr);
+                        d1[qq] = iou_screen_d(bk, tk, b1, tc1, cthr);
+                    }
+                    dmax0 = fmax3(fmax3(dmax0, d0[0], d0[1]), d0[2], d0[3]);
+                    dmax1 = fmax3(fmax3(dmax1, d1[0], d1[1]), d1[2], d1[3]);
+                }
+            };
             PROFW_MARK(0);
+            const int cnt_known = share(nk_known);
+            screen(0, cnt_known, nk_known);   // first instalment: no dependence on the release
             int nk = 0;  // boxes kept in tiles <= u-kDepth
             if (u >= kDepth) {
                 asm volatile("bar.sync %0, %1;" ::"r"(3 + (u % kDepth)), "r"(rel_threads) : "memory");
-                nk = s_nk[(u - kDepth) & 3];
+                nk = s_nk[(u - kDepth) & (kRing - 1)];
                 if (nk >= max_out) {
                     // the resolver stops before tile u-kDepth+1.  The row warps have already sent rows(u): complete the tile's
                     // transaction set with empty partials so that the final drain can wait for it
@@ -203,35 +293,15 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
                 }
             }
             PROFW_MARK(1);
-            // cnt = ceil((nk - k0) / nsrc) without the integer-division sequence (operands < 2^14: exact in fp32)
-            int cnt = 0;
-            if (nk > k0) {
-                const int x = nk - k0 + nsrc - 1;
-                cnt = (int)__fmul_rn((float)x, inv_src);
-                cnt += ((cnt + 1) * nsrc <= x) - (cnt * nsrc > x);
-            }
-            float dmax0 = -3.0e38f, dmax1 = -3.0e38f, tkmax = 0.0f;
-            for (int j = 0; j < cnt; j += 4) {  // four kept boxes per round: independent IoU chains; a round that runs
-                float d0[4], d1[4];             // past the list repeats its last box (harmless)
-#pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    const int k = min(k0 + (j + qq) * nsrc, nk - 1);
-                    float4 bk;
-                    float tk;
-                    if (COMPACT) { bk = kb[k]; tk = kt[k]; }
-                    else { const int ki = sel[k]; bk = sb[ki]; tk = __fmul_rn(thr, sa[ki]); }
-                    tkmax = fmaxf(tkmax, tk);
-                    d0[qq] = iou_screen_d(bk, tk, b0, tc0, cthr);
-                    d1[qq] = iou_screen_d(bk, tk, b1, tc1, cthr);
-                }
-                dmax0 = fmax3(fmax3(dmax0, d0[0], d0[1]), d0[2], d0[3]);
-                dmax1 = fmax3(fmax3(dmax1, d1[0], d1[1]), d1[2], d1[3]);
-            }
+            const int cnt = share(nk);
+            screen(cnt_known, cnt, nk);       // second instalment: the boxes kept in tile u-2
+            nk_known = nk;
             const float m0 = __fmul_rn(__fadd_rn(tkmax, tc0), kScreenBand), m1 = __fmul_rn(__fadd_rn(tkmax, tc1), kScreenBand);
             bool r0 = dmax0 > m0, r1 = dmax1 > m1;
             const bool unsure = (!r0 && dmax0 >= -m0) || (!r1 && dmax1 >= -m1);
             if (__any_sync(0xffffffffu, unsure)) {  // a pair within 2^-20 of the threshold: exact division
                 PROFW_COUNT;
+                PROF_FALLBACK;
                 r0 = false; r1 = false;
                 for (int k = k0; k < nk; k += nsrc) {
                     const int ki = sel[k];
@@ -248,7 +318,7 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
     } else {
         // ================= row warps: diag(v) + cross(v), one tile ahead of the far warps =================
         // Rows do not depend on the kept list; the release barrier only provides flow control: rows(u+1) goes into ring
-        // slot (u+1) & 3 of every CTA, last read by resolve(u-3), and is sent once resolve(u-kDepth) has released tile u.
+        // slot (u+1) % kRing of every CTA and is sent once resolve(u-kDepth) has released tile u (ring depth: nms_dev.cuh).
         const int rw = ri - nfar;  // 0..nrow-1
         const float cthr = __fadd_rn(1.0f, thr);
         auto send_rows = [&](int v) {
@@ -256,13 +326,13 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
             const int c0 = vbase + lane, c1 = c0 + 32;
             const float4 b0 = (c0 < n) ? sb[c0] : kNone, b1 = (c1 < n) ? sb[c1] : kNone;
             const float a0 = (c0 < n) ? sa[c0] : 1.0f, a1 = (c1 < n) ? sa[c1] : 1.0f;
-            const uint32_t bar_v = bar_base + 8u * (uint32_t)(v & 3);
+            const uint32_t bar_v = bar_base + 8u * (uint32_t)(v & (kRing - 1));
             const float tc0 = __fmul_rn(thr, a0), tc1 = __fmul_rn(thr, a1);
             // this CTA owns the contiguous rows [crank * rpc, (crank + 1) * rpc) of the tile (0..63 diag, 64 d + i:
             // candidate i of tile v-d against tile v); they are staged locally and travel as ONE bulk copy per peer:
             // the receivers' mbarriers see csize transactions per tile instead of one per row
             const int rpc = kRows / csize;
-            unsigned long long* stage = &s_stage[v & 7][0];
+            unsigned long long* stage = &s_stage[v & (kRing - 1)][0];
             for (int j = rw; j < rpc; j += nrow) {  // (four rows per pass with one vote was measured: slower, 135 -> 147 us)
                 const int r = crank * rpc + j;
                 const int i = r & (kTile - 1);
@@ -274,6 +344,7 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
                 const float m0 = __fmul_rn(__fadd_rn(ti, tc0), kScreenBand), m1 = __fmul_rn(__fadd_rn(ti, tc1), kScreenBand);
                 bool h0 = e0 > m0, h1 = e1 > m1;
                 if (__any_sync(0xffffffffu, fabsf(e0) <= m0 || fabsf(e1) <= m1)) {
+                    PROF_FALLBACK;
                     h0 = iou_gt(bi, ai, b0, a0, thr);
                     h1 = iou_gt(bi, ai, b1, a1, thr);
                 }
@@ -284,14 +355,14 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async-proxy reads
             named_barrier(1, nrow * 32);
             if (rw == 0 && lane < csize)
-                bulk_copy_to_peer(mapa_u32(smem_u32(&s_rows[v & 3][crank * rpc]), (uint32_t)lane), smem_u32(stage),
+                bulk_copy_to_peer(mapa_u32(smem_u32(&s_rows[v & (kRing - 1)][crank * rpc]), (uint32_t)lane), smem_u32(stage),
                                   (uint32_t)rpc * 8u, mapa_u32(bar_v, (uint32_t)lane));
         };
         if (tiles > 1) send_rows(1);
         for (int u = 1; u < tiles; ++u) {
             if (u >= kDepth) {
                 asm volatile("bar.sync %0, %1;" ::"r"(3 + (u % kDepth)), "r"(rel_threads) : "memory");
-                if (s_nk[(u - kDepth) & 3] >= max_out) break;  // same test as the far warps: both leave at the same tile
+                if (s_nk[(u - kDepth) & (kRing - 1)] >= max_out) break;  // same test as the far warps: both leave at the same tile
             }
             if (u + 1 < tiles) send_rows(u + 1);
         }
@@ -307,77 +378,91 @@ nms_lazy_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ va
     if (warp == 0) {
         for (int d = t; d < t + kDepth; ++d)
             if (d >= 1 && d < tiles)
-                mbar_wait(bar_base + 8u * (uint32_t)(d & 3), (uint32_t)(((d >> 2) - ((d & 3) == 0 ? 1 : 0)) & 1));
+                mbar_wait(bar_base + 8u * (uint32_t)(d & (kRing - 1)),
+                          (uint32_t)(((d >> 3) - ((d & (kRing - 1)) == 0 ? 1 : 0)) & 1));
     }
     cluster.sync();
     if (crank != 0) return;
     const int total = nkept;
-    nms_write_outputs(epi, bx, b, M, max_out, total, sel, eidx, rel_threads);
+    nms_write_outputs(epi, bx, b, M, max_out, total, sel, FUSED ? s_orig : nullptr, eidx, rel_threads);
 }
 
-// cluster size: spread one image over as many SMs as the batch leaves free (148 SMs, 1 CTA per SM), up to the
-// portable maximum of 8 (16-CTA clusters do not co-schedule for 8 images on this part: measured); small candidate
-// sets do not amortise the exchange
-static int nms_cluster_size(int B, int M, size_t smem, bool compact) {
-    if (M <= 2048) return 1;
-    static int cache[2][4][2] = {};
-    if (compact)
-        return pick_cluster_size(nms_lazy_kernel<true>, kNmsThreads, B, 8, [smem](int) { return smem; }, cache[1]);
-    return pick_cluster_size(nms_lazy_kernel<false>, kNmsThreads, B, 8, [smem](int) { return smem; }, cache[0]);
+template <bool COMPACT, bool FUSED>
+static const void* nms_kernel_ptr() { return (const void*)nms_lazy_kernel<COMPACT, FUSED>; }
+
+// Launch.  in.scores / in.keys != NULL selects the fused-ordering kernel (the caller has checked that it applies:
+// nms_fused_applies).  Cluster size: spread one image over as many SMs as the batch leaves free (1 CTA per SM), up to
+// the portable maximum of 8 (16-CTA clusters do not co-schedule for 8 images on this part: measured); small candidate
+// sets do not amortise the exchange.
+static bool nms_compact_fits(int M, int max_out, bool fused, size_t* smem_out) {
+    const void* k = fused ? nms_kernel_ptr<true, true>() : nms_kernel_ptr<true, false>();
+    const size_t max_dyn = (size_t)device_props().smem_optin - static_smem_bytes(k) - 256;
+    const size_t c = fused ? nms_fused_smem_bytes(M, max_out, true) : nms_smem_bytes(M, max_out, true);
+    const bool compact = c <= max_dyn;
+    *smem_out = compact ? c : (fused ? nms_fused_smem_bytes(M, max_out, false) : nms_smem_bytes(M, max_out, false));
+    return compact;
 }
 
-int launch_nms_sorted(const float4* boxes_sorted, const int32_t* valid, int B, int M, int max_out, float thr,
-                      const NmsEpilogue& epi, cudaStream_t stream) {
-    // dense copies of the kept boxes (24 more bytes per output slot) whenever they fit beside the candidates
-    static const bool env_indirect = getenv("MRCNN_NMS_INDIRECT") != nullptr;  // test knob: force the index-list path
-    // dynamic shared memory left beside the kernel's static arrays (queried, not assumed; pure query results, so the
-    // unsynchronised cache is harmless)
-    static size_t max_dyn = 0;
-    if (max_dyn == 0) {
-        cudaFuncAttributes fa;
-        int dev_id = 0, optin = 227 * 1024;
-        if (cudaGetDevice(&dev_id) == cudaSuccess)
-            cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev_id);
-        size_t stat = 20 * 1024;
-        if (cudaFuncGetAttributes(&fa, nms_lazy_kernel<true>) == cudaSuccess) stat = fa.sharedSizeBytes;
-        (void)cudaGetLastError();
-        max_dyn = (size_t)optin - stat - 256;
+bool nms_fused_applies(int M, int max_out) {
+    if (M > 2048) return false;  // cluster size 1 only: every CTA of a cluster would repeat the ordering
+    size_t smem;
+    (void)nms_compact_fits(M, max_out, true, &smem);
+    const size_t max_dyn = (size_t)device_props().smem_optin - static_smem_bytes(nms_kernel_ptr<false, true>()) - 256;
+    return smem <= max_dyn;
+}
+
+int launch_nms(const NmsInput& in, int B, int M, int max_out, float thr, const NmsEpilogue& epi, cudaStream_t stream) {
+    const bool fused = in.scores != nullptr || in.keys != nullptr;
+    size_t smem;
+    const bool compact = nms_compact_fits(M, max_out, fused, &smem);
+    const void* kernel = fused ? (compact ? nms_kernel_ptr<true, true>() : nms_kernel_ptr<false, true>())
+                               : (compact ? nms_kernel_ptr<true, false>() : nms_kernel_ptr<false, false>());
+    int cs = 1;
+    if (!fused && M > 2048) cs = pick_cluster_size(kernel, kNmsThreads, B, 8, [smem](int) { return smem; });
+    {   // per launch: the occupancy cache above may have set another problem's (smaller) limit last
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
     }
-    const bool compact = !env_indirect && nms_smem_bytes(M, max_out, true) <= max_dyn;
-    const size_t smem = nms_smem_bytes(M, max_out, compact);
-    cudaError_t e = compact ? cudaFuncSetAttribute(nms_lazy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                            : cudaFuncSetAttribute(nms_lazy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    const int cs = nms_cluster_size(B, M, smem, compact);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * cs));
     cfg.blockDim = dim3(kNmsThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 1 + (unsigned)pdl_attr(attr + 1);
     // warp roles: 1 resolver, nfar far warps (the kept list x tile tests), nrow row warps (diag + cross blocks: 128 rows
     // per tile dealt over the cluster); the remaining warps only help with the staging and exit.  Few, fat workers:
     // the per-tile work of a warp is a latency-bound chain (~5 cycles per instruction), so fixed overhead per warp
-    // costs more than it buys.
-    static const int env_far = getenv("MRCNN_NMS_NFAR") ? atoi(getenv("MRCNN_NMS_NFAR")) : 0;
-    static const int env_row = getenv("MRCNN_NMS_NROW") ? atoi(getenv("MRCNN_NMS_NROW")) : 0;
-    // measured at config 2 (ProposalLayer, B=8 / B=16): (8,4) 134.5 / 200 us, (6,8) 129.2 / 194, (6,12) 130.4 / 192,
-    // (8,12) 132.4 / 198, (10,14) 136.6 / 202; the single-CTA detection NMS does not react to the split (13.1-13.6 us)
-    int nfar = cs >= 4 ? 6 : 12, nrow = cs >= 4 ? 8 : (cs == 2 ? 8 : 12);
-    if (env_far > 0 && env_row > 0 && env_far + env_row <= 24 && env_far * cs <= kMaxFarSrc) {  // tuning knob
-        nfar = env_far;
-        nrow = env_row;
-    }
-    if (compact) e = cudaLaunchKernelEx(&cfg, nms_lazy_kernel<true>, boxes_sorted, valid, M, max_out, thr, nfar, nrow, epi);
-    else e = cudaLaunchKernelEx(&cfg, nms_lazy_kernel<false>, boxes_sorted, valid, M, max_out, thr, nfar, nrow, epi);
+    // costs more than it buys.  Measured at config 2 (ProposalLayer, B=8 / B=16): (8,4) 134.5 / 200 us, (6,8) 129.2 /
+    // 194, (6,12) 130.4 / 192, (8,12) 132.4 / 198, (10,14) 136.6 / 202; the single-CTA detection NMS does not react.
+    const int nfar = cs >= 4 ? 6 : 12, nrow = cs >= 4 ? 8 : (cs == 2 ? 8 : 12);
+    void* args[] = {(void*)&in, (void*)&M, (void*)&max_out, (void*)&thr, (void*)&nfar, (void*)&nrow, (void*)&epi};
+    cudaError_t e = cudaLaunchKernelExC(&cfg, kernel, args);
     if (e != cudaSuccess) return (int)e;
     return last_error();
+}
+
+int launch_nms_sorted(const float4* boxes_sorted, const int32_t* valid, int B, int M, int max_out, float thr,
+                      const NmsEpilogue& epi, cudaStream_t stream) {
+    NmsInput in{};
+    in.boxes = boxes_sorted;
+    in.valid = valid;
+    return launch_nms(in, B, M, max_out, thr, epi, stream);
+}
+
+int launch_nms_unsorted(const float4* boxes, const float* scores, const uint32_t* keys, const int32_t* valid, int B, int M,
+                        int max_out, float thr, const NmsEpilogue& epi, cudaStream_t stream) {
+    NmsInput in{};
+    in.boxes = boxes;
+    in.valid = valid;
+    in.scores = scores;
+    in.keys = keys;
+    return launch_nms(in, B, M, max_out, thr, epi, stream);
 }
 
 // generic entry: sort candidates (score > -inf) by (score desc, index asc); one CTA per image
@@ -387,6 +472,8 @@ nms_sort_kernel(const float4* __restrict__ boxes, const float* __restrict__ scor
     extern __shared__ __align__(16) uint64_t s[];
     __shared__ int s_n;
     const int b = blockIdx.x, tid = threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     const int n = valid ? min(max(valid[b], 0), M) : M;
     const int sort_n = max(32, 1 << (32 - __clz(max(M, 1) - 1)));
     if (tid == 0) s_n = 0;
@@ -435,6 +522,13 @@ MRCNN_EXPORT int mrcnn_debug_nms_profile(long long* host_out8) {
     if (e == cudaSuccess) e = cudaMemcpyFromSymbol(host_out8 + 16, g_nms_tl, sizeof(long long) * 16);
     return (int)e;
 }
+// number of exact-division fallbacks of the threshold screen since the last call (far and row warps, all CTAs)
+MRCNN_EXPORT int mrcnn_debug_nms_fallbacks(unsigned long long* host_out, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(host_out, g_nms_fallbacks, sizeof(unsigned long long));
+    const unsigned long long zero = 0;
+    if (e == cudaSuccess && reset) e = cudaMemcpyToSymbol(g_nms_fallbacks, &zero, sizeof(zero));
+    return (int)e;
+}
 #endif
 
 MRCNN_EXPORT int mrcnn_nms_workspace_bytes(int B, int M, size_t* bytes) {
@@ -452,6 +546,13 @@ MRCNN_EXPORT int mrcnn_nms_forward(const float* boxes, const float* scores, cons
     if (ws_bytes < nms_ws_bytes(B, M)) return MRCNN_ERR_WORKSPACE;
     if (!aligned16(boxes) || !aligned16(ws)) return MRCNN_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
+    NmsEpilogue epi{};
+    epi.mode = 0;
+    epi.keep = keep;
+    epi.count = count;
+    // single-CTA problems: the NMS kernel orders its candidates itself (one launch, no workspace traffic)
+    if (nms_fused_applies(M, max_out))
+        return launch_nms_unsorted((const float4*)boxes, scores, nullptr, valid, B, M, max_out, thr, epi, st);
     NmsWs w;
     char* p = (char*)ws;
     w.boxes_sorted = (float4*)p; p += align_up((size_t)B * M * sizeof(float4), 256);
@@ -463,11 +564,9 @@ MRCNN_EXPORT int mrcnn_nms_forward(const float* boxes, const float* scores, cons
         cudaError_t e = cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    nms_sort_kernel<<<B, 1024, smem, st>>>((const float4*)boxes, scores, valid, M, w.boxes_sorted, w.orig_idx, w.ncand);
-    NmsEpilogue epi{};
-    epi.mode = 0;
+    cudaError_t e = launch_pdl(nms_sort_kernel, dim3(B), dim3(1024), smem, st, (const float4*)boxes, scores, valid, M,
+                               w.boxes_sorted, w.orig_idx, w.ncand);
+    if (e != cudaSuccess) return (int)e;
     epi.orig_idx = w.orig_idx;
-    epi.keep = keep;
-    epi.count = count;
     return launch_nms_sorted(w.boxes_sorted, w.ncand, B, M, max_out, thr, epi, st);
 }

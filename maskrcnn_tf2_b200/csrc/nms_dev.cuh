@@ -19,6 +19,8 @@ static __device__ long long g_nms_profw[8];  // far warp 1 of CTA 0: prologue, w
 #define PROFW_COUNT ++w_acc[6]
 #define PROFW_MARK(i) do { const long long w_now = clock64(); w_acc[i] += w_now - w_t0; w_t0 = w_now; } while (0)
 static __device__ long long g_nms_tl[16];    // spare slots for ad-hoc clock64 stamps
+static __device__ unsigned long long g_nms_fallbacks;   // exact-division fallbacks taken (all warps, all CTAs)
+#define PROF_FALLBACK do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_nms_fallbacks, 1ull); } while (0)
 #define PROFW_DUMP do { if (blockIdx.x == 0 && threadIdx.x == 32) { for (int q = 0; q < 7; ++q) g_nms_profw[q] = w_acc[q]; } } while (0)
 #else
 #define PROF_DECL
@@ -29,23 +31,39 @@ static __device__ long long g_nms_tl[16];    // spare slots for ad-hoc clock64 s
 #define PROFW_MARK(i)
 #define PROFW_DUMP
 #define PROFW_COUNT
+#define PROF_FALLBACK
 #endif
 
 constexpr int kTile = 64;
 // Pipeline depth: far(u) covers the boxes kept in tiles <= u - kDepth, so the far warps run kDepth tiles ahead of the
-// resolver; the tiles in between are covered by kDepth - 1 precomputed cross blocks.  The ring of 4 slots per tile
-// (rows, far partials, mbarriers, kept counts) requires kDepth <= 3.
+// resolver; the tiles in between are covered by kDepth - 1 precomputed cross blocks.
 constexpr int kDepth = 2;
 constexpr int kRows = kDepth * kTile;              // rows per tile: diag + (kDepth - 1) cross blocks
+// Per-tile slots (rows, far partials, mbarriers, kept counts) are rings of kRing entries, tile t uses slot t % kRing.
+// What the ring depth has to cover (cluster size > 1): a sender writes the set of tile v into every peer once its OWN
+// resolver has finished tile v - 3 (rows, sent one tile ahead) or v - 2 (far partials).  For that the sender needed the
+// peer's far partials of tile v - 3, which the peer produced after ITS resolver finished tile v - 5: the peer is then
+// at tile v - 4 or later, and slot v % 8 was last read (and its mbarrier phase last completed) for tile v - 8.
+constexpr int kRing = 8;
 constexpr int kNmsThreads = 1024;
 constexpr int kNmsWarps = kNmsThreads / 32;
 
-constexpr int kMaxFarSrc = 16 * 12;                // far partials per tile: cluster size x far warps per CTA
+constexpr int kMaxFarSrc = 8 * 12;                 // far partials per tile: cluster size (<= 8) x far warps per CTA
 
 static size_t nms_smem_bytes(int M, int max_out, bool compact) {
     const size_t cap = (size_t)(max_out < M ? max_out : M);
     return (size_t)M * (sizeof(float4) + sizeof(float)) + cap * sizeof(int32_t) +
            (compact ? cap * (sizeof(float4) + sizeof(float)) : 0);
+}
+// Fused candidate ordering (single-CTA problems): the kernel first builds (score key, ~index) composites of the
+// candidates in shared memory, sorts them and stages the boxes in candidate order itself.
+// Layout: [composites: sort_n x 8 B][candidate -> original row: M x 4 B][union(NMS arrays, sort exchange buffers)]
+static int nms_sort_n(int M) { int p = 32; while (p < M) p <<= 1; return p; }
+static size_t nms_fused_smem_bytes(int M, int max_out, bool compact) {
+    const int sort_n = nms_sort_n(M);
+    const size_t xch = sort_n >= 1024 ? block_sort_xch_bytes(sort_n / 1024) : 0;
+    const size_t body = nms_smem_bytes(M, max_out, compact);
+    return (size_t)sort_n * 8 + align_up((size_t)M * 4, 16) + (body > xch ? body : xch);
 }
 
 __device__ __forceinline__ uint64_t ballot64(bool lo, bool hi) {
@@ -99,12 +117,15 @@ __device__ __forceinline__ void or_into(unsigned long long* word, uint64_t bits)
 }
 
 // fixed-size padded outputs, no host round trip; `sel` = kept candidate positions (shared memory), `total` of them
+// `orig` (shared memory, fused ordering) or epi.orig_idx (global) maps a candidate position to its input row
 __device__ __forceinline__ void nms_write_outputs(const NmsEpilogue& epi, const float4* __restrict__ bx, int b, int M,
-                                                  int max_out, int total, const int32_t* sel, int tid, int nthreads) {
+                                                  int max_out, int total, const int32_t* sel, const int32_t* orig,
+                                                  int tid, int nthreads) {
+    auto row_of = [&](int pos) { return orig ? orig[pos] : (epi.orig_idx ? epi.orig_idx[(size_t)b * M + pos] : pos); };
     if (epi.mode == 0) {
         for (int r = tid; r < max_out; r += nthreads) {
             int32_t v = -1;
-            if (r < total) v = epi.orig_idx ? epi.orig_idx[(size_t)b * M + sel[r]] : sel[r];
+            if (r < total) v = row_of(sel[r]);
             epi.keep[(size_t)b * max_out + r] = v;
         }
         if (tid == 0 && epi.count) epi.count[b] = total;
@@ -118,7 +139,7 @@ __device__ __forceinline__ void nms_write_outputs(const NmsEpilogue& epi, const 
         for (int r = tid; r < max_out; r += nthreads) {
             float* o = epi.detections + ((size_t)b * max_out + r) * 6;
             if (r < total) {
-                const int i = epi.orig_idx[(size_t)b * M + sel[r]];
+                const int i = row_of(sel[r]);
                 const float4 v = epi.refined[(size_t)b * epi.N + i];
                 o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
                 o[4] = (float)epi.class_ids[(size_t)b * epi.N + i];

@@ -33,7 +33,7 @@ struct GradTable {
     int W[4];
 };
 
-constexpr int kPrepThreads = 256;
+constexpr int kPrepThreads = 1024; // ROIs per prep CTA = ROIs per entry of the first-appearance partial list
 constexpr int kRoiThreads = 256;   // 8 warps per CTA
 
 __device__ __forceinline__ int roi_level_of(float4 b, float denom) {
@@ -46,11 +46,17 @@ __device__ __forceinline__ int roi_level_of(float4 b, float denom) {
     return min(max(level, 2), 5);
 }
 
-// level per ROI + first flattened index at which each level appears (tf.unique order, L:613)
+// level per ROI + first flattened index at which each level appears (tf.unique order, L:613).  Every CTA writes the
+// minima of its own kPrepThreads ROIs to partial[blockIdx.x] (INT_MAX = level absent); the consumers reduce the
+// partial list themselves (first_appearance below: one int4 per lane at B*N <= 32768) -- no atomics, so no memset node
+// in front of the kernel, and the launch chain stays eligible for programmatic dependent launch.
 __global__ void __launch_bounds__(kPrepThreads)
 roialign_prep_kernel(const float4* __restrict__ boxes, const float* __restrict__ image_meta, int BN,
-                     float denominator, int32_t* __restrict__ level_ws, int* __restrict__ first,
+                     float denominator, int32_t* __restrict__ level_ws, int4* __restrict__ partial,
                      int32_t* __restrict__ roi_level) {
+    __shared__ int s_min[kPrepThreads / 32][4];
+    pdl_launch_dependents();
+    pdl_wait();
     const int f = blockIdx.x * kPrepThreads + threadIdx.x;
     const float image_area = __fmul_rn(image_meta[4], image_meta[5]);               // L:600,604 (image 0)
     const float denom = __fdiv_rn(denominator, __fsqrt_rn(image_area));
@@ -63,8 +69,29 @@ roialign_prep_kernel(const float4* __restrict__ boxes, const float* __restrict__
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
         const int m = __reduce_min_sync(0xffffffffu, (level == l + 2) ? f : INT_MAX);
-        if ((threadIdx.x & 31) == 0 && m != INT_MAX) atomicMin(&first[l], m);
+        if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5][l] = m;
     }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        int m = INT_MAX;
+#pragma unroll
+        for (int w = 0; w < kPrepThreads / 32; ++w) m = min(m, s_min[w][threadIdx.x]);
+        reinterpret_cast<int*>(partial + blockIdx.x)[threadIdx.x] = m;
+    }
+}
+
+// the four first-appearance indices, reduced from the prep kernel's per-CTA minima; every lane of the warp must call
+__device__ __forceinline__ int4 first_appearance(const int4* __restrict__ partial, int nparts) {
+    int4 m = make_int4(INT_MAX, INT_MAX, INT_MAX, INT_MAX);
+    for (int i = threadIdx.x & 31; i < nparts; i += 32) {
+        const int4 p = __ldg(partial + i);
+        m.x = min(m.x, p.x); m.y = min(m.y, p.y); m.z = min(m.z, p.z); m.w = min(m.w, p.w);
+    }
+    m.x = __reduce_min_sync(0xffffffffu, m.x);
+    m.y = __reduce_min_sync(0xffffffffu, m.y);
+    m.z = __reduce_min_sync(0xffffffffu, m.z);
+    m.w = __reduce_min_sync(0xffffffffu, m.w);
+    return m;
 }
 
 // Sampling geometry of one ROI on its feature map, computed once per warp (all lanes redundantly, no divergence):
@@ -104,9 +131,8 @@ __device__ __forceinline__ AxisTap axis_tap(float c0, float scale, int t, int si
 }
 
 // map index of a ROI from its level and the four first-appearance indices (L:613-619), or level-2 (map_mode 1)
-__device__ __forceinline__ int roi_map_index(int level, const int* __restrict__ first, int map_mode) {
+__device__ __forceinline__ int roi_map_index(int level, const int4& fa, int map_mode) {
     if (map_mode != 0) return level - 2;
-    const int4 fa = *reinterpret_cast<const int4*>(first);
     const int mine = (level == 2) ? fa.x : (level == 3) ? fa.y : (level == 4) ? fa.z : fa.w;
     return (fa.x < mine) + (fa.y < mine) + (fa.z < mine) + (fa.w < mine);
 }
@@ -117,17 +143,20 @@ __device__ __forceinline__ int roi_map_index(int level, const int* __restrict__ 
 template <int VPL, int XSPLIT>
 __global__ void __launch_bounds__(kRoiThreads, 5)
 roialign_fwd_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ level_ws,
-                    const int* __restrict__ first, int map_mode, MapTable tbl, int C, int N, int ph, int pw,
+                    const int4* __restrict__ partial, int nparts, int map_mode, MapTable tbl, int C, int N, int ph, int pw,
                     int total_rows, float* __restrict__ out, int32_t* __restrict__ roi_map) {
     constexpr int xsplit = XSPLIT;
     const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int4 fa = first_appearance(partial, nparts);  // every warp, before the early exit (warp-uniform anyway)
     // a warp owns one output row, or 1/xsplit of it (wide crops: more, shorter warps fill the last wave better)
     const int unit = blockIdx.x * (kRoiThreads / 32) + (threadIdx.x >> 5);
     if (unit >= total_rows * xsplit) return;
     const int row = unit / xsplit, part = unit - row * xsplit;
     const int x_begin = part * pw / xsplit, x_end = (part + 1) * pw / xsplit;
     const int f = row / ph, y = row - f * ph;
-    const int m = roi_map_index(level_ws[f], first, map_mode);
+    const int m = roi_map_index(level_ws[f], fa, map_mode);
     const RoiGeom g = roi_geom(__ldg(boxes + f), m, tbl.H, tbl.W, ph, pw);
     if (y == 0 && part == 0 && lane == 0) roi_map[f] = m;
     const int c4 = C >> 2;
@@ -210,10 +239,10 @@ struct RowCtx {        // everything about one output row (roi f, row y) that do
 };
 
 __device__ __forceinline__ RowCtx make_row_ctx(int row, const float4* __restrict__ boxes,
-                                               const int32_t* __restrict__ level_ws, const int* __restrict__ first,
+                                               const int32_t* __restrict__ level_ws, const int4& fa,
                                                int map_mode, const MapTable& tbl, int N, int ph, int pw, int& m_out) {
     const int f = row / ph, y = row - f * ph;
-    const int m = roi_map_index(level_ws[f], first, map_mode);
+    const int m = roi_map_index(level_ws[f], fa, map_mode);
     const RoiGeom g = roi_geom(__ldg(boxes + f), m, tbl.H, tbl.W, ph, pw);
     const AxisTap ty = axis_tap(g.y0, g.hs, y, g.H);
     RowCtx c;
@@ -228,10 +257,13 @@ __device__ __forceinline__ RowCtx make_row_ctx(int row, const float4* __restrict
 template <int WARPS, int STAGES>
 __global__ void __launch_bounds__(WARPS * 32)
 roialign_fwd_tma_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ level_ws,
-                        const int* __restrict__ first, int map_mode, MapTable tbl, int N, int ph, int pw,
+                        const int4* __restrict__ partial, int nparts, int map_mode, MapTable tbl, int N, int ph, int pw,
                         int total_rows, float* __restrict__ out, int32_t* __restrict__ roi_map) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int4 fa = first_appearance(partial, nparts);
     float4* ring = reinterpret_cast<float4*>(smem_raw) + (size_t)warp * STAGES * 256;        // [STAGES][4 corners][64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)WARPS * STAGES * 4096) + warp * STAGES;
     if (lane == 0) {
@@ -247,7 +279,7 @@ roialign_fwd_tma_kernel(const float4* __restrict__ boxes, const int32_t* __restr
     const int my_bins = my_rows * pw;
 
     int m_dummy;
-    RowCtx pc = make_row_ctx(w0, boxes, level_ws, first, map_mode, tbl, N, ph, pw, m_dummy);  // producer cursor
+    RowCtx pc = make_row_ctx(w0, boxes, level_ws, fa, map_mode, tbl, N, ph, pw, m_dummy);  // producer cursor
     int p_row = 0, p_x = 0, issued = 0;
     auto produce = [&]() {  // bin `issued` of this warp's stream -> stage issued % STAGES
         const AxisTap tx = axis_tap(pc.x0, pc.ws, p_x, pc.W);
@@ -270,7 +302,7 @@ roialign_fwd_tma_kernel(const float4* __restrict__ boxes, const int32_t* __restr
         if (++p_x == pw) {
             p_x = 0;
             if (++p_row < my_rows)
-                pc = make_row_ctx(w0 + p_row * nwarps, boxes, level_ws, first, map_mode, tbl, N, ph, pw, m_dummy);
+                pc = make_row_ctx(w0 + p_row * nwarps, boxes, level_ws, fa, map_mode, tbl, N, ph, pw, m_dummy);
         }
     };
     for (int k = 0; k < STAGES - 1 && issued < my_bins; ++k) produce();
@@ -280,7 +312,7 @@ roialign_fwd_tma_kernel(const float4* __restrict__ boxes, const int32_t* __restr
     for (int r = 0; r < my_rows; ++r) {
         const int row = w0 + r * nwarps;
         int m;
-        const RowCtx cc = make_row_ctx(row, boxes, level_ws, first, map_mode, tbl, N, ph, pw, m);
+        const RowCtx cc = make_row_ctx(row, boxes, level_ws, fa, map_mode, tbl, N, ph, pw, m);
         if (lane == 0 && row % ph == 0) roi_map[row / ph] = m;
         float4* o = reinterpret_cast<float4*>(out) + (size_t)row * pw * 64;
         const float ly = cc.ly;
@@ -719,7 +751,11 @@ roialign_bwd_gather_kernel(const float4* __restrict__ grad_out, GradTable tbl, P
     }
 }
 
-static size_t roialign_ws_bytes(int B, int N) { return align_up((size_t)B * N * sizeof(int32_t), 256) + 256; }
+// workspace: [first-appearance partial list: one int4 per kPrepThreads ROIs][level per ROI]
+static int roialign_nparts(int BN) { return (BN + kPrepThreads - 1) / kPrepThreads; }
+static size_t roialign_ws_bytes(int B, int N) {
+    return align_up((size_t)roialign_nparts(B * N) * sizeof(int4), 256) + align_up((size_t)B * N * sizeof(int32_t), 256);
+}
 
 }  // namespace mrcnn
 
@@ -766,12 +802,12 @@ MRCNN_EXPORT int mrcnn_roialign_forward(const float* boxes, const float* image_m
     MapTable tbl;
     for (int l = 0; l < 4; ++l) { tbl.ptr[l] = fmaps[l]; tbl.H[l] = H[l]; tbl.W[l] = W[l]; }
     const int BN = B * N;
-    int* first = (int*)ws;                                   // 4 ints, 16-byte aligned
-    int32_t* level_ws = (int32_t*)((char*)ws + 256);
-    cudaError_t e = cudaMemsetAsync(first, 0x7f, 4 * sizeof(int), st);
+    const int nparts = roialign_nparts(BN);
+    int4* partial = (int4*)ws;
+    int32_t* level_ws = (int32_t*)((char*)ws + align_up((size_t)nparts * sizeof(int4), 256));
+    cudaError_t e = launch_pdl(roialign_prep_kernel, dim3(nparts), dim3(kPrepThreads), 0, st, (const float4*)boxes,
+                               image_meta, BN, denominator, level_ws, partial, roi_level);
     if (e != cudaSuccess) return (int)e;
-    roialign_prep_kernel<<<(BN + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, st>>>(
-        (const float4*)boxes, image_meta, BN, denominator, level_ws, first, roi_level);
     const int total_rows = BN * ph;
     // two warps per output row for wide crops on large maps (memory-latency-bound: 14x14 at S=1024 62 -> 58 us at B=8,
     // 236 -> 232 at B=32); 7x7 and the small, cache-resident maps of config 4 (S=512 / 256: 189 -> 195, 150 -> 162 us)
@@ -781,11 +817,11 @@ MRCNN_EXPORT int mrcnn_roialign_forward(const float* boxes, const float* image_m
 #define MRCNN_FWD(V)                                                                                              \
     do {                                                                                                          \
         if (xsplit == 2)                                                                                          \
-            roialign_fwd_kernel<V, 2><<<grid, kRoiThreads, 0, st>>>((const float4*)boxes, level_ws, first, map_mode, \
-                                                                    tbl, C, N, ph, pw, total_rows, out, roi_map);  \
+            e = launch_pdl(roialign_fwd_kernel<V, 2>, dim3(grid), dim3(kRoiThreads), 0, st, (const float4*)boxes,  \
+                           level_ws, partial, nparts, map_mode, tbl, C, N, ph, pw, total_rows, out, roi_map);     \
         else                                                                                                      \
-            roialign_fwd_kernel<V, 1><<<grid, kRoiThreads, 0, st>>>((const float4*)boxes, level_ws, first, map_mode, \
-                                                                    tbl, C, N, ph, pw, total_rows, out, roi_map);  \
+            e = launch_pdl(roialign_fwd_kernel<V, 1>, dim3(grid), dim3(kRoiThreads), 0, st, (const float4*)boxes,  \
+                           level_ws, partial, nparts, map_mode, tbl, C, N, ph, pw, total_rows, out, roi_map);     \
     } while (0)
     const int variant = fwd_variant();
     if (C == 256 && variant != 0) {
@@ -798,8 +834,9 @@ MRCNN_EXPORT int mrcnn_roialign_forward(const float* boxes, const float* image_m
                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
             if (e2 != cudaSuccess) return (int)e2;                                                                 \
             const int g2 = min((total_rows + WARPS - 1) / WARPS, CTAS * sms);                                      \
-            roialign_fwd_tma_kernel<WARPS, STAGES><<<g2, WARPS * 32, smem, st>>>(                                  \
-                (const float4*)boxes, level_ws, first, map_mode, tbl, N, ph, pw, total_rows, out, roi_map);        \
+            e = launch_pdl(roialign_fwd_tma_kernel<WARPS, STAGES>, dim3(g2), dim3(WARPS * 32), smem, st,           \
+                           (const float4*)boxes, level_ws, partial, nparts, map_mode, tbl, N, ph, pw, total_rows,  \
+                           out, roi_map);                                                                          \
         }
         // measured on B200, config 2 (profiles/r1_roialign_fwd_tma.md): 4 warps x 2 stages x 6 CTAs/SM is the best
         // of the shapes tried and ties the LDG kernel at 7x7 (138.8 vs 140.0 us) but loses at 14x14 (103 vs 59 us)
@@ -807,14 +844,14 @@ MRCNN_EXPORT int mrcnn_roialign_forward(const float* boxes, const float* image_m
         else if (variant == 3) MRCNN_TMA(4, 3, 4)
         else MRCNN_TMA(4, 2, 6)
 #undef MRCNN_TMA
-        return last_error();
+        return e != cudaSuccess ? (int)e : last_error();
     }
     if (C == 128) MRCNN_FWD(1);
     else if (C == 256) MRCNN_FWD(2);
     else if (C == 512) MRCNN_FWD(4);
     else MRCNN_FWD(0);
 #undef MRCNN_FWD
-    return last_error();
+    return e != cudaSuccess ? (int)e : last_error();
 }
 
 static int pixel_space(const int* H, const int* W, int B, PixelSpace* ps) {
@@ -933,12 +970,13 @@ namespace mrcnn {
 
 __global__ void __launch_bounds__(256)
 roialign_mark_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ level_ws,
-                     const int* __restrict__ first, int map_mode, MapTable tbl, PixelSpace ps, int N, int ph, int pw,
-                     int total_bins, const uint32_t* __restrict__ resident, uint32_t* __restrict__ need) {
+                     const int4* __restrict__ partial, int nparts, int map_mode, MapTable tbl, PixelSpace ps, int N, int ph,
+                     int pw, int total_bins, const uint32_t* __restrict__ resident, uint32_t* __restrict__ need) {
     const int s = blockIdx.x * 256 + threadIdx.x;
+    const int4 fa = first_appearance(partial, nparts);  // all lanes, before the exit
     if (s >= total_bins) return;
     const int f = s / (ph * pw), r = s - f * (ph * pw), y = r / pw, x = r - y * pw;
-    const int m = roi_map_index(level_ws[f], first, map_mode);
+    const int m = roi_map_index(level_ws[f], fa, map_mode);
     const RoiGeom g = roi_geom(__ldg(boxes + f), m, tbl.H, tbl.W, ph, pw);
     const AxisTap ty = axis_tap(g.y0, g.hs, y, g.H), tx = axis_tap(g.x0, g.ws, x, g.W);
     if (!(ty.valid && tx.valid)) return;  // the forward kernel writes zeros without reading
@@ -1054,18 +1092,18 @@ MRCNN_EXPORT int mrcnn_roialign_fetch_hostmaps(const float* boxes, const float* 
         dev.ptr[l] = dev_fmaps[l]; dev.H[l] = H[l]; dev.W[l] = W[l];
     }
     const int BN = B * N, words = (ps.base[4] + 31) / 32;
-    int* first = (int*)ws;
-    int32_t* level_ws = (int32_t*)((char*)ws + 256);
+    const int nparts = roialign_nparts(BN);
+    int4* partial = (int4*)ws;
+    int32_t* level_ws = (int32_t*)((char*)ws + align_up((size_t)nparts * sizeof(int4), 256));
     uint32_t* need = (uint32_t*)((char*)ws + roialign_ws_bytes(B, N));
-    cudaError_t e = cudaMemsetAsync(first, 0x7f, 4 * sizeof(int), st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(need, 0, (size_t)words * sizeof(uint32_t), st);
+    cudaError_t e = cudaMemsetAsync(need, 0, (size_t)words * sizeof(uint32_t), st);
     if (e == cudaSuccess && reset) e = cudaMemsetAsync(resident, 0, (size_t)words * sizeof(uint32_t), st);
     if (e != cudaSuccess) return (int)e;
-    roialign_prep_kernel<<<(BN + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, st>>>(
-        (const float4*)boxes, image_meta, BN, denominator, level_ws, first, nullptr);
+    roialign_prep_kernel<<<nparts, kPrepThreads, 0, st>>>((const float4*)boxes, image_meta, BN, denominator, level_ws,
+                                                         partial, nullptr);
     const int bins = BN * ph * pw;
-    roialign_mark_kernel<<<(bins + 255) / 256, 256, 0, st>>>((const float4*)boxes, level_ws, first, map_mode, host, ps, N,
-                                                            ph, pw, bins, resident, need);
+    roialign_mark_kernel<<<(bins + 255) / 256, 256, 0, st>>>((const float4*)boxes, level_ws, partial, nparts, map_mode,
+                                                            host, ps, N, ph, pw, bins, resident, need);
     int devid = 0, sms = 148;
     if (cudaGetDevice(&devid) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devid);
     const int grid = min((words + 7) / 8, 8 * sms);

@@ -2,19 +2,29 @@
 // Replaces tf.nn.top_k at mrcnn_layers.py:246, the per-image gathers at L:247-250 and (fused epilogue) the box
 // decode / clip of utils.py:830-869.
 //
-// A thread-block cluster of 1..8 CTAs (1024 threads each) owns an image; every CTA streams one contiguous slice
-// of the scores (128-bit loads, L2-resident after the first pass) and everything else stays on chip:
-//   1. radix select, up to three levels (12 + 12 + 8 bits of an order-preserving key): per-CTA shared-memory
-//      histogram, cluster-wide reduction where CTA s sums bin slice s from all peers through distributed shared
-//      memory, the CTA whose slice holds the K-th element resolves the digit and stores it into every CTA; the
-//      descent stops as soon as "above + boundary bin" fits the 8192-entry sort;
-//   2. compaction of the candidates as 64-bit (key, ~index) composites into shared memory, exclusive offsets from
-//      the per-CTA counts, then a scatter of every candidate to its sort slot in the owning CTA (DSMEM stores);
-//      if more than 8192 candidates share all 32 key bits the equal keys are taken in index order instead (ordered
-//      block scans per CTA, quotas from the per-CTA counts);
-//   3. cluster-wide bitonic sort: 8192 / (1024 * CTAs) keys per thread in registers, shuffles inside a warp, padded
-//      shared memory across warps, DSMEM reads across CTAs (log2(CTAs)*(log2(CTAs)+1)/2 cluster barriers in total);
-//   4. epilogue: indices / values, and for ProposalLayer the gather + std-dev scale + decode + clip of the winners.
+// A thread-block cluster of 1..8 CTAs (1024 threads each) owns an image.  The scores are dealt to the CTAs in units of
+// one warp-wide 128-bit load (64 anchors of rpn_probs), round robin -- NOT in contiguous slices: the anchors are
+// level-major and a trained RPN puts most of its top scores on the coarse levels at the end of the list (5000 of the
+// 6000 winners sat in the last eighth on the synthetic COCO-shape input), which would leave one CTA with the whole
+// sort.  Every CTA streams its share (L2-resident after the first pass) and everything else stays on chip:
+//   1. radix select on the 64-bit composite (order-preserving score key, ~index), 12 + 12 + 8 bits of the key and, only
+//      if more than 8192 candidates share all 32 key bits (tie floods, e.g. saturated probabilities), 12 + 12 + 8 bits
+//      of the index -- lower index first, TopKV2's tie rule, by the same mechanism: per-CTA shared-memory
+//      histogram, ONE cluster barrier per level, after which every CTA sums all the peers' histograms through
+//      distributed shared memory (128-bit loads, four bins per thread) and resolves the digit for itself -- identical
+//      integer sums, so no broadcast of the result is needed; the histograms are double buffered so that the next
+//      level can be zeroed while peers still read the previous one.  The descent stops as soon as "above + boundary
+//      bin" fits the 8192-entry sort;
+//   2. compaction of the CTA's candidates (composite >= the resolved prefix) into its own shared-memory list;
+//   3. every CTA sorts ITS OWN list (register-blocked bitonic network, no cluster traffic), publishes its length, and
+//      after one cluster barrier copies the peers' sorted lists into local shared memory; the global rank of an
+//      element is its local rank plus, per peer, the number of that peer's elements above it (binary search in the
+//      local copy).  The cluster-wide bitonic network this replaces needed six cluster barriers for its cross-CTA
+//      stages alone;
+//   4. epilogue at the element's global rank: indices / values, and for ProposalLayer the gather + std-dev scale +
+//      decode + clip of the winners.
+// Cluster barriers per launch: one per radix level (two on COCO-shape RPN scores) + one before the merge + the exit
+// barrier (split arrive / wait, so it costs no waiting).
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -24,13 +34,17 @@ namespace cg = cooperative_groups;
 namespace mrcnn {
 
 constexpr int kTkThreads = 1024;
+constexpr size_t kTkListBytes = (size_t)kMaxSort * 8;                 // the CTA's own candidates
+constexpr size_t kTkScratchBytes = block_sort_xch_bytes(8);           // sort exchange buffers / gathered peer lists
+constexpr size_t kTkHistOffset = kTkScratchBytes - 2 * 4096 * sizeof(uint32_t);  // two histograms at the scratch's end,
+// out of reach of every sort's exchange buffers (<= 96 KB from the scratch's start for <= 4096 keys; the 8192-key sort
+// holds the list in registers and uses the list's own 64 KB + the first 96 KB of the scratch): a slow peer may still
+// be reading this CTA's last histogram while it sorts
 
-struct TkControl {                 // static shared memory, one per CTA; the *_from arrays are written by the peers
-    uint32_t slice_sum[8];         // [source CTA] total of that CTA's bin slice
-    uint32_t sel[4];               // digit, need left, boundary-bin count, -- (stored by the owner into every CTA)
-    uint32_t cnt_a[8], cnt_b[8];   // [source CTA] candidates above / on the boundary
-    uint32_t cnt_eq[8];            // [source CTA] tie path: elements equal to the K-th key
-    uint32_t n_a, n_b;
+struct TkControl {                 // static shared memory, one per CTA; cnt / cnt_eq are written by the peers
+    uint32_t sel[4];               // digit, need left, boundary-bin count
+    uint32_t cnt[8];               // [source CTA] length of that CTA's candidate list
+    uint32_t n_list;
     int warp_sums[32];
     int scan_total;
 };
@@ -40,118 +54,182 @@ __device__ __forceinline__ uint32_t tk_load_key(const float* __restrict__ scores
     return score_key(__ldg(scores + ((size_t)b * A + a) * stride + offset));
 }
 
-// visits every score index in [lo, hi) once across the block (order unspecified); lo, hi multiples of 4 or == A
+// Visits every score index of this CTA's share once (order unspecified).  Unit = 32 consecutive vectors (one warp-wide
+// load: 512 B); unit q belongs to CTA q % csize, and the CTA deals its units to its 32 warps round robin.
 template <int MODE, typename F>
 __device__ __forceinline__ void for_each_key(const float* __restrict__ scores, int stride, int offset, int A, int b,
-                                             int lo, int hi, F f) {
-    const int tid = threadIdx.x;
+                                             int crank, int csize, F f) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int PER = (MODE == 2) ? 2 : (MODE == 1) ? 4 : 1;   // scores per vector
+    const int V = A / PER;                                        // MODE 1 / 2 are only selected when PER divides A
+    const int units = (V + 31) >> 5;
     if (MODE == 2) {  // two interleaved columns (rpn_probs [B,A,2]): one float4 = two anchors
         const float4* p4 = reinterpret_cast<const float4*>(scores + (size_t)b * A * 2);
 #pragma unroll 4
-        for (int a = lo + tid * 2; a < hi; a += kTkThreads * 2) {
-            const float4 q = __ldg(p4 + (a >> 1));
-            f(score_key(offset ? q.y : q.x), a);
-            f(score_key(offset ? q.w : q.z), a + 1);
+        for (int q = warp * csize + crank; q < units; q += 32 * csize) {
+            const int g = q * 32 + lane;
+            if (g < V) {
+                const float4 v = __ldg(p4 + g);
+                f(score_key(offset ? v.y : v.x), 2 * g);
+                f(score_key(offset ? v.w : v.z), 2 * g + 1);
+            }
         }
     } else if (MODE == 1) {  // dense [B,A]
         const float4* p4 = reinterpret_cast<const float4*>(scores + (size_t)b * A);
 #pragma unroll 4
-        for (int a = lo + tid * 4; a < hi; a += kTkThreads * 4) {
-            const float4 q = __ldg(p4 + (a >> 2));
-            f(score_key(q.x), a);
-            f(score_key(q.y), a + 1);
-            f(score_key(q.z), a + 2);
-            f(score_key(q.w), a + 3);
+        for (int q = warp * csize + crank; q < units; q += 32 * csize) {
+            const int g = q * 32 + lane;
+            if (g < V) {
+                const float4 v = __ldg(p4 + g);
+                f(score_key(v.x), 4 * g);
+                f(score_key(v.y), 4 * g + 1);
+                f(score_key(v.z), 4 * g + 2);
+                f(score_key(v.w), 4 * g + 3);
+            }
         }
     } else {
 #pragma unroll 4
-        for (int a = lo + tid; a < hi; a += kTkThreads) f(tk_load_key(scores, stride, offset, A, b, a), a);
-    }
-}
-
-// cluster-wide bitonic sort, descending; thread t of CTA r holds ranks (r*1024 + t)*E .. +E-1
-template <int E>
-__device__ __forceinline__ void cluster_sort_desc(uint64_t (&v)[E], uint64_t* xch_local, uint64_t* xch_remote,
-                                                  cg::cluster_group& cluster, int crank, int csize) {
-    constexpr int LOG_E = (E == 1) ? 0 : (E == 2) ? 1 : (E == 4) ? 2 : 3;
-    constexpr int ROW = E + 2;
-    constexpr int NCTA = 1024 * E;
-    const int N = NCTA * csize;
-    const int t = threadIdx.x;
-    const int gbase = (crank * 1024 + t) << LOG_E;
-    int buf = 0, rbuf = 0;
-    for (int k = 2; k <= N; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j >= NCTA) {  // partner element lives in another CTA of the cluster
-                const int dc = j / NCTA;
-                uint64_t* mine = xch_remote + (size_t)rbuf * NCTA + (size_t)t * E;
-#pragma unroll
-                for (int e = 0; e < E; ++e) mine[e] = v[e];
-                cluster.sync();
-                const uint64_t* theirs = cluster.map_shared_rank(mine, crank ^ dc);
-                const bool lower = (crank & dc) == 0;
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const uint64_t p = theirs[e];
-                    const bool desc = ((gbase | e) & k) == 0;
-                    const bool take_max = (lower == desc);
-                    v[e] = take_max ? (v[e] > p ? v[e] : p) : (v[e] < p ? v[e] : p);
-                }
-                rbuf ^= 1;
-            } else if (j >= 32 * E) {  // another warp of this CTA
-                const int dm = j >> LOG_E;
-                uint64_t* mine = xch_local + (size_t)buf * (1024 * ROW) + (size_t)t * ROW;
-#pragma unroll
-                for (int e = 0; e < E; ++e) mine[e] = v[e];
-                __syncthreads();
-                const uint64_t* theirs = xch_local + (size_t)buf * (1024 * ROW) + (size_t)(t ^ dm) * ROW;
-                const bool lower = (t & dm) == 0;
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const uint64_t p = theirs[e];
-                    const bool desc = ((gbase | e) & k) == 0;
-                    const bool take_max = (lower == desc);
-                    v[e] = take_max ? (v[e] > p ? v[e] : p) : (v[e] < p ? v[e] : p);
-                }
-                buf ^= 1;
-            } else if (j >= E) {  // another lane of this warp
-                const int lm = j >> LOG_E;
-                const bool lower = (t & lm) == 0;
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const uint64_t p = __shfl_xor_sync(0xffffffffu, v[e], lm);
-                    const bool desc = ((gbase | e) & k) == 0;
-                    const bool take_max = (lower == desc);
-                    v[e] = take_max ? (v[e] > p ? v[e] : p) : (v[e] < p ? v[e] : p);
-                }
-            } else {  // both elements in this thread's registers
-                // sort_local_stage derives the direction from (t << LOG_E | e) & k; add the CTA offset through t
-                const int tt = crank * 1024 + t;
-                if (j == 4) sort_local_stage<E, 4>(v, k, tt, LOG_E);
-                else if (j == 2) sort_local_stage<E, 2>(v, k, tt, LOG_E);
-                else sort_local_stage<E, 1>(v, k, tt, LOG_E);
-            }
+        for (int q = warp * csize + crank; q < units; q += 32 * csize) {
+            const int g = q * 32 + lane;
+            if (g < V) f(tk_load_key(scores, stride, offset, A, b, g), g);
         }
     }
 }
 
-template <int E>
-__device__ __forceinline__ void tk_sort_emit(const uint64_t* slots, uint64_t* xch_local, uint64_t* xch_remote,
-                                             cg::cluster_group& cluster, int crank, int csize, int A, int K, int b,
-                                             int32_t* idx_out, float* vals_out, const TopkDecode& dec, bool has_dec) {
-    const int tid = threadIdx.x;
-    uint64_t v[E];
+// number of elements of the descending list s[0, n) that are greater than x (all elements are distinct)
+__device__ __forceinline__ int count_greater(const uint64_t* __restrict__ s, int n, uint64_t x) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s[mid] > x) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kTkThreads, 1)
+topk_cluster_kernel(const float* __restrict__ scores, int stride, int offset, int A, int K,
+                    int32_t* __restrict__ idx_out, float* __restrict__ vals_out, TopkDecode dec, bool has_dec) {
+    extern __shared__ __align__(16) unsigned char tk_smem[];
+    __shared__ TkControl ctl;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int csize = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
+    const int b = blockIdx.x / csize, tid = threadIdx.x;
+    uint64_t* list = reinterpret_cast<uint64_t*>(tk_smem);                                  // [8192] own candidates
+    unsigned char* scratch = tk_smem + kTkListBytes;
+    uint32_t* hist2 = reinterpret_cast<uint32_t*>(scratch + kTkHistOffset);                 // [2][4096]
+    pdl_launch_dependents();
+    if (tid == 0) ctl.n_list = 0;
+    pdl_wait();
+
+    // ---- 1. radix select on the composite (key << 32 | ~index) -----------------------------------------
+    uint64_t prefix = 0;               // the resolved leading bits of the K-th composite (== composite >> shift)
+    uint32_t need = (uint32_t)K, above_total = 0, in_bin = 0;
+    int shift = 64;
+    for (int level = 0; level < 6; ++level) {
+        const int bits = (level % 3 < 2) ? 12 : 8;   // key: 12 + 12 + 8, then (tie floods only) index: 12 + 12 + 8
+        const int nb = 1 << bits;
+        const int pshift = shift;  // bits above `pshift` are resolved (== prefix)
+        shift -= bits;
+        uint32_t* hist = hist2 + (level & 1) * 4096;
+        for (int i = tid; i < nb; i += kTkThreads) hist[i] = 0;
+        __syncthreads();
+        for_each_key<MODE>(scores, stride, offset, A, b, crank, csize, [&](uint32_t key, int a) {
+            const uint64_t c = make_composite(key, (uint32_t)a);
+            if (level == 0 || (c >> pshift) == prefix) atomicAdd(&hist[(uint32_t)(c >> shift) & (uint32_t)(nb - 1)], 1u);
+        });
+        cluster.sync();  // every CTA's histogram of this level is complete (and nobody reads the other buffer any more)
+        // every CTA sums the whole histogram over the cluster: thread t owns bins 4t .. 4t+3
+        uint4 tot = make_uint4(0u, 0u, 0u, 0u);
+        if (4 * tid < nb) {
+            for (int r = 0; r < csize; ++r) {
+                const uint4 p = *reinterpret_cast<const uint4*>(cluster.map_shared_rank(hist, r) + 4 * tid);
+                tot.x += p.x; tot.y += p.y; tot.z += p.z; tot.w += p.w;
+            }
+        }
+        const uint32_t tsum = tot.x + tot.y + tot.z + tot.w;
+        const int before = block_exclusive_scan((int)tsum, ctl.warp_sums, &ctl.scan_total);
+        const uint32_t above_t = (uint32_t)ctl.scan_total - (uint32_t)before - tsum;  // bins owned by higher threads
+        if (above_t < need && need <= above_t + tsum) {  // exactly one thread: its bins hold the K-th element
+            const uint32_t c[4] = {tot.x, tot.y, tot.z, tot.w};
+            uint32_t acc = above_t;
 #pragma unroll
-    for (int e = 0; e < E; ++e) v[e] = slots[tid * E + e];
-    __syncthreads();  // the exchange buffers alias the slot array
-    cluster_sort_desc<E>(v, xch_local, xch_remote, cluster, crank, csize);
+            for (int i = 3; i >= 0; --i) {
+                if (acc < need && need <= acc + c[i]) {
+                    ctl.sel[0] = (uint32_t)(4 * tid + i);
+                    ctl.sel[1] = need - acc;
+                    ctl.sel[2] = c[i];
+                }
+                acc += c[i];
+            }
+        }
+        __syncthreads();
+        const uint32_t digit = ctl.sel[0], need_left = ctl.sel[1];
+        in_bin = ctl.sel[2];
+        prefix = (prefix << bits) | (uint64_t)digit;
+        above_total += need - need_left;
+        need = need_left;
+        if (above_total + in_bin <= (uint32_t)kMaxSort) break;   // certain at the last level: composites are distinct
+    }
+
+    // ---- 2. compaction of this CTA's candidates into its own list ---------------------------------------
+    for_each_key<MODE>(scores, stride, offset, A, b, crank, csize, [&](uint32_t key, int a) {
+        const uint64_t c = make_composite(key, (uint32_t)a);
+        if ((c >> shift) >= prefix) list[atomicAdd(&ctl.n_list, 1u)] = c;
+    });
+    __syncthreads();
+    const int n_mine = (int)ctl.n_list;
+
+    // ---- 3. local sort, exchange of the sorted lists, global ranks ----------------------------------------
+    const int sort_n = max(32, 1 << (32 - __clz(max(n_mine, 1) - 1)));
+    for (int i = n_mine + tid; i < sort_n; i += kTkThreads) list[i] = 0ull;  // padding sorts last
+    __syncthreads();
+    if (sort_n <= 4096) {
+        block_sort_desc_any(list, sort_n, reinterpret_cast<uint64_t*>(scratch));
+    } else {  // 8192 keys: eight per thread in registers; the exchange buffers start at the (then dead) list itself
+        uint64_t v[8];
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const int r = (crank * 1024 + tid) * E + e;
+        for (int e = 0; e < 8; ++e) v[e] = list[tid * 8 + e];
+        __syncthreads();
+        block_sort_desc_blocked<8>(v, reinterpret_cast<uint64_t*>(tk_smem));
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) list[tid * 8 + e] = v[e];
+        __syncthreads();
+    }
+    if (tid < csize) cluster.map_shared_rank(&ctl.cnt[0], tid)[crank] = (uint32_t)n_mine;
+    cluster.sync();  // every list is sorted, every length is known everywhere
+    uint64_t* gathered = reinterpret_cast<uint64_t*>(scratch);   // peers' lists, back to back (total <= 8192 entries)
+    int off[8];
+    {
+        int acc = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            off[r] = acc;
+            if (r < csize && r != crank) acc += (int)ctl.cnt[r];
+        }
+    }
+    for (int r = 0; r < csize; ++r) {
+        if (r == crank) continue;
+        const uint64_t* src = cluster.map_shared_rank(list, r);
+        const int n = (int)ctl.cnt[r];
+        for (int i = tid; i < n; i += kTkThreads) gathered[off[r] + i] = src[i];
+    }
+    // this CTA no longer reads its peers' shared memory: arrive now, wait at exit
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    __syncthreads();
+
+    // ---- 4. emit at the global rank ------------------------------------------------------------------------
+    for (int i = tid; i < n_mine; i += kTkThreads) {
+        const uint64_t v = list[i];
+        int r = i;
+        for (int p = 0; p < csize; ++p)
+            if (p != crank) r += count_greater(gathered + off[p], (int)ctl.cnt[p], v);
         if (r >= K) continue;
-        const uint32_t a = composite_idx(v[e]);
+        const uint32_t a = composite_idx(v);
         if (idx_out) idx_out[(size_t)b * K + r] = (int32_t)a;
-        if (vals_out) vals_out[(size_t)b * K + r] = key_score(composite_key(v[e]));
+        if (vals_out) vals_out[(size_t)b * K + r] = key_score(composite_key(v));
         if (has_dec) {
             // L:247-261: gather anchors / deltas by index, scale by std_dev (L:238), decode, clip to [0,1]
             const float4 an = __ldg(dec.anchors + (size_t)b * A + a);
@@ -161,184 +239,26 @@ __device__ __forceinline__ void tk_sort_emit(const uint64_t* slots, uint64_t* xc
             if (dec.pre_nms_boxes) dec.pre_nms_boxes[(size_t)b * K + r] = bx;
         }
     }
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // no CTA leaves while a peer may still read its list
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kTkThreads, 1)
-topk_cluster_kernel(const float* __restrict__ scores, int stride, int offset, int A, int K, int chunk,
-                    int32_t* __restrict__ idx_out, float* __restrict__ vals_out, TopkDecode dec, bool has_dec) {
-    extern __shared__ __align__(16) unsigned char tk_smem[];
-    __shared__ TkControl ctl;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int csize = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
-    const int b = blockIdx.x / csize, tid = threadIdx.x;
-    const int E = kMaxSort / (csize * kTkThreads);
-    uint32_t* hist = reinterpret_cast<uint32_t*>(tk_smem);                  // [4096]
-    uint32_t* slice_tot = hist + 4096;                                      // [4096 / csize]
-    uint64_t* region = reinterpret_cast<uint64_t*>(slice_tot + 4096);
-    uint64_t* staging = region;                                             // [8192] above from the front, boundary from the back
-    uint64_t* slots = region + kMaxSort;                                    // [1024 * E] this CTA's sort input
-    uint64_t* xch_local = region;                                           // sort: aliases staging / slots (both dead by then)
-    uint64_t* xch_remote = region + 2 * 1024 * (E + 2);
-    const int lo = min(A, crank * chunk), hi = min(A, lo + chunk);
+static size_t tk_smem_bytes() { return kTkListBytes + kTkScratchBytes; }
 
-    // ---- 1. radix select -----------------------------------------------------------------------------
-    uint32_t prefix = 0, need = (uint32_t)K, above_total = 0, in_bin = 0;
-    int shift = 32;
-    bool fits = false;
-    for (int level = 0; level < 3; ++level) {
-        const int bits = (level < 2) ? 12 : 8;
-        const int nb = 1 << bits;
-        const int W = nb / csize;  // bins per slice
-        const int pshift = shift;  // bits above `pshift` are resolved (== prefix)
-        shift -= bits;
-        for (int i = tid; i < nb; i += kTkThreads) hist[i] = 0;
-        __syncthreads();
-        for_each_key<MODE>(scores, stride, offset, A, b, lo, hi, [&](uint32_t key, int) {
-            if (level == 0 || (key >> pshift) == prefix) atomicAdd(&hist[(key >> shift) & (uint32_t)(nb - 1)], 1u);
-        });
-        __syncthreads();
-        cluster.sync();  // every CTA's histogram is complete
-        // CTA `crank` sums bin slice `crank` over the cluster
-        uint32_t part = 0;
-        for (int i = tid; i < W; i += kTkThreads) {
-            uint32_t tot = 0;
-            for (int r = 0; r < csize; ++r) tot += cluster.map_shared_rank(hist, r)[crank * W + i];
-            slice_tot[i] = tot;
-            part += tot;
-        }
-        {
-            const int excl = block_exclusive_scan((int)part, ctl.warp_sums, &ctl.scan_total);
-            (void)excl;
-        }
-        if (tid < csize) cluster.map_shared_rank(&ctl.slice_sum[0], tid)[crank] = (uint32_t)ctl.scan_total;
-        cluster.sync();  // slice totals of every CTA are visible everywhere
-        uint32_t above_s = 0;
-        for (int r = crank + 1; r < csize; ++r) above_s += ctl.slice_sum[r];
-        const uint32_t mine = ctl.slice_sum[crank];
-        if (above_s < need && need <= above_s + mine) {  // this CTA's slice holds the K-th element (CTA-uniform)
-            const int per = (W + kTkThreads - 1) / kTkThreads;  // bins per thread (1..4)
-            uint32_t tsum = 0;
-            for (int i = tid * per; i < min(W, (tid + 1) * per); ++i) tsum += slice_tot[i];
-            const int before = block_exclusive_scan((int)tsum, ctl.warp_sums, &ctl.scan_total);
-            const uint32_t above_t = above_s + (mine - (uint32_t)before - tsum);  // bins of higher threads
-            if (above_t < need && need <= above_t + tsum) {
-                uint32_t acc = above_t;
-                for (int i = min(W, (tid + 1) * per) - 1; i >= tid * per; --i) {
-                    const uint32_t c = slice_tot[i];
-                    if (need <= acc + c) {
-                        for (int r = 0; r < csize; ++r) {
-                            uint32_t* dst = cluster.map_shared_rank(&ctl.sel[0], r);
-                            dst[0] = (uint32_t)(crank * W + i);
-                            dst[1] = need - acc;
-                            dst[2] = c;
-                        }
-                        break;
-                    }
-                    acc += c;
-                }
-            }
-        }
-        cluster.sync();  // the selection is visible in every CTA
-        const uint32_t digit = ctl.sel[0], need_left = ctl.sel[1];
-        in_bin = ctl.sel[2];
-        prefix = (level == 0) ? digit : ((prefix << bits) | digit);
-        above_total += need - need_left;
-        need = need_left;
-        if (above_total + in_bin <= (uint32_t)kMaxSort) { fits = true; break; }
-    }
-
-    // ---- 2. compaction into shared memory, offsets, scatter to the sort slots ----------------------------
-    if (tid == 0) { ctl.n_a = 0; ctl.n_b = 0; }
-    for (int i = tid; i < kTkThreads * E; i += kTkThreads) slots[i] = 0ull;
-    __syncthreads();
-    if (fits) {
-        for_each_key<MODE>(scores, stride, offset, A, b, lo, hi, [&](uint32_t key, int a) {
-            const uint32_t kp = key >> shift;
-            if (kp > prefix) staging[atomicAdd(&ctl.n_a, 1u)] = make_composite(key, (uint32_t)a);
-            else if (kp == prefix) staging[kMaxSort - 1 - atomicAdd(&ctl.n_b, 1u)] = make_composite(key, (uint32_t)a);
-        });
-        __syncthreads();
-    } else {
-        // tie flood: all 32 key bits resolved (prefix = K-th key, need = how many of its copies belong to the
-        // top K); copies are taken in index order
-        uint32_t eq_local = 0;
-        for_each_key<MODE>(scores, stride, offset, A, b, lo, hi, [&](uint32_t key, int a) {
-            if (key > prefix) staging[atomicAdd(&ctl.n_a, 1u)] = make_composite(key, (uint32_t)a);
-            else if (key == prefix) ++eq_local;
-        });
-        (void)block_exclusive_scan((int)eq_local, ctl.warp_sums, &ctl.scan_total);
-        if (tid < csize) cluster.map_shared_rank(&ctl.cnt_eq[0], tid)[crank] = (uint32_t)ctl.scan_total;
-        cluster.sync();
-        uint32_t eq_before = 0;
-        for (int r = 0; r < crank; ++r) eq_before += ctl.cnt_eq[r];
-        const uint32_t quota = (need > eq_before) ? min(need - eq_before, ctl.cnt_eq[crank]) : 0u;
-        uint32_t taken = 0;  // uniform
-        for (int a0 = lo; a0 < hi && taken < quota; a0 += kTkThreads) {
-            const int a = a0 + tid;
-            const bool eq = (a < hi) && tk_load_key(scores, stride, offset, A, b, a) == prefix;
-            const int rank = block_exclusive_scan(eq ? 1 : 0, ctl.warp_sums, &ctl.scan_total);
-            if (eq && taken + (uint32_t)rank < quota)
-                staging[kMaxSort - 1 - (taken + (uint32_t)rank)] = make_composite(prefix, (uint32_t)a);
-            taken += (uint32_t)ctl.scan_total;
-            __syncthreads();
-        }
-        if (tid == 0) ctl.n_b = quota;
-        __syncthreads();
-    }
-    const uint32_t n_a = ctl.n_a, n_b = ctl.n_b;
-    if (tid < csize) {
-        cluster.map_shared_rank(&ctl.cnt_a[0], tid)[crank] = n_a;
-        cluster.map_shared_rank(&ctl.cnt_b[0], tid)[crank] = n_b;
-    }
-    cluster.sync();  // counts visible everywhere, every CTA's slot array is zeroed
-    uint32_t off_a = 0, tot_a = 0, off_b = 0;
-    for (int r = 0; r < csize; ++r) {
-        if (r < crank) { off_a += ctl.cnt_a[r]; off_b += ctl.cnt_b[r]; }
-        tot_a += ctl.cnt_a[r];
-    }
-    off_b += tot_a;
-    const uint32_t per_cta = (uint32_t)(kTkThreads * E);
-    for (uint32_t i = tid; i < n_a + n_b; i += kTkThreads) {
-        const bool is_a = i < n_a;
-        const uint32_t pos = is_a ? off_a + i : off_b + (i - n_a);
-        const uint64_t comp = is_a ? staging[i] : staging[kMaxSort - 1 - (i - n_a)];
-        if (pos < (uint32_t)kMaxSort) cluster.map_shared_rank(slots, pos / per_cta)[pos % per_cta] = comp;
-    }
-    cluster.sync();  // every candidate sits in its slot
-
-    // ---- 3 + 4. sort and emit ---------------------------------------------------------------------------
-    if (E == 1) tk_sort_emit<1>(slots, xch_local, xch_remote, cluster, crank, csize, A, K, b, idx_out, vals_out, dec, has_dec);
-    else if (E == 2) tk_sort_emit<2>(slots, xch_local, xch_remote, cluster, crank, csize, A, K, b, idx_out, vals_out, dec, has_dec);
-    else if (E == 4) tk_sort_emit<4>(slots, xch_local, xch_remote, cluster, crank, csize, A, K, b, idx_out, vals_out, dec, has_dec);
-    else tk_sort_emit<8>(slots, xch_local, xch_remote, cluster, crank, csize, A, K, b, idx_out, vals_out, dec, has_dec);
-    cluster.sync();  // no CTA leaves while a peer may still read its exchange buffers
-}
-
-static size_t tk_smem_bytes(int cs);
 template <int M> static int tk_cluster_size_for(int B) {
-    static int cache[4][2] = {};
-    return pick_cluster_size(topk_cluster_kernel<M>, kTkThreads, B, 8, [](int cs) { return tk_smem_bytes(cs); }, cache);
+    return pick_cluster_size((const void*)topk_cluster_kernel<M>, kTkThreads, B, 8, [](int) { return tk_smem_bytes(); });
 }
 
-static size_t tk_smem_bytes(int cs) {
-    const int E = kMaxSort / (cs * kTkThreads);
-    const size_t stage = (size_t)(kMaxSort + kTkThreads * E) * 8;
-    const size_t sort = (size_t)2 * 1024 * (E + 2) * 8 + (cs > 1 ? (size_t)2 * 1024 * E * 8 : 0);
-    return 2 * 4096 * sizeof(uint32_t) + (stage > sort ? stage : sort);
-}
+size_t topk_ws_bytes(int /*B*/) { return 256; }  // the cluster kernel keeps everything on chip
 
-int launch_topk_cluster(const float* scores, int stride, int offset, int B, int A, int K, int32_t* idx, float* vals,
-                        const TopkDecode* dec, cudaStream_t stream) {
+int launch_topk(const float* scores, int stride, int offset, int B, int A, int K, int32_t* idx, float* vals,
+                const TopkDecode* dec, void* /*ws*/, cudaStream_t stream) {
     int mode = 0;
     if (aligned16(scores)) {
         if (stride == 2 && (A % 2) == 0) mode = 2;
         else if (stride == 1 && (A % 4) == 0) mode = 1;
     }
     const int cs = (mode == 2) ? tk_cluster_size_for<2>(B) : (mode == 1) ? tk_cluster_size_for<1>(B) : tk_cluster_size_for<0>(B);
-    const size_t smem = tk_smem_bytes(cs);
-    int chunk = (A + cs - 1) / cs;
-    chunk = (chunk + 3) & ~3;
+    const size_t smem = tk_smem_bytes();
     TopkDecode d{};
     if (dec) d = *dec;
     const bool has_dec = dec != nullptr;
@@ -347,19 +267,19 @@ int launch_topk_cluster(const float* scores, int stride, int offset, int B, int 
     cfg.blockDim = dim3(kTkThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 1 + (unsigned)pdl_attr(attr + 1);
     cudaError_t e;
 #define MRCNN_TK(M)                                                                                                   \
     do {                                                                                                              \
         e = cudaFuncSetAttribute(topk_cluster_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
         if (e != cudaSuccess) return (int)e;                                                                          \
-        e = cudaLaunchKernelEx(&cfg, topk_cluster_kernel<M>, scores, stride, offset, A, K, chunk, idx, vals, d, has_dec); \
+        e = cudaLaunchKernelEx(&cfg, topk_cluster_kernel<M>, scores, stride, offset, A, K, idx, vals, d, has_dec); \
     } while (0)
     if (mode == 2) MRCNN_TK(2);
     else if (mode == 1) MRCNN_TK(1);
@@ -370,3 +290,23 @@ int launch_topk_cluster(const float* scores, int stride, int offset, int B, int 
 }
 
 }  // namespace mrcnn
+
+using namespace mrcnn;
+
+MRCNN_EXPORT int mrcnn_topk_workspace_bytes(int B, int A, int K, size_t* bytes) {
+    if (!bytes) return MRCNN_ERR_NULL;
+    if (B < 1 || A < 1 || K < 1 || K > A || K > kMaxSort) return MRCNN_ERR_RANGE;
+    *bytes = topk_ws_bytes(B);
+    return MRCNN_OK;
+}
+
+MRCNN_EXPORT int mrcnn_topk_forward(const float* scores, int stride, int offset, int B, int A, int K, int32_t* idx,
+                                    float* vals, void* ws, size_t ws_bytes, void* stream) {
+    if (!scores || !idx || !ws) return MRCNN_ERR_NULL;
+    if (B < 1 || A < 1 || K < 1 || K > A || K > kMaxSort || stride < 1 || offset < 0 || offset >= stride)
+        return MRCNN_ERR_RANGE;
+    if ((size_t)B * A * stride > 0x7fffffffull * 4) return MRCNN_ERR_RANGE;
+    if (ws_bytes < topk_ws_bytes(B)) return MRCNN_ERR_WORKSPACE;
+    if (!aligned16(ws)) return MRCNN_ERR_ALIGN;
+    return launch_topk(scores, stride, offset, B, A, K, idx, vals, nullptr, ws, (cudaStream_t)stream);
+}
