@@ -79,6 +79,10 @@ bool pdl_enabled() {
     static const bool on = [] { const char* e = getenv("MRCNN_PDL"); return !(e && strcmp(e, "0") == 0); }();
     return on;
 }
+int tuning_knob(const char* name, int fallback) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : fallback;
+}
 }  // namespace mrcnn
 
 MRCNN_EXPORT const char* mrcnn_roi_b200_version(void) { return "mrcnn_roi_b200 0.1.0 (sm_100a)"; }

@@ -36,6 +36,8 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __attribute__((visibility("hidden"))) bool pdl_enabled();   // api.cu: getenv("MRCNN_PDL") != "0", read once
+// integer tuning knob for measurements (getenv on every call: no cached state); `fallback` when unset
+__attribute__((visibility("hidden"))) int tuning_knob(const char* name, int fallback);
 
 // fills `attr[0]` with the PDL attribute when enabled; returns the number of attributes written
 static inline int pdl_attr(cudaLaunchAttribute* attr) {
@@ -323,6 +325,54 @@ __device__ __forceinline__ float iou_screen_d(const float4& bk, float tak, const
     const float dh = fmaxf(__fsub_rn(fminf(bk.z, bc.z), fmaxf(bk.x, bc.x)), 0.0f);
     const float dw = __fsub_rn(fminf(bk.w, bc.w), fmaxf(bk.y, bc.y));
     return __fmaf_rn(__fmul_rn(dh, dw), c1, -__fadd_rn(tak, tac));
+}
+// Two candidates per lane, packed for the f32x2 pipe (FADD2 / FMUL2 / FFMA2 on sm_100): the screen of one kept box
+// against both costs 8 FMNMX + 2 clamps + 5 packed operations instead of 20 scalar ones, with the SAME roundings as
+// iou_screen_d (sub, mul, add, fma individually rounded; (-a) + (-b) == -(a + b) exactly).
+__device__ __forceinline__ unsigned long long pack_f2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long sub_f2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long add_f2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul_f2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma_f2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+struct CandPair {   // candidates c0 (low halves) and c1 (high halves) of one lane
+    float y1a, x1a, y2a, x2a, y1b, x1b, y2b, x2b;
+    unsigned long long ntac;   // (-thr * area_c0, -thr * area_c1)
+};
+// d = inter * (1 + thr) - (tak + tac) for both candidates; ntak = -thr * area_k, c1 = (1 + thr, 1 + thr)
+__device__ __forceinline__ void iou_screen_d2(const float4& bk, float ntak, const CandPair& c, unsigned long long c1,
+                                              float& d0, float& d1) {
+    const unsigned long long top = pack_f2(fminf(bk.z, c.y2a), fminf(bk.z, c.y2b));
+    const unsigned long long bot = pack_f2(fmaxf(bk.x, c.y1a), fmaxf(bk.x, c.y1b));
+    float h0, h1;
+    unpack_f2(sub_f2(top, bot), h0, h1);
+    const unsigned long long dh = pack_f2(fmaxf(h0, 0.0f), fmaxf(h1, 0.0f));
+    const unsigned long long rgt = pack_f2(fminf(bk.w, c.x2a), fminf(bk.w, c.x2b));
+    const unsigned long long lft = pack_f2(fmaxf(bk.y, c.x1a), fmaxf(bk.y, c.x1b));
+    const unsigned long long inter = mul_f2(dh, sub_f2(rgt, lft));
+    unpack_f2(fma_f2(inter, c1, add_f2(pack_f2(ntak, ntak), c.ntac)), d0, d1);
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {  // FMNMX3 (sm_100)
     float d;

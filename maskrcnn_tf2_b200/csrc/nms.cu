@@ -49,7 +49,7 @@ struct NmsInput {
 // FUSED: order the candidates in the kernel (cluster size 1 only).
 template <bool COMPACT, bool FUSED>
 __global__ void __launch_bounds__(kNmsThreads, 1)
-nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, NmsEpilogue epi) {
+nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, int roles, NmsEpilogue epi) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
     const int cap = min(max_out, M);
     // fused ordering: composites and the candidate -> row map sit in front of the NMS arrays
@@ -58,10 +58,13 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
     int32_t* s_orig = reinterpret_cast<int32_t*>(nms_smem + (size_t)sort_n_max * 8);
     unsigned char* body = nms_smem + (FUSED ? (size_t)sort_n_max * 8 + (((size_t)M * 4 + 15) & ~(size_t)15) : 0);
     float4* sb = reinterpret_cast<float4*>(body);              // [M] min/max-normalised corners
-    float4* kb = sb + M;                                        // [cap] kept boxes in selection order (COMPACT)
-    float* sa = reinterpret_cast<float*>(kb + (COMPACT ? cap : 0));  // [M] areas
-    float* kt = sa + M;                                         // [cap] thr * area of the kept boxes (COMPACT)
-    int32_t* sel = reinterpret_cast<int32_t*>(kt + (COMPACT ? cap : 0));  // [cap] kept candidate positions
+    // COMPACT: kept box k of the selection order belongs to far warp (k % nsrc) of the cluster; the far warps of THIS CTA
+    // get dense private copies [far warp][k / nsrc] of (box, -thr * area), so that a far warp streams its share with
+    // consecutive shared-memory loads (capacity kCompactSlack entries above cap: nms_smem_bytes)
+    float4* kb = sb + M;                                        // [nfar][wcap]
+    float* sa = reinterpret_cast<float*>(kb + (COMPACT ? cap + kCompactSlack : 0));  // [M] areas
+    float* kt = sa + M;                                         // [nfar][wcap]
+    int32_t* sel = reinterpret_cast<int32_t*>(kt + (COMPACT ? cap + kCompactSlack : 0));  // [cap] kept candidate positions
     __shared__ __align__(16) unsigned long long s_rows[kRing][kRows];   // [tile % kRing][0..63 diag rows, 64 d + i: cross_d rows]
     __shared__ __align__(16) unsigned long long s_stage[kRing][kRows];  // this CTA's rows on their way out
     __shared__ unsigned long long s_far[kRing][kMaxFarSrc];     // [tile % kRing][source CTA * nfar + far warp], written by the peers
@@ -75,6 +78,8 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
     const uint32_t bar_base = smem_u32(&s_bar[0]);
     const int rel_threads = 32 * (1 + nfar + nrow);  // the release barrier: resolver (arrives) + far and row warps (wait)
     const int nsrc = csize * nfar;                   // far partials per tile: one per far warp of the cluster
+    const int wcap = (cap + nsrc - 1) / nsrc + 1;    // entries of one far warp's private kept list
+    const uint32_t nsrc_magic = ((1u << 20) + (uint32_t)nsrc - 1u) / (uint32_t)nsrc;  // k / nsrc == (k * magic) >> 20, k < 2^13
     // per tile every CTA receives one 64-bit far partial from each far warp of the cluster and, as one bulk copy per
     // CTA, the rows of the tile's diag + cross blocks
     const uint32_t far_bytes = (uint32_t)nsrc * 8u + (uint32_t)kRows * 8u;
@@ -108,20 +113,37 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
         }
         __syncthreads();
         const int nc = s_ncand;
-        const int sort_n = max(32, 1 << (32 - __clz(max(nc, 1) - 1)));
-        for (int i = nc + tid; i < sort_n; i += kNmsThreads) s_comp[i] = 0ull;
-        __syncthreads();
-        block_sort_desc_any(s_comp, sort_n, reinterpret_cast<uint64_t*>(body));  // exchange buffers alias the NMS arrays
-        __syncthreads();
         n = nc;
-        for (int r = tid; r < n; r += kNmsThreads) {
-            const int i = (int)composite_idx(s_comp[r]);
-            s_orig[r] = i;
-            float a;
-            float4 t = normalise_box(__ldg(bx + i), a);
-            if (!(a > 0.0f)) { t = kNone; a = 1.0f; }
-            sb[r] = t;
-            sa[r] = a;
+        if (nc <= 512) {
+            // few candidates (DetectionLayer: ~150 of 1000 ROIs): rank by counting -- thread r counts the composites above
+            // its own (broadcast shared-memory loads, no barrier) and stages its box at that rank directly
+            for (int r = tid; r < nc; r += kNmsThreads) {
+                const uint64_t x = s_comp[r];
+                int rank = 0;
+                for (int j = 0; j < nc; ++j) rank += (s_comp[j] > x);
+                const int i = (int)composite_idx(x);
+                s_orig[rank] = i;
+                float a;
+                float4 t = normalise_box(__ldg(bx + i), a);
+                if (!(a > 0.0f)) { t = kNone; a = 1.0f; }
+                sb[rank] = t;
+                sa[rank] = a;
+            }
+        } else {
+            const int sort_n = max(32, 1 << (32 - __clz(max(nc, 1) - 1)));
+            for (int i = nc + tid; i < sort_n; i += kNmsThreads) s_comp[i] = 0ull;
+            __syncthreads();
+            block_sort_desc_any(s_comp, sort_n, reinterpret_cast<uint64_t*>(body));  // exchange buffers alias the NMS arrays
+            __syncthreads();
+            for (int r = tid; r < n; r += kNmsThreads) {
+                const int i = (int)composite_idx(s_comp[r]);
+                s_orig[r] = i;
+                float a;
+                float4 t = normalise_box(__ldg(bx + i), a);
+                if (!(a > 0.0f)) { t = kNone; a = 1.0f; }
+                sb[r] = t;
+                sa[r] = a;
+            }
         }
     } else {
         for (int i = tid; i < n; i += kNmsThreads) {
@@ -152,7 +174,9 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
     // is the serial part of the kernel.  The other 24 warps are numbered 0..23 in order: the first nfar are far warps,
     // the next nrow row warps; the rest only helped with the staging and exit (exited threads count as arrived at the
     // barriers below).
-    const int ri = (warp & 3) ? (warp >> 2) * 3 + (warp & 3) - 1 : -1;
+    // roles == 1: the workers are warps 1, 2, 3, ... in order, i.e. two far and two row warps share the resolver's
+    // scheduler (the resolver waits for its workers about half of the time: measured).
+    const int ri = roles ? warp - 1 : ((warp & 3) ? (warp >> 2) * 3 + (warp & 3) - 1 : -1);
     if (warp != 0 && (ri < 0 || ri >= nfar + nrow)) return;
     const int eidx = (warp == 0) ? lane : (1 + ri) * 32 + lane;  // dense index of the surviving threads (epilogue)
     int nkept = 0, t = 0;
@@ -172,8 +196,8 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
             float4 mb0 = kNone, mb1 = kNone;
             float mt0 = thr, mt1 = thr;
             if (COMPACT) {
-                if (c0 < n) { mb0 = sb[c0]; mt0 = __fmul_rn(thr, sa[c0]); }
-                if (c1 < n) { mb1 = sb[c1]; mt1 = __fmul_rn(thr, sa[c1]); }
+                if (c0 < n) { mb0 = sb[c0]; mt0 = -__fmul_rn(thr, sa[c0]); }
+                if (c1 < n) { mb1 = sb[c1]; mt1 = -__fmul_rn(thr, sa[c1]); }
             }
             uint64_t removed = 0;
             if (t >= 1) {  // slot j serves tiles j, j + 8, ...; tile 0 has no far / cross set
@@ -209,12 +233,20 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
             if ((kept >> lane) & 1ull) {
                 const int pos = nkept + __popcll(kept & ((1ull << lane) - 1ull));
                 sel[pos] = c0;
-                if (COMPACT) { kb[pos] = mb0; kt[pos] = mt0; }
+                if (COMPACT) {
+                    const uint32_t q = ((uint32_t)pos * nsrc_magic) >> 20;
+                    const uint32_t lw = (uint32_t)pos - q * (uint32_t)nsrc - (uint32_t)(crank * nfar);
+                    if (lw < (uint32_t)nfar) { kb[lw * wcap + q] = mb0; kt[lw * wcap + q] = mt0; }
+                }
             }
             if ((kept >> (lane + 32)) & 1ull) {
                 const int pos = nkept + __popcll(kept & ((1ull << (lane + 32)) - 1ull));
                 sel[pos] = c1;
-                if (COMPACT) { kb[pos] = mb1; kt[pos] = mt1; }
+                if (COMPACT) {
+                    const uint32_t q = ((uint32_t)pos * nsrc_magic) >> 20;
+                    const uint32_t lw = (uint32_t)pos - q * (uint32_t)nsrc - (uint32_t)(crank * nfar);
+                    if (lw < (uint32_t)nfar) { kb[lw * wcap + q] = mb1; kt[lw * wcap + q] = mt1; }
+                }
             }
             nkept += __popcll(kept);
 #pragma unroll
@@ -251,28 +283,42 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
         };
         PROFW_DECL;
         int nk_known = 0;  // kept count after tile u-3 (read at the previous release)
+        float tkmax = 0.0f;  // largest thr * area over this warp's share so far (the list only grows)
+        const float4* kbw = kb + fw * wcap;
+        const float* ktw = kt + fw * wcap;
+        const unsigned long long c1_2 = pack_f2(cthr, cthr);
         for (int u = 1; u < tiles; ++u) {
             const int ubase = u * kTile;
             const int c0 = ubase + lane, c1 = c0 + 32;
             const float4 b0 = (c0 < n) ? sb[c0] : kNone, b1 = (c1 < n) ? sb[c1] : kNone;
             const float a0 = (c0 < n) ? sa[c0] : 1.0f, a1 = (c1 < n) ? sa[c1] : 1.0f;
             const float tc0 = __fmul_rn(thr, a0), tc1 = __fmul_rn(thr, a1);
+            CandPair cp;
+            cp.y1a = b0.x; cp.x1a = b0.y; cp.y2a = b0.z; cp.x2a = b0.w;
+            cp.y1b = b1.x; cp.x1b = b1.y; cp.y2b = b1.z; cp.x2b = b1.w;
+            cp.ntac = pack_f2(-tc0, -tc1);
             const uint32_t bar_u = bar_base + 8u * (uint32_t)(u & (kRing - 1));
             const uint32_t my_far = smem_u32(&s_far[u & (kRing - 1)][k0]);
-            float dmax0 = -3.0e38f, dmax1 = -3.0e38f, tkmax = 0.0f;
-            auto screen = [&](int j_begin, int j_end, int nk_lim) {  // this warp's boxes j_begin <= j < j_end of kept[0, nk_lim)
+            float dmax0 = -3.0e38f, dmax1 = -3.0e38f;
+            auto screen = [&](int j_begin, int j_end, int nk_lim, bool fresh) {  // this warp's boxes j_begin <= j < j_end
                 for (int j = j_begin; j < j_end; j += 4) {  // four kept boxes per round: independent IoU chains; a round
                     float d0[4], d1[4];                      // that runs past the list repeats its last box (harmless)
 #pragma unroll
                     for (int qq = 0; qq < 4; ++qq) {
-                        const int k = min(k0 + (j + qq) * nsrc, nk_lim - 1);
-                        float4 bk;
-                        float tk;
-                        if (COMPACT) { bk = kb[k]; tk = kt[k]; }
-                        else { const int ki = sel[k]; bk = sb[ki]; tk = __fmul_rn(thr, sa[ki]); }
-                        tkmax = fmaxf(tkmax, tk);
-                        d0[qq] = iou_screen_d(bk, tk, b0, tc0, cthr);
-                        d1[qq] = iou_screen_d(bk, tk, b1, tc1, cthr);
+                        if (COMPACT) {
+                            const int jj = min(j + qq, j_end - 1);
+                            const float4 bk = kbw[jj];
+                            const float ntk = ktw[jj];
+                            if (fresh) tkmax = fmaxf(tkmax, -ntk);
+                            iou_screen_d2(bk, ntk, cp, c1_2, d0[qq], d1[qq]);
+                        } else {
+                            const int ki = sel[min(k0 + (j + qq) * nsrc, nk_lim - 1)];
+                            const float4 bk = sb[ki];
+                            const float tk = __fmul_rn(thr, sa[ki]);
+                            tkmax = fmaxf(tkmax, tk);
+                            d0[qq] = iou_screen_d(bk, tk, b0, tc0, cthr);
+                            d1[qq] = iou_screen_d(bk, tk, b1, tc1, cthr);
+                        }
                     }
                     dmax0 = fmax3(fmax3(dmax0, d0[0], d0[1]), d0[2], d0[3]);
                     dmax1 = fmax3(fmax3(dmax1, d1[0], d1[1]), d1[2], d1[3]);
@@ -280,7 +326,7 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
             };
             PROFW_MARK(0);
             const int cnt_known = share(nk_known);
-            screen(0, cnt_known, nk_known);   // first instalment: no dependence on the release
+            screen(0, cnt_known, nk_known, false);   // first instalment: no dependence on the release
             int nk = 0;  // boxes kept in tiles <= u-kDepth
             if (u >= kDepth) {
                 asm volatile("bar.sync %0, %1;" ::"r"(3 + (u % kDepth)), "r"(rel_threads) : "memory");
@@ -294,7 +340,7 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
             }
             PROFW_MARK(1);
             const int cnt = share(nk);
-            screen(cnt_known, cnt, nk);       // second instalment: the boxes kept in tile u-2
+            screen(cnt_known, cnt, nk, true);         // second instalment: the boxes kept in tile u-2
             nk_known = nk;
             const float m0 = __fmul_rn(__fadd_rn(tkmax, tc0), kScreenBand), m1 = __fmul_rn(__fadd_rn(tkmax, tc1), kScreenBand);
             bool r0 = dmax0 > m0, r1 = dmax1 > m1;
@@ -321,6 +367,7 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
         // slot (u+1) % kRing of every CTA and is sent once resolve(u-kDepth) has released tile u (ring depth: nms_dev.cuh).
         const int rw = ri - nfar;  // 0..nrow-1
         const float cthr = __fadd_rn(1.0f, thr);
+        const unsigned long long c1_2 = pack_f2(cthr, cthr);
         auto send_rows = [&](int v) {
             const int vbase = v * kTile;
             const int c0 = vbase + lane, c1 = c0 + 32;
@@ -328,6 +375,10 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
             const float a0 = (c0 < n) ? sa[c0] : 1.0f, a1 = (c1 < n) ? sa[c1] : 1.0f;
             const uint32_t bar_v = bar_base + 8u * (uint32_t)(v & (kRing - 1));
             const float tc0 = __fmul_rn(thr, a0), tc1 = __fmul_rn(thr, a1);
+            CandPair cp;
+            cp.y1a = b0.x; cp.x1a = b0.y; cp.y2a = b0.z; cp.x2a = b0.w;
+            cp.y1b = b1.x; cp.x1b = b1.y; cp.y2b = b1.z; cp.x2b = b1.w;
+            cp.ntac = pack_f2(-tc0, -tc1);
             // this CTA owns the contiguous rows [crank * rpc, (crank + 1) * rpc) of the tile (0..63 diag, 64 d + i:
             // candidate i of tile v-d against tile v); they are staged locally and travel as ONE bulk copy per peer:
             // the receivers' mbarriers see csize transactions per tile instead of one per row
@@ -340,7 +391,8 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
                 const float4 bi = (ci >= 0 && ci < n) ? sb[ci] : kNone;
                 const float ai = (ci >= 0 && ci < n) ? sa[ci] : 1.0f;
                 const float ti = __fmul_rn(thr, ai);  // screen first; the exact division only inside the 2^-20 band
-                const float e0 = iou_screen_d(bi, ti, b0, tc0, cthr), e1 = iou_screen_d(bi, ti, b1, tc1, cthr);
+                float e0, e1;
+                iou_screen_d2(bi, -ti, cp, c1_2, e0, e1);
                 const float m0 = __fmul_rn(__fadd_rn(ti, tc0), kScreenBand), m1 = __fmul_rn(__fadd_rn(ti, tc1), kScreenBand);
                 bool h0 = e0 > m0, h1 = e1 > m1;
                 if (__any_sync(0xffffffffu, fabsf(e0) <= m0 || fabsf(e1) <= m1)) {
@@ -440,8 +492,15 @@ int launch_nms(const NmsInput& in, int B, int M, int max_out, float thr, const N
     // the per-tile work of a warp is a latency-bound chain (~5 cycles per instruction), so fixed overhead per warp
     // costs more than it buys.  Measured at config 2 (ProposalLayer, B=8 / B=16): (8,4) 134.5 / 200 us, (6,8) 129.2 /
     // 194, (6,12) 130.4 / 192, (8,12) 132.4 / 198, (10,14) 136.6 / 202; the single-CTA detection NMS does not react.
-    const int nfar = cs >= 4 ? 6 : 12, nrow = cs >= 4 ? 8 : (cs == 2 ? 8 : 12);
-    void* args[] = {(void*)&in, (void*)&M, (void*)&max_out, (void*)&thr, (void*)&nfar, (void*)&nrow, (void*)&epi};
+    int nfar = cs >= 4 ? 8 : 12, nrow = cs >= 4 ? 8 : (cs == 2 ? 8 : 12), roles = 1;
+    {   // measurement knobs (no cached state): MRCNN_NMS_NFAR / _NROW / _ROLES
+        const int kf = tuning_knob("MRCNN_NMS_NFAR", 0), kr = tuning_knob("MRCNN_NMS_NROW", 0);
+        roles = tuning_knob("MRCNN_NMS_ROLES", 1) ? 1 : 0;
+        const int max_workers = roles ? 31 : 24;
+        if (kf > 0 && kr > 0 && kf + kr <= max_workers && kf * cs <= kMaxFarSrc && kf <= 12) { nfar = kf; nrow = kr; }
+    }
+    void* args[] = {(void*)&in, (void*)&M, (void*)&max_out, (void*)&thr, (void*)&nfar, (void*)&nrow, (void*)&roles,
+                    (void*)&epi};
     cudaError_t e = cudaLaunchKernelExC(&cfg, kernel, args);
     if (e != cudaSuccess) return (int)e;
     return last_error();

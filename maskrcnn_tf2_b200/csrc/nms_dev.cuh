@@ -50,10 +50,11 @@ constexpr int kNmsWarps = kNmsThreads / 32;
 
 constexpr int kMaxFarSrc = 8 * 12;                 // far partials per tile: cluster size (<= 8) x far warps per CTA
 
+constexpr int kCompactSlack = 32;                  // the far warps' private kept lists: sum of the roundings-up (<= 2 each)
 static size_t nms_smem_bytes(int M, int max_out, bool compact) {
     const size_t cap = (size_t)(max_out < M ? max_out : M);
     return (size_t)M * (sizeof(float4) + sizeof(float)) + cap * sizeof(int32_t) +
-           (compact ? cap * (sizeof(float4) + sizeof(float)) : 0);
+           (compact ? (cap + kCompactSlack) * (sizeof(float4) + sizeof(float)) : 0);
 }
 // Fused candidate ordering (single-CTA problems): the kernel first builds (score key, ~index) composites of the
 // candidates in shared memory, sorts them and stages the boxes in candidate order itself.

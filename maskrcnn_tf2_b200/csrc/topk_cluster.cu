@@ -36,6 +36,7 @@ namespace mrcnn {
 constexpr int kTkThreads = 1024;
 constexpr size_t kTkListBytes = (size_t)kMaxSort * 8;                 // the CTA's own candidates
 constexpr size_t kTkScratchBytes = block_sort_xch_bytes(8);           // sort exchange buffers / gathered peer lists
+constexpr int kTkCacheKeys = 32768;                                   // key cache: the first 128 KB of the scratch
 constexpr size_t kTkHistOffset = kTkScratchBytes - 2 * 4096 * sizeof(uint32_t);  // two histograms at the scratch's end,
 // out of reach of every sort's exchange buffers (<= 96 KB from the scratch's start for <= 4096 keys; the 8192-key sort
 // holds the list in registers and uses the list's own 64 KB + the first 96 KB of the scratch): a slow peer may still
@@ -56,42 +57,70 @@ __device__ __forceinline__ uint32_t tk_load_key(const float* __restrict__ scores
 
 // Visits every score index of this CTA's share once (order unspecified).  Unit = 32 consecutive vectors (one warp-wide
 // load: 512 B); unit q belongs to CTA q % csize, and the CTA deals its units to its 32 warps round robin.
-template <int MODE, typename F>
+// The first pass (FIRST) computes the order-preserving keys from global memory and parks them in shared memory
+// (`cache`: kTkCacheKeys keys, the part of the scratch area that is idle until the sort); later passes read the keys
+// back (one LDS.64 per two anchors) instead of re-reading and re-encoding the scores.  Shares larger than the cache
+// re-read their tail from global memory (L2).
+template <int MODE, bool FIRST, typename F>
 __device__ __forceinline__ void for_each_key(const float* __restrict__ scores, int stride, int offset, int A, int b,
-                                             int crank, int csize, F f) {
+                                             int crank, int csize, uint32_t* __restrict__ cache, F f) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int PER = (MODE == 2) ? 2 : (MODE == 1) ? 4 : 1;   // scores per vector
+    constexpr int kSlots = kTkCacheKeys / PER;                    // vectors the cache holds
     const int V = A / PER;                                        // MODE 1 / 2 are only selected when PER divides A
     const int units = (V + 31) >> 5;
+    int slot = threadIdx.x;                                       // this thread's vectors sit at slot, slot + 1024, ...
     if (MODE == 2) {  // two interleaved columns (rpn_probs [B,A,2]): one float4 = two anchors
         const float4* p4 = reinterpret_cast<const float4*>(scores + (size_t)b * A * 2);
+        uint2* c2 = reinterpret_cast<uint2*>(cache);
 #pragma unroll 4
-        for (int q = warp * csize + crank; q < units; q += 32 * csize) {
+        for (int q = warp * csize + crank; q < units; q += 32 * csize, slot += kTkThreads) {
             const int g = q * 32 + lane;
             if (g < V) {
-                const float4 v = __ldg(p4 + g);
-                f(score_key(offset ? v.y : v.x), 2 * g);
-                f(score_key(offset ? v.w : v.z), 2 * g + 1);
+                uint2 k;
+                if (!FIRST && slot < kSlots) k = c2[slot];
+                else {
+                    const float4 v = __ldg(p4 + g);
+                    k = make_uint2(score_key(offset ? v.y : v.x), score_key(offset ? v.w : v.z));
+                    if (FIRST && slot < kSlots) c2[slot] = k;
+                }
+                f(k.x, 2 * g);
+                f(k.y, 2 * g + 1);
             }
         }
     } else if (MODE == 1) {  // dense [B,A]
         const float4* p4 = reinterpret_cast<const float4*>(scores + (size_t)b * A);
+        uint4* c4 = reinterpret_cast<uint4*>(cache);
 #pragma unroll 4
-        for (int q = warp * csize + crank; q < units; q += 32 * csize) {
+        for (int q = warp * csize + crank; q < units; q += 32 * csize, slot += kTkThreads) {
             const int g = q * 32 + lane;
             if (g < V) {
-                const float4 v = __ldg(p4 + g);
-                f(score_key(v.x), 4 * g);
-                f(score_key(v.y), 4 * g + 1);
-                f(score_key(v.z), 4 * g + 2);
-                f(score_key(v.w), 4 * g + 3);
+                uint4 k;
+                if (!FIRST && slot < kSlots) k = c4[slot];
+                else {
+                    const float4 v = __ldg(p4 + g);
+                    k = make_uint4(score_key(v.x), score_key(v.y), score_key(v.z), score_key(v.w));
+                    if (FIRST && slot < kSlots) c4[slot] = k;
+                }
+                f(k.x, 4 * g);
+                f(k.y, 4 * g + 1);
+                f(k.z, 4 * g + 2);
+                f(k.w, 4 * g + 3);
             }
         }
     } else {
 #pragma unroll 4
-        for (int q = warp * csize + crank; q < units; q += 32 * csize) {
+        for (int q = warp * csize + crank; q < units; q += 32 * csize, slot += kTkThreads) {
             const int g = q * 32 + lane;
-            if (g < V) f(tk_load_key(scores, stride, offset, A, b, g), g);
+            if (g < V) {
+                uint32_t k;
+                if (!FIRST && slot < kSlots) k = cache[slot];
+                else {
+                    k = tk_load_key(scores, stride, offset, A, b, g);
+                    if (FIRST && slot < kSlots) cache[slot] = k;
+                }
+                f(k, g);
+            }
         }
     }
 }
@@ -119,6 +148,8 @@ topk_cluster_kernel(const float* __restrict__ scores, int stride, int offset, in
     uint64_t* list = reinterpret_cast<uint64_t*>(tk_smem);                                  // [8192] own candidates
     unsigned char* scratch = tk_smem + kTkListBytes;
     uint32_t* hist2 = reinterpret_cast<uint32_t*>(scratch + kTkHistOffset);                 // [2][4096]
+    uint32_t* cache = reinterpret_cast<uint32_t*>(scratch);                                  // [kTkCacheKeys] (until the sort)
+    static_assert((size_t)kTkCacheKeys * 4 <= kTkHistOffset, "the key cache must end before the histograms");
     pdl_launch_dependents();
     if (tid == 0) ctl.n_list = 0;
     pdl_wait();
@@ -135,10 +166,15 @@ topk_cluster_kernel(const float* __restrict__ scores, int stride, int offset, in
         uint32_t* hist = hist2 + (level & 1) * 4096;
         for (int i = tid; i < nb; i += kTkThreads) hist[i] = 0;
         __syncthreads();
-        for_each_key<MODE>(scores, stride, offset, A, b, crank, csize, [&](uint32_t key, int a) {
-            const uint64_t c = make_composite(key, (uint32_t)a);
-            if (level == 0 || (c >> pshift) == prefix) atomicAdd(&hist[(uint32_t)(c >> shift) & (uint32_t)(nb - 1)], 1u);
-        });
+        if (level == 0) {
+            for_each_key<MODE, true>(scores, stride, offset, A, b, crank, csize, cache,
+                                     [&](uint32_t key, int) { atomicAdd(&hist[key >> 20], 1u); });
+        } else {
+            for_each_key<MODE, false>(scores, stride, offset, A, b, crank, csize, cache, [&](uint32_t key, int a) {
+                const uint64_t c = make_composite(key, (uint32_t)a);
+                if ((c >> pshift) == prefix) atomicAdd(&hist[(uint32_t)(c >> shift) & (uint32_t)(nb - 1)], 1u);
+            });
+        }
         cluster.sync();  // every CTA's histogram of this level is complete (and nobody reads the other buffer any more)
         // every CTA sums the whole histogram over the cluster: thread t owns bins 4t .. 4t+3
         uint4 tot = make_uint4(0u, 0u, 0u, 0u);
@@ -174,7 +210,7 @@ topk_cluster_kernel(const float* __restrict__ scores, int stride, int offset, in
     }
 
     // ---- 2. compaction of this CTA's candidates into its own list ---------------------------------------
-    for_each_key<MODE>(scores, stride, offset, A, b, crank, csize, [&](uint32_t key, int a) {
+    for_each_key<MODE, false>(scores, stride, offset, A, b, crank, csize, cache, [&](uint32_t key, int a) {
         const uint64_t c = make_composite(key, (uint32_t)a);
         if ((c >> shift) >= prefix) list[atomicAdd(&ctl.n_list, 1u)] = c;
     });
