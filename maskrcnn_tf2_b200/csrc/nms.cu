@@ -327,6 +327,7 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
             PROFW_MARK(0);
             const int cnt_known = share(nk_known);
             screen(0, cnt_known, nk_known, false);   // first instalment: no dependence on the release
+            PROFW_MARK(4);
             int nk = 0;  // boxes kept in tiles <= u-kDepth
             if (u >= kDepth) {
                 asm volatile("bar.sync %0, %1;" ::"r"(3 + (u % kDepth)), "r"(rel_threads) : "memory");

@@ -22,6 +22,7 @@ v = list(buf)
 tiles = max(v[4], 1)
 print(f"B={B} {regime}: tiles {v[4]} kept {v[5]}  cycles/tile: wait far {v[0]/tiles:.0f}  resolve {v[1]/tiles:.0f}  "
       f"total {sum(v[:4])/tiles:.0f}")
-w = v[8:12]
-print("  far warp 1 of CTA 0, cycles/tile: prologue %.0f  wait release %.0f  far loop %.0f  send %.0f  total %.0f; exact-division fallbacks: %d"
+w = v[8:13]
+print("  far warp 1 of CTA 0, cycles/tile: prologue %.0f  wait release %.0f  second instalment + vote %.0f  send %.0f  "
+      "first instalment %.0f  total %.0f; exact-division fallbacks: %d"
       % tuple([x / tiles for x in w] + [sum(w) / tiles, v[14]]))

@@ -126,9 +126,10 @@ def test_stress_2000_rois_per_image_through_roialign(orc, dev, pool, B):
         for l in range(4):
             tol = 1e-6 + 1e-5 * np.maximum(np.abs(ref_b[l]), mag[l])
             assert np.all(np.abs(N(got[l]) - ref_b[l]) <= tol), (deterministic, l)
-            if deterministic:   # bit-identical except under the zero-padded rows' pixel (0,0) (documented exception)
-                same = (N(got[l]) == ref_b[l]).all(-1)
-                assert same.mean() > 0.9999, (l, same.mean())
+            if deterministic:   # bit-identical except the ONE pixel per image under the zero-padded rows (their taps
+                same = (N(got[l]) == ref_b[l]).all(-1)      # are (0,0): pre-reduced, DESIGN.md "Backward")
+                assert (~same).sum() <= B, (l, int((~same).sum()))
+                assert same[:, 1:, :].all() and same[:, :, 1:].all(), l
         del got
         torch.cuda.empty_cache()
 
