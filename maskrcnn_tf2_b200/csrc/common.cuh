@@ -487,10 +487,11 @@ struct NmsEpilogue {
     int N;
 };
 
-// boxes_sorted [B,M] in candidate order; valid [B] or NULL (= M)
+// boxes_sorted [B,M] in candidate order; valid [B] or NULL (= M); rows_ws: nms_rows_ws_bytes(B, M) of scratch or NULL
+__attribute__((visibility("hidden"))) size_t nms_rows_ws_bytes(int B, int M);
 __attribute__((visibility("hidden"))) int launch_nms_sorted(const float4* boxes_sorted, const int32_t* valid, int B,
                                                             int M, int max_out, float thr, const NmsEpilogue& epi,
-                                                            cudaStream_t stream);
+                                                            void* rows_ws, cudaStream_t stream);
 
 // candidates in input order: the kernel orders them itself by `keys` ([B,M] order-preserving score keys, 0 = not a
 // candidate) or else by `scores` ([B,M]); only where nms_fused_applies(M, max_out) (single-CTA problems)

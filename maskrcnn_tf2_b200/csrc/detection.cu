@@ -165,5 +165,5 @@ MRCNN_EXPORT int mrcnn_detection_forward(const float* rois, const float* probs, 
                    (const uint32_t*)w.keep_key, N, w.boxes_sorted, w.orig_idx, w.ncand);
     if (e != cudaSuccess) return (int)e;
     epi.orig_idx = w.orig_idx;
-    return launch_nms_sorted(w.boxes_sorted, w.ncand, B, N, max_inst, nms_thr, epi, st);
+    return launch_nms_sorted(w.boxes_sorted, w.ncand, B, N, max_inst, nms_thr, epi, nullptr, st);
 }

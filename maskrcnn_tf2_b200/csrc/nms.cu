@@ -41,7 +41,67 @@ struct NmsInput {
     const int32_t* valid;
     const float* scores;
     const uint32_t* keys;
+    // ordered input only: the diag / cross rows of every tile, precomputed by nms_rows_kernel ([B][tiles][kRows] words);
+    // NULL = the kernel's own row warps compute them
+    const unsigned long long* rows;
 };
+
+// The rows of a tile -- its own symmetric 64 x 64 block and tile v-1 (rows) x tile v (columns) -- do not depend on what is
+// kept, only on the candidate order.  For ordered input they are computed ahead of the sweep by this kernel, over the
+// whole GPU (one CTA per tile, one warp per 32 rows), instead of by row warps inside the 8-CTA clusters of the sweep,
+// whose issue slots are what bounds it (measured: 25 % of the sweep's instructions were row work).  The sweep fetches a
+// tile's 1 KB of rows with one bulk copy, eight tiles ahead.
+__global__ void __launch_bounds__(128)
+nms_rows_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ valid, int M, int tiles_max, float thr,
+                unsigned long long* __restrict__ rows) {
+    __shared__ float4 s_b[2 * kTile];
+    __shared__ float s_a[2 * kTile];
+    const int v = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int n = valid ? min(max(valid[b], 0), M) : M;
+    const float4 kNone = make_float4(1.0e18f, 1.0e18f, -1.0e18f, -1.0e18f);
+    {   // s_b[0..63] = tile v, s_b[64..127] = tile v-1
+        const int c = (tid < kTile) ? v * kTile + tid : (v - 1) * kTile + (tid - kTile);
+        float a = 1.0f;
+        float4 t = kNone;
+        if (c >= 0 && c < n) {
+            t = normalise_box(__ldg(boxes + (size_t)b * M + c), a);
+            if (!(a > 0.0f)) { t = kNone; a = 1.0f; }
+        }
+        s_b[tid] = t;
+        s_a[tid] = a;
+    }
+    __syncthreads();
+    const float4 b0 = s_b[lane], b1 = s_b[lane + 32];
+    const float a0 = s_a[lane], a1 = s_a[lane + 32];
+    const float tc0 = __fmul_rn(thr, a0), tc1 = __fmul_rn(thr, a1);
+    const float cthr = __fadd_rn(1.0f, thr);
+    CandPair cp;
+    cp.y1a = b0.x; cp.x1a = b0.y; cp.y2a = b0.z; cp.x2a = b0.w;
+    cp.y1b = b1.x; cp.x1b = b1.y; cp.y2b = b1.z; cp.x2b = b1.w;
+    cp.ntac = pack_f2(-tc0, -tc1);
+    const unsigned long long c1_2 = pack_f2(cthr, cthr);
+    unsigned long long mine = 0ull;   // lane j keeps row 32 * warp + j
+    for (int j = 0; j < 32; ++j) {
+        const int r = warp * 32 + j;  // 0..63 diag rows, 64..127 cross rows
+        const float4 bi = s_b[r];
+        const float ai = s_a[r], ti = __fmul_rn(thr, ai);
+        float e0, e1;
+        iou_screen_d2(bi, -ti, cp, c1_2, e0, e1);
+        const float m0 = __fmul_rn(__fadd_rn(ti, tc0), kScreenBand), m1 = __fmul_rn(__fadd_rn(ti, tc1), kScreenBand);
+        bool h0 = e0 > m0, h1 = e1 > m1;
+        if (__any_sync(0xffffffffu, fabsf(e0) <= m0 || fabsf(e1) <= m1)) {
+            PROF_FALLBACK;
+            h0 = iou_gt(bi, ai, b0, a0, thr);
+            h1 = iou_gt(bi, ai, b1, a1, thr);
+        }
+        uint64_t row = ballot64(h0, h1);
+        if (r < kTile) row &= ~(1ull << r);
+        if (lane == j) mine = row;
+    }
+    rows[((size_t)b * tiles_max + v) * kRows + warp * 32 + lane] = mine;
+}
 
 // COMPACT: the kept boxes are also appended, by the resolver, to dense arrays (box, thr * area) so that the far loop
 // streams them with plain strided shared-memory loads; false (shared memory too small for the copies): the far loop
@@ -69,6 +129,7 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
     __shared__ __align__(16) unsigned long long s_stage[kRing][kRows];  // this CTA's rows on their way out
     __shared__ unsigned long long s_far[kRing][kMaxFarSrc];     // [tile % kRing][source CTA * nfar + far warp], written by the peers
     __shared__ __align__(8) uint64_t s_bar[kRing];              // mbarriers, [tile % kRing] (ring depth: nms_dev.cuh)
+    __shared__ __align__(8) uint64_t s_rbar[kRing];             // precomputed rows (in.rows): their bulk copies land here
     __shared__ int s_nk[kRing];                                 // [tile % kRing] kept count after that tile's resolve
     __shared__ int s_final[2];
     __shared__ int s_ncand;
@@ -76,16 +137,19 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
     const int csize = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
     const int b = blockIdx.x / csize, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t bar_base = smem_u32(&s_bar[0]);
-    const int rel_threads = 32 * (1 + nfar + nrow);  // the release barrier: resolver (arrives) + far and row warps (wait)
     const int nsrc = csize * nfar;                   // far partials per tile: one per far warp of the cluster
     const int wcap = (cap + nsrc - 1) / nsrc + 1;    // entries of one far warp's private kept list
     const uint32_t nsrc_magic = ((1u << 20) + (uint32_t)nsrc - 1u) / (uint32_t)nsrc;  // k / nsrc == (k * magic) >> 20, k < 2^13
     // per tile every CTA receives one 64-bit far partial from each far warp of the cluster and, as one bulk copy per
     // CTA, the rows of the tile's diag + cross blocks
-    const uint32_t far_bytes = (uint32_t)nsrc * 8u + (uint32_t)kRows * 8u;
+    const bool grows = in.rows != nullptr;          // rows precomputed in global memory: no row warps in this kernel
+    if (grows) nrow = 0;
+    const int rel_threads = 32 * (1 + nfar + nrow);  // the release barrier: resolver (arrives) + far and row warps (wait)
+    const uint32_t far_bytes = (uint32_t)nsrc * 8u + (grows ? 0u : (uint32_t)kRows * 8u);
+    const uint32_t rbar_base = smem_u32(&s_rbar[0]);
     pdl_launch_dependents();
     if (tid == 0) {
-        for (int j = 0; j < kRing; ++j) { mbar_init(bar_base + 8u * j, 1); s_nk[j] = 0; }
+        for (int j = 0; j < kRing; ++j) { mbar_init(bar_base + 8u * j, 1); mbar_init(rbar_base + 8u * j, 1); s_nk[j] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int j = 1; j < kRing; ++j) mbar_arm(bar_base + 8u * j, far_bytes);  // tiles 1..7; tile 8 is armed in tile 0
         s_ncand = 0;
@@ -155,6 +219,14 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
         }
     }
     const int tiles = (n + kTile - 1) / kTile;
+    const int tiles_max = (M + kTile - 1) / kTile;
+    const unsigned long long* rows_b = grows ? in.rows + (size_t)b * tiles_max * kRows : nullptr;
+    if (grows && tid == 0) {
+        for (int v = 1; v < kRing && v < tiles; ++v) {
+            mbar_arm(rbar_base + 8u * v, (uint32_t)kRows * 8u);
+            bulk_copy_from_global(smem_u32(&s_rows[v][0]), rows_b + (size_t)v * kRows, (uint32_t)kRows * 8u, rbar_base + 8u * v);
+        }
+    }
     __syncthreads();
     // diag(0): rows 2*warp, 2*warp+1 of tile 0, every CTA for itself
     {
@@ -201,7 +273,9 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
             }
             uint64_t removed = 0;
             if (t >= 1) {  // slot j serves tiles j, j + 8, ...; tile 0 has no far / cross set
-                mbar_wait(bar_t, (uint32_t)(((t >> 3) - (slot == 0 ? 1 : 0)) & 1));
+                const uint32_t parity = (uint32_t)(((t >> 3) - (slot == 0 ? 1 : 0)) & 1);
+                if (grows) mbar_wait(rbar_base + 8u * (uint32_t)slot, parity);   // fetched eight tiles ago: long complete
+                mbar_wait(bar_t, parity);
                 PROF_MARK(0);
                 uint64_t v = 0ull;
 #pragma unroll
@@ -256,6 +330,12 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
             if (lane == 0) {
                 s_nk[slot] = nkept;
                 mbar_arm(bar_t, far_bytes);  // phase of tile t + kRing
+                if (grows && t + kRing < tiles) {   // this tile's rows have been consumed: fetch those of tile t + kRing
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arm(rbar_base + 8u * (uint32_t)slot, (uint32_t)kRows * 8u);
+                    bulk_copy_from_global(smem_u32(&s_rows[slot][0]), rows_b + (size_t)(t + kRing) * kRows,
+                                          (uint32_t)kRows * 8u, rbar_base + 8u * (uint32_t)slot);
+                }
             }
             __threadfence_block();
             // release the workers for tile t+kDepth (they need the kept list through tile t)
@@ -433,6 +513,10 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
             if (d >= 1 && d < tiles)
                 mbar_wait(bar_base + 8u * (uint32_t)(d & (kRing - 1)),
                           (uint32_t)(((d >> 3) - ((d & (kRing - 1)) == 0 ? 1 : 0)) & 1));
+        if (grows)   // row copies issued for tiles t .. t + kRing - 1 (resolve(d - kRing) fetched tile d) and never consumed
+            for (int d = max(t, 1); d < t + kRing && d < tiles; ++d)
+                mbar_wait(rbar_base + 8u * (uint32_t)(d & (kRing - 1)),
+                          (uint32_t)(((d >> 3) - ((d & (kRing - 1)) == 0 ? 1 : 0)) & 1));
     }
     cluster.sync();
     if (crank != 0) return;
@@ -507,11 +591,23 @@ int launch_nms(const NmsInput& in, int B, int M, int max_out, float thr, const N
     return last_error();
 }
 
+size_t nms_rows_ws_bytes(int B, int M) {
+    return align_up((size_t)B * ((M + kTile - 1) / kTile) * kRows * sizeof(unsigned long long), 256);
+}
+
+// rows_ws: nms_rows_ws_bytes(B, M) of scratch for the precomputed rows (cluster problems, M > 2048), or NULL
 int launch_nms_sorted(const float4* boxes_sorted, const int32_t* valid, int B, int M, int max_out, float thr,
-                      const NmsEpilogue& epi, cudaStream_t stream) {
+                      const NmsEpilogue& epi, void* rows_ws, cudaStream_t stream) {
     NmsInput in{};
     in.boxes = boxes_sorted;
     in.valid = valid;
+    if (rows_ws != nullptr && M > 2048 && tuning_knob("MRCNN_NMS_GLOBAL_ROWS", 1)) {
+        const int tiles_max = (M + kTile - 1) / kTile;
+        cudaError_t e = launch_pdl(nms_rows_kernel, dim3(tiles_max, B), dim3(128), 0, stream, boxes_sorted, valid, M,
+                                   tiles_max, thr, (unsigned long long*)rows_ws);
+        if (e != cudaSuccess) return (int)e;
+        in.rows = (const unsigned long long*)rows_ws;
+    }
     return launch_nms(in, B, M, max_out, thr, epi, stream);
 }
 
@@ -568,7 +664,7 @@ struct NmsWs {
 };
 static size_t nms_ws_bytes(int B, int M) {
     return align_up((size_t)B * M * sizeof(float4), 256) + align_up((size_t)B * M * sizeof(int32_t), 256) +
-           align_up((size_t)B * sizeof(int32_t), 256);
+           align_up((size_t)B * sizeof(int32_t), 256) + nms_rows_ws_bytes(B, M);
 }
 
 }  // namespace mrcnn
@@ -617,7 +713,8 @@ MRCNN_EXPORT int mrcnn_nms_forward(const float* boxes, const float* scores, cons
     char* p = (char*)ws;
     w.boxes_sorted = (float4*)p; p += align_up((size_t)B * M * sizeof(float4), 256);
     w.orig_idx = (int32_t*)p;    p += align_up((size_t)B * M * sizeof(int32_t), 256);
-    w.ncand = (int32_t*)p;
+    w.ncand = (int32_t*)p;       p += align_up((size_t)B * sizeof(int32_t), 256);
+    void* rows_ws = p;
     const int sort_n = next_pow2(M < 32 ? 32 : M);
     const size_t smem = (size_t)sort_n * sizeof(uint64_t) + (sort_n >= 1024 ? block_sort_xch_bytes(sort_n / 1024) : 0);
     if (smem > 48 * 1024) {
@@ -628,5 +725,5 @@ MRCNN_EXPORT int mrcnn_nms_forward(const float* boxes, const float* scores, cons
                                w.boxes_sorted, w.orig_idx, w.ncand);
     if (e != cudaSuccess) return (int)e;
     epi.orig_idx = w.orig_idx;
-    return launch_nms_sorted(w.boxes_sorted, w.ncand, B, M, max_out, thr, epi, st);
+    return launch_nms_sorted(w.boxes_sorted, w.ncand, B, M, max_out, thr, epi, rows_ws, st);
 }

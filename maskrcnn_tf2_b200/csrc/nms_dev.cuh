@@ -108,6 +108,11 @@ __device__ __forceinline__ void bulk_copy_to_peer(uint32_t peer_dst, uint32_t lo
     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(peer_dst), "r"(local_src), "r"(bytes), "r"(peer_bar) : "memory");
 }
+// bulk copy of `bytes` (multiple of 16) from global memory into this CTA's shared memory, completing on its mbarrier
+__device__ __forceinline__ void bulk_copy_from_global(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void named_barrier(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

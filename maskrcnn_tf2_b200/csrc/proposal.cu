@@ -13,7 +13,7 @@ struct ProposalWs {
     float4* boxes_sorted;  // [B,K]
 };
 size_t proposal_ws_bytes(int B, int K) {
-    return align_up(topk_ws_bytes(B), 256) + align_up((size_t)B * K * sizeof(float4), 256);
+    return align_up(topk_ws_bytes(B), 256) + align_up((size_t)B * K * sizeof(float4), 256) + nms_rows_ws_bytes(B, K);
 }
 }  // namespace
 
@@ -96,7 +96,8 @@ MRCNN_EXPORT int mrcnn_proposal_forward(const float* rpn_probs, const float* rpn
     ProposalWs w;
     char* p = (char*)ws;
     w.topk = p;                  p += align_up(topk_ws_bytes(B), 256);
-    w.boxes_sorted = (float4*)p;
+    w.boxes_sorted = (float4*)p; p += align_up((size_t)B * K * sizeof(float4), 256);
+    void* rows_ws = p;
 
     TopkDecode dec{};
     dec.anchors = (const float4*)anchors;
@@ -112,7 +113,7 @@ MRCNN_EXPORT int mrcnn_proposal_forward(const float* rpn_probs, const float* rpn
     epi.proposals = (float4*)proposals;
     epi.keep = keep_idx;
     epi.count = keep_count;
-    return launch_nms_sorted(w.boxes_sorted, nullptr, B, K, P, nms_thr, epi, st);
+    return launch_nms_sorted(w.boxes_sorted, nullptr, B, K, P, nms_thr, epi, rows_ws, st);
 }
 
 
@@ -187,6 +188,7 @@ MRCNN_EXPORT int mrcnn_proposal_forward_levels(const float* const* rpn_class_log
     char* p = (char*)ws;
     void* topk_ws = p;            p += align_up(topk_ws_bytes(B), 256);
     float4* boxes_sorted = (float4*)p; p += align_up((size_t)B * K * sizeof(float4), 256);
+    void* rows_ws = p;                 p += nms_rows_ws_bytes(B, K);
     float* fg = (float*)p;
     rpn_fg_score_kernel<<<dim3((A + 255) / 256, B), 256, 0, st>>>(lv, A, fg, (float2*)rpn_probs);
     dec.anchors = (const float4*)anchors;
@@ -201,5 +203,5 @@ MRCNN_EXPORT int mrcnn_proposal_forward_levels(const float* const* rpn_class_log
     epi.proposals = (float4*)proposals;
     epi.keep = keep_idx;
     epi.count = keep_count;
-    return launch_nms_sorted(boxes_sorted, nullptr, B, K, P, nms_thr, epi, st);
+    return launch_nms_sorted(boxes_sorted, nullptr, B, K, P, nms_thr, epi, rows_ws, st);
 }

@@ -368,11 +368,14 @@ struct PixelSpace {   // global pixel id = base[m] + (b * H[m] + y) * W[m] + x ;
 
 constexpr int kTileH = 4, kTileW = 8; // gradient-map tile of the deterministic mode: 4 rows x 8 columns of pixels
 constexpr int kTilePix = kTileH * kTileW;
-constexpr int kTileRoiMax = 1024;    // ROIs one tile orders in shared memory; fuller tiles fall back to the scatter kernel
+constexpr int kTileCap = 4096;       // samples one tile orders in shared memory per round
 constexpr int kTileThreads = 64;     // one thread per four channels (256 channels per pass)
 constexpr int kTileChunk = 64;       // float4 channel vectors per pass
-constexpr int kTileQueue = 192;      // bin entries staged per consume round
-constexpr int kTileBuckets = 4;      // work lists by ROI count (>= 32, >= 8, >= 2, >= 1): heavy tiles start first
+constexpr int kTileQueue = 192;      // samples decoded per consume round
+constexpr int kTileBuckets = 4;      // work lists by sample count (>= 512, >= 64, >= 8, >= 1): heavy tiles start first
+constexpr int kTileFBuckets = 256;   // a tile with more than kTileCap samples is taken in rounds of ROI-index ranges
+// sample key: ROI index << 14 | output row << 7 | output column -- ascending key = TF's accumulation order
+constexpr int kKeyXBits = 7, kKeyYBits = 7, kKeyFBits = 18;
 
 struct TileSpace {    // tile id = base[m] + (b * ty[m] + tile_y) * tx[m] + tile_x ; base[4] = number of tiles
     int base[5];
@@ -491,35 +494,60 @@ roialign_bwd_kernel(const float4* __restrict__ grad_out, const float4* __restric
 }
 
 // ---- deterministic backward: tile-owner accumulation ------------------------------------------------------------
-// Every gradient map is cut into 8 x 8-pixel tiles and every tile is written exactly once, by ONE CTA that adds up all
-// the samples landing on it in TF CropAndResizeGradImage's own order -- ROI index ascending, then output row, column,
+// Every gradient map is cut into tiles of 4 x 8 pixels and every tile is written exactly once, by ONE CTA that adds up
+// all the samples landing on it in TF CropAndResizeGradImage's own order -- ROI index ascending, then output row, column,
 // corner -- with every product and sum individually rounded: the result is bit-identical to the sequential CPU kernel
 // and reproducible, and the zero-fill of the maps (713 MB per 8 images at 1024^2) and the accumulation are the same
 // HBM write.  Steps:
+//   roialign_bwd_taps_kernel    thread per (ROI, output row or column): the TF sampling tap (lo, hi, lerp, valid) -- the
+//                               only place the ROI geometry (two fp32 divisions per axis) is evaluated;
 //   roialign_bwd_const_kernel   zero-size ROIs (zero-padded target rows, quirk Q5: all ph*pw bins on the same four taps)
-//                               are pre-reduced to one gradient row each (fixed order), see below;
-//   roialign_bwd_bin_kernel<0>  thread per ROI: the tile rows / columns its taps touch (two 64-bit masks), one count
-//                               per touched tile;
-//   roialign_bwd_alloc_kernel   thread per tile: a segment of the (tile, ROI) entry list, and the tile goes on one of
-//                               four work lists by ROI count (the heavy tiles are started first);
-//   roialign_bwd_bin_kernel<1>  the same walk, now storing the ROI index into the segments;
+//                               are pre-reduced to one gradient row each (fixed order) and enter as ONE sample;
+//   roialign_bwd_bin_kernel<0>  thread per sample: one count per tile its (up to four) corners land on;
+//   roialign_bwd_alloc_kernel   a segment of the (tile, sample) list per tile (block scan, one atomic per CTA), and the
+//                               tile goes on one of four work lists by sample count (the heavy tiles are started first);
+//   roialign_bwd_bin_kernel<1>  the same walk, now storing the sample key into the segments;
 //   roialign_bwd_tile_kernel    CTAs [0, NT): the ranked non-empty tiles; CTAs [NT, 2 NT): zero-fill of the empty ones.
-//                               A tile CTA orders its ROIs (shared memory), then walks them: group g of 64 threads owns
-//                               tile rows 2g, 2g+1 (no synchronisation between the groups), a thread owns four channels
-//                               of every pixel of those rows in a shared-memory accumulator; gradient rows are fetched
-//                               four bins ahead.  A gradient row is read once per tile it touches (1.2-1.3 x in all)
-//                               instead of once per corner (4 x).
+//                               A tile CTA (64 threads, a thread owns four channels of every pixel of the tile in a
+//                               32 KB shared-memory accumulator) sorts its sample keys, then alternates: 64 threads
+//                               decode 192 samples (taps -> which corner lands on which tile pixel with which weight),
+//                               then all of them walk those samples in order, gradient rows fetched eight samples
+//                               ahead.  A gradient row is read once per tile it touches (1.4 x in all at 1024^2, from
+//                               L2) instead of once per corner (4 x).  More than kTileCap samples on a tile (thousands of
+//                               ROIs per image): rounds over ROI-index ranges chosen from a 256-bucket histogram.
 // Not bit-identical to the sequential order, but still deterministic: pixels under zero-size ROIs (their pre-reduced
 // row is added as one sample) -- thousands of samples on one pixel cannot be added one after the other at any speed;
-// non-deterministic: tiles touched by more than kTileRoiMax ROIs of one image (atomic scatter fallback).
-// Maps up to 512 x 512 (64 tiles per axis: the masks).
+// non-deterministic: a tile where ONE histogram bucket of ROI indices holds more than kTileCap samples (atomic scatter
+// fallback; needs > 5000 ROIs per image on the same 32 pixels).
+// Maps up to 512 x 512 pixels, ph, pw <= 128, B * N < 2^18.
+struct TapWord {   // .x = lo | (hi - lo) << 16 | valid << 17 | zero-size ROI << 18 ; .y = lerp bits
+    uint32_t x, y;
+};
+__device__ __forceinline__ int tap_lo(const TapWord& t) { return (int)(t.x & 0xffffu); }
+__device__ __forceinline__ int tap_hi(const TapWord& t) { return (int)(t.x & 0xffffu) + (int)((t.x >> 16) & 1u); }
+__device__ __forceinline__ bool tap_valid(const TapWord& t) { return (t.x >> 17) & 1u; }
+__device__ __forceinline__ bool tap_const(const TapWord& t) { return (t.x >> 18) & 1u; }
+
+__global__ void __launch_bounds__(256)
+roialign_bwd_taps_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ roi_map, GradTable tbl, int BN,
+                         int ph, int pw, TapWord* __restrict__ taps /*[BN][ph + pw]*/) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= BN * (ph + pw)) return;
+    const int f = i / (ph + pw), t = i - f * (ph + pw);
+    const RoiGeom g = roi_geom(__ldg(boxes + f), roi_map[f], tbl.H, tbl.W, ph, pw);
+    const AxisTap a = (t < ph) ? axis_tap(g.y0, g.hs, t, g.H) : axis_tap(g.x0, g.ws, t - ph, g.W);
+    TapWord w;
+    w.x = (uint32_t)a.lo | ((uint32_t)(a.hi - a.lo) << 16) | (a.valid ? 1u << 17 : 0u) |
+          ((g.hs == 0.0f && g.ws == 0.0f) ? 1u << 18 : 0u);
+    w.y = __float_as_uint(a.lerp);
+    taps[i] = w;
+}
+
 __global__ void __launch_bounds__(64)
-roialign_bwd_const_kernel(const float4* __restrict__ grad_out, const float4* __restrict__ boxes,
-                          const int32_t* __restrict__ roi_map, GradTable tbl, int C, int ph, int pw,
+roialign_bwd_const_kernel(const float4* __restrict__ grad_out, const TapWord* __restrict__ taps, int C, int ph, int pw,
                           float4* __restrict__ partial /*[BN][C/4]*/) {
     const int f = blockIdx.x;
-    const RoiGeom g = roi_geom(__ldg(boxes + f), roi_map[f], tbl.H, tbl.W, ph, pw);
-    if (!(g.hs == 0.0f && g.ws == 0.0f)) return;
+    if (!tap_const(taps[(size_t)f * (ph + pw)])) return;
     const int c4 = C >> 2, bins = ph * pw;
     const float4* gr = grad_out + (size_t)f * bins * c4;
     for (int i = threadIdx.x; i < c4; i += 64) {
@@ -544,45 +572,48 @@ roialign_bwd_const_kernel(const float4* __restrict__ grad_out, const float4* __r
     }
 }
 
-// tile rows / columns touched by the taps of one axis (tile extent `tdim` pixels): bit t of (lo, hi) = tile index t
-struct Mask128 { unsigned long long lo, hi; };
-__device__ __forceinline__ Mask128 axis_tile_mask(float c0, float scale, int crop, int size, int tdim) {
-    Mask128 m{0ull, 0ull};
-    auto set = [&](int t) { if (t < 64) m.lo |= 1ull << t; else m.hi |= 1ull << (t - 64); };
-    for (int t = 0; t < crop; ++t) {
-        const AxisTap a = axis_tap(c0, scale, t, size);
-        if (!a.valid) continue;
-        if (__fsub_rn(1.0f, a.lerp) != 0.0f) set(a.lo / tdim);
-        if (a.lerp != 0.0f) set(a.hi / tdim);
-    }
-    return m;
+// the (up to four) distinct tiles the corners of one sample land on with non-zero weight; returns their number
+__device__ __forceinline__ int sample_tiles(const TapWord& ty, const TapWord& tx, int tbase, int TX, int (&tiles)[4]) {
+    if (!(tap_valid(ty) && tap_valid(tx))) return 0;
+    const float ly = __uint_as_float(ty.y), lx = __uint_as_float(tx.y);
+    const bool t_on = __fsub_rn(1.0f, ly) != 0.0f, b_on = ly != 0.0f, l_on = __fsub_rn(1.0f, lx) != 0.0f, r_on = lx != 0.0f;
+    const int r0 = tap_lo(ty) / kTileH, r1 = tap_hi(ty) / kTileH, c0 = tap_lo(tx) / kTileW, c1 = tap_hi(tx) / kTileW;
+    int n = 0;
+    auto add = [&](int r, int c) {
+        const int t = tbase + r * TX + c;
+        for (int i = 0; i < n; ++i)
+            if (tiles[i] == t) return;
+        tiles[n++] = t;
+    };
+    if (t_on && l_on) add(r0, c0);
+    if (t_on && r_on) add(r0, c1);
+    if (b_on && l_on) add(r1, c0);
+    if (b_on && r_on) add(r1, c1);
+    return n;
 }
 
 template <int PASS>
-__global__ void __launch_bounds__(128)
-roialign_bwd_bin_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ roi_map, GradTable tbl,
-                        TileSpace ts, int N, int BN, int ph, int pw, int* __restrict__ count,
-                        const int* __restrict__ start, int* __restrict__ cursor, int* __restrict__ entries) {
-    const int f = blockIdx.x * 128 + threadIdx.x;
-    if (f >= BN) return;
+__global__ void __launch_bounds__(256)
+roialign_bwd_bin_kernel(const TapWord* __restrict__ taps, const int32_t* __restrict__ roi_map, TileSpace ts, int N,
+                        int ph, int pw, int total_bins, int* __restrict__ count, const int* __restrict__ start,
+                        int* __restrict__ cursor, uint32_t* __restrict__ entries) {
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= total_bins) return;
+    const int bins = ph * pw;
+    const int f = s / bins, r = s - f * bins, y = r / pw, x = r - y * pw;
+    const TapWord* tf = taps + (size_t)f * (ph + pw);
+    const TapWord ty = tf[y], tx = tf[ph + x];
+    if (tap_const(ty) && r != 0) return;           // a zero-size ROI is ONE sample (its pre-reduced row)
     const int m = roi_map[f];
-    const RoiGeom g = roi_geom(__ldg(boxes + f), m, tbl.H, tbl.W, ph, pw);
-    const Mask128 rows = axis_tile_mask(g.y0, g.hs, ph, g.H, kTileH);
-    const Mask128 cols = axis_tile_mask(g.x0, g.ws, pw, g.W, kTileW);   // at most 64 tile columns: cols.hi == 0
-    const int tbase = tile_of_pixel(ts, m, f / N, 0, 0);
-    const int tx = (m == 0) ? ts.tx[0] : (m == 1) ? ts.tx[1] : (m == 2) ? ts.tx[2] : ts.tx[3];
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        for (unsigned long long r = half ? rows.hi : rows.lo; r; r &= r - 1) {
-            const int row = 64 * half + __ffsll((long long)r) - 1;
-            for (unsigned long long c = cols.lo; c; c &= c - 1) {
-                const int t = tbase + row * tx + (__ffsll((long long)c) - 1);
-                if (PASS == 0) atomicAdd(count + t, 1);
-                else {
-                    const int seg = start[t];
-                    if (seg >= 0) entries[seg + atomicAdd(cursor + t, 1)] = f;
-                }
-            }
+    const int TX = (m == 0) ? ts.tx[0] : (m == 1) ? ts.tx[1] : (m == 2) ? ts.tx[2] : ts.tx[3];
+    int tiles[4];
+    const int n = sample_tiles(ty, tx, tile_of_pixel(ts, m, f / N, 0, 0), TX, tiles);
+    const uint32_t key = ((uint32_t)f << (kKeyXBits + kKeyYBits)) | ((uint32_t)y << kKeyXBits) | (uint32_t)x;
+    for (int i = 0; i < n; ++i) {
+        if (PASS == 0) atomicAdd(count + tiles[i], 1);
+        else {
+            const int seg = start[tiles[i]];
+            if (seg >= 0) entries[seg + atomicAdd(cursor + tiles[i], 1)] = key;
         }
     }
 }
@@ -590,17 +621,24 @@ roialign_bwd_bin_kernel(const float4* __restrict__ boxes, const int32_t* __restr
 __global__ void __launch_bounds__(256)
 roialign_bwd_alloc_kernel(const int* __restrict__ count, int NT, int* __restrict__ start, int* __restrict__ misc,
                           int* __restrict__ lists /*[kTileBuckets][NT]*/) {
+    __shared__ int warp_sums[32];
+    __shared__ int block_total, block_base;
     const int t = blockIdx.x * 256 + threadIdx.x;
+    const int c = (t < NT) ? count[t] : 0;
+    int off = block_exclusive_scan(c, warp_sums, &block_total);
+    if (threadIdx.x == 0) block_base = block_total > 0 ? atomicAdd(&misc[kMiscBump], block_total) : 0;
+    __syncthreads();
     if (t >= NT) return;
-    const int c = count[t];
-    int seg = 0;
-    if (c > kTileRoiMax) { seg = -1; misc[kMiscOverflow] = 1; }
-    else if (c > 0) {
-        seg = atomicAdd(&misc[kMiscBump], c);
-        const int bucket = (c >= 32) ? 0 : (c >= 8) ? 1 : (c >= 2) ? 2 : 3;
-        lists[(size_t)bucket * NT + atomicAdd(&misc[kMiscBucket0 + bucket], 1)] = t;
+    start[t] = block_base + off;
+    if (c > 0) {   // one atomic per bucket and warp
+        const int bucket = (c >= 512) ? 0 : (c >= 64) ? 1 : (c >= 8) ? 2 : 3;
+        const unsigned peers = __match_any_sync(__activemask(), bucket);
+        const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&misc[kMiscBucket0 + bucket], __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        lists[(size_t)bucket * NT + base + __popc(peers & ((1u << lane) - 1u))] = t;
     }
-    start[t] = seg;
 }
 
 __device__ __forceinline__ void acc_corner(float4* acc, const float4& d, float w) {
@@ -612,9 +650,9 @@ __device__ __forceinline__ void acc_corner(float4* acc, const float4& d, float w
     *acc = a;
 }
 
-// One sample of the tile's queue: where its gradient row lies and which of its four corners land on which tile pixel.
-// pk: bits 0-4 pixel of the top-left corner's ROW start (row * 8), 5-7 column lo, 8-10 column hi, 11-15 bottom row
-// start, 16 tl, 17 tr, 18 bl, 19 br (corner lands in the tile with non-zero weight), 20 pre-reduced row (zero-size ROI)
+// One decoded sample of the tile's queue: where its gradient row lies and which of its four corners land on which tile
+// pixel.  pk: bits 0-4 top row's first pixel (row * 8), 5-7 column lo, 8-10 column hi, 11-15 bottom row's first pixel,
+// 16 tl, 17 tr, 18 bl, 19 br (corner lands in the tile with non-zero weight), 20 pre-reduced row (zero-size ROI)
 struct TileQueue {
     int off[kTileQueue];
     uint32_t pk[kTileQueue];
@@ -622,16 +660,16 @@ struct TileQueue {
 };
 
 __global__ void __launch_bounds__(kTileThreads)
-roialign_bwd_tile_kernel(const float4* __restrict__ grad_out, const float4* __restrict__ boxes,
-                         const int32_t* __restrict__ roi_map, const float4* __restrict__ const_partial, GradTable tbl,
-                         TileSpace ts, int C, int N, int ph, int pw, const int* __restrict__ count,
-                         const int* __restrict__ start, const int* __restrict__ entries, const int* __restrict__ misc,
-                         const int* __restrict__ lists) {
-    __shared__ __align__(16) float4 acc[kTilePix * kTileChunk];   // [pixel][channel vector]: 32 KB
-    __shared__ int s_roi[kTileRoiMax];
+roialign_bwd_tile_kernel(const float4* __restrict__ grad_out, const TapWord* __restrict__ taps,
+                         const float4* __restrict__ const_partial, GradTable tbl, TileSpace ts, int C, int ph, int pw,
+                         const int* __restrict__ count, int* __restrict__ start, const uint32_t* __restrict__ entries,
+                         int* __restrict__ misc, const int* __restrict__ lists) {
+    extern __shared__ __align__(16) float4 acc[];                 // [pixel][channel vector]: 32 KB (dynamic)
+    __shared__ uint32_t s_key[kTileCap];
     __shared__ TileQueue q;
-    __shared__ int s_wcount[2];
-    const int NT = ts.base[4], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int s_hist[kTileFBuckets];
+    __shared__ int s_n;
+    const int NT = ts.base[4], tid = threadIdx.x;
     const int c4 = C >> 2;
     int tile, n = 0;
     if ((int)blockIdx.x < NT) {   // ranked work item: the blockIdx-th non-empty tile, heaviest bucket first
@@ -645,10 +683,9 @@ roialign_bwd_tile_kernel(const float4* __restrict__ grad_out, const float4* __re
         if (bucket == kTileBuckets) return;
         tile = lists[(size_t)bucket * NT + w];
         n = count[tile];
-    } else {                      // zero-fill: tiles nobody samples, and overflowed tiles (the scatter kernel adds to them)
+    } else {                      // zero-fill: the tiles nobody samples
         tile = blockIdx.x - NT;
-        const int c = count[tile];
-        if (c > 0 && c <= kTileRoiMax) return;
+        if (count[tile] > 0) return;
     }
     const int m = (tile >= ts.base[3]) ? 3 : (tile >= ts.base[2]) ? 2 : (tile >= ts.base[1]) ? 1 : 0;
     const int H = tbl.H[m], W = tbl.W[m], TY = ts.ty[m], TX = ts.tx[m];
@@ -664,127 +701,138 @@ roialign_bwd_tile_kernel(const float4* __restrict__ grad_out, const float4* __re
         }
         return;
     }
-    // ---- order the tile's ROIs ascending (= TF's accumulation order) ----
-    {
-        const int seg = start[tile];
-        const int np2 = max(32, 1 << (32 - __clz(n - 1)));
-        for (int i = tid; i < np2; i += kTileThreads) s_roi[i] = (i < n) ? __ldg(entries + seg + i) : INT_MAX;
+    const uint32_t* seg = entries + start[tile];
+    // ---- rounds: all samples at once when they fit, else ranges of ROI indices of at most kTileCap samples ----
+    uint32_t f_lo = 0u, f_width = 1u;   // histogram bucket of a key: ((key >> 14) - f_lo) / f_width
+    bool overflow = false;
+    if (n > kTileCap) {
+        uint32_t mn = 0xffffffffu, mx = 0u;
+        for (int i = tid; i < n; i += kTileThreads) { const uint32_t f = seg[i] >> (kKeyXBits + kKeyYBits); mn = min(mn, f); mx = max(mx, f); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+        for (int i = tid; i < kTileFBuckets; i += kTileThreads) s_hist[i] = 0;
+        if (tid == 0) { s_key[0] = 0xffffffffu; s_key[1] = 0u; }
         __syncthreads();
-        for (int k = 2; k <= np2; k <<= 1)
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int t = tid; t < (np2 >> 1); t += kTileThreads) {
-                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), p = i | j;
-                    const bool up = ((i & k) == 0);
-                    const int a = s_roi[i], c = s_roi[p];
-                    if ((a > c) == up) { s_roi[i] = c; s_roi[p] = a; }
-                }
-                __syncthreads();
-            }
+        if ((tid & 31) == 0) { atomicMin(&s_key[0], mn); atomicMax(&s_key[1], mx); }
+        __syncthreads();
+        f_lo = s_key[0];
+        f_width = (s_key[1] - f_lo) / kTileFBuckets + 1u;
+        __syncthreads();
+        for (int i = tid; i < n; i += kTileThreads) atomicAdd(&s_hist[((seg[i] >> (kKeyXBits + kKeyYBits)) - f_lo) / f_width], 1);
+        __syncthreads();
+        for (int i = tid; i < kTileFBuckets; i += kTileThreads) overflow |= s_hist[i] > kTileCap;
+        overflow = __syncthreads_or(overflow);
     }
-    const float fy_lo = (float)(y0 - 1), fy_hi = (float)(y0 + kTileH);   // taps within one pixel of the tile
-    const float fx_lo = (float)(x0 - 1), fx_hi = (float)(x0 + kTileW);
+    if (overflow) {   // (pathological) zero the tile, flag it: the scatter kernel adds this tile's samples atomically
+        if (tid == 0) { start[tile] = -1; misc[kMiscOverflow] = 1; }
+        for (int r = 0; r < rows_in; ++r) {
+            float4* dst = gmap + ((size_t)(y0 + r) * W + x0) * c4;
+            for (int v = tid; v < cols_in * c4; v += kTileThreads) __stcs(dst + v, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        return;
+    }
     for (int cc = 0; cc < c4; cc += kTileChunk) {   // 256 channels per pass
         const int v = cc + tid;
         const bool have_v = v < c4;
         for (int i = tid; i < kTilePix * kTileChunk; i += kTileThreads) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        int idx = 0, kbase = 0;     // builder cursor: ROI idx of the sorted list, first candidate bin of its next pass
-        while (idx < n) {
-            // ---- build: the bins of the next ROIs that land on this tile, in (ROI, y, x) order ----
-            int nq = 0;             // uniform
-            while (idx < n && nq + kTileThreads <= kTileQueue) {
-                const int f = s_roi[idx];
-                const RoiGeom g = roi_geom(__ldg(boxes + f), m, tbl.H, tbl.W, ph, pw);
-                const bool constant = (g.hs == 0.0f && g.ws == 0.0f);
-                // conservative bin ranges whose taps can reach the tile
-                int ya = 0, yb = constant ? 0 : ph - 1, xa = 0, xb = constant ? 0 : pw - 1;
-                if (!constant && fabsf(g.hs) > 1e-12f) {
-                    const float t0 = __fdiv_rn(fy_lo - g.y0, g.hs), t1 = __fdiv_rn(fy_hi - g.y0, g.hs);
-                    ya = max(0, (int)fmaxf(floorf(fminf(t0, t1)) - 1.0f, -1.0f));
-                    yb = min(ph - 1, (int)fminf(ceilf(fmaxf(t0, t1)) + 1.0f, (float)ph));
+        int bkt = 0;
+        while (bkt < kTileFBuckets) {
+            // ---- this round's samples -> s_key, ascending ----
+            int nr;
+            if (n <= kTileCap) {
+                for (int i = tid; i < n; i += kTileThreads) s_key[i] = __ldg(seg + i);
+                nr = n;
+                bkt = kTileFBuckets;
+            } else {
+                int b1 = bkt, sum = 0;
+                while (b1 < kTileFBuckets && sum + s_hist[b1] <= kTileCap) sum += s_hist[b1++];   // uniform
+                if (tid == 0) s_n = 0;
+                __syncthreads();
+                for (int i = tid; i < n; i += kTileThreads) {
+                    const uint32_t key = __ldg(seg + i);
+                    const int kb = (int)(((key >> (kKeyXBits + kKeyYBits)) - f_lo) / f_width);
+                    if (kb >= bkt && kb < b1) s_key[atomicAdd(&s_n, 1)] = key;
                 }
-                if (!constant && fabsf(g.ws) > 1e-12f) {
-                    const float t0 = __fdiv_rn(fx_lo - g.x0, g.ws), t1 = __fdiv_rn(fx_hi - g.x0, g.ws);
-                    xa = max(0, (int)fmaxf(floorf(fminf(t0, t1)) - 1.0f, -1.0f));
-                    xb = min(pw - 1, (int)fminf(ceilf(fmaxf(t0, t1)) + 1.0f, (float)pw));
-                }
-                const int ny = yb - ya + 1, nx = xb - xa + 1;
-                const int total = (ny > 0 && nx > 0) ? ny * nx : 0;
-                bool roi_done = true;
-                for (; kbase < total; kbase += kTileThreads) {
-                    if (nq + kTileThreads > kTileQueue) { roi_done = false; break; }   // queue full: resume here
-                    const int k = kbase + tid;
-                    bool active = false;
-                    int off = 0;
-                    uint32_t pk = 0;
-                    float4 wt = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (k < total) {
-                        const int y = ya + k / nx, x = xa + (k - (k / nx) * nx);
-                        const AxisTap ty = axis_tap(g.y0, g.hs, y, H), tx = axis_tap(g.x0, g.ws, x, W);
-                        const float wy0 = __fsub_rn(1.0f, ty.lerp), wx0 = __fsub_rn(1.0f, tx.lerp);
-                        const int rt = ty.lo - y0, rb = ty.hi - y0, cl = tx.lo - x0, cr = tx.hi - x0;
-                        const bool ok = ty.valid && tx.valid;
-                        const bool t_in = ok && wy0 != 0.0f && (unsigned)rt < (unsigned)kTileH;
-                        const bool b_in = ok && ty.lerp != 0.0f && (unsigned)rb < (unsigned)kTileH;
-                        const bool l_in = wx0 != 0.0f && (unsigned)cl < (unsigned)kTileW;
-                        const bool r_in = tx.lerp != 0.0f && (unsigned)cr < (unsigned)kTileW;
-                        const uint32_t fl = (t_in && l_in ? 1u : 0u) | (t_in && r_in ? 2u : 0u) | (b_in && l_in ? 4u : 0u) |
-                                            (b_in && r_in ? 8u : 0u);
-                        active = fl != 0u;
-                        off = constant ? f : (f * ph + y) * pw + x;
-                        pk = (uint32_t)((rt & 3) * kTileW) | ((uint32_t)(cl & 7) << 5) | ((uint32_t)(cr & 7) << 8) |
-                             ((uint32_t)((rb & 3) * kTileW) << 11) | (fl << 16) | (constant ? (1u << 20) : 0u);
-                        wt = make_float4(wy0, ty.lerp, wx0, tx.lerp);
+                __syncthreads();
+                nr = s_n;
+                bkt = b1;
+            }
+            const int np2 = max(32, 1 << (32 - __clz(max(nr, 1) - 1)));
+            for (int i = nr + tid; i < np2; i += kTileThreads) s_key[i] = 0xffffffffu;
+            __syncthreads();
+            for (int k = 2; k <= np2; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = tid; t < (np2 >> 1); t += kTileThreads) {
+                        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), p = i | j;
+                        const bool up = ((i & k) == 0);
+                        const uint32_t a = s_key[i], c = s_key[p];
+                        if ((a > c) == up) { s_key[i] = c; s_key[p] = a; }
                     }
-                    const unsigned vote = __ballot_sync(0xffffffffu, active);
-                    if (lane == 0) s_wcount[warp] = __popc(vote);
-                    __syncthreads();
-                    const int pos = nq + (warp ? s_wcount[0] : 0) + __popc(vote & ((1u << lane) - 1u));
-                    if (active) { q.off[pos] = off; q.pk[pos] = pk; q.w[pos] = wt; }
-                    nq += s_wcount[0] + s_wcount[1];
                     __syncthreads();
                 }
-                if (!roi_done) break;
-                ++idx;
-                kbase = 0;
-            }
-            // ---- consume: gradient rows eight samples ahead, accumulation strictly in queue order ----
-            auto row_ptr = [&](int i) {
-                const int o = q.off[i];
-                return ((q.pk[i] >> 20) & 1u) ? const_partial + (size_t)o * c4 + v : grad_out + (size_t)o * c4 + v;
-            };
-            float4 val[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (u < nq && have_v) val[u] = __ldg(row_ptr(u));
-            for (int i0 = 0; i0 < nq; i0 += 8) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int i = i0 + u;
-                    if (i < nq && have_v) {
-                        const uint32_t pk = q.pk[i];
-                        const float4 wt = q.w[i];
-                        const float4 gv = val[u];
-                        float4* at = acc + (size_t)(pk & 31u) * kTileChunk + tid;
-                        float4* ab = acc + (size_t)((pk >> 11) & 31u) * kTileChunk + tid;
-                        const int cl = (pk >> 5) & 7u, cr = (pk >> 8) & 7u;
-                        if (pk & (3u << 16)) {
-                            const float4 d = make_float4(__fmul_rn(wt.x, gv.x), __fmul_rn(wt.x, gv.y), __fmul_rn(wt.x, gv.z),
-                                                         __fmul_rn(wt.x, gv.w));
-                            if (pk & (1u << 16)) acc_corner(at + cl * kTileChunk, d, wt.z);
-                            if (pk & (2u << 16)) acc_corner(at + cr * kTileChunk, d, wt.w);
-                        }
-                        if (pk & (12u << 16)) {
-                            const float4 d = make_float4(__fmul_rn(wt.y, gv.x), __fmul_rn(wt.y, gv.y), __fmul_rn(wt.y, gv.z),
-                                                         __fmul_rn(wt.y, gv.w));
-                            if (pk & (4u << 16)) acc_corner(ab + cl * kTileChunk, d, wt.z);
-                            if (pk & (8u << 16)) acc_corner(ab + cr * kTileChunk, d, wt.w);
-                        }
-                    }
-                    const int j = i + 8;
-                    if (j < nq && have_v) val[u] = __ldg(row_ptr(j));
+            // ---- decode kTileQueue samples, then walk them in order ----
+            for (int base = 0; base < nr; base += kTileQueue) {
+                const int nq = min(kTileQueue, nr - base);
+                for (int k = tid; k < nq; k += kTileThreads) {
+                    const uint32_t key = s_key[base + k];
+                    const int f = (int)(key >> (kKeyXBits + kKeyYBits)), y = (int)((key >> kKeyXBits) & ((1u << kKeyYBits) - 1u)),
+                              x = (int)(key & ((1u << kKeyXBits) - 1u));
+                    const TapWord* tf = taps + (size_t)f * (ph + pw);
+                    const TapWord ty = tf[y], tx = tf[ph + x];
+                    const float ly = __uint_as_float(ty.y), lx = __uint_as_float(tx.y);
+                    const float wy0 = __fsub_rn(1.0f, ly), wx0 = __fsub_rn(1.0f, lx);
+                    const int rt = tap_lo(ty) - y0, rb = tap_hi(ty) - y0, cl = tap_lo(tx) - x0, cr = tap_hi(tx) - x0;
+                    const bool t_in = wy0 != 0.0f && (unsigned)rt < (unsigned)kTileH;
+                    const bool b_in = ly != 0.0f && (unsigned)rb < (unsigned)kTileH;
+                    const bool l_in = wx0 != 0.0f && (unsigned)cl < (unsigned)kTileW;
+                    const bool r_in = lx != 0.0f && (unsigned)cr < (unsigned)kTileW;
+                    const uint32_t fl = (t_in && l_in ? 1u : 0u) | (t_in && r_in ? 2u : 0u) | (b_in && l_in ? 4u : 0u) |
+                                        (b_in && r_in ? 8u : 0u);
+                    const bool constant = tap_const(ty);
+                    q.off[k] = constant ? f : (f * ph + y) * pw + x;
+                    q.pk[k] = (uint32_t)((rt & 3) * kTileW) | ((uint32_t)(cl & 7) << 5) | ((uint32_t)(cr & 7) << 8) |
+                              ((uint32_t)((rb & 3) * kTileW) << 11) | (fl << 16) | (constant ? (1u << 20) : 0u);
+                    q.w[k] = make_float4(wy0, ly, wx0, lx);
                 }
+                __syncthreads();
+                auto row_ptr = [&](int i) {
+                    const int o = q.off[i];
+                    return ((q.pk[i] >> 20) & 1u) ? const_partial + (size_t)o * c4 + v : grad_out + (size_t)o * c4 + v;
+                };
+                float4 val[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (u < nq && have_v) val[u] = __ldg(row_ptr(u));
+                for (int i0 = 0; i0 < nq; i0 += 8) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u;
+                        if (i < nq && have_v) {
+                            const uint32_t pk = q.pk[i];
+                            const float4 wt = q.w[i];
+                            const float4 gv = val[u];
+                            float4* at = acc + (size_t)(pk & 31u) * kTileChunk + tid;
+                            float4* ab = acc + (size_t)((pk >> 11) & 31u) * kTileChunk + tid;
+                            const int cl = (pk >> 5) & 7u, cr = (pk >> 8) & 7u;
+                            if (pk & (3u << 16)) {
+                                const float4 d = make_float4(__fmul_rn(wt.x, gv.x), __fmul_rn(wt.x, gv.y),
+                                                             __fmul_rn(wt.x, gv.z), __fmul_rn(wt.x, gv.w));
+                                if (pk & (1u << 16)) acc_corner(at + cl * kTileChunk, d, wt.z);
+                                if (pk & (2u << 16)) acc_corner(at + cr * kTileChunk, d, wt.w);
+                            }
+                            if (pk & (12u << 16)) {
+                                const float4 d = make_float4(__fmul_rn(wt.y, gv.x), __fmul_rn(wt.y, gv.y),
+                                                             __fmul_rn(wt.y, gv.z), __fmul_rn(wt.y, gv.w));
+                                if (pk & (4u << 16)) acc_corner(ab + cl * kTileChunk, d, wt.z);
+                                if (pk & (8u << 16)) acc_corner(ab + cr * kTileChunk, d, wt.w);
+                            }
+                        }
+                        const int j = i + 8;
+                        if (j < nq && have_v) val[u] = __ldg(row_ptr(j));
+                    }
+                }
+                __syncthreads();   // the queue is rewritten next
             }
-            __syncthreads();   // the queue is rebuilt next
         }
         // every pixel of the tile exactly once
         if (have_v)
@@ -921,24 +969,20 @@ static int tile_space(const int* H, const int* W, int B, TileSpace* ts) {
 }
 
 // workspace of the deterministic backward:
-// [count NT | cursor NT | misc] (zeroed per call) [start NT] [work lists 4 NT] [(tile, ROI) entries] [pre-reduced rows of
-// the zero-size ROIs: BN x C floats]
+// [count NT | cursor NT | misc] (zeroed per call) [start NT] [work lists 4 NT] [taps BN (ph + pw)] [(tile, sample) keys:
+// 4 per sample] [pre-reduced rows of the zero-size ROIs: BN x C floats]
 struct BwdWsLayout {
-    size_t zeroed, start, lists, entries, partial, total;
+    size_t zeroed, start, lists, taps, entries, partial, total;
 };
 static BwdWsLayout roialign_bwd_ws_layout(const TileSpace& ts, int B, int N, int ph, int pw, int C) {
     const size_t NT = (size_t)ts.base[4], BN = (size_t)B * N;
-    size_t per_roi = 0;   // tiles one ROI can touch on its map: at most two tile rows / columns per output row / column
-    for (int l = 0; l < 4; ++l) {
-        const size_t r = (size_t)(2 * ph < ts.ty[l] ? 2 * ph : ts.ty[l]), c = (size_t)(2 * pw < ts.tx[l] ? 2 * pw : ts.tx[l]);
-        if (r * c > per_roi) per_roi = r * c;
-    }
     BwdWsLayout w;
     w.zeroed = align_up((2 * NT + kMiscWords) * sizeof(int), 256);
     w.start = w.zeroed;
     w.lists = w.start + align_up(NT * sizeof(int), 256);
-    w.entries = w.lists + align_up((size_t)kTileBuckets * NT * sizeof(int), 256);
-    w.partial = w.entries + align_up(BN * per_roi * sizeof(int), 256);
+    w.taps = w.lists + align_up((size_t)kTileBuckets * NT * sizeof(int), 256);
+    w.entries = w.taps + align_up(BN * (size_t)(ph + pw) * sizeof(TapWord), 256);
+    w.partial = w.entries + align_up(BN * (size_t)ph * pw * 4 * sizeof(uint32_t), 256);
     w.total = w.partial + align_up(BN * (size_t)C * sizeof(float), 256);
     return w;
 }
@@ -952,7 +996,9 @@ MRCNN_EXPORT int mrcnn_roialign_backward_workspace_bytes(int B, int N, int ph, i
     TileSpace ts;
     const int rc = tile_space(H, W, B, &ts);
     if (rc != MRCNN_OK) return rc;
-    if ((long long)B * N * ph * pw >= (1LL << 29)) return MRCNN_ERR_RANGE;
+    if ((long long)B * N * ph * pw >= (1LL << 29) || ph > (1 << kKeyYBits) || pw > (1 << kKeyXBits) ||
+        (long long)B * N >= (1LL << kKeyFBits))
+        return MRCNN_ERR_RANGE;
     *bytes = roialign_bwd_ws_layout(ts, B, N, ph, pw, C).total;
     return MRCNN_OK;
 }
@@ -987,32 +1033,38 @@ MRCNN_EXPORT int mrcnn_roialign_backward(const float* grad_out, const float* box
         return last_error();
     }
     // deterministic mode
-    if ((long long)B * N * ph * pw >= (1LL << 29)) return MRCNN_ERR_RANGE;
+    if ((long long)B * N * ph * pw >= (1LL << 29) || ph > (1 << kKeyYBits) || pw > (1 << kKeyXBits) ||
+        (long long)B * N >= (1LL << kKeyFBits))
+        return MRCNN_ERR_RANGE;
     rc = tile_space(H, W, B, &ts);
     if (rc != MRCNN_OK) return rc;
     if (!aligned16(ws)) return MRCNN_ERR_ALIGN;
     const BwdWsLayout lay = roialign_bwd_ws_layout(ts, B, N, ph, pw, C);
     if (ws_bytes < lay.total) return MRCNN_ERR_WORKSPACE;
-    const int NT = ts.base[4], BN = B * N;
+    const int NT = ts.base[4], BN = B * N, bins = BN * ph * pw;
     int* count = (int*)ws;
     int* cursor = count + NT;
     int* misc = count + 2 * (size_t)NT;
     int* start = (int*)((char*)ws + lay.start);
     int* lists = (int*)((char*)ws + lay.lists);
-    int* entries = (int*)((char*)ws + lay.entries);
+    TapWord* taps = (TapWord*)((char*)ws + lay.taps);
+    uint32_t* entries = (uint32_t*)((char*)ws + lay.entries);
     float4* partial = (float4*)((char*)ws + lay.partial);
     cudaError_t e = cudaMemsetAsync(ws, 0, lay.zeroed, st);
     if (e != cudaSuccess) return (int)e;
-    roialign_bwd_const_kernel<<<BN, 64, 0, st>>>((const float4*)grad_out, (const float4*)boxes, roi_map, tbl, C, ph, pw,
-                                                 partial);
-    roialign_bwd_bin_kernel<0><<<(BN + 127) / 128, 128, 0, st>>>((const float4*)boxes, roi_map, tbl, ts, N, BN, ph, pw,
-                                                                count, start, cursor, entries);
+    roialign_bwd_taps_kernel<<<(BN * (ph + pw) + 255) / 256, 256, 0, st>>>((const float4*)boxes, roi_map, tbl, BN, ph, pw,
+                                                                           taps);
+    roialign_bwd_const_kernel<<<BN, 64, 0, st>>>((const float4*)grad_out, taps, C, ph, pw, partial);
+    roialign_bwd_bin_kernel<0><<<(bins + 255) / 256, 256, 0, st>>>(taps, roi_map, ts, N, ph, pw, bins, count, start,
+                                                                  cursor, entries);
     roialign_bwd_alloc_kernel<<<(NT + 255) / 256, 256, 0, st>>>(count, NT, start, misc, lists);
-    roialign_bwd_bin_kernel<1><<<(BN + 127) / 128, 128, 0, st>>>((const float4*)boxes, roi_map, tbl, ts, N, BN, ph, pw,
-                                                                count, start, cursor, entries);
-    roialign_bwd_tile_kernel<<<2 * NT, kTileThreads, 0, st>>>((const float4*)grad_out, (const float4*)boxes,
-                                                                       roi_map, partial, tbl, ts, C, N, ph, pw, count,
-                                                                       start, entries, misc, lists);
+    roialign_bwd_bin_kernel<1><<<(bins + 255) / 256, 256, 0, st>>>(taps, roi_map, ts, N, ph, pw, bins, count, start,
+                                                                  cursor, entries);
+    const size_t tile_smem = (size_t)kTilePix * kTileChunk * sizeof(float4);
+    e = cudaFuncSetAttribute(roialign_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem);
+    if (e != cudaSuccess) return (int)e;
+    roialign_bwd_tile_kernel<<<2 * NT, kTileThreads, tile_smem, st>>>((const float4*)grad_out, taps, partial, tbl, ts, C, ph, pw,
+                                                              count, start, entries, misc, lists);
     roialign_bwd_kernel<<<B * N * groups, kRoiThreads, smem, st>>>((const float4*)grad_out, (const float4*)boxes, roi_map,
                                                                   tbl, C, N, ph, pw, groups, rows_per_group, ts, start,
                                                                   misc + kMiscOverflow);
