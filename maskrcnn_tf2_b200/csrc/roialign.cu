@@ -368,11 +368,12 @@ struct PixelSpace {   // global pixel id = base[m] + (b * H[m] + y) * W[m] + x ;
 
 constexpr int kTileH = 4, kTileW = 8; // gradient-map tile of the deterministic mode: 4 rows x 8 columns of pixels
 constexpr int kTilePix = kTileH * kTileW;
-constexpr int kTileCap = 4096;       // samples one tile orders in shared memory per round
+constexpr int kTileCap = 1024;       // samples one tile orders in shared memory per round
 constexpr int kTileThreads = 64;     // one thread per four channels (256 channels per pass)
 constexpr int kTileChunk = 64;       // float4 channel vectors per pass
-constexpr int kTileQueue = 192;      // samples decoded per consume round
-constexpr int kTileBuckets = 4;      // work lists by sample count (>= 512, >= 64, >= 8, >= 1): heavy tiles start first
+constexpr int kTileQueue = 128;      // samples decoded per consume round
+constexpr int kTileBuckets = 2;      // work lists by sample count (>= 128 / fewer): the heavy tiles are started first
+constexpr int kTileCtasPerSm = 5;    // persistent grid of the tile kernel (42 KB of shared memory per CTA)
 constexpr int kTileFBuckets = 256;   // a tile with more than kTileCap samples is taken in rounds of ROI-index ranges
 // sample key: ROI index << 14 | output row << 7 | output column -- ascending key = TF's accumulation order
 constexpr int kKeyXBits = 7, kKeyYBits = 7, kKeyFBits = 18;
@@ -620,7 +621,7 @@ roialign_bwd_bin_kernel(const TapWord* __restrict__ taps, const int32_t* __restr
 
 __global__ void __launch_bounds__(256)
 roialign_bwd_alloc_kernel(const int* __restrict__ count, int NT, int* __restrict__ start, int* __restrict__ misc,
-                          int* __restrict__ lists /*[kTileBuckets][NT]*/) {
+                          int4* __restrict__ lists /*[kTileBuckets][NT]: (tile, segment start, samples, -)*/) {
     __shared__ int warp_sums[32];
     __shared__ int block_total, block_base;
     const int t = blockIdx.x * 256 + threadIdx.x;
@@ -631,13 +632,13 @@ roialign_bwd_alloc_kernel(const int* __restrict__ count, int NT, int* __restrict
     if (t >= NT) return;
     start[t] = block_base + off;
     if (c > 0) {   // one atomic per bucket and warp
-        const int bucket = (c >= 512) ? 0 : (c >= 64) ? 1 : (c >= 8) ? 2 : 3;
+        const int bucket = (c >= 128) ? 0 : 1;
         const unsigned peers = __match_any_sync(__activemask(), bucket);
         const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
         int base = 0;
         if (lane == leader) base = atomicAdd(&misc[kMiscBucket0 + bucket], __popc(peers));
         base = __shfl_sync(peers, base, leader);
-        lists[(size_t)bucket * NT + base + __popc(peers & ((1u << lane) - 1u))] = t;
+        lists[(size_t)bucket * NT + base + __popc(peers & ((1u << lane) - 1u))] = make_int4(t, block_base + off, c, 0);
     }
 }
 
@@ -659,187 +660,218 @@ struct TileQueue {
     float4 w[kTileQueue];   // (1 - ly, ly, 1 - lx, lx)
 };
 
+// geometry of a tile: which map, which image, first pixel, extent
+struct TileGeom {
+    float4* gmap;
+    int W, y0, x0, rows_in, cols_in;
+};
+__device__ __forceinline__ TileGeom tile_geom(const GradTable& tbl, const TileSpace& ts, int tile, int c4) {
+    const int m = (tile >= ts.base[3]) ? 3 : (tile >= ts.base[2]) ? 2 : (tile >= ts.base[1]) ? 1 : 0;
+    const int H = tbl.H[m], W = tbl.W[m], TY = ts.ty[m], TX = ts.tx[m];
+    const int local = tile - ts.base[m];
+    const int b = local / (TY * TX), rem = local - b * (TY * TX);
+    TileGeom g;
+    g.W = W;
+    g.y0 = (rem / TX) * kTileH;
+    g.x0 = (rem - (rem / TX) * TX) * kTileW;
+    g.rows_in = min(kTileH, H - g.y0);
+    g.cols_in = min(kTileW, W - g.x0);
+    g.gmap = reinterpret_cast<float4*>(tbl.ptr[m]) + (size_t)b * H * W * c4;
+    return g;
+}
+__device__ __forceinline__ void tile_zero(const TileGeom& g, int c4, int tid) {
+    for (int r = 0; r < g.rows_in; ++r) {
+        float4* dst = g.gmap + ((size_t)(g.y0 + r) * g.W + g.x0) * c4;
+        for (int v = tid; v < g.cols_in * c4; v += kTileThreads) __stcs(dst + v, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+}
+
+// Persistent grid (kTileCtasPerSm CTAs per SM): every CTA first takes non-empty tiles off the two work lists (heavy
+// tiles first, static round robin), then zero-fills its share of the tiles nobody samples.
 __global__ void __launch_bounds__(kTileThreads)
 roialign_bwd_tile_kernel(const float4* __restrict__ grad_out, const TapWord* __restrict__ taps,
                          const float4* __restrict__ const_partial, GradTable tbl, TileSpace ts, int C, int ph, int pw,
                          const int* __restrict__ count, int* __restrict__ start, const uint32_t* __restrict__ entries,
-                         int* __restrict__ misc, const int* __restrict__ lists) {
+                         int* __restrict__ misc, const int4* __restrict__ lists) {
     extern __shared__ __align__(16) float4 acc[];                 // [pixel][channel vector]: 32 KB (dynamic)
-    __shared__ uint32_t s_key[kTileCap];
+    __shared__ uint32_t s_key[kTileCap], s_tmp[kTileCap];
     __shared__ TileQueue q;
     __shared__ int s_hist[kTileFBuckets];
     __shared__ int s_n;
     const int NT = ts.base[4], tid = threadIdx.x;
     const int c4 = C >> 2;
-    int tile, n = 0;
-    if ((int)blockIdx.x < NT) {   // ranked work item: the blockIdx-th non-empty tile, heaviest bucket first
-        int w = blockIdx.x, bucket = 0;
+    const int n_heavy = misc[kMiscBucket0], n_items = n_heavy + misc[kMiscBucket0 + 1];
+    auto item_of = [&](int w) { return __ldg(lists + (w < n_heavy ? (size_t)w : (size_t)NT + (w - n_heavy))); };
+    int4 next = make_int4(0, 0, 0, 0);
+    if ((int)blockIdx.x < n_items) next = item_of(blockIdx.x);
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const int4 item = next;
+        if (w + (int)gridDim.x < n_items) next = item_of(w + gridDim.x);     // the next header is in flight during this tile
+        const int tile = item.x, n = item.z;
+        const TileGeom tg = tile_geom(tbl, ts, tile, c4);
+        const int y0 = tg.y0, x0 = tg.x0;
+        const uint32_t* seg = entries + item.y;
+        // ---- rounds: all samples at once when they fit, else ranges of ROI indices of at most kTileCap samples ----
+        uint32_t f_lo = 0u, f_width = 1u;   // histogram bucket of a key: ((key >> 14) - f_lo) / f_width
+        bool overflow = false;
+        __syncthreads();                    // the previous tile is done with the shared arrays
+        if (n > kTileCap) {
+            uint32_t mn = 0xffffffffu, mx = 0u;
+            for (int i = tid; i < n; i += kTileThreads) { const uint32_t f = seg[i] >> (kKeyXBits + kKeyYBits); mn = min(mn, f); mx = max(mx, f); }
 #pragma unroll
-        for (; bucket < kTileBuckets; ++bucket) {
-            const int nb = misc[kMiscBucket0 + bucket];
-            if (w < nb) break;
-            w -= nb;
-        }
-        if (bucket == kTileBuckets) return;
-        tile = lists[(size_t)bucket * NT + w];
-        n = count[tile];
-    } else {                      // zero-fill: the tiles nobody samples
-        tile = blockIdx.x - NT;
-        if (count[tile] > 0) return;
-    }
-    const int m = (tile >= ts.base[3]) ? 3 : (tile >= ts.base[2]) ? 2 : (tile >= ts.base[1]) ? 1 : 0;
-    const int H = tbl.H[m], W = tbl.W[m], TY = ts.ty[m], TX = ts.tx[m];
-    const int local = tile - ts.base[m];
-    const int b = local / (TY * TX), rem = local - b * (TY * TX);
-    const int y0 = (rem / TX) * kTileH, x0 = (rem - (rem / TX) * TX) * kTileW;
-    const int rows_in = min(kTileH, H - y0), cols_in = min(kTileW, W - x0);
-    float4* gmap = reinterpret_cast<float4*>(tbl.ptr[m]) + (size_t)b * H * W * c4;
-    if (n == 0) {
-        for (int r = 0; r < rows_in; ++r) {
-            float4* dst = gmap + ((size_t)(y0 + r) * W + x0) * c4;
-            for (int v = tid; v < cols_in * c4; v += kTileThreads) __stcs(dst + v, make_float4(0.f, 0.f, 0.f, 0.f));
-        }
-        return;
-    }
-    const uint32_t* seg = entries + start[tile];
-    // ---- rounds: all samples at once when they fit, else ranges of ROI indices of at most kTileCap samples ----
-    uint32_t f_lo = 0u, f_width = 1u;   // histogram bucket of a key: ((key >> 14) - f_lo) / f_width
-    bool overflow = false;
-    if (n > kTileCap) {
-        uint32_t mn = 0xffffffffu, mx = 0u;
-        for (int i = tid; i < n; i += kTileThreads) { const uint32_t f = seg[i] >> (kKeyXBits + kKeyYBits); mn = min(mn, f); mx = max(mx, f); }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
-        for (int i = tid; i < kTileFBuckets; i += kTileThreads) s_hist[i] = 0;
-        if (tid == 0) { s_key[0] = 0xffffffffu; s_key[1] = 0u; }
-        __syncthreads();
-        if ((tid & 31) == 0) { atomicMin(&s_key[0], mn); atomicMax(&s_key[1], mx); }
-        __syncthreads();
-        f_lo = s_key[0];
-        f_width = (s_key[1] - f_lo) / kTileFBuckets + 1u;
-        __syncthreads();
-        for (int i = tid; i < n; i += kTileThreads) atomicAdd(&s_hist[((seg[i] >> (kKeyXBits + kKeyYBits)) - f_lo) / f_width], 1);
-        __syncthreads();
-        for (int i = tid; i < kTileFBuckets; i += kTileThreads) overflow |= s_hist[i] > kTileCap;
-        overflow = __syncthreads_or(overflow);
-    }
-    if (overflow) {   // (pathological) zero the tile, flag it: the scatter kernel adds this tile's samples atomically
-        if (tid == 0) { start[tile] = -1; misc[kMiscOverflow] = 1; }
-        for (int r = 0; r < rows_in; ++r) {
-            float4* dst = gmap + ((size_t)(y0 + r) * W + x0) * c4;
-            for (int v = tid; v < cols_in * c4; v += kTileThreads) __stcs(dst + v, make_float4(0.f, 0.f, 0.f, 0.f));
-        }
-        return;
-    }
-    for (int cc = 0; cc < c4; cc += kTileChunk) {   // 256 channels per pass
-        const int v = cc + tid;
-        const bool have_v = v < c4;
-        for (int i = tid; i < kTilePix * kTileChunk; i += kTileThreads) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        int bkt = 0;
-        while (bkt < kTileFBuckets) {
-            // ---- this round's samples -> s_key, ascending ----
-            int nr;
-            if (n <= kTileCap) {
-                for (int i = tid; i < n; i += kTileThreads) s_key[i] = __ldg(seg + i);
-                nr = n;
-                bkt = kTileFBuckets;
-            } else {
-                int b1 = bkt, sum = 0;
-                while (b1 < kTileFBuckets && sum + s_hist[b1] <= kTileCap) sum += s_hist[b1++];   // uniform
-                if (tid == 0) s_n = 0;
-                __syncthreads();
-                for (int i = tid; i < n; i += kTileThreads) {
-                    const uint32_t key = __ldg(seg + i);
-                    const int kb = (int)(((key >> (kKeyXBits + kKeyYBits)) - f_lo) / f_width);
-                    if (kb >= bkt && kb < b1) s_key[atomicAdd(&s_n, 1)] = key;
-                }
-                __syncthreads();
-                nr = s_n;
-                bkt = b1;
-            }
-            const int np2 = max(32, 1 << (32 - __clz(max(nr, 1) - 1)));
-            for (int i = nr + tid; i < np2; i += kTileThreads) s_key[i] = 0xffffffffu;
+            for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+            for (int i = tid; i < kTileFBuckets; i += kTileThreads) s_hist[i] = 0;
+            if (tid == 0) { s_key[0] = 0xffffffffu; s_key[1] = 0u; }
             __syncthreads();
-            for (int k = 2; k <= np2; k <<= 1)
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    for (int t = tid; t < (np2 >> 1); t += kTileThreads) {
-                        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), p = i | j;
-                        const bool up = ((i & k) == 0);
-                        const uint32_t a = s_key[i], c = s_key[p];
-                        if ((a > c) == up) { s_key[i] = c; s_key[p] = a; }
+            if ((tid & 31) == 0) { atomicMin(&s_key[0], mn); atomicMax(&s_key[1], mx); }
+            __syncthreads();
+            f_lo = s_key[0];
+            f_width = (s_key[1] - f_lo) / kTileFBuckets + 1u;
+            __syncthreads();
+            for (int i = tid; i < n; i += kTileThreads) atomicAdd(&s_hist[((seg[i] >> (kKeyXBits + kKeyYBits)) - f_lo) / f_width], 1);
+            __syncthreads();
+            for (int i = tid; i < kTileFBuckets; i += kTileThreads) overflow |= s_hist[i] > kTileCap;
+            overflow = __syncthreads_or(overflow);
+        }
+        if (overflow) {   // (pathological) zero the tile, flag it: the scatter kernel adds this tile's samples atomically
+            if (tid == 0) { start[tile] = -1; misc[kMiscOverflow] = 1; }
+            tile_zero(tg, c4, tid);
+            continue;
+        }
+        for (int cc = 0; cc < c4; cc += kTileChunk) {   // 256 channels per pass
+            const int v = cc + tid;
+            const bool have_v = v < c4;
+            for (int i = tid; i < kTilePix * kTileChunk; i += kTileThreads) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            int bkt = 0;
+            while (bkt < kTileFBuckets) {
+                // ---- this round's samples -> s_key, ascending ----
+                int nr;
+                if (n <= kTileCap) {
+                    for (int i = tid; i < n; i += kTileThreads) s_tmp[i] = __ldg(seg + i);
+                    nr = n;
+                    bkt = kTileFBuckets;
+                } else {
+                    int b1 = bkt, sum = 0;
+                    while (b1 < kTileFBuckets && sum + s_hist[b1] <= kTileCap) sum += s_hist[b1++];   // uniform
+                    if (tid == 0) s_n = 0;
+                    __syncthreads();
+                    for (int i = tid; i < n; i += kTileThreads) {
+                        const uint32_t key = __ldg(seg + i);
+                        const int kb = (int)(((key >> (kKeyXBits + kKeyYBits)) - f_lo) / f_width);
+                        if (kb >= bkt && kb < b1) s_tmp[atomicAdd(&s_n, 1)] = key;
                     }
                     __syncthreads();
-                }
-            // ---- decode kTileQueue samples, then walk them in order ----
-            for (int base = 0; base < nr; base += kTileQueue) {
-                const int nq = min(kTileQueue, nr - base);
-                for (int k = tid; k < nq; k += kTileThreads) {
-                    const uint32_t key = s_key[base + k];
-                    const int f = (int)(key >> (kKeyXBits + kKeyYBits)), y = (int)((key >> kKeyXBits) & ((1u << kKeyYBits) - 1u)),
-                              x = (int)(key & ((1u << kKeyXBits) - 1u));
-                    const TapWord* tf = taps + (size_t)f * (ph + pw);
-                    const TapWord ty = tf[y], tx = tf[ph + x];
-                    const float ly = __uint_as_float(ty.y), lx = __uint_as_float(tx.y);
-                    const float wy0 = __fsub_rn(1.0f, ly), wx0 = __fsub_rn(1.0f, lx);
-                    const int rt = tap_lo(ty) - y0, rb = tap_hi(ty) - y0, cl = tap_lo(tx) - x0, cr = tap_hi(tx) - x0;
-                    const bool t_in = wy0 != 0.0f && (unsigned)rt < (unsigned)kTileH;
-                    const bool b_in = ly != 0.0f && (unsigned)rb < (unsigned)kTileH;
-                    const bool l_in = wx0 != 0.0f && (unsigned)cl < (unsigned)kTileW;
-                    const bool r_in = lx != 0.0f && (unsigned)cr < (unsigned)kTileW;
-                    const uint32_t fl = (t_in && l_in ? 1u : 0u) | (t_in && r_in ? 2u : 0u) | (b_in && l_in ? 4u : 0u) |
-                                        (b_in && r_in ? 8u : 0u);
-                    const bool constant = tap_const(ty);
-                    q.off[k] = constant ? f : (f * ph + y) * pw + x;
-                    q.pk[k] = (uint32_t)((rt & 3) * kTileW) | ((uint32_t)(cl & 7) << 5) | ((uint32_t)(cr & 7) << 8) |
-                              ((uint32_t)((rb & 3) * kTileW) << 11) | (fl << 16) | (constant ? (1u << 20) : 0u);
-                    q.w[k] = make_float4(wy0, ly, wx0, lx);
+                    nr = s_n;
+                    bkt = b1;
                 }
                 __syncthreads();
-                auto row_ptr = [&](int i) {
-                    const int o = q.off[i];
-                    return ((q.pk[i] >> 20) & 1u) ? const_partial + (size_t)o * c4 + v : grad_out + (size_t)o * c4 + v;
-                };
-                float4 val[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (u < nq && have_v) val[u] = __ldg(row_ptr(u));
-                for (int i0 = 0; i0 < nq; i0 += 8) {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int i = i0 + u;
-                        if (i < nq && have_v) {
-                            const uint32_t pk = q.pk[i];
-                            const float4 wt = q.w[i];
-                            const float4 gv = val[u];
-                            float4* at = acc + (size_t)(pk & 31u) * kTileChunk + tid;
-                            float4* ab = acc + (size_t)((pk >> 11) & 31u) * kTileChunk + tid;
-                            const int cl = (pk >> 5) & 7u, cr = (pk >> 8) & 7u;
-                            if (pk & (3u << 16)) {
-                                const float4 d = make_float4(__fmul_rn(wt.x, gv.x), __fmul_rn(wt.x, gv.y),
-                                                             __fmul_rn(wt.x, gv.z), __fmul_rn(wt.x, gv.w));
-                                if (pk & (1u << 16)) acc_corner(at + cl * kTileChunk, d, wt.z);
-                                if (pk & (2u << 16)) acc_corner(at + cr * kTileChunk, d, wt.w);
-                            }
-                            if (pk & (12u << 16)) {
-                                const float4 d = make_float4(__fmul_rn(wt.y, gv.x), __fmul_rn(wt.y, gv.y),
-                                                             __fmul_rn(wt.y, gv.z), __fmul_rn(wt.y, gv.w));
-                                if (pk & (4u << 16)) acc_corner(ab + cl * kTileChunk, d, wt.z);
-                                if (pk & (8u << 16)) acc_corner(ab + cr * kTileChunk, d, wt.w);
-                            }
-                        }
-                        const int j = i + 8;
-                        if (j < nq && have_v) val[u] = __ldg(row_ptr(j));
+                if (nr <= 128) {   // the usual case: rank by counting (broadcast loads), one barrier
+                    for (int i = tid; i < nr; i += kTileThreads) {
+                        const uint32_t x = s_tmp[i];
+                        int rank = 0;
+                        for (int j = 0; j < nr; ++j) rank += (s_tmp[j] < x);
+                        s_key[rank] = x;
                     }
+                    __syncthreads();
+                } else {
+                    const int np2 = 1 << (32 - __clz(nr - 1));
+                    for (int i = tid; i < np2; i += kTileThreads) s_key[i] = (i < nr) ? s_tmp[i] : 0xffffffffu;
+                    __syncthreads();
+                    for (int k = 2; k <= np2; k <<= 1)
+                        for (int j = k >> 1; j > 0; j >>= 1) {
+                            for (int t = tid; t < (np2 >> 1); t += kTileThreads) {
+                                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), p = i | j;
+                                const bool up = ((i & k) == 0);
+                                const uint32_t a = s_key[i], c = s_key[p];
+                                if ((a > c) == up) { s_key[i] = c; s_key[p] = a; }
+                            }
+                            __syncthreads();
+                        }
                 }
-                __syncthreads();   // the queue is rewritten next
+                // ---- decode kTileQueue samples, then walk them in order ----
+                for (int base = 0; base < nr; base += kTileQueue) {
+                    const int nq = min(kTileQueue, nr - base);
+                    for (int k = tid; k < nq; k += kTileThreads) {
+                        const uint32_t key = s_key[base + k];
+                        const int f = (int)(key >> (kKeyXBits + kKeyYBits)), y = (int)((key >> kKeyXBits) & ((1u << kKeyYBits) - 1u)),
+                                  x = (int)(key & ((1u << kKeyXBits) - 1u));
+                        const TapWord* tf = taps + (size_t)f * (ph + pw);
+                        const TapWord ty = tf[y], tx = tf[ph + x];
+                        const float ly = __uint_as_float(ty.y), lx = __uint_as_float(tx.y);
+                        const float wy0 = __fsub_rn(1.0f, ly), wx0 = __fsub_rn(1.0f, lx);
+                        const int rt = tap_lo(ty) - y0, rb = tap_hi(ty) - y0, cl = tap_lo(tx) - x0, cr = tap_hi(tx) - x0;
+                        const bool t_in = wy0 != 0.0f && (unsigned)rt < (unsigned)kTileH;
+                        const bool b_in = ly != 0.0f && (unsigned)rb < (unsigned)kTileH;
+                        const bool l_in = wx0 != 0.0f && (unsigned)cl < (unsigned)kTileW;
+                        const bool r_in = lx != 0.0f && (unsigned)cr < (unsigned)kTileW;
+                        const uint32_t fl = (t_in && l_in ? 1u : 0u) | (t_in && r_in ? 2u : 0u) | (b_in && l_in ? 4u : 0u) |
+                                            (b_in && r_in ? 8u : 0u);
+                        const bool constant = tap_const(ty);
+                        q.off[k] = constant ? f : (f * ph + y) * pw + x;
+                        q.pk[k] = (uint32_t)((rt & 3) * kTileW) | ((uint32_t)(cl & 7) << 5) | ((uint32_t)(cr & 7) << 8) |
+                                  ((uint32_t)((rb & 3) * kTileW) << 11) | (fl << 16) | (constant ? (1u << 20) : 0u);
+                        q.w[k] = make_float4(wy0, ly, wx0, lx);
+                    }
+                    __syncthreads();
+                    auto row_ptr = [&](int i) {
+                        const int o = q.off[i];
+                        return ((q.pk[i] >> 20) & 1u) ? const_partial + (size_t)o * c4 + v : grad_out + (size_t)o * c4 + v;
+                    };
+                    float4 val[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (u < nq && have_v) val[u] = __ldg(row_ptr(u));
+                    for (int i0 = 0; i0 < nq; i0 += 8) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int i = i0 + u;
+                            if (i < nq && have_v) {
+                                const uint32_t pk = q.pk[i];
+                                const float4 wt = q.w[i];
+                                const float4 gv = val[u];
+                                float4* at = acc + (size_t)(pk & 31u) * kTileChunk + tid;
+                                float4* ab = acc + (size_t)((pk >> 11) & 31u) * kTileChunk + tid;
+                                const int cl = (pk >> 5) & 7u, cr = (pk >> 8) & 7u;
+                                if (pk & (3u << 16)) {
+                                    const float4 d = make_float4(__fmul_rn(wt.x, gv.x), __fmul_rn(wt.x, gv.y),
+                                                                 __fmul_rn(wt.x, gv.z), __fmul_rn(wt.x, gv.w));
+                                    if (pk & (1u << 16)) acc_corner(at + cl * kTileChunk, d, wt.z);
+                                    if (pk & (2u << 16)) acc_corner(at + cr * kTileChunk, d, wt.w);
+                                }
+                                if (pk & (12u << 16)) {
+                                    const float4 d = make_float4(__fmul_rn(wt.y, gv.x), __fmul_rn(wt.y, gv.y),
+                                                                 __fmul_rn(wt.y, gv.z), __fmul_rn(wt.y, gv.w));
+                                    if (pk & (4u << 16)) acc_corner(ab + cl * kTileChunk, d, wt.z);
+                                    if (pk & (8u << 16)) acc_corner(ab + cr * kTileChunk, d, wt.w);
+                                }
+                            }
+                            const int j = i + 8;
+                            if (j < nq && have_v) val[u] = __ldg(row_ptr(j));
+                        }
+                    }
+                    __syncthreads();   // the queue is rewritten next
+                }
             }
+            // every pixel of the tile exactly once
+            if (have_v)
+                for (int r = 0; r < tg.rows_in; ++r)
+                    for (int px = 0; px < tg.cols_in; ++px)
+                        __stcs(tg.gmap + ((size_t)(y0 + r) * tg.W + x0 + px) * c4 + v,
+                               acc[(size_t)(r * kTileW + px) * kTileChunk + tid]);
+            __syncthreads();
         }
-        // every pixel of the tile exactly once
-        if (have_v)
-            for (int r = 0; r < rows_in; ++r)
-                for (int px = 0; px < cols_in; ++px)
-                    __stcs(gmap + ((size_t)(y0 + r) * W + x0 + px) * c4 + v, acc[(size_t)(r * kTileW + px) * kTileChunk + tid]);
+    }
+    // ---- zero-fill: the tiles nobody samples, 64 candidates per step (one count per thread) ----
+    for (int base = blockIdx.x * kTileThreads; base < NT; base += gridDim.x * kTileThreads) {
+        const int t = base + tid;
+        const bool empty = (t < NT) && count[t] == 0;
+        const unsigned vote = __ballot_sync(0xffffffffu, empty);
+        __syncthreads();                                   // s_hist is free (previous step / the tile loop)
+        if ((tid & 31) == 0) s_hist[tid >> 5] = (int)vote;
         __syncthreads();
+        const unsigned long long all = (unsigned long long)(unsigned)s_hist[0] | ((unsigned long long)(unsigned)s_hist[1] << 32);
+        for (unsigned long long mm = all; mm; mm &= mm - 1)
+            tile_zero(tile_geom(tbl, ts, base + __ffsll((long long)mm) - 1, c4), c4, tid);
     }
 }
 
@@ -980,7 +1012,7 @@ static BwdWsLayout roialign_bwd_ws_layout(const TileSpace& ts, int B, int N, int
     w.zeroed = align_up((2 * NT + kMiscWords) * sizeof(int), 256);
     w.start = w.zeroed;
     w.lists = w.start + align_up(NT * sizeof(int), 256);
-    w.taps = w.lists + align_up((size_t)kTileBuckets * NT * sizeof(int), 256);
+    w.taps = w.lists + align_up((size_t)kTileBuckets * NT * sizeof(int4), 256);
     w.entries = w.taps + align_up(BN * (size_t)(ph + pw) * sizeof(TapWord), 256);
     w.partial = w.entries + align_up(BN * (size_t)ph * pw * 4 * sizeof(uint32_t), 256);
     w.total = w.partial + align_up(BN * (size_t)C * sizeof(float), 256);
@@ -1046,7 +1078,7 @@ MRCNN_EXPORT int mrcnn_roialign_backward(const float* grad_out, const float* box
     int* cursor = count + NT;
     int* misc = count + 2 * (size_t)NT;
     int* start = (int*)((char*)ws + lay.start);
-    int* lists = (int*)((char*)ws + lay.lists);
+    int4* lists = (int4*)((char*)ws + lay.lists);
     TapWord* taps = (TapWord*)((char*)ws + lay.taps);
     uint32_t* entries = (uint32_t*)((char*)ws + lay.entries);
     float4* partial = (float4*)((char*)ws + lay.partial);
@@ -1063,7 +1095,8 @@ MRCNN_EXPORT int mrcnn_roialign_backward(const float* grad_out, const float* box
     const size_t tile_smem = (size_t)kTilePix * kTileChunk * sizeof(float4);
     e = cudaFuncSetAttribute(roialign_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem);
     if (e != cudaSuccess) return (int)e;
-    roialign_bwd_tile_kernel<<<2 * NT, kTileThreads, tile_smem, st>>>((const float4*)grad_out, taps, partial, tbl, ts, C, ph, pw,
+    const int tile_grid = min(2 * NT, device_props().sms * kTileCtasPerSm);
+    roialign_bwd_tile_kernel<<<tile_grid, kTileThreads, tile_smem, st>>>((const float4*)grad_out, taps, partial, tbl, ts, C, ph, pw,
                                                               count, start, entries, misc, lists);
     roialign_bwd_kernel<<<B * N * groups, kRoiThreads, smem, st>>>((const float4*)grad_out, (const float4*)boxes, roi_map,
                                                                   tbl, C, N, ph, pw, groups, rows_per_group, ts, start,
