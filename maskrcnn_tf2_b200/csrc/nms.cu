@@ -421,7 +421,19 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
             }
             PROFW_MARK(1);
             const int cnt = share(nk);
-            screen(cnt_known, cnt, nk, true);         // second instalment: the boxes kept in tile u-2
+            if (COMPACT) {   // second instalment: the boxes kept in tile u-2 -- one or two per far warp, taken one by one
+                for (int j = cnt_known; j < cnt; ++j) {
+                    const float4 bk = kbw[j];
+                    const float ntk = ktw[j];
+                    tkmax = fmaxf(tkmax, -ntk);
+                    float e0, e1;
+                    iou_screen_d2(bk, ntk, cp, c1_2, e0, e1);
+                    dmax0 = fmaxf(dmax0, e0);
+                    dmax1 = fmaxf(dmax1, e1);
+                }
+            } else {
+                screen(cnt_known, cnt, nk, true);
+            }
             nk_known = nk;
             const float m0 = __fmul_rn(__fadd_rn(tkmax, tc0), kScreenBand), m1 = __fmul_rn(__fadd_rn(tkmax, tc1), kScreenBand);
             bool r0 = dmax0 > m0, r1 = dmax1 > m1;

@@ -352,81 +352,54 @@ __device__ __forceinline__ void red_add_v4(float* addr, float x, float y, float 
 
 // TF CropAndResizeGradImage: dtop = (1-ly) g; tl += (1-lx) dtop; tr += lx dtop; dbot = ly g; bl += (1-lx) dbot;
 // br += lx dbot -- skipped exactly where the forward pass extrapolated.
-//
-// Atomic mode (no workspace): memset of the maps, then roialign_bwd_kernel scatters with 16-byte vector reductions.
 // One CTA per (ROI, group of <= 8 output rows), one warp per row, lanes over channels.  Contention control:
 //   * a corner whose weight is exactly 0 is not touched (finite gradients: adding 0 changes nothing);
 //   * bins of a row that hit the same pixels (zero width scale) are summed in registers before one reduction;
 //   * ROIs whose taps are constant in both axes (zero-padded ROIs: every bin samples pixel (0,0), quirk Q5) are
 //     summed across the CTA's rows in shared memory and issue ONE reduction per CTA and corner, which keeps the
 //     thousands of padded rows of a training batch from serialising on a single L2 line.
-//
-// Deterministic mode (workspace): tile-owner accumulation, see roialign_bwd_tile_kernel below.
+constexpr int kLightMax = 32;       // samples a pixel may collect and still be summed, in TF's order, by one warp
+constexpr int kMediumMax = 1024;    // ... or, thread per channel, by one CTA, in ONE round; more samples: several rounds
+constexpr int kHeavyMax = 1 << 20;  // pixels above this (never seen) go to the atomic fallback
+constexpr int kHeavyBuckets = 1024; // sample-index histogram of a pixel with more than kMediumMax samples
+constexpr int kMediumCtas = 296;    // CTAs at the head of the gather grid that walk the list of such pixels
+
 struct PixelSpace {   // global pixel id = base[m] + (b * H[m] + y) * W[m] + x ; base[4] = number of pixels
     int base[5];
 };
 
-constexpr int kTileH = 4, kTileW = 8; // gradient-map tile of the deterministic mode: 4 rows x 8 columns of pixels
-constexpr int kTilePix = kTileH * kTileW;
-constexpr int kTileCap = 1024;       // samples one tile orders in shared memory per round
-constexpr int kTileThreads = 64;     // one thread per four channels (256 channels per pass)
-constexpr int kTileChunk = 64;       // float4 channel vectors per pass
-constexpr int kTileQueue = 128;      // samples decoded per consume round
-constexpr int kTileBuckets = 2;      // work lists by sample count (>= 128 / fewer): the heavy tiles are started first
-constexpr int kTileCtasPerSm = 5;    // persistent grid of the tile kernel (42 KB of shared memory per CTA)
-constexpr int kTileFBuckets = 256;   // a tile with more than kTileCap samples is taken in rounds of ROI-index ranges
-// sample key: ROI index << 14 | output row << 7 | output column -- ascending key = TF's accumulation order
-constexpr int kKeyXBits = 7, kKeyYBits = 7, kKeyFBits = 18;
-
-struct TileSpace {    // tile id = base[m] + (b * ty[m] + tile_y) * tx[m] + tile_x ; base[4] = number of tiles
-    int base[5];
-    int ty[4], tx[4];
-};
-// misc words of the deterministic workspace
-enum { kMiscBump = 0, kMiscOverflow = 1, kMiscBucket0 = 2 /* .. 5 */, kMiscWords = 16 };
-
-__device__ __forceinline__ int tile_of_pixel(const TileSpace& ts, int m, int b, int y, int x) {
-    const int ty = (m == 0) ? ts.ty[0] : (m == 1) ? ts.ty[1] : (m == 2) ? ts.ty[2] : ts.ty[3];
-    const int tx = (m == 0) ? ts.tx[0] : (m == 1) ? ts.tx[1] : (m == 2) ? ts.tx[2] : ts.tx[3];
-    const int base = (m == 0) ? ts.base[0] : (m == 1) ? ts.base[1] : (m == 2) ? ts.base[2] : ts.base[3];
-    return base + (b * ty + y / kTileH) * tx + x / kTileW;
+// `count` == nullptr: every corner is scattered (atomic mode).  Otherwise only corners whose pixel was left to the
+// atomic fallback (more than kLightMax samples, or a constant-tap ROI) are; the gather kernel owns the rest.
+// (cursor[q] < 0: the gather kernel handed the pixel over -- one bucket of its sample histogram overflowed a round)
+__device__ __forceinline__ bool corner_is_ours(const uint32_t* __restrict__ count, int q) {
+    return count == nullptr || __ldg(count + q) > (uint32_t)kHeavyMax || (__ldg(count + q) & 0x40000000u) != 0u;
 }
 
-// `tile_start` == nullptr: every corner is scattered (atomic mode).  Otherwise only corners whose pixel lies in a tile
-// that overflowed kTileRoiMax (tile_start < 0) are; the tile kernel owns the rest.
-struct ScatterFilter {
-    const int* tile_start;
-    TileSpace ts;
-    int m, b, W;
-    __device__ __forceinline__ bool ours(int p) const {   // p = pixel index inside the (image, map) plane
-        if (tile_start == nullptr) return true;
-        return __ldg(tile_start + tile_of_pixel(ts, m, b, p / W, p - (p / W) * W)) < 0;
-    }
-};
-
-__device__ __forceinline__ void scatter_corners(float* gimg, int C, const ScatterFilter& flt, int ptl, int ptr_, int pbl,
-                                                int pbr, int i, const float4& v, float wy0, float ly, float wx0, float lx) {
+__device__ __forceinline__ void scatter_corners(float* gimg, int C, const uint32_t* __restrict__ count, int qbase,
+                                                int ptl, int ptr_, int pbl, int pbr, int i, const float4& v,
+                                                float wy0, float ly, float wx0, float lx) {
     const float4 dt = make_float4(__fmul_rn(wy0, v.x), __fmul_rn(wy0, v.y), __fmul_rn(wy0, v.z), __fmul_rn(wy0, v.w));
     const float4 db = make_float4(__fmul_rn(ly, v.x), __fmul_rn(ly, v.y), __fmul_rn(ly, v.z), __fmul_rn(ly, v.w));
-    if (wy0 != 0.0f && wx0 != 0.0f && flt.ours(ptl))
+    if (wy0 != 0.0f && wx0 != 0.0f && corner_is_ours(count, qbase + ptl))
         red_add_v4(gimg + (size_t)ptl * C + 4 * i, __fmul_rn(wx0, dt.x), __fmul_rn(wx0, dt.y), __fmul_rn(wx0, dt.z), __fmul_rn(wx0, dt.w));
-    if (wy0 != 0.0f && lx != 0.0f && flt.ours(ptr_))
+    if (wy0 != 0.0f && lx != 0.0f && corner_is_ours(count, qbase + ptr_))
         red_add_v4(gimg + (size_t)ptr_ * C + 4 * i, __fmul_rn(lx, dt.x), __fmul_rn(lx, dt.y), __fmul_rn(lx, dt.z), __fmul_rn(lx, dt.w));
-    if (ly != 0.0f && wx0 != 0.0f && flt.ours(pbl))
+    if (ly != 0.0f && wx0 != 0.0f && corner_is_ours(count, qbase + pbl))
         red_add_v4(gimg + (size_t)pbl * C + 4 * i, __fmul_rn(wx0, db.x), __fmul_rn(wx0, db.y), __fmul_rn(wx0, db.z), __fmul_rn(wx0, db.w));
-    if (ly != 0.0f && lx != 0.0f && flt.ours(pbr))
+    if (ly != 0.0f && lx != 0.0f && corner_is_ours(count, qbase + pbr))
         red_add_v4(gimg + (size_t)pbr * C + 4 * i, __fmul_rn(lx, db.x), __fmul_rn(lx, db.y), __fmul_rn(lx, db.z), __fmul_rn(lx, db.w));
 }
 
 __global__ void __launch_bounds__(kRoiThreads)
 roialign_bwd_kernel(const float4* __restrict__ grad_out, const float4* __restrict__ boxes,
                     const int32_t* __restrict__ roi_map, GradTable tbl, int C, int N, int ph, int pw, int groups,
-                    int rows_per_group, TileSpace ts, const int* __restrict__ tile_start,
-                    const int* __restrict__ overflow) {
+                    int rows_per_group, PixelSpace ps, const uint32_t* __restrict__ count,
+                    const int* __restrict__ heavy_normal) {
     extern __shared__ __align__(16) float4 s_acc[];  // [8 warps][C/4], constant-tap ROIs only
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // deterministic mode: nothing to do unless some tile overflowed kTileRoiMax
-    if (tile_start != nullptr && *overflow == 0) return;
+    // gather mode: nothing to do unless some pixel was left to the fallback (more than kHeavyMax samples, or more than
+    // kMediumMax of them inside one bucket of its sample-index histogram)
+    if (count != nullptr && *heavy_normal == 0) return;
     const int f = blockIdx.x / groups, grp = blockIdx.x - f * groups;
     const int y = grp * rows_per_group + warp;
     const bool has_row = (warp < rows_per_group) && (y < ph);
@@ -436,14 +409,13 @@ roialign_bwd_kernel(const float4* __restrict__ grad_out, const float4* __restric
     const int b = f / N;
     float* gimg = ((m == 0) ? tbl.ptr[0] : (m == 1) ? tbl.ptr[1] : (m == 2) ? tbl.ptr[2] : tbl.ptr[3]) +
                   (size_t)b * g.H * g.W * C;
-    ScatterFilter flt;
-    flt.tile_start = tile_start; flt.ts = ts; flt.m = m; flt.b = b; flt.W = g.W;
+    const int qbase = ps.base[m] + b * g.H * g.W;
     const bool constant = (g.hs == 0.0f && g.ws == 0.0f);  // CTA-uniform
     const AxisTap ty = axis_tap(g.y0, g.hs, has_row ? y : 0, g.H);
     const float4* gr = grad_out + ((size_t)f * ph + (has_row ? y : 0)) * pw * c4;
     const int top = ty.lo * g.W, bot = ty.hi * g.W;
     const float ly = ty.lerp, wy0 = __fsub_rn(1.0f, ty.lerp);
-    if (constant) {
+    if (constant) {  // its pixels carry kConstFlag, so in gather mode they are always ours
         const AxisTap tx = axis_tap(g.x0, g.ws, 0, g.W);
         for (int i = lane; i < c4; i += 32) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -463,12 +435,13 @@ roialign_bwd_kernel(const float4* __restrict__ grad_out, const float4* __restric
                 const float4 v = s_acc[w * c4 + i];
                 acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
             }
-            scatter_corners(gimg, C, flt, top + tx.lo, top + tx.hi, bot + tx.lo, bot + tx.hi, i, acc, wy0, ly, wx0, lx);
+            scatter_corners(gimg, C, count, qbase, top + tx.lo, top + tx.hi, bot + tx.lo, bot + tx.hi, i, acc, wy0, ly,
+                            wx0, lx);
         }
         return;
     }
     if (!has_row || !ty.valid) return;
-    if (g.ws == 0.0f && tile_start == nullptr) {  // every bin of the row hits the same pixels: sum the row first
+    if (g.ws == 0.0f && count == nullptr) {  // every bin of the row hits the same pixels: sum the row first
         const AxisTap tx = axis_tap(g.x0, g.ws, 0, g.W);
         if (!tx.valid) return;
         const float lx = tx.lerp, wx0 = __fsub_rn(1.0f, tx.lerp);
@@ -478,7 +451,8 @@ roialign_bwd_kernel(const float4* __restrict__ grad_out, const float4* __restric
                 const float4 v = __ldcs(gr + (size_t)x * c4 + i);
                 acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
             }
-            scatter_corners(gimg, C, flt, top + tx.lo, top + tx.hi, bot + tx.lo, bot + tx.hi, i, acc, wy0, ly, wx0, lx);
+            scatter_corners(gimg, C, nullptr, qbase, top + tx.lo, top + tx.hi, bot + tx.lo, bot + tx.hi, i, acc, wy0, ly,
+                            wx0, lx);
         }
         return;
     }
@@ -486,69 +460,115 @@ roialign_bwd_kernel(const float4* __restrict__ grad_out, const float4* __restric
         const AxisTap tx = axis_tap(g.x0, g.ws, x, g.W);
         if (!tx.valid) continue;
         const int ptl = top + tx.lo, ptr_ = top + tx.hi, pbl = bot + tx.lo, pbr = bot + tx.hi;
-        if (tile_start != nullptr && !(flt.ours(ptl) || flt.ours(ptr_) || flt.ours(pbl) || flt.ours(pbr)))
-            continue;  // warp-uniform: no gradient row is read for bins the tile kernel owns entirely
+        if (count != nullptr && !(corner_is_ours(count, qbase + ptl) || corner_is_ours(count, qbase + ptr_) ||
+                                  corner_is_ours(count, qbase + pbl) || corner_is_ours(count, qbase + pbr)))
+            continue;  // warp-uniform: no gradient row is read for bins the gather kernel owns entirely
         const float lx = tx.lerp, wx0 = __fsub_rn(1.0f, tx.lerp);
         for (int i = lane; i < c4; i += 32)
-            scatter_corners(gimg, C, flt, ptl, ptr_, pbl, pbr, i, __ldcs(gr + i), wy0, ly, wx0, lx);
+            scatter_corners(gimg, C, count, qbase, ptl, ptr_, pbl, pbr, i, __ldcs(gr + i), wy0, ly, wx0, lx);
     }
 }
 
-// ---- deterministic backward: tile-owner accumulation ------------------------------------------------------------
-// Every gradient map is cut into tiles of 4 x 8 pixels and every tile is written exactly once, by ONE CTA that adds up
-// all the samples landing on it in TF CropAndResizeGradImage's own order -- ROI index ascending, then output row, column,
-// corner -- with every product and sum individually rounded: the result is bit-identical to the sequential CPU kernel
-// and reproducible, and the zero-fill of the maps (713 MB per 8 images at 1024^2) and the accumulation are the same
-// HBM write.  Steps:
-//   roialign_bwd_taps_kernel    thread per (ROI, output row or column): the TF sampling tap (lo, hi, lerp, valid) -- the
-//                               only place the ROI geometry (two fp32 divisions per axis) is evaluated;
-//   roialign_bwd_const_kernel   zero-size ROIs (zero-padded target rows, quirk Q5: all ph*pw bins on the same four taps)
-//                               are pre-reduced to one gradient row each (fixed order) and enter as ONE sample;
-//   roialign_bwd_bin_kernel<0>  thread per sample: one count per tile its (up to four) corners land on;
-//   roialign_bwd_alloc_kernel   a segment of the (tile, sample) list per tile (block scan, one atomic per CTA), and the
-//                               tile goes on one of four work lists by sample count (the heavy tiles are started first);
-//   roialign_bwd_bin_kernel<1>  the same walk, now storing the sample key into the segments;
-//   roialign_bwd_tile_kernel    CTAs [0, NT): the ranked non-empty tiles; CTAs [NT, 2 NT): zero-fill of the empty ones.
-//                               A tile CTA (64 threads, a thread owns four channels of every pixel of the tile in a
-//                               32 KB shared-memory accumulator) sorts its sample keys, then alternates: 64 threads
-//                               decode 192 samples (taps -> which corner lands on which tile pixel with which weight),
-//                               then all of them walk those samples in order, gradient rows fetched eight samples
-//                               ahead.  A gradient row is read once per tile it touches (1.4 x in all at 1024^2, from
-//                               L2) instead of once per corner (4 x).  More than kTileCap samples on a tile (thousands of
-//                               ROIs per image): rounds over ROI-index ranges chosen from a 256-bucket histogram.
-// Not bit-identical to the sequential order, but still deterministic: pixels under zero-size ROIs (their pre-reduced
-// row is added as one sample) -- thousands of samples on one pixel cannot be added one after the other at any speed;
-// non-deterministic: a tile where ONE histogram bucket of ROI indices holds more than kTileCap samples (atomic scatter
-// fallback; needs > 5000 ROIs per image on the same 32 pixels).
-// Maps up to 512 x 512 pixels, ph, pw <= 128, B * N < 2^18.
-struct TapWord {   // .x = lo | (hi - lo) << 16 | valid << 17 | zero-size ROI << 18 ; .y = lerp bits
-    uint32_t x, y;
+// ---- deterministic gather backward -------------------------------------------------------------------------
+// One thread per output bin (f, y, x): the up-to-four gradient-map pixels its gradient lands on.
+struct BinTaps {
+    int q[4];      // global pixel ids: tl, tr, bl, br
+    bool on[4];    // weight != 0 and the forward pass did not extrapolate
+    bool constant; // zero-size ROI: every bin of the ROI samples the same pixels
+    float wy[2], wx[2];  // (1 - ly, ly), (1 - lx, lx): corner c weighs wx[c & 1] * (wy[c >> 1] * g)
 };
-__device__ __forceinline__ int tap_lo(const TapWord& t) { return (int)(t.x & 0xffffu); }
-__device__ __forceinline__ int tap_hi(const TapWord& t) { return (int)(t.x & 0xffffu) + (int)((t.x >> 16) & 1u); }
-__device__ __forceinline__ bool tap_valid(const TapWord& t) { return (t.x >> 17) & 1u; }
-__device__ __forceinline__ bool tap_const(const TapWord& t) { return (t.x >> 18) & 1u; }
 
-__global__ void __launch_bounds__(256)
-roialign_bwd_taps_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ roi_map, GradTable tbl, int BN,
-                         int ph, int pw, TapWord* __restrict__ taps /*[BN][ph + pw]*/) {
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= BN * (ph + pw)) return;
-    const int f = i / (ph + pw), t = i - f * (ph + pw);
-    const RoiGeom g = roi_geom(__ldg(boxes + f), roi_map[f], tbl.H, tbl.W, ph, pw);
-    const AxisTap a = (t < ph) ? axis_tap(g.y0, g.hs, t, g.H) : axis_tap(g.x0, g.ws, t - ph, g.W);
-    TapWord w;
-    w.x = (uint32_t)a.lo | ((uint32_t)(a.hi - a.lo) << 16) | (a.valid ? 1u << 17 : 0u) |
-          ((g.hs == 0.0f && g.ws == 0.0f) ? 1u << 18 : 0u);
-    w.y = __float_as_uint(a.lerp);
-    taps[i] = w;
+__device__ __forceinline__ BinTaps bin_taps(const float4* __restrict__ boxes, const int32_t* __restrict__ roi_map,
+                                            const GradTable& tbl, const PixelSpace& ps, int N, int ph, int pw, int s) {
+    const int bins = ph * pw;
+    const int f = s / bins, r = s - f * bins, y = r / pw, x = r - y * pw;
+    const int m = roi_map[f];
+    const RoiGeom g = roi_geom(__ldg(boxes + f), m, tbl.H, tbl.W, ph, pw);
+    const AxisTap ty = axis_tap(g.y0, g.hs, y, g.H), tx = axis_tap(g.x0, g.ws, x, g.W);
+    const int qbase = ps.base[m] + (f / N) * g.H * g.W;
+    const float wy0 = __fsub_rn(1.0f, ty.lerp), wx0 = __fsub_rn(1.0f, tx.lerp);
+    const bool valid = ty.valid && tx.valid;
+    BinTaps t;
+    t.wy[0] = wy0; t.wy[1] = ty.lerp; t.wx[0] = wx0; t.wx[1] = tx.lerp;
+    t.constant = (g.hs == 0.0f && g.ws == 0.0f);
+    t.q[0] = qbase + ty.lo * g.W + tx.lo; t.on[0] = valid && wy0 != 0.0f && wx0 != 0.0f;
+    t.q[1] = qbase + ty.lo * g.W + tx.hi; t.on[1] = valid && wy0 != 0.0f && tx.lerp != 0.0f;
+    t.q[2] = qbase + ty.hi * g.W + tx.lo; t.on[2] = valid && ty.lerp != 0.0f && wx0 != 0.0f;
+    t.q[3] = qbase + ty.hi * g.W + tx.hi; t.on[3] = valid && ty.lerp != 0.0f && tx.lerp != 0.0f;
+    return t;
 }
 
+__global__ void __launch_bounds__(256)
+roialign_bwd_count_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ roi_map, GradTable tbl,
+                          PixelSpace ps, int N, int ph, int pw, int total_bins, uint32_t* __restrict__ count,
+                          int* __restrict__ misc) {
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= total_bins) return;
+    const BinTaps t = bin_taps(boxes, roi_map, tbl, ps, N, ph, pw, s);
+    if (t.constant && s % (ph * pw) != 0) return;  // a zero-size ROI is ONE sample: its pre-reduced gradient row
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (t.on[c]) atomicAdd(count + t.q[c], 1u);
+}
+
+// Four pixels per thread: a segment of the key list for every pixel the gather kernel will sum (1..kMediumMax samples);
+// pixels above kLightMax are also appended to the medium list.  Segment order is whatever the atomics give; only the
+// order INSIDE a segment matters and that is sorted later.  misc: [0] key-list bump pointer, [1] "the atomic fallback
+// has work" (a constant-tap ROI, or ordinary samples on a pixel above kMediumMax), [2] length of the medium list.
+__global__ void __launch_bounds__(256)
+roialign_bwd_alloc_kernel(const uint32_t* __restrict__ count, int NP, int* __restrict__ start, int* __restrict__ misc,
+                          int* __restrict__ medium) {
+    __shared__ int warp_sums[32];
+    __shared__ int block_total, block_base;
+    const int q0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    uint32_t c[4];
+    int n[4], mine = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        c[i] = (q0 + i < NP) ? count[q0 + i] : 0u;
+        n[i] = (c[i] <= (uint32_t)kHeavyMax) ? (int)c[i] : 0;
+        mine += n[i];
+        if (c[i] > (uint32_t)kHeavyMax) misc[1] = 1;
+        if (n[i] > kLightMax) medium[atomicAdd(&misc[2], 1)] = q0 + i;
+    }
+    int off = block_exclusive_scan(mine, warp_sums, &block_total);
+    if (threadIdx.x == 0) block_base = (block_total > 0) ? atomicAdd(&misc[0], block_total) : 0;
+    __syncthreads();
+    off += block_base;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (q0 + i < NP) start[q0 + i] = off;
+        off += n[i];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+roialign_bwd_fill_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ roi_map, GradTable tbl,
+                         PixelSpace ps, int N, int ph, int pw, int total_bins, const uint32_t* __restrict__ count,
+                         const int* __restrict__ start, int* __restrict__ cursor, int4* __restrict__ entries) {
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= total_bins) return;
+    const BinTaps t = bin_taps(boxes, roi_map, tbl, ps, N, ph, pw, s);
+    if (t.constant && s % (ph * pw) != 0) return;
+    const int fetch = t.constant ? total_bins + s / (ph * pw) : s;   // rows >= total_bins: the pre-reduced rows, by ROI
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (t.on[c] && count[t.q[c]] <= (uint32_t)kHeavyMax)
+            entries[start[t.q[c]] + atomicAdd(cursor + t.q[c], 1)] =  // key order = TF's accumulation order
+                make_int4((s << 2) | c, __float_as_int(t.wy[c >> 1]), __float_as_int(t.wx[c & 1]), fetch);
+}
+
+// zero-size ROIs (zero-padded target rows, quirk Q5): all ph*pw bins sample the same four taps.  Thousands of them can
+// sit on one pixel, and that many rows cannot be added one after the other at any speed, so each such ROI is reduced
+// to ONE row first (its bins in order, fixed) and enters the pixel sums as one sample at the position of its first bin:
+// deterministic, and bit-identical to the sequential order everywhere except on the pixels under such ROIs.
 __global__ void __launch_bounds__(64)
-roialign_bwd_const_kernel(const float4* __restrict__ grad_out, const TapWord* __restrict__ taps, int C, int ph, int pw,
+roialign_bwd_const_kernel(const float4* __restrict__ grad_out, const float4* __restrict__ boxes,
+                          const int32_t* __restrict__ roi_map, GradTable tbl, int C, int ph, int pw,
                           float4* __restrict__ partial /*[BN][C/4]*/) {
     const int f = blockIdx.x;
-    if (!tap_const(taps[(size_t)f * (ph + pw)])) return;
+    const RoiGeom g = roi_geom(__ldg(boxes + f), roi_map[f], tbl.H, tbl.W, ph, pw);
+    if (!(g.hs == 0.0f && g.ws == 0.0f)) return;
     const int c4 = C >> 2, bins = ph * pw;
     const float4* gr = grad_out + (size_t)f * bins * c4;
     for (int i = threadIdx.x; i < c4; i += 64) {
@@ -573,305 +593,252 @@ roialign_bwd_const_kernel(const float4* __restrict__ grad_out, const TapWord* __
     }
 }
 
-// the (up to four) distinct tiles the corners of one sample land on with non-zero weight; returns their number
-__device__ __forceinline__ int sample_tiles(const TapWord& ty, const TapWord& tx, int tbase, int TX, int (&tiles)[4]) {
-    if (!(tap_valid(ty) && tap_valid(tx))) return 0;
-    const float ly = __uint_as_float(ty.y), lx = __uint_as_float(tx.y);
-    const bool t_on = __fsub_rn(1.0f, ly) != 0.0f, b_on = ly != 0.0f, l_on = __fsub_rn(1.0f, lx) != 0.0f, r_on = lx != 0.0f;
-    const int r0 = tap_lo(ty) / kTileH, r1 = tap_hi(ty) / kTileH, c0 = tap_lo(tx) / kTileW, c1 = tap_hi(tx) / kTileW;
-    int n = 0;
-    auto add = [&](int r, int c) {
-        const int t = tbase + r * TX + c;
-        for (int i = 0; i < n; ++i)
-            if (tiles[i] == t) return;
-        tiles[n++] = t;
-    };
-    if (t_on && l_on) add(r0, c0);
-    if (t_on && r_on) add(r0, c1);
-    if (b_on && l_on) add(r1, c0);
-    if (b_on && r_on) add(r1, c1);
-    return n;
-}
-
-template <int PASS>
-__global__ void __launch_bounds__(256)
-roialign_bwd_bin_kernel(const TapWord* __restrict__ taps, const int32_t* __restrict__ roi_map, TileSpace ts, int N,
-                        int ph, int pw, int total_bins, int* __restrict__ count, const int* __restrict__ start,
-                        int* __restrict__ cursor, uint32_t* __restrict__ entries) {
-    const int s = blockIdx.x * 256 + threadIdx.x;
-    if (s >= total_bins) return;
-    const int bins = ph * pw;
-    const int f = s / bins, r = s - f * bins, y = r / pw, x = r - y * pw;
-    const TapWord* tf = taps + (size_t)f * (ph + pw);
-    const TapWord ty = tf[y], tx = tf[ph + x];
-    if (tap_const(ty) && r != 0) return;           // a zero-size ROI is ONE sample (its pre-reduced row)
-    const int m = roi_map[f];
-    const int TX = (m == 0) ? ts.tx[0] : (m == 1) ? ts.tx[1] : (m == 2) ? ts.tx[2] : ts.tx[3];
-    int tiles[4];
-    const int n = sample_tiles(ty, tx, tile_of_pixel(ts, m, f / N, 0, 0), TX, tiles);
-    const uint32_t key = ((uint32_t)f << (kKeyXBits + kKeyYBits)) | ((uint32_t)y << kKeyXBits) | (uint32_t)x;
-    for (int i = 0; i < n; ++i) {
-        if (PASS == 0) atomicAdd(count + tiles[i], 1);
-        else {
-            const int seg = start[tiles[i]];
-            if (seg >= 0) entries[seg + atomicAdd(cursor + tiles[i], 1)] = key;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256)
-roialign_bwd_alloc_kernel(const int* __restrict__ count, int NT, int* __restrict__ start, int* __restrict__ misc,
-                          int4* __restrict__ lists /*[kTileBuckets][NT]: (tile, segment start, samples, -)*/) {
-    __shared__ int warp_sums[32];
-    __shared__ int block_total, block_base;
-    const int t = blockIdx.x * 256 + threadIdx.x;
-    const int c = (t < NT) ? count[t] : 0;
-    int off = block_exclusive_scan(c, warp_sums, &block_total);
-    if (threadIdx.x == 0) block_base = block_total > 0 ? atomicAdd(&misc[kMiscBump], block_total) : 0;
-    __syncthreads();
-    if (t >= NT) return;
-    start[t] = block_base + off;
-    if (c > 0) {   // one atomic per bucket and warp
-        const int bucket = (c >= 128) ? 0 : 1;
-        const unsigned peers = __match_any_sync(__activemask(), bucket);
-        const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(&misc[kMiscBucket0 + bucket], __popc(peers));
-        base = __shfl_sync(peers, base, leader);
-        lists[(size_t)bucket * NT + base + __popc(peers & ((1u << lane) - 1u))] = make_int4(t, block_base + off, c, 0);
-    }
-}
-
-__device__ __forceinline__ void acc_corner(float4* acc, const float4& d, float w) {
-    float4 a = *acc;   // acc += w * d with the product and the sum individually rounded (TF's two statements)
-    a.x = __fadd_rn(a.x, __fmul_rn(w, d.x));
-    a.y = __fadd_rn(a.y, __fmul_rn(w, d.y));
-    a.z = __fadd_rn(a.z, __fmul_rn(w, d.z));
-    a.w = __fadd_rn(a.w, __fmul_rn(w, d.w));
-    *acc = a;
-}
-
-// One decoded sample of the tile's queue: where its gradient row lies and which of its four corners land on which tile
-// pixel.  pk: bits 0-4 top row's first pixel (row * 8), 5-7 column lo, 8-10 column hi, 11-15 bottom row's first pixel,
-// 16 tl, 17 tr, 18 bl, 19 br (corner lands in the tile with non-zero weight), 20 pre-reduced row (zero-size ROI)
-struct TileQueue {
-    int off[kTileQueue];
-    uint32_t pk[kTileQueue];
-    float4 w[kTileQueue];   // (1 - ly, ly, 1 - lx, lx)
-};
-
-// geometry of a tile: which map, which image, first pixel, extent
-struct TileGeom {
-    float4* gmap;
-    int W, y0, x0, rows_in, cols_in;
-};
-__device__ __forceinline__ TileGeom tile_geom(const GradTable& tbl, const TileSpace& ts, int tile, int c4) {
-    const int m = (tile >= ts.base[3]) ? 3 : (tile >= ts.base[2]) ? 2 : (tile >= ts.base[1]) ? 1 : 0;
-    const int H = tbl.H[m], W = tbl.W[m], TY = ts.ty[m], TX = ts.tx[m];
-    const int local = tile - ts.base[m];
-    const int b = local / (TY * TX), rem = local - b * (TY * TX);
-    TileGeom g;
-    g.W = W;
-    g.y0 = (rem / TX) * kTileH;
-    g.x0 = (rem - (rem / TX) * TX) * kTileW;
-    g.rows_in = min(kTileH, H - g.y0);
-    g.cols_in = min(kTileW, W - g.x0);
-    g.gmap = reinterpret_cast<float4*>(tbl.ptr[m]) + (size_t)b * H * W * c4;
-    return g;
-}
-__device__ __forceinline__ void tile_zero(const TileGeom& g, int c4, int tid) {
-    for (int r = 0; r < g.rows_in; ++r) {
-        float4* dst = g.gmap + ((size_t)(g.y0 + r) * g.W + g.x0) * c4;
-        for (int v = tid; v < g.cols_in * c4; v += kTileThreads) __stcs(dst + v, make_float4(0.f, 0.f, 0.f, 0.f));
-    }
-}
-
-// Persistent grid (kTileCtasPerSm CTAs per SM): every CTA first takes non-empty tiles off the two work lists (heavy
-// tiles first, static round robin), then zero-fills its share of the tiles nobody samples.
-__global__ void __launch_bounds__(kTileThreads)
-roialign_bwd_tile_kernel(const float4* __restrict__ grad_out, const TapWord* __restrict__ taps,
-                         const float4* __restrict__ const_partial, GradTable tbl, TileSpace ts, int C, int ph, int pw,
-                         const int* __restrict__ count, int* __restrict__ start, const uint32_t* __restrict__ entries,
-                         int* __restrict__ misc, const int4* __restrict__ lists) {
-    extern __shared__ __align__(16) float4 acc[];                 // [pixel][channel vector]: 32 KB (dynamic)
-    __shared__ uint32_t s_key[kTileCap], s_tmp[kTileCap];
-    __shared__ TileQueue q;
-    __shared__ int s_hist[kTileFBuckets];
-    __shared__ int s_n;
-    const int NT = ts.base[4], tid = threadIdx.x;
-    const int c4 = C >> 2;
-    const int n_heavy = misc[kMiscBucket0], n_items = n_heavy + misc[kMiscBucket0 + 1];
-    auto item_of = [&](int w) { return __ldg(lists + (w < n_heavy ? (size_t)w : (size_t)NT + (w - n_heavy))); };
-    int4 next = make_int4(0, 0, 0, 0);
-    if ((int)blockIdx.x < n_items) next = item_of(blockIdx.x);
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-        const int4 item = next;
-        if (w + (int)gridDim.x < n_items) next = item_of(w + gridDim.x);     // the next header is in flight during this tile
-        const int tile = item.x, n = item.z;
-        const TileGeom tg = tile_geom(tbl, ts, tile, c4);
-        const int y0 = tg.y0, x0 = tg.x0;
-        const uint32_t* seg = entries + item.y;
-        // ---- rounds: all samples at once when they fit, else ranges of ROI indices of at most kTileCap samples ----
-        uint32_t f_lo = 0u, f_width = 1u;   // histogram bucket of a key: ((key >> 14) - f_lo) / f_width
-        bool overflow = false;
-        __syncthreads();                    // the previous tile is done with the shared arrays
-        if (n > kTileCap) {
-            uint32_t mn = 0xffffffffu, mx = 0u;
-            for (int i = tid; i < n; i += kTileThreads) { const uint32_t f = seg[i] >> (kKeyXBits + kKeyYBits); mn = min(mn, f); mx = max(mx, f); }
+__device__ __forceinline__ int warp_sort_asc(int v, int lane) {  // bitonic network over the 32 lanes
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
-            for (int i = tid; i < kTileFBuckets; i += kTileThreads) s_hist[i] = 0;
-            if (tid == 0) { s_key[0] = 0xffffffffu; s_key[1] = 0u; }
-            __syncthreads();
-            if ((tid & 31) == 0) { atomicMin(&s_key[0], mn); atomicMax(&s_key[1], mx); }
-            __syncthreads();
-            f_lo = s_key[0];
-            f_width = (s_key[1] - f_lo) / kTileFBuckets + 1u;
-            __syncthreads();
-            for (int i = tid; i < n; i += kTileThreads) atomicAdd(&s_hist[((seg[i] >> (kKeyXBits + kKeyYBits)) - f_lo) / f_width], 1);
-            __syncthreads();
-            for (int i = tid; i < kTileFBuckets; i += kTileThreads) overflow |= s_hist[i] > kTileCap;
-            overflow = __syncthreads_or(overflow);
+    for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int o = __shfl_xor_sync(0xffffffffu, v, j);
+            const bool up = ((lane & k) == 0), lower = ((lane & j) == 0);
+            v = (lower == up) ? min(v, o) : max(v, o);
         }
-        if (overflow) {   // (pathological) zero the tile, flag it: the scatter kernel adds this tile's samples atomically
-            if (tid == 0) { start[tile] = -1; misc[kMiscOverflow] = 1; }
-            tile_zero(tg, c4, tid);
-            continue;
-        }
-        for (int cc = 0; cc < c4; cc += kTileChunk) {   // 256 channels per pass
-            const int v = cc + tid;
-            const bool have_v = v < c4;
-            for (int i = tid; i < kTilePix * kTileChunk; i += kTileThreads) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return v;
+}
+
+__device__ __forceinline__ void fma_in_order(float4& acc, const float4& v, float a, float b) {
+    acc.x = __fadd_rn(acc.x, __fmul_rn(b, __fmul_rn(a, v.x)));  // acc += wx * (wy * g): TF's two products, then the add
+    acc.y = __fadd_rn(acc.y, __fmul_rn(b, __fmul_rn(a, v.y)));
+    acc.z = __fadd_rn(acc.z, __fmul_rn(b, __fmul_rn(a, v.z)));
+    acc.w = __fadd_rn(acc.w, __fmul_rn(b, __fmul_rn(a, v.w)));
+}
+
+__device__ __forceinline__ int c4_of(int C) { return C >> 2; }
+__device__ __forceinline__ float4* pixel_ptr(const GradTable& tbl, const PixelSpace& ps, int q, int c4) {
+    const int m = (q >= ps.base[3]) ? 3 : (q >= ps.base[2]) ? 2 : (q >= ps.base[1]) ? 1 : 0;
+    return reinterpret_cast<float4*>((m == 0) ? tbl.ptr[0] : (m == 1) ? tbl.ptr[1] : (m == 2) ? tbl.ptr[2] : tbl.ptr[3]) +
+           (size_t)(q - ps.base[m]) * c4;
+}
+
+// The gather pass.  Every pixel of every gradient map is written exactly once.  An entry is (key, wy, wx): sample
+// s = key >> 2 (= its row of grad_out), corner = key & 3; ascending key = TF's accumulation order.
+//   * CTAs [kMediumCtas, grid): persistent warps stream over the pixels -- zeros, or (<= kLightMax samples) the sum
+//     in TF's order: each lane ranks its entry among the pixel's (n shuffles), then the rows are fetched two at a
+//     time and added strictly in rank order;
+//   * CTAs [0, kMediumCtas): walk the medium list, one CTA per pixel: (key, slot) pairs sorted in shared memory, then
+//     one thread per channel adds the rows strictly in order, sixteen loads in flight.  They sit at the head of the
+//     grid so these long sums start first and overlap the streaming pass.
+template <int VPL>
+__global__ void __launch_bounds__(256, 4)
+roialign_bwd_gather_kernel(const float4* __restrict__ grad_out, const float4* __restrict__ const_partial, int total_bins,
+                           GradTable tbl, PixelSpace ps, int C, uint32_t* __restrict__ count,
+                           const int* __restrict__ start, const int4* __restrict__ entries, int* __restrict__ misc,
+                           const int* __restrict__ medium) {
+    constexpr int V = VPL > 0 ? VPL : 1;
+    __shared__ uint64_t s_sort[kMediumMax];
+    __shared__ int s_row[kMediumMax];
+    __shared__ float s_wy[kMediumMax], s_wx[kMediumMax];
+    __shared__ int s_hist[kHeavyBuckets];
+    __shared__ int s_n, s_lohi[2];
+    // a gradient row: rows < total_bins are rows of grad_out, the others the pre-reduced rows of the zero-size ROIs
+    auto row_ptr = [&](int r) { return r < total_bins ? grad_out + (size_t)r * c4_of(C) : const_partial + (size_t)(r - total_bins) * c4_of(C); };
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c4 = C >> 2;
+    if (blockIdx.x < kMediumCtas) {
+        const int n_medium = misc[2];
+        for (int mi = blockIdx.x; mi < n_medium; mi += kMediumCtas) {
+            const int q = medium[mi];
+            const int n = (int)count[q], seg = start[q];
+            float* dst = reinterpret_cast<float*>(pixel_ptr(tbl, ps, q, c4));
+            // More than kMediumMax samples: rounds over ranges of the sample index, chosen from a histogram so that each
+            // round holds at most kMediumMax entries; the per-channel sums run on across the rounds (C <= 1024).
+            int s_lo = 0, s_width = 1;
+            bool hand_over = false;
+            if (n > kMediumMax) {
+                int mn = INT_MAX, mx = 0;
+                for (int e = threadIdx.x; e < n; e += 256) { const int smp = __ldg(&entries[seg + e].x) >> 2; mn = min(mn, smp); mx = max(mx, smp); }
+                mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+                for (int i = threadIdx.x; i < kHeavyBuckets; i += 256) s_hist[i] = 0;
+                if (threadIdx.x == 0) { s_lohi[0] = INT_MAX; s_lohi[1] = 0; }
+                __syncthreads();
+                if (lane == 0) { atomicMin(&s_lohi[0], mn); atomicMax(&s_lohi[1], mx); }
+                __syncthreads();
+                s_lo = s_lohi[0];
+                s_width = (s_lohi[1] - s_lo) / kHeavyBuckets + 1;
+                for (int e = threadIdx.x; e < n; e += 256) atomicAdd(&s_hist[((__ldg(&entries[seg + e].x) >> 2) - s_lo) / s_width], 1);
+                __syncthreads();
+                bool over = false;
+                for (int i = threadIdx.x; i < kHeavyBuckets; i += 256) over |= s_hist[i] > kMediumMax;
+                hand_over = __syncthreads_or(over) || C > 1024;
+            }
+            if (hand_over) {   // (never seen) the atomic fallback adds this pixel's samples: zero it and flag it
+                if (threadIdx.x == 0) { count[q] |= 0x40000000u; misc[1] = 1; }
+                for (int ch = threadIdx.x; ch < C; ch += 256) __stcs(dst + ch, 0.0f);
+                __syncthreads();
+                continue;
+            }
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // channels threadIdx.x + 256 k
             int bkt = 0;
-            while (bkt < kTileFBuckets) {
-                // ---- this round's samples -> s_key, ascending ----
+            while (bkt < kHeavyBuckets) {
                 int nr;
-                if (n <= kTileCap) {
-                    for (int i = tid; i < n; i += kTileThreads) s_tmp[i] = __ldg(seg + i);
+                if (n <= kMediumMax) {
+                    for (int e = threadIdx.x; e < n; e += 256)
+                        s_sort[e] = (((uint64_t)(uint32_t)__ldg(&entries[seg + e].x) << 21) | (uint32_t)e) + 1u;
                     nr = n;
-                    bkt = kTileFBuckets;
+                    bkt = kHeavyBuckets;
                 } else {
                     int b1 = bkt, sum = 0;
-                    while (b1 < kTileFBuckets && sum + s_hist[b1] <= kTileCap) sum += s_hist[b1++];   // uniform
-                    if (tid == 0) s_n = 0;
+                    while (b1 < kHeavyBuckets && sum + s_hist[b1] <= kMediumMax) sum += s_hist[b1++];   // uniform
+                    if (threadIdx.x == 0) s_n = 0;
                     __syncthreads();
-                    for (int i = tid; i < n; i += kTileThreads) {
-                        const uint32_t key = __ldg(seg + i);
-                        const int kb = (int)(((key >> (kKeyXBits + kKeyYBits)) - f_lo) / f_width);
-                        if (kb >= bkt && kb < b1) s_tmp[atomicAdd(&s_n, 1)] = key;
+                    for (int e = threadIdx.x; e < n; e += 256) {
+                        const uint32_t key = (uint32_t)__ldg(&entries[seg + e].x);
+                        const int kb = ((int)(key >> 2) - s_lo) / s_width;
+                        if (kb >= bkt && kb < b1) s_sort[atomicAdd(&s_n, 1)] = (((uint64_t)key << 21) | (uint32_t)e) + 1u;
                     }
                     __syncthreads();
                     nr = s_n;
                     bkt = b1;
                 }
+                const int np2 = max(64, 1 << (32 - __clz(max(nr, 1) - 1)));
+                for (int e = nr + threadIdx.x; e < np2; e += 256) s_sort[e] = 0ull;
                 __syncthreads();
-                if (nr <= 128) {   // the usual case: rank by counting (broadcast loads), one barrier
-                    for (int i = tid; i < nr; i += kTileThreads) {
-                        const uint32_t x = s_tmp[i];
-                        int rank = 0;
-                        for (int j = 0; j < nr; ++j) rank += (s_tmp[j] < x);
-                        s_key[rank] = x;
-                    }
-                    __syncthreads();
-                } else {
-                    const int np2 = 1 << (32 - __clz(nr - 1));
-                    for (int i = tid; i < np2; i += kTileThreads) s_key[i] = (i < nr) ? s_tmp[i] : 0xffffffffu;
-                    __syncthreads();
-                    for (int k = 2; k <= np2; k <<= 1)
-                        for (int j = k >> 1; j > 0; j >>= 1) {
-                            for (int t = tid; t < (np2 >> 1); t += kTileThreads) {
-                                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), p = i | j;
-                                const bool up = ((i & k) == 0);
-                                const uint32_t a = s_key[i], c = s_key[p];
-                                if ((a > c) == up) { s_key[i] = c; s_key[p] = a; }
-                            }
-                            __syncthreads();
-                        }
+                block_bitonic_sort_desc(s_sort, np2);  // descending, zero padding last: ascending rank e sits at nr - 1 - e
+                for (int e = threadIdx.x; e < nr; e += 256) {
+                    const int4 ent = __ldg(entries + seg + (int)((s_sort[nr - 1 - e] - 1u) & 0x1fffffu));
+                    s_row[e] = ent.w;
+                    s_wy[e] = __int_as_float(ent.y);
+                    s_wx[e] = __int_as_float(ent.z);
                 }
-                // ---- decode kTileQueue samples, then walk them in order ----
-                for (int base = 0; base < nr; base += kTileQueue) {
-                    const int nq = min(kTileQueue, nr - base);
-                    for (int k = tid; k < nq; k += kTileThreads) {
-                        const uint32_t key = s_key[base + k];
-                        const int f = (int)(key >> (kKeyXBits + kKeyYBits)), y = (int)((key >> kKeyXBits) & ((1u << kKeyYBits) - 1u)),
-                                  x = (int)(key & ((1u << kKeyXBits) - 1u));
-                        const TapWord* tf = taps + (size_t)f * (ph + pw);
-                        const TapWord ty = tf[y], tx = tf[ph + x];
-                        const float ly = __uint_as_float(ty.y), lx = __uint_as_float(tx.y);
-                        const float wy0 = __fsub_rn(1.0f, ly), wx0 = __fsub_rn(1.0f, lx);
-                        const int rt = tap_lo(ty) - y0, rb = tap_hi(ty) - y0, cl = tap_lo(tx) - x0, cr = tap_hi(tx) - x0;
-                        const bool t_in = wy0 != 0.0f && (unsigned)rt < (unsigned)kTileH;
-                        const bool b_in = ly != 0.0f && (unsigned)rb < (unsigned)kTileH;
-                        const bool l_in = wx0 != 0.0f && (unsigned)cl < (unsigned)kTileW;
-                        const bool r_in = lx != 0.0f && (unsigned)cr < (unsigned)kTileW;
-                        const uint32_t fl = (t_in && l_in ? 1u : 0u) | (t_in && r_in ? 2u : 0u) | (b_in && l_in ? 4u : 0u) |
-                                            (b_in && r_in ? 8u : 0u);
-                        const bool constant = tap_const(ty);
-                        q.off[k] = constant ? f : (f * ph + y) * pw + x;
-                        q.pk[k] = (uint32_t)((rt & 3) * kTileW) | ((uint32_t)(cl & 7) << 5) | ((uint32_t)(cr & 7) << 8) |
-                                  ((uint32_t)((rb & 3) * kTileW) << 11) | (fl << 16) | (constant ? (1u << 20) : 0u);
-                        q.w[k] = make_float4(wy0, ly, wx0, lx);
-                    }
-                    __syncthreads();
-                    auto row_ptr = [&](int i) {
-                        const int o = q.off[i];
-                        return ((q.pk[i] >> 20) & 1u) ? const_partial + (size_t)o * c4 + v : grad_out + (size_t)o * c4 + v;
-                    };
-                    float4 val[8];
+                __syncthreads();
+                // one thread per channel (a warp covers 128 B of every gradient row), sixteen rows in flight, strict order
 #pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        if (u < nq && have_v) val[u] = __ldg(row_ptr(u));
-                    for (int i0 = 0; i0 < nq; i0 += 8) {
+                for (int k = 0; k < 4; ++k) {
+                    const int ch = threadIdx.x + 256 * k;
+                    if (ch >= C) break;
+                    float a = acc[k];
+                    int e = 0;
+                    for (; e + 16 <= nr; e += 16) {
+                        float val[16];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int i = i0 + u;
-                            if (i < nq && have_v) {
-                                const uint32_t pk = q.pk[i];
-                                const float4 wt = q.w[i];
-                                const float4 gv = val[u];
-                                float4* at = acc + (size_t)(pk & 31u) * kTileChunk + tid;
-                                float4* ab = acc + (size_t)((pk >> 11) & 31u) * kTileChunk + tid;
-                                const int cl = (pk >> 5) & 7u, cr = (pk >> 8) & 7u;
-                                if (pk & (3u << 16)) {
-                                    const float4 d = make_float4(__fmul_rn(wt.x, gv.x), __fmul_rn(wt.x, gv.y),
-                                                                 __fmul_rn(wt.x, gv.z), __fmul_rn(wt.x, gv.w));
-                                    if (pk & (1u << 16)) acc_corner(at + cl * kTileChunk, d, wt.z);
-                                    if (pk & (2u << 16)) acc_corner(at + cr * kTileChunk, d, wt.w);
-                                }
-                                if (pk & (12u << 16)) {
-                                    const float4 d = make_float4(__fmul_rn(wt.y, gv.x), __fmul_rn(wt.y, gv.y),
-                                                                 __fmul_rn(wt.y, gv.z), __fmul_rn(wt.y, gv.w));
-                                    if (pk & (4u << 16)) acc_corner(ab + cl * kTileChunk, d, wt.z);
-                                    if (pk & (8u << 16)) acc_corner(ab + cr * kTileChunk, d, wt.w);
-                                }
-                            }
-                            const int j = i + 8;
-                            if (j < nq && have_v) val[u] = __ldg(row_ptr(j));
-                        }
+                        for (int u = 0; u < 16; ++u) val[u] = __ldg(reinterpret_cast<const float*>(row_ptr(s_row[e + u])) + ch);
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) a = __fadd_rn(a, __fmul_rn(s_wx[e + u], __fmul_rn(s_wy[e + u], val[u])));
                     }
-                    __syncthreads();   // the queue is rewritten next
+                    for (; e < nr; ++e)
+                        a = __fadd_rn(a, __fmul_rn(s_wx[e], __fmul_rn(s_wy[e], __ldg(reinterpret_cast<const float*>(row_ptr(s_row[e])) + ch))));
+                    acc[k] = a;
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (threadIdx.x + 256 * k < C) __stcs(dst + threadIdx.x + 256 * k, acc[k]);
+        }
+        return;
+    }
+    // persistent streaming pass: a CTA walks 32-pixel chunks (32 KB of contiguous gradient map at C = 256, 4 pixels per
+    // warp); the next chunk's headers are fetched one iteration ahead and the entry lists of a warp's four pixels are
+    // requested together, so a touched pixel costs one gradient-row latency, not three dependent ones.
+    const int NP = ps.base[4];
+    const int nctas = gridDim.x - kMediumCtas, chunks = (NP + 31) >> 5;
+    int chunk = blockIdx.x - kMediumCtas;
+    auto header = [&](int ch, uint32_t& cnt, int& st) {
+        const int q = ch * 32 + warp * 4 + lane;
+        const bool ok = (lane < 4) && (ch < chunks) && (q < NP);
+        cnt = ok ? __ldg(count + q) : 0u;
+        st = ok ? __ldg(start + q) : 0;
+    };
+    uint32_t c_next;
+    int seg_next;
+    header(chunk, c_next, seg_next);
+#pragma unroll 1
+    for (; chunk < chunks; chunk += nctas) {
+        const uint32_t my_count = c_next;
+        const int my_start = seg_next;
+        header(chunk + nctas, c_next, seg_next);
+        const int q0 = chunk * 32 + warp * 4;
+        // fast path (most of the fine maps): none of the warp's four pixels has a sample and they are contiguous in
+        // one map -> eight stores
+        if (__all_sync(0xffffffffu, my_count == 0u) && q0 + 3 < NP &&
+            (q0 + 3 < ps.base[1] || (q0 >= ps.base[1] && q0 + 3 < ps.base[2]) || (q0 >= ps.base[2] && q0 + 3 < ps.base[3]) ||
+             q0 >= ps.base[3])) {
+            float4* dst = pixel_ptr(tbl, ps, q0, c4);
+            for (int v = lane; v < 4 * c4; v += 32) __stcs(dst + v, make_float4(0.f, 0.f, 0.f, 0.f));
+            continue;
+        }
+        // -1: a medium CTA writes this pixel; 0: zeros (untouched, or the atomic fallback adds to it later)
+        auto samples_of = [&](int i) {
+            const uint32_t c = __shfl_sync(0xffffffffu, my_count, i);
+            return (c <= (uint32_t)kLightMax) ? (int)c : (c <= (uint32_t)kHeavyMax) ? -1 : 0;
+        };
+        auto entry_of = [&](int i, int n) {
+            const int seg = __shfl_sync(0xffffffffu, my_start, i);
+            return (lane < n) ? __ldg(entries + seg + lane) : make_int4(INT_MAX, 0, 0, 0);
+        };
+        int n_next = samples_of(0);
+        int4 ent_next = entry_of(0, n_next);
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+            const int q = q0 + i, n = n_next;
+            const int4 ent = ent_next;
+            if (i < 3) { n_next = samples_of(i + 1); ent_next = entry_of(i + 1, n_next); }  // one pixel ahead
+            if (q >= NP || n < 0) continue;
+            float4* dst = pixel_ptr(tbl, ps, q, c4);
+            if (n == 0) {
+                if (VPL > 0) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) __stcs(dst + lane + 32 * v, make_float4(0.f, 0.f, 0.f, 0.f));
+                } else {
+                    for (int v = lane; v < c4; v += 32) __stcs(dst + v, make_float4(0.f, 0.f, 0.f, 0.f));
+                }
+                continue;
+            }
+            int rank = 0;
+            for (int j = 0; j < n; ++j) rank += (__shfl_sync(0xffffffffu, ent.x, j) < ent.x);
+            if (lane >= n) rank = -1;
+            const int row = ent.w;   // the gradient row to fetch (a pre-reduced row for a zero-size ROI)
+            const float wy = __int_as_float(ent.y), wx = __int_as_float(ent.z);
+            auto lane_of_rank = [&](int j) { return __ffs(__ballot_sync(0xffffffffu, rank == j)) - 1; };
+            if (VPL > 0) {
+                float4 acc[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                int j = 0;
+                for (; j + 2 <= n; j += 2) {  // two gradient rows in flight, added strictly in order
+                    const int s0 = lane_of_rank(j), s1 = lane_of_rank(j + 1);
+                    const float4* g0 = row_ptr(__shfl_sync(0xffffffffu, row, s0));
+                    const float4* g1 = row_ptr(__shfl_sync(0xffffffffu, row, s1));
+                    const float a0 = __shfl_sync(0xffffffffu, wy, s0), b0 = __shfl_sync(0xffffffffu, wx, s0);
+                    const float a1 = __shfl_sync(0xffffffffu, wy, s1), b1 = __shfl_sync(0xffffffffu, wx, s1);
+                    float4 v0[V], v1[V];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) { v0[v] = __ldg(g0 + lane + 32 * v); v1[v] = __ldg(g1 + lane + 32 * v); }
+#pragma unroll
+                    for (int v = 0; v < V; ++v) { fma_in_order(acc[v], v0[v], a0, b0); fma_in_order(acc[v], v1[v], a1, b1); }
+                }
+                if (j < n) {
+                    const int s0 = lane_of_rank(j);
+                    const float4* g0 = row_ptr(__shfl_sync(0xffffffffu, row, s0));
+                    const float a0 = __shfl_sync(0xffffffffu, wy, s0), b0 = __shfl_sync(0xffffffffu, wx, s0);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) fma_in_order(acc[v], __ldg(g0 + lane + 32 * v), a0, b0);
+                }
+#pragma unroll
+                for (int v = 0; v < V; ++v) __stcs(dst + lane + 32 * v, acc[v]);
+            } else {
+                for (int v0 = 0; v0 < c4; v0 += 32) {  // warp-uniform trip count: the shuffles need every lane
+                    const int v = v0 + lane;
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int j = 0; j < n; ++j) {
+                        const int s0 = lane_of_rank(j);
+                        const float4* gr = row_ptr(__shfl_sync(0xffffffffu, row, s0));
+                        const float a0 = __shfl_sync(0xffffffffu, wy, s0), b0 = __shfl_sync(0xffffffffu, wx, s0);
+                        if (v < c4) fma_in_order(acc, __ldg(gr + v), a0, b0);
+                    }
+                    if (v < c4) __stcs(dst + v, acc);
                 }
             }
-            // every pixel of the tile exactly once
-            if (have_v)
-                for (int r = 0; r < tg.rows_in; ++r)
-                    for (int px = 0; px < tg.cols_in; ++px)
-                        __stcs(tg.gmap + ((size_t)(y0 + r) * tg.W + x0 + px) * c4 + v,
-                               acc[(size_t)(r * kTileW + px) * kTileChunk + tid]);
-            __syncthreads();
         }
-    }
-    // ---- zero-fill: the tiles nobody samples, 64 candidates per step (one count per thread) ----
-    for (int base = blockIdx.x * kTileThreads; base < NT; base += gridDim.x * kTileThreads) {
-        const int t = base + tid;
-        const bool empty = (t < NT) && count[t] == 0;
-        const unsigned vote = __ballot_sync(0xffffffffu, empty);
-        __syncthreads();                                   // s_hist is free (previous step / the tile loop)
-        if ((tid & 31) == 0) s_hist[tid >> 5] = (int)vote;
-        __syncthreads();
-        const unsigned long long all = (unsigned long long)(unsigned)s_hist[0] | ((unsigned long long)(unsigned)s_hist[1] << 32);
-        for (unsigned long long mm = all; mm; mm &= mm - 1)
-            tile_zero(tile_geom(tbl, ts, base + __ffsll((long long)mm) - 1, c4), c4, tid);
     }
 }
 
@@ -986,37 +953,13 @@ static int pixel_space(const int* H, const int* W, int B, PixelSpace* ps) {
     return MRCNN_OK;
 }
 
-static int tile_space(const int* H, const int* W, int B, TileSpace* ts) {
-    long long acc = 0;
-    for (int l = 0; l < 4; ++l) {
-        ts->ty[l] = (H[l] + kTileH - 1) / kTileH;
-        ts->tx[l] = (W[l] + kTileW - 1) / kTileW;
-        if (ts->ty[l] > 128 || ts->tx[l] > 64) return MRCNN_ERR_RANGE;   // the tile masks: 128 rows, 64 columns (512 x 512 maps)
-        ts->base[l] = (int)acc;
-        acc += (long long)B * ts->ty[l] * ts->tx[l];
-    }
-    if (acc > INT_MAX / 8) return MRCNN_ERR_RANGE;
-    ts->base[4] = (int)acc;
-    return MRCNN_OK;
-}
-
 // workspace of the deterministic backward:
-// [count NT | cursor NT | misc] (zeroed per call) [start NT] [work lists 4 NT] [taps BN (ph + pw)] [(tile, sample) keys:
-// 4 per sample] [pre-reduced rows of the zero-size ROIs: BN x C floats]
-struct BwdWsLayout {
-    size_t zeroed, start, lists, taps, entries, partial, total;
-};
-static BwdWsLayout roialign_bwd_ws_layout(const TileSpace& ts, int B, int N, int ph, int pw, int C) {
-    const size_t NT = (size_t)ts.base[4], BN = (size_t)B * N;
-    BwdWsLayout w;
-    w.zeroed = align_up((2 * NT + kMiscWords) * sizeof(int), 256);
-    w.start = w.zeroed;
-    w.lists = w.start + align_up(NT * sizeof(int), 256);
-    w.taps = w.lists + align_up((size_t)kTileBuckets * NT * sizeof(int4), 256);
-    w.entries = w.taps + align_up(BN * (size_t)(ph + pw) * sizeof(TapWord), 256);
-    w.partial = w.entries + align_up(BN * (size_t)ph * pw * 4 * sizeof(uint32_t), 256);
-    w.total = w.partial + align_up(BN * (size_t)C * sizeof(float), 256);
-    return w;
+// [count NP | cursor NP | misc 64] (zeroed per call) [start NP] [medium list] [entries 4*bins x 16 B] [pre-reduced rows of
+// the zero-size ROIs: BN x C floats]
+static size_t roialign_bwd_ws_bytes(int NP, long long bins, int C, long long BN) {
+    return align_up((2 * (size_t)NP + 64) * sizeof(int), 256) + align_up((size_t)NP * sizeof(int), 256) +
+           align_up(((size_t)NP / 32 + 1 + 4 * (size_t)bins / 32) * sizeof(int), 256) +
+           align_up(4 * (size_t)bins * sizeof(int4), 256) + align_up((size_t)BN * C * sizeof(float), 256);
 }
 
 MRCNN_EXPORT int mrcnn_roialign_backward_workspace_bytes(int B, int N, int ph, int pw, const int* H, const int* W,
@@ -1025,13 +968,10 @@ MRCNN_EXPORT int mrcnn_roialign_backward_workspace_bytes(int B, int N, int ph, i
     if (B < 1 || N < 1 || ph < 1 || pw < 1 || C < 4 || (C & 3) || C > 8192) return MRCNN_ERR_RANGE;
     for (int l = 0; l < 4; ++l)
         if (H[l] < 1 || W[l] < 1) return MRCNN_ERR_RANGE;
-    TileSpace ts;
-    const int rc = tile_space(H, W, B, &ts);
-    if (rc != MRCNN_OK) return rc;
-    if ((long long)B * N * ph * pw >= (1LL << 29) || ph > (1 << kKeyYBits) || pw > (1 << kKeyXBits) ||
-        (long long)B * N >= (1LL << kKeyFBits))
-        return MRCNN_ERR_RANGE;
-    *bytes = roialign_bwd_ws_layout(ts, B, N, ph, pw, C).total;
+    PixelSpace ps;
+    const long long bins = (long long)B * N * ph * pw;
+    if (pixel_space(H, W, B, &ps) != MRCNN_OK || bins >= (1LL << 29)) return MRCNN_ERR_RANGE;
+    *bytes = roialign_bwd_ws_bytes(ps.base[4], bins, C, (long long)B * N);
     return MRCNN_OK;
 }
 
@@ -1046,6 +986,9 @@ MRCNN_EXPORT int mrcnn_roialign_backward(const float* grad_out, const float* box
     cudaStream_t st = (cudaStream_t)stream;
     GradTable tbl;
     for (int l = 0; l < 4; ++l) { tbl.ptr[l] = grad_fmaps[l]; tbl.H[l] = H[l]; tbl.W[l] = W[l]; }
+    PixelSpace ps;
+    rc = pixel_space(H, W, B, &ps);
+    if (rc != MRCNN_OK) return rc;
     const int groups = (ph + kRoiThreads / 32 - 1) / (kRoiThreads / 32);
     const int rows_per_group = (ph + groups - 1) / groups;  // 7x7 -> 1 x 7 rows, 14x14 -> 2 x 7, 28x28 -> 4 x 7
     const size_t smem = (size_t)(kRoiThreads / 32) * C * sizeof(float);
@@ -1053,7 +996,6 @@ MRCNN_EXPORT int mrcnn_roialign_backward(const float* grad_out, const float* box
         cudaError_t e = cudaFuncSetAttribute(roialign_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    TileSpace ts{};
     if (ws == nullptr) {  // atomic mode: zero-fill, then scatter every sample with vector reductions
         for (int l = 0; l < 4; ++l) {
             cudaError_t e = cudaMemsetAsync(grad_fmaps[l], 0, (size_t)B * H[l] * W[l] * C * sizeof(float), st);
@@ -1061,46 +1003,47 @@ MRCNN_EXPORT int mrcnn_roialign_backward(const float* grad_out, const float* box
         }
         roialign_bwd_kernel<<<B * N * groups, kRoiThreads, smem, st>>>((const float4*)grad_out, (const float4*)boxes,
                                                                       roi_map, tbl, C, N, ph, pw, groups, rows_per_group,
-                                                                      ts, nullptr, nullptr);
+                                                                      ps, nullptr, nullptr);
         return last_error();
     }
     // deterministic mode
-    if ((long long)B * N * ph * pw >= (1LL << 29) || ph > (1 << kKeyYBits) || pw > (1 << kKeyXBits) ||
-        (long long)B * N >= (1LL << kKeyFBits))
-        return MRCNN_ERR_RANGE;
-    rc = tile_space(H, W, B, &ts);
-    if (rc != MRCNN_OK) return rc;
+    const long long bins_ll = (long long)B * N * ph * pw;
+    if (bins_ll >= (1LL << 29)) return MRCNN_ERR_RANGE;
+    const int NP = ps.base[4], bins = (int)bins_ll;
     if (!aligned16(ws)) return MRCNN_ERR_ALIGN;
-    const BwdWsLayout lay = roialign_bwd_ws_layout(ts, B, N, ph, pw, C);
-    if (ws_bytes < lay.total) return MRCNN_ERR_WORKSPACE;
-    const int NT = ts.base[4], BN = B * N, bins = BN * ph * pw;
-    int* count = (int*)ws;
-    int* cursor = count + NT;
-    int* misc = count + 2 * (size_t)NT;
-    int* start = (int*)((char*)ws + lay.start);
-    int4* lists = (int4*)((char*)ws + lay.lists);
-    TapWord* taps = (TapWord*)((char*)ws + lay.taps);
-    uint32_t* entries = (uint32_t*)((char*)ws + lay.entries);
-    float4* partial = (float4*)((char*)ws + lay.partial);
-    cudaError_t e = cudaMemsetAsync(ws, 0, lay.zeroed, st);
+    if (ws_bytes < roialign_bwd_ws_bytes(NP, bins_ll, C, (long long)B * N)) return MRCNN_ERR_WORKSPACE;
+    const size_t zeroed = align_up((2 * (size_t)NP + 64) * sizeof(int), 256);
+    uint32_t* count = (uint32_t*)ws;
+    int* cursor = (int*)ws + NP;
+    int* misc = (int*)ws + 2 * (size_t)NP;  // [0] key-list bump pointer, [1] "ordinary samples on a fallback pixel"
+    int* start = (int*)((char*)ws + zeroed);
+    // a medium pixel holds > kLightMax of the <= 4*bins keys, and there are at most NP pixels
+    int* medium = (int*)((char*)start + align_up((size_t)NP * sizeof(int), 256));
+    int4* entries = (int4*)((char*)medium + align_up(((size_t)NP / 32 + 1 + 4 * (size_t)bins / 32) * sizeof(int), 256));
+    float4* partial = (float4*)((char*)entries + align_up(4 * (size_t)bins * sizeof(int4), 256));
+    cudaError_t e = cudaMemsetAsync(ws, 0, zeroed, st);
     if (e != cudaSuccess) return (int)e;
-    roialign_bwd_taps_kernel<<<(BN * (ph + pw) + 255) / 256, 256, 0, st>>>((const float4*)boxes, roi_map, tbl, BN, ph, pw,
-                                                                           taps);
-    roialign_bwd_const_kernel<<<BN, 64, 0, st>>>((const float4*)grad_out, taps, C, ph, pw, partial);
-    roialign_bwd_bin_kernel<0><<<(bins + 255) / 256, 256, 0, st>>>(taps, roi_map, ts, N, ph, pw, bins, count, start,
-                                                                  cursor, entries);
-    roialign_bwd_alloc_kernel<<<(NT + 255) / 256, 256, 0, st>>>(count, NT, start, misc, lists);
-    roialign_bwd_bin_kernel<1><<<(bins + 255) / 256, 256, 0, st>>>(taps, roi_map, ts, N, ph, pw, bins, count, start,
-                                                                  cursor, entries);
-    const size_t tile_smem = (size_t)kTilePix * kTileChunk * sizeof(float4);
-    e = cudaFuncSetAttribute(roialign_bwd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem);
-    if (e != cudaSuccess) return (int)e;
-    const int tile_grid = min(2 * NT, device_props().sms * kTileCtasPerSm);
-    roialign_bwd_tile_kernel<<<tile_grid, kTileThreads, tile_smem, st>>>((const float4*)grad_out, taps, partial, tbl, ts, C, ph, pw,
-                                                              count, start, entries, misc, lists);
+    roialign_bwd_const_kernel<<<B * N, 64, 0, st>>>((const float4*)grad_out, (const float4*)boxes, roi_map, tbl, C, ph, pw,
+                                                    partial);
+    const int bin_grid = (bins + 255) / 256;
+    roialign_bwd_count_kernel<<<bin_grid, 256, 0, st>>>((const float4*)boxes, roi_map, tbl, ps, N, ph, pw, bins, count,
+                                                        misc);
+    roialign_bwd_alloc_kernel<<<(NP + 1023) / 1024, 256, 0, st>>>(count, NP, start, misc, medium);
+    roialign_bwd_fill_kernel<<<bin_grid, 256, 0, st>>>((const float4*)boxes, roi_map, tbl, ps, N, ph, pw, bins, count,
+                                                      start, cursor, entries);
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int gather_grid = kMediumCtas + min((NP + 31) / 32, 4 * sms);  // 4 resident CTAs per SM (__launch_bounds__)
+#define MRCNN_GATHER(V) roialign_bwd_gather_kernel<V><<<gather_grid, 256, 0, st>>>((const float4*)grad_out, partial, bins, \
+        tbl, ps, C, count, start, entries, misc, medium)
+    if (C == 128) MRCNN_GATHER(1);
+    else if (C == 256) MRCNN_GATHER(2);
+    else if (C == 512) MRCNN_GATHER(4);
+    else MRCNN_GATHER(0);
+#undef MRCNN_GATHER
     roialign_bwd_kernel<<<B * N * groups, kRoiThreads, smem, st>>>((const float4*)grad_out, (const float4*)boxes, roi_map,
-                                                                  tbl, C, N, ph, pw, groups, rows_per_group, ts, start,
-                                                                  misc + kMiscOverflow);
+                                                                  tbl, C, N, ph, pw, groups, rows_per_group, ps, count,
+                                                                  misc + 1);
     return last_error();
 }
 

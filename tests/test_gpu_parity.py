@@ -661,3 +661,22 @@ def test_proposal_from_per_level_rpn_outputs(orc, dev, S, B):
     same = layer([probs, t(deltas), t(an)])
     assert torch.equal(same, rois)
     assert torch.equal(layer.call_levels(lv_logits, lv_deltas, t(an)), rois)   # without the optional rpn_probs output
+
+
+def test_pooled_layout_is_already_the_gemm_operand_of_the_heads_first_conv(F, dev):
+    """the classifier head starts with TimeDistributed(Conv2D(fc, (7, 7), 'valid')) over the pooled
+    [B,N,7,7,C] tensor (mrcnn_layers.py:1151-1153).  A 7x7 VALID convolution over a 7x7 input is one dot product per
+    filter over (y, x, c) -- exactly the row-major order PyramidROIAlign writes -- so pooled.view(B*N, 49*C) IS the A
+    operand of the head's first GEMM against the Keras kernel [7,7,C,F] viewed as [49*C, F]: no re-layout pass exists
+    between the ROIAlign kernel and the head."""
+    rng = np.random.default_rng(140)
+    B, Nr, C, Fc = 2, 24, 256, 32
+    boxes = T(_roi_boxes(rng, B, Nr, pad=2), dev)
+    fm = [torch.randn((B, s, s, C), device=dev) for s in (64, 32, 16, 8)]
+    pooled, _ = F.roialign_forward(boxes, T(_meta(B, 1024), dev), fm, (7, 7))
+    assert pooled.is_contiguous()
+    keras_kernel = torch.randn((7, 7, C, Fc), device=dev) * 0.05             # Conv2D kernel layout: [kh, kw, in, out]
+    gemm = pooled.view(B * Nr, 7 * 7 * C) @ keras_kernel.reshape(7 * 7 * C, Fc)
+    conv = torch.nn.functional.conv2d(pooled.view(B * Nr, 7, 7, C).permute(0, 3, 1, 2),
+                                      keras_kernel.permute(3, 2, 0, 1)).reshape(B * Nr, Fc)
+    assert torch.allclose(gemm, conv, rtol=1e-3, atol=1e-3)
