@@ -483,9 +483,9 @@ def main():
                                        cfg["rpn_bbox_std_dev"], cfg["rpn_nms_threshold"])
         d["proposals"] = proposals
         host["proposals"] = proposals.cpu().pin_memory()
-        # dt_select + dt_mask, 2 x (prep + fwd), 2 x deterministic backward (memset node + count / alloc / fill / gather
-        # / fallback scatter)
-        KERNELS_PER_STEP = 2 + 2 * 2 + 2 * 5
+        # dt_select + dt_mask, 2 x (prep + fwd), 2 x deterministic backward (const + count + alloc + fill + gather +
+        # fallback scatter; the memset node in front of them is not counted)
+        KERNELS_PER_STEP = 2 + 2 * 2 + 2 * 6
 
         def stage(t, maps, step=None, host_stage=None):
             rois, cls, deltas, masks = targets([t["proposals"], t["gt_class_ids"], t["gt_boxes"], t["gt_masks"]],
@@ -752,7 +752,7 @@ def main():
             stage_alg = stage_bytes(S, A, NC=NC)
         else:
             bytes_roof = B * backward_algorithmic_bytes(S, TRAIN_T, 14, 14)
-            roof_kernel = "PyramidROIAlign backward 14x14, T=%d (deterministic: memset + count + alloc + fill + gather)" % TRAIN_T
+            roof_kernel = "PyramidROIAlign backward 14x14, T=%d (deterministic: roialign_bwd_gather_kernel<2> + its count / alloc / fill passes)" % TRAIN_T
             roof_extra = {"definition": "SURVEY 8(d): gradient read once + every gradient-map pixel written once + boxes"}
             stage_alg = None
         achieved = bytes_roof / (ms_roof_avg * 1e-3) / 1e9

@@ -47,10 +47,11 @@ struct NmsInput {
 };
 
 // The rows of a tile -- its own symmetric 64 x 64 block and tile v-1 (rows) x tile v (columns) -- do not depend on what is
-// kept, only on the candidate order.  For ordered input they are computed ahead of the sweep by this kernel, over the
-// whole GPU (one CTA per tile, one warp per 32 rows), instead of by row warps inside the 8-CTA clusters of the sweep,
-// whose issue slots are what bounds it (measured: 25 % of the sweep's instructions were row work).  The sweep fetches a
-// tile's 1 KB of rows with one bulk copy, eight tiles ahead.
+// kept, only on the candidate order.  For ordered input they CAN be computed ahead of the sweep by this kernel, over the
+// whole GPU (one CTA per tile, one warp per 32 rows), instead of by row warps inside the 8-CTA clusters of the sweep
+// (25 % of the sweep's instructions are row work); the sweep then fetches a tile's 1 KB of rows with one bulk copy,
+// eight tiles ahead.  Opt-in (MRCNN_NMS_GLOBAL_ROWS=1): measured on B200 at config 2 it is NOT faster (ProposalLayer
+// 132-136 us against 130 us with the row warps: the sweep is bound by the far warps' loop, not by the rows).
 __global__ void __launch_bounds__(128)
 nms_rows_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ valid, int M, int tiles_max, float thr,
                 unsigned long long* __restrict__ rows) {
@@ -613,7 +614,7 @@ int launch_nms_sorted(const float4* boxes_sorted, const int32_t* valid, int B, i
     NmsInput in{};
     in.boxes = boxes_sorted;
     in.valid = valid;
-    if (rows_ws != nullptr && M > 2048 && tuning_knob("MRCNN_NMS_GLOBAL_ROWS", 1)) {
+    if (rows_ws != nullptr && M > 2048 && tuning_knob("MRCNN_NMS_GLOBAL_ROWS", 0)) {
         const int tiles_max = (M + kTile - 1) / kTile;
         cudaError_t e = launch_pdl(nms_rows_kernel, dim3(tiles_max, B), dim3(128), 0, stream, boxes_sorted, valid, M,
                                    tiles_max, thr, (unsigned long long*)rows_ws);
