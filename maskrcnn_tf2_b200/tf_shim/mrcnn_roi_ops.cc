@@ -150,6 +150,9 @@ class MrcnnProposalGradOp : public tf::OpKernel {
     const tf::Tensor& keep = ctx->input(4);
     OP_REQUIRES(ctx, bbox.dims() == 3 && bbox.dim_size(2) == 4 && anchors.shape() == bbox.shape(),
                 tf::errors::InvalidArgument("rpn_bbox / anchors must be [B,A,4]"));
+    OP_REQUIRES(ctx, topk.dims() == 2 && keep.dims() == 2 && topk.dim_size(0) == bbox.dim_size(0) &&
+                         keep.dim_size(0) == bbox.dim_size(0),
+                tf::errors::InvalidArgument("topk_idx [B,K] and keep_idx [B,P] must have the batch size of rpn_bbox"));
     const int B = bbox.dim_size(0), A = bbox.dim_size(1), K = topk.dim_size(1), P = keep.dim_size(1);
     OP_REQUIRES(ctx, grad.shape() == tf::TensorShape({B, P, 4}), tf::errors::InvalidArgument("grad_proposals [B,P,4]"));
     tf::Tensor* out = nullptr;
@@ -198,8 +201,11 @@ class MrcnnPyramidRoiAlignOp : public tf::OpKernel {
     const tf::Tensor& meta = ctx->input(1);
     OP_REQUIRES(ctx, boxes.dims() == 3 && boxes.dim_size(2) == 4, tf::errors::InvalidArgument("boxes [B,N,4]"));
     const int B = boxes.dim_size(0), N = boxes.dim_size(1);
+    OP_REQUIRES(ctx, meta.dims() == 2 && meta.dim_size(0) == B && meta.dim_size(1) >= 6,
+                tf::errors::InvalidArgument("image_meta [B,meta] with meta >= 6 and the batch size of boxes"));
     const float* maps[4];
     int H[4], W[4];
+    OP_REQUIRES(ctx, ctx->input(2).dims() == 4, tf::errors::InvalidArgument("feature maps must be [B,H,W,C]"));
     const int C = ctx->input(2).dim_size(3);
     for (int l = 0; l < 4; ++l) {
       const tf::Tensor& m = ctx->input(2 + l);
@@ -251,9 +257,14 @@ class MrcnnPyramidRoiAlignGradOp : public tf::OpKernel {
     OP_REQUIRES(ctx, grad.dims() == 5, tf::errors::InvalidArgument("grad [B,N,ph,pw,C]"));
     const int B = grad.dim_size(0), N = grad.dim_size(1), ph = grad.dim_size(2), pw = grad.dim_size(3);
     const int C = grad.dim_size(4);
+    OP_REQUIRES(ctx, boxes.shape() == tf::TensorShape({B, N, 4}) && roi_map.shape() == tf::TensorShape({B, N}),
+                tf::errors::InvalidArgument("boxes [B,N,4] and roi_map [B,N] must match grad [B,N,ph,pw,C]"));
     float* grads[4];
     int H[4], W[4];
     for (int l = 0; l < 4; ++l) {
+      const tf::Tensor& fm = ctx->input(3 + l);
+      OP_REQUIRES(ctx, fm.dims() == 4 && fm.dim_size(0) == B && fm.dim_size(3) == C,
+                  tf::errors::InvalidArgument("feature maps must be [B,H,W,C] with the batch size and channels of grad"));
       tf::Tensor* g = nullptr;
       OP_REQUIRES_OK(ctx, ctx->allocate_output(l, ctx->input(3 + l).shape(), &g));
       grads[l] = g->flat<float>().data();
@@ -376,10 +387,15 @@ class MrcnnDetectionTargetOp : public tf::OpKernel {
     const tf::Tensor& boxes = ctx->input(2);
     const tf::Tensor& masks = ctx->input(3);
     const tf::Tensor& keys = ctx->input(4);
-    OP_REQUIRES(ctx, props.dims() == 3 && props.dim_size(1) > 0,
+    OP_REQUIRES(ctx, props.dims() == 3 && props.dim_size(1) > 0 && props.dim_size(2) == 4,
                 tf::errors::InvalidArgument("roi_assertion: at least one proposal (mrcnn_layers.py:866-868)"));
+    OP_REQUIRES(ctx, cls.dims() == 2 && masks.dims() == 4, tf::errors::InvalidArgument("gt_class_ids [B,G], gt_masks [B,H,W,G]"));
     const int B = props.dim_size(0), P = props.dim_size(1), G = cls.dim_size(1);
     const int MH = masks.dim_size(1), MW = masks.dim_size(2);
+    OP_REQUIRES(ctx, cls.dim_size(0) == B && boxes.shape() == tf::TensorShape({B, G, 4}) && masks.dim_size(0) == B &&
+                         masks.dim_size(3) == G && keys.shape() == tf::TensorShape({B, P}),
+                tf::errors::InvalidArgument("expected gt_class_ids [B,G], gt_boxes [B,G,4], gt_masks [B,H,W,G] and rand_keys "
+                                            "[B,P] for proposals [B,P,4]"));
     tf::Tensor *rois, *ids, *deltas, *out_masks;
     OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({B, t_, 4}), &rois));
     OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({B, t_}), &ids));
@@ -445,6 +461,8 @@ class MrcnnRpnTargetsOp : public tf::OpKernel {
     OP_REQUIRES(ctx, anchors.dims() == 2 && anchors.dim_size(1) == 4 && cls.dims() == 2 && boxes.dims() == 3,
                 tf::errors::InvalidArgument("expected anchors [A,4], gt_class_ids [B,G], gt_boxes [B,G,4]"));
     const int A = anchors.dim_size(0), B = cls.dim_size(0), G = cls.dim_size(1);
+    OP_REQUIRES(ctx, boxes.shape() == tf::TensorShape({B, G, 4}) && keys.shape() == tf::TensorShape({B, A}),
+                tf::errors::InvalidArgument("expected gt_boxes [B,G,4] and rand_keys [B,A]"));
     tf::Tensor *match, *bbox, *bbox32;
     OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({B, A, 1}), &match));
     OP_REQUIRES_OK(ctx, ctx->allocate_output(1, tf::TensorShape({B, r_, 4}), &bbox));

@@ -272,6 +272,43 @@ def test_training_side_ops_run_through_the_shim(F, dev, stub_ready):
     assert torch.equal(bbox, w_bbox) and torch.equal(bbox32, w_bbox32)
 
 
+@pytest.mark.gpu
+def test_shim_rejects_mismatched_input_shapes_before_any_launch(F, dev, stub_ready):
+    """Every OpKernel::Compute checks the shapes its launcher dereferences (OP_REQUIRES -> InvalidArgument), so a
+    mismatch -- e.g. a different max_gt_instances for gt_masks and gt_class_ids -- is an error status, never an
+    out-of-bounds device read."""
+    rng = np.random.default_rng(44)
+    B, P, G, MH = 2, 64, 8, 16
+    props = T(np.stack([random_boxes(rng, P) for _ in range(B)]), dev)
+    cls = T(rng.integers(0, 5, (B, G)).astype(np.int32), dev)
+    boxes = T(np.stack([random_boxes(rng, G) for _ in range(B)]), dev)
+    masks = T(rng.uniform(0, 1, (B, MH, MH, G)) < 0.5, dev)
+    keys = T(rng.integers(0, 2 ** 31, (B, P)).astype(np.int32), dev)
+    op = tf_stub.StubOp("MrcnnDetectionTarget", train_rois_per_image=16, roi_positive_ratio=0.33, mask_height=28,
+                        mask_width=28, use_mini_masks=False, std_dev=SD)
+    op(props, cls, boxes, masks, keys)                                              # the matching call is fine
+    bad_masks = T(rng.uniform(0, 1, (B, MH, MH, G + 3)) < 0.5, dev)                  # another max_gt_instances
+    for args in ((props, cls, boxes, bad_masks, keys), (props, cls, boxes[:, :5], masks, keys),
+                 (props, cls, boxes, masks, keys[:, :10]), (props, cls[:1], boxes, masks, keys)):
+        with pytest.raises(RuntimeError, match="status"):
+            op(*args)
+    fm = [torch.zeros((B, s, s, 8), device=dev) for s in (16, 8, 4, 2)]
+    meta = T(np.zeros((B, 17), np.float32) + 64.0, dev)
+    ra = tf_stub.StubOp("MrcnnPyramidRoiAlign", pool_height=7, pool_width=7, denominator=244.0, map_mode=0)
+    ra(props, meta, *fm)
+    with pytest.raises(RuntimeError, match="status"):
+        ra(props, meta[:1], *fm)                                                     # image_meta of another batch size
+    with pytest.raises(RuntimeError, match="status"):
+        ra(props, meta[:, :4], *fm)                                                  # image_meta too short
+    pooled, roi_map = ra(props, meta, *fm)
+    grad_op = tf_stub.StubOp("MrcnnPyramidRoiAlignGrad")
+    grad_op(torch.ones_like(pooled), props, roi_map, *fm)
+    with pytest.raises(RuntimeError, match="status"):
+        grad_op(torch.ones_like(pooled), props[:, :10], roi_map, *fm)                # boxes of another N
+    with pytest.raises(RuntimeError, match="status"):
+        grad_op(torch.ones_like(pooled), props, roi_map[:, :10], *fm)                # roi_map of another N
+
+
 # ------------------------------------------------------------------------ the Python side, executed (fake `tensorflow`)
 def test_python_shim_executes_under_the_fake_tensorflow_and_keeps_the_reference_surface():
     """tf_shim/mrcnn_layers_b200.py is run as it is against tests/tf_stub/fake_tf.py: the module body (op library,
