@@ -30,7 +30,8 @@ static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p;
 // kernel waits on ALL paths, completion is transitive along the stream (kernel N done => N-1 done), so a kernel
 // may also safely overwrite buffers an earlier kernel read.  What overlaps is launch latency, CTA scheduling and
 // the shared-memory / barrier set-up of kernel N+1 with the tail of kernel N.  MRCNN_PDL=0 disables the attribute
-// (the device-side calls are then no-ops); a launch behind a memset or a foreign kernel degrades to a plain launch.
+// (the device-side calls are then no-ops); a launch behind a memset or a foreign kernel degrades to a plain launch;
+// launches captured into a CUDA graph are plain as well (pdl_attr).
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -39,9 +40,15 @@ __attribute__((visibility("hidden"))) bool pdl_enabled();   // api.cu: getenv("M
 // integer tuning knob for measurements (getenv on every call: no cached state); `fallback` when unset
 __attribute__((visibility("hidden"))) int tuning_knob(const char* name, int fallback);
 
-// fills `attr[0]` with the PDL attribute when enabled; returns the number of attributes written
-static inline int pdl_attr(cudaLaunchAttribute* attr) {
+// fills `attr[0]` with the PDL attribute when enabled; returns the number of attributes written.  Not while `stream` is
+// being captured into a CUDA graph: programmatic edges inside a replayed graph measured slower than plain edges
+// (config 4, B = 32: 35.6 k against 39.9 k images/s; config 2: no difference), whereas on a live stream the attribute
+// hides the launch gaps (config 2 eager: 23.4 k against 22.4 k) -- profiles/r2_pdl_graph.md.
+static inline int pdl_attr(cudaLaunchAttribute* attr, cudaStream_t stream) {
     if (!pdl_enabled()) return 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    if (cap != cudaStreamCaptureStatusNone) return 0;
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     return 1;
@@ -57,7 +64,7 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
-    cfg.numAttrs = (unsigned)pdl_attr(attr);
+    cfg.numAttrs = (unsigned)pdl_attr(attr, stream);
     cfg.attrs = attr;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }

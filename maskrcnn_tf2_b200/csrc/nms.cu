@@ -584,7 +584,7 @@ int launch_nms(const NmsInput& in, int B, int M, int max_out, float thr, const N
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1 + (unsigned)pdl_attr(attr + 1);
+    cfg.numAttrs = 1 + (unsigned)pdl_attr(attr + 1, stream);
     // warp roles: 1 resolver, nfar far warps (the kept list x tile tests), nrow row warps (diag + cross blocks: 128 rows
     // per tile dealt over the cluster); the remaining warps only help with the staging and exit.  Few, fat workers:
     // the per-tile work of a warp is a latency-bound chain (~5 cycles per instruction), so fixed overhead per warp

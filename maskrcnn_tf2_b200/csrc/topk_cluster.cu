@@ -309,7 +309,7 @@ int launch_topk(const float* scores, int stride, int offset, int B, int A, int K
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1 + (unsigned)pdl_attr(attr + 1);
+    cfg.numAttrs = 1 + (unsigned)pdl_attr(attr + 1, stream);
     cudaError_t e;
 #define MRCNN_TK(M)                                                                                                   \
     do {                                                                                                              \
