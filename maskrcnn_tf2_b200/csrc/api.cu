@@ -52,7 +52,8 @@ int max_active_clusters(const void* kernel, int threads, int cs, size_t smem) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+    if ((cs > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ||
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
         cudaOccupancyMaxActiveClusters(&active, kernel, &cfg) != cudaSuccess) {
         (void)cudaGetLastError();
         active = -1;

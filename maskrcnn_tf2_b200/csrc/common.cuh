@@ -467,7 +467,7 @@ __attribute__((visibility("hidden"))) size_t static_smem_bytes(const void* kerne
 // more than the wider clusters gain.  smem_for(cs) gives the dynamic shared memory of a CTA at that size.
 template <typename SmemFn>
 static int pick_cluster_size(const void* kernel, int threads, int B, int max_cs, SmemFn smem_for) {
-    for (int cs = 8; cs > 1; cs >>= 1) {
+    for (int cs = 16; cs > 1; cs >>= 1) {   // 16: non-portable cluster size (max_active_clusters opts the kernel in)
         if (cs > max_cs) continue;
         int active = max_active_clusters(kernel, threads, cs, smem_for(cs));
         if (active < 0) active = device_props().sms / cs;  // the query failed: assume one CTA per SM

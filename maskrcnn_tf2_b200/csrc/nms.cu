@@ -568,7 +568,8 @@ int launch_nms(const NmsInput& in, int B, int M, int max_out, float thr, const N
     const void* kernel = fused ? (compact ? nms_kernel_ptr<true, true>() : nms_kernel_ptr<false, true>())
                                : (compact ? nms_kernel_ptr<true, false>() : nms_kernel_ptr<false, false>());
     int cs = 1;
-    if (!fused && M > 2048) cs = pick_cluster_size(kernel, kNmsThreads, B, 8, [smem](int) { return smem; });
+    if (!fused && M > 2048)
+        cs = pick_cluster_size(kernel, kNmsThreads, B, tuning_knob("MRCNN_NMS_MAX_CLUSTER", 8), [smem](int) { return smem; });
     {   // per launch: the occupancy cache above may have set another problem's (smaller) limit last
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
@@ -590,7 +591,7 @@ int launch_nms(const NmsInput& in, int B, int M, int max_out, float thr, const N
     // the per-tile work of a warp is a latency-bound chain (~5 cycles per instruction), so fixed overhead per warp
     // costs more than it buys.  Measured at config 2 (ProposalLayer, B=8 / B=16): (8,4) 134.5 / 200 us, (6,8) 129.2 /
     // 194, (6,12) 130.4 / 192, (8,12) 132.4 / 198, (10,14) 136.6 / 202; the single-CTA detection NMS does not react.
-    int nfar = cs >= 4 ? 8 : 12, nrow = cs >= 4 ? 8 : (cs == 2 ? 8 : 12), roles = 1;
+    int nfar = cs >= 16 ? 6 : (cs >= 4 ? 8 : 12), nrow = cs >= 4 ? 8 : (cs == 2 ? 8 : 12), roles = 1;
     {   // measurement knobs (no cached state): MRCNN_NMS_NFAR / _NROW / _ROLES
         const int kf = tuning_knob("MRCNN_NMS_NFAR", 0), kr = tuning_knob("MRCNN_NMS_NROW", 0);
         roles = tuning_knob("MRCNN_NMS_ROLES", 1) ? 1 : 0;

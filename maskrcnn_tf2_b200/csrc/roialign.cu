@@ -178,15 +178,25 @@ roialign_fwd_kernel(const float4* __restrict__ boxes, const int32_t* __restrict_
         const float4* bl = img + (size_t)(bot + tx.lo) * c4;
         const float4* br = img + (size_t)(bot + tx.hi) * c4;
         const float lx = tx.lerp;
-        // TF's three lerps per element, every subtraction, product and sum individually rounded.  The subtractions and
-        // sums run on the f32x2 pipe (FADD2: two elements per instruction, same IEEE rounding); the products stay
-        // scalar -- ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would change the rounding.
+        // TF's three lerps per element, every subtraction, product and sum individually rounded.
+        auto lerp1 = [&](float a, float b, float c, float d) {
+            const float t = __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), lx));
+            const float u = __fadd_rn(c, __fmul_rn(__fsub_rn(d, c), lx));
+            return __fadd_rn(t, __fmul_rn(__fsub_rn(u, t), ly));
+        };
+        // Wide crops (XSPLIT == 2: 14x14 and up, L1 hit rate 66 %, issue slots 56 % busy) run the subtractions and sums on
+        // the f32x2 pipe (FADD2: two elements per instruction, same IEEE rounding); the products stay scalar -- ptxas
+        // contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would change the rounding.  Measured on B200: 14x14
+        // 60.4 -> 58.4 us; the memory-bound 7x7 kernel loses with it (140.3 -> 144.4 us) and keeps the scalar form.
         auto lerp2 = [&](unsigned long long a, unsigned long long b, float w) {   // a + (b - a) * w on two elements
             float d0, d1;
             unpack_f2(sub_f2(b, a), d0, d1);
             return add_f2(a, pack_f2(__fmul_rn(d0, w), __fmul_rn(d1, w)));
         };
         auto lerp4 = [&](const float4& a, const float4& b, const float4& c, const float4& d) {
+            if (XSPLIT == 1)
+                return make_float4(lerp1(a.x, b.x, c.x, d.x), lerp1(a.y, b.y, c.y, d.y), lerp1(a.z, b.z, c.z, d.z),
+                                   lerp1(a.w, b.w, c.w, d.w));
             const unsigned long long t0 = lerp2(pack_f2(a.x, a.y), pack_f2(b.x, b.y), lx);
             const unsigned long long t1 = lerp2(pack_f2(a.z, a.w), pack_f2(b.z, b.w), lx);
             const unsigned long long u0 = lerp2(pack_f2(c.x, c.y), pack_f2(d.x, d.y), lx);
