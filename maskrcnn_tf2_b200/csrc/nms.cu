@@ -261,6 +261,7 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
         for (int d = 0; d < kDepth - 1; ++d) kept_hist[d] = 0ull;
         for (; t < tiles && nkept < max_out; ++t) {
             PROF_TILE;
+            PROF_TL(t, 0);
             const int base = t * kTile;
             const int slot = t & (kRing - 1);
             const uint32_t bar_t = bar_base + 8u * (uint32_t)slot;
@@ -278,6 +279,7 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
                 if (grows) mbar_wait(rbar_base + 8u * (uint32_t)slot, parity);   // fetched eight tiles ago: long complete
                 mbar_wait(bar_t, parity);
                 PROF_MARK(0);
+                PROF_TL(t, 1);
                 uint64_t v = 0ull;
 #pragma unroll
                 for (int q = 0; q < kMaxFarSrc / 32; ++q)  // far(t): fixed trip count, predicated loads (a generic
@@ -305,6 +307,7 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
             }
             const int room = max_out - nkept;
             while (__popcll(kept) > room) kept &= ~(1ull << (63 - __clzll(kept)));
+            PROF_TL(t, 2);
             if ((kept >> lane) & 1ull) {
                 const int pos = nkept + __popcll(kept & ((1ull << lane) - 1ull));
                 sel[pos] = c0;
@@ -342,6 +345,7 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
             // release the workers for tile t+kDepth (they need the kept list through tile t)
             if (t + kDepth < tiles) asm volatile("bar.arrive %0, %1;" ::"r"(3 + (t % kDepth)), "r"(rel_threads) : "memory");
             PROF_MARK(1);
+            PROF_TL(t, 3);
         }
     } else if (ri < nfar) {
         // ================= far warps: far(u) share, u = 1 .. tiles-1 =================
@@ -406,6 +410,7 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
                 }
             };
             PROFW_MARK(0);
+            if (fw == 0) PROF_TL(u, 7);
             const int cnt_known = share(nk_known);
             screen(0, cnt_known, nk_known, false);   // first instalment: no dependence on the release
             PROFW_MARK(4);
@@ -421,6 +426,7 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
                 }
             }
             PROFW_MARK(1);
+            if (fw == 0) PROF_TL(u, 4);
             const int cnt = share(nk);
             if (COMPACT) {   // second instalment: the boxes kept in tile u-2 -- one or two per far warp, taken one by one
                 for (int j = cnt_known; j < cnt; ++j) {
@@ -453,6 +459,7 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
             PROFW_MARK(2);
             if (lane < csize) st_async_u64(mapa_u32(my_far, (uint32_t)lane), hit, mapa_u32(bar_u, (uint32_t)lane));
             PROFW_MARK(3);
+            if (fw == 0) PROF_TL(u, 5);
         }
         PROFW_DUMP;
     } else {
@@ -503,6 +510,7 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
             if (rw == 0 && lane < csize)
                 bulk_copy_to_peer(mapa_u32(smem_u32(&s_rows[v & (kRing - 1)][crank * rpc]), (uint32_t)lane), smem_u32(stage),
                                   (uint32_t)rpc * 8u, mapa_u32(bar_v, (uint32_t)lane));
+            if (rw == 0) PROF_TL(v, 6);
         };
         if (tiles > 1) send_rows(1);
         for (int u = 1; u < tiles; ++u) {
@@ -691,6 +699,9 @@ MRCNN_EXPORT int mrcnn_debug_nms_profile(long long* host_out8) {
     if (e == cudaSuccess) e = cudaMemcpyFromSymbol(host_out8 + 8, g_nms_profw, sizeof(long long) * 8);
     if (e == cudaSuccess) e = cudaMemcpyFromSymbol(host_out8 + 16, g_nms_tl, sizeof(long long) * 16);
     return (int)e;
+}
+MRCNN_EXPORT int mrcnn_debug_nms_timeline(long long* host_out_128x8) {
+    return (int)cudaMemcpyFromSymbol(host_out_128x8, g_nms_timeline, sizeof(long long) * 128 * 8);
 }
 // number of exact-division fallbacks of the threshold screen since the last call (far and row warps, all CTAs)
 MRCNN_EXPORT int mrcnn_debug_nms_fallbacks(unsigned long long* host_out, int reset) {

@@ -19,6 +19,8 @@ static __device__ long long g_nms_profw[8];  // far warp 1 of CTA 0: prologue, w
 #define PROFW_COUNT ++w_acc[6]
 #define PROFW_MARK(i) do { const long long w_now = clock64(); w_acc[i] += w_now - w_t0; w_t0 = w_now; } while (0)
 static __device__ long long g_nms_tl[16];    // spare slots for ad-hoc clock64 stamps
+static __device__ long long g_nms_timeline[128 * 8];    // clock64 stamps of CTA 0, [tile][event], scripts/profile_nms.py
+#define PROF_TL(tile, ev) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (tile) < 128) g_nms_timeline[(tile) * 8 + (ev)] = clock64(); } while (0)
 static __device__ unsigned long long g_nms_fallbacks;   // exact-division fallbacks taken (all warps, all CTAs)
 #define PROF_FALLBACK do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_nms_fallbacks, 1ull); } while (0)
 #define PROFW_DUMP do { if (blockIdx.x == 0 && threadIdx.x == 32) { for (int q = 0; q < 7; ++q) g_nms_profw[q] = w_acc[q]; } } while (0)
@@ -32,6 +34,7 @@ static __device__ unsigned long long g_nms_fallbacks;   // exact-division fallba
 #define PROFW_DUMP
 #define PROFW_COUNT
 #define PROF_FALLBACK
+#define PROF_TL(tile, ev)
 #endif
 
 constexpr int kTile = 64;

@@ -26,3 +26,14 @@ w = v[8:13]
 print("  far warp 1 of CTA 0, cycles/tile: prologue %.0f  wait release %.0f  second instalment + vote %.0f  send %.0f  "
       "first instalment %.0f  total %.0f; exact-division fallbacks: %d"
       % tuple([x / tiles for x in w] + [sum(w) / tiles, v[14]]))
+
+tl = (ctypes.c_longlong * (128 * 8))()
+L.mrcnn_debug_nms_timeline.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
+L.mrcnn_debug_nms_timeline(tl)
+tl = np.array(list(tl), dtype=np.int64).reshape(128, 8)
+t0 = tl[20, 0]
+print("timeline of CTA 0 (cycles since resolve(20) started); columns: resolver start | far set arrived | kept known | released "
+      "|| far warp 0: loop top | release seen | sent || row warp 0: rows sent")
+for t in range(20, 32):
+    r = tl[t] - t0
+    print(f"  tile {t}: {r[0]:7d} {r[1]:7d} {r[2]:7d} {r[3]:7d} || {r[7]:7d} {r[4]:7d} {r[5]:7d} || {r[6]:7d}")
