@@ -381,6 +381,33 @@ __device__ __forceinline__ void iou_screen_d2(const float4& bk, float ntak, cons
     const unsigned long long inter = mul_f2(dh, sub_f2(rgt, lft));
     unpack_f2(fma_f2(inter, c1, add_f2(pack_f2(ntak, ntak), c.ntac)), d0, d1);
 }
+// The same for boxes known to lie inside the unit square (ProposalLayer: clip_boxes_graph U:854-869 clips to [0,0,1,1]):
+// the overlap height top - bot is then <= 1, so the saturating subtract (FADD.SAT, fma pipe) IS max(top - bot, 0) -- same
+// value, two FMNMX fewer on the alu pipe, which is what bounds the NMS sweep.
+__device__ __forceinline__ float sub_sat(float a, float b) {
+    float r;
+    asm("sub.rn.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+template <bool UNIT>
+__device__ __forceinline__ void iou_screen_d2t(const float4& bk, float ntak, const CandPair& c, unsigned long long c1,
+                                               float& d0, float& d1) {
+    if (UNIT) {
+        const unsigned long long dh = pack_f2(sub_sat(fminf(bk.z, c.y2a), fmaxf(bk.x, c.y1a)),
+                                              sub_sat(fminf(bk.z, c.y2b), fmaxf(bk.x, c.y1b)));
+        const unsigned long long rgt = pack_f2(fminf(bk.w, c.x2a), fminf(bk.w, c.x2b));
+        const unsigned long long lft = pack_f2(fmaxf(bk.y, c.x1a), fmaxf(bk.y, c.x1b));
+        const unsigned long long inter = mul_f2(dh, sub_f2(rgt, lft));
+        unpack_f2(fma_f2(inter, c1, add_f2(pack_f2(ntak, ntak), c.ntac)), d0, d1);
+    } else {
+        iou_screen_d2(bk, ntak, c, c1, d0, d1);
+    }
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {  // FMNMX3 (sm_100)
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {  // FMNMX3 (sm_100)
     float d;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -498,7 +525,8 @@ struct NmsEpilogue {
 __attribute__((visibility("hidden"))) size_t nms_rows_ws_bytes(int B, int M);
 __attribute__((visibility("hidden"))) int launch_nms_sorted(const float4* boxes_sorted, const int32_t* valid, int B,
                                                             int M, int max_out, float thr, const NmsEpilogue& epi,
-                                                            void* rows_ws, cudaStream_t stream);
+                                                            void* rows_ws, cudaStream_t stream,
+                                                            bool unit_boxes = false);
 
 // candidates in input order: the kernel orders them itself by `keys` ([B,M] order-preserving score keys, 0 = not a
 // candidate) or else by `scores` ([B,M]); only where nms_fused_applies(M, max_out) (single-CTA problems)

@@ -44,6 +44,7 @@ struct NmsInput {
     // ordered input only: the diag / cross rows of every tile, precomputed by nms_rows_kernel ([B][tiles][kRows] words);
     // NULL = the kernel's own row warps compute them
     const unsigned long long* rows;
+    bool unit;   // every box lies inside the unit square (ProposalLayer's clipped boxes)
 };
 
 // The rows of a tile -- its own symmetric 64 x 64 block and tile v-1 (rows) x tile v (columns) -- do not depend on what is
@@ -571,6 +572,10 @@ bool nms_fused_applies(int M, int max_out) {
 
 int launch_nms(const NmsInput& in, int B, int M, int max_out, float thr, const NmsEpilogue& epi, cudaStream_t stream) {
     const bool fused = in.scores != nullptr || in.keys != nullptr;
+    if (!fused && M > 2048 && in.rows == nullptr && tuning_knob("MRCNN_NMS_SWEEP", 1)) {   // cluster problems: nms_sweep.cu
+        const int rc = launch_nms_sweep(in.boxes, in.valid, B, M, max_out, thr, epi, stream, in.unit);
+        if (rc != -1) return rc;
+    }
     size_t smem;
     const bool compact = nms_compact_fits(M, max_out, fused, &smem);
     const void* kernel = fused ? (compact ? nms_kernel_ptr<true, true>() : nms_kernel_ptr<false, true>())
@@ -619,10 +624,11 @@ size_t nms_rows_ws_bytes(int B, int M) {
 
 // rows_ws: nms_rows_ws_bytes(B, M) of scratch for the precomputed rows (cluster problems, M > 2048), or NULL
 int launch_nms_sorted(const float4* boxes_sorted, const int32_t* valid, int B, int M, int max_out, float thr,
-                      const NmsEpilogue& epi, void* rows_ws, cudaStream_t stream) {
+                      const NmsEpilogue& epi, void* rows_ws, cudaStream_t stream, bool unit_boxes) {
     NmsInput in{};
     in.boxes = boxes_sorted;
     in.valid = valid;
+    in.unit = unit_boxes;
     if (rows_ws != nullptr && M > 2048 && tuning_knob("MRCNN_NMS_GLOBAL_ROWS", 0)) {
         const int tiles_max = (M + kTile - 1) / kTile;
         cudaError_t e = launch_pdl(nms_rows_kernel, dim3(tiles_max, B), dim3(128), 0, stream, boxes_sorted, valid, M,

@@ -113,7 +113,7 @@ MRCNN_EXPORT int mrcnn_proposal_forward(const float* rpn_probs, const float* rpn
     epi.proposals = (float4*)proposals;
     epi.keep = keep_idx;
     epi.count = keep_count;
-    return launch_nms_sorted(w.boxes_sorted, nullptr, B, K, P, nms_thr, epi, rows_ws, st);
+    return launch_nms_sorted(w.boxes_sorted, nullptr, B, K, P, nms_thr, epi, rows_ws, st, /*unit_boxes=*/true);
 }
 
 
@@ -203,5 +203,5 @@ MRCNN_EXPORT int mrcnn_proposal_forward_levels(const float* const* rpn_class_log
     epi.proposals = (float4*)proposals;
     epi.keep = keep_idx;
     epi.count = keep_count;
-    return launch_nms_sorted(boxes_sorted, nullptr, B, K, P, nms_thr, epi, rows_ws, st);
+    return launch_nms_sorted(boxes_sorted, nullptr, B, K, P, nms_thr, epi, rows_ws, st, /*unit_boxes=*/true);
 }

@@ -1,0 +1,101 @@
+"""The cluster NMS sweep (csrc/nms_sweep.cu) against the oracle, through every shape of the kernel the launcher can pick:
+cluster sizes 1..10 (incl. the non-power-of-two ones), both pipeline depths, both warp layouts, other worker splits,
+the unit-box screen of ProposalLayer and the general one, ragged / tiny / empty candidate lists and stops in the first
+tiles.  Keep indices bit-exact (BASELINE.json north_star; replaces tf.image.non_max_suppression, mrcnn_layers.py:225)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import random_boxes
+
+pytestmark = pytest.mark.gpu
+SD = np.array([0.1, 0.1, 0.2, 0.2], np.float32)
+
+
+def T(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def _check(orc, dev, boxes, scores, max_out, thr, valid=None):
+    from maskrcnn_tf2_b200 import functional as F
+    keep, count = F.nms(T(boxes, dev), T(scores, dev), max_out, thr,
+                        None if valid is None else T(np.asarray(valid, np.int32), dev))
+    keep, count = N(keep), N(count)
+    for b in range(boxes.shape[0]):
+        n = boxes.shape[1] if valid is None else valid[b]
+        ref = orc.nms(boxes[b, :n], scores[b, :n], max_out, thr)
+        assert count[b] == len(ref), (b, count[b], len(ref))
+        assert np.array_equal(keep[b, :len(ref)], ref)
+        assert np.all(keep[b, len(ref):] == -1)
+
+
+KNOBS = [
+    {},                                                                   # the launcher's own choice
+    {"MRCNN_NMS_MAX_CLUSTER": "1"}, {"MRCNN_NMS_MAX_CLUSTER": "2"}, {"MRCNN_NMS_MAX_CLUSTER": "3"},
+    {"MRCNN_NMS_MAX_CLUSTER": "4"}, {"MRCNN_NMS_MAX_CLUSTER": "6"}, {"MRCNN_NMS_MAX_CLUSTER": "8"},
+    {"MRCNN_SWEEP_DEPTH": "2"}, {"MRCNN_SWEEP_DEPTH": "2", "MRCNN_NMS_MAX_CLUSTER": "3"},
+    {"MRCNN_SWEEP_LAYOUT": "0"},
+    {"MRCNN_SWEEP_NFAR": "6", "MRCNN_SWEEP_NTAIL": "1", "MRCNN_SWEEP_NROW": "1"},
+    {"MRCNN_SWEEP_NFAR": "10", "MRCNN_SWEEP_NTAIL": "5", "MRCNN_SWEEP_NROW": "5", "MRCNN_SWEEP_LOOK": "4"},
+]
+
+
+@pytest.mark.parametrize("knobs", KNOBS, ids=lambda k: ",".join(f"{a[6:]}={b}" for a, b in k.items()) or "default")
+def test_sweep_keep_indices_bit_exact_in_every_configuration(orc, dev, monkeypatch, knobs):
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(77)
+    B, M = 3, 4100
+    boxes = np.stack([random_boxes(rng, M, clusters=30) for _ in range(B)])
+    scores = rng.uniform(0, 1, (B, M)).astype(np.float32)
+    _check(orc, dev, boxes, scores, 1000, 0.7)                       # stops on max_out somewhere in the middle
+    _check(orc, dev, boxes, scores, M, 0.5)                          # never stops: every tile is resolved
+    _check(orc, dev, boxes, scores, 700, 0.7, valid=[0, 65, 4100])   # empty, two tiles, full
+
+
+def test_sweep_ragged_and_tiny_candidate_lists(orc, dev):
+    rng = np.random.default_rng(78)
+    B, M = 8, 2500
+    boxes = np.stack([random_boxes(rng, M, clusters=12) for _ in range(B)])
+    scores = rng.uniform(0, 1, (B, M)).astype(np.float32)
+    boxes[:, 40:60] = boxes[:, 0:20]                                 # exact duplicates inside the first tile
+    boxes[:, 300:330, 2] = boxes[:, 300:330, 0]                      # zero-height boxes: IoU 0 with everything, always kept
+    for valid in ([0, 1, 2, 63, 64, 65, 127, 128], [129, 191, 192, 193, 1000, 2499, 2500, 640]):
+        _check(orc, dev, boxes, scores, 300, 0.7, valid=valid)
+    for max_out in (1, 5, 64, 65):                                   # stop inside tile 0, at its end, in tile 1
+        _check(orc, dev, boxes, scores, max_out, 0.7)
+    for thr in (0.0, 0.05, 0.3, 1.0):                                # thr = 0: the per-candidate band cap degenerates
+        _check(orc, dev, boxes, scores, 400, thr)
+
+
+def test_sweep_heavy_suppression_and_long_dependency_chains(orc, dev):
+    # every tile is dense in overlaps: 6000 boxes jittered around 4 objects -> almost everything is suppressed, the sweep
+    # runs through all 94 tiles and keeps a few dozen; plus a sliding row (keep, drop, keep, ... along the whole list)
+    rng = np.random.default_rng(79)
+    B, M = 2, 6000
+    boxes = np.stack([random_boxes(rng, M, clusters=4) for _ in range(B)])
+    scores = rng.uniform(0, 1, (B, M)).astype(np.float32)
+    _check(orc, dev, boxes, scores, 1000, 0.7)
+    x = np.arange(M, dtype=np.float32) * np.float32(0.0001)
+    row = np.stack([np.full(M, 0.1, np.float32), x, np.full(M, 0.2, np.float32), x + np.float32(0.0004)], 1)[None]
+    _check(orc, dev, row.astype(np.float32), (1.0 - np.arange(M, dtype=np.float32) / M)[None], M, 0.5)
+
+
+@pytest.mark.parametrize("knobs", [{}, {"MRCNN_SWEEP_UNIT": "0"}, {"MRCNN_SWEEP_DEPTH": "2"},
+                                   {"MRCNN_NMS_MAX_CLUSTER": "4"}, {"MRCNN_NMS_SWEEP": "0"}],
+                         ids=["default", "general-screen", "depth2", "cluster4", "lazy-kernel"])
+def test_proposal_layer_through_the_sweep_matches_the_oracle(orc, dev, monkeypatch, knobs):
+    from maskrcnn_tf2_b200 import functional as F, synth
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    x = synth.inference_batch(7, 3, img_size=512, num_classes=3, regime="clustered", n_rois=10, channels=4)
+    out = F.proposal_forward(T(x["rpn_probs"], dev), T(x["rpn_bbox"], dev), T(x["anchors"], dev), 6000, 1000, SD, 0.7,
+                             debug=True)
+    ref = orc.proposal_layer(x["rpn_probs"], x["rpn_bbox"], x["anchors"], 6000, 1000, SD, 0.7)
+    assert np.array_equal(N(out["proposals"]), ref["proposals"])
+    assert np.array_equal(N(out["keep_idx"]), ref["keep_idx"])
+    assert np.array_equal(N(out["keep_count"]), ref["keep_count"])
