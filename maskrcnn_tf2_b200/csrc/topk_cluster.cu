@@ -33,9 +33,17 @@ namespace cg = cooperative_groups;
 
 namespace mrcnn {
 
+#ifdef MRCNN_NMS_PROFILE   // debug build only (scripts/profile_topk.py): clock64 stamps of thread 0 of CTA 0
+static __device__ long long g_tk_timeline[32];
+#define TK_TL(ev) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_tk_timeline[ev] = clock64(); } while (0)
+#else
+#define TK_TL(ev)
+#endif
+
 constexpr int kTkThreads = 1024;
 constexpr size_t kTkListBytes = (size_t)kMaxSort * 8;                 // the CTA's own candidates
 constexpr size_t kTkScratchBytes = block_sort_xch_bytes(8);           // sort exchange buffers / gathered peer lists
+constexpr int kTkBinLimit = 256;                                      // largest bin the counting rank accepts
 constexpr int kTkCacheKeys = 32768;                                   // key cache: the first 128 KB of the scratch
 constexpr size_t kTkHistOffset = kTkScratchBytes - 2 * 4096 * sizeof(uint32_t);  // two histograms at the scratch's end,
 // out of reach of every sort's exchange buffers (<= 96 KB from the scratch's start for <= 4096 keys; the 8192-key sort
@@ -44,7 +52,7 @@ constexpr size_t kTkHistOffset = kTkScratchBytes - 2 * 4096 * sizeof(uint32_t); 
 
 struct TkControl {                 // static shared memory, one per CTA; cnt / cnt_eq are written by the peers
     uint32_t sel[4];               // digit, need left, boundary-bin count
-    uint32_t cnt[8];               // [source CTA] length of that CTA's candidate list
+    uint32_t cnt[16];              // [source CTA] length of that CTA's candidate list
     uint32_t n_list;
     int warp_sums[32];
     int scan_total;
@@ -150,9 +158,11 @@ topk_cluster_kernel(const float* __restrict__ scores, int stride, int offset, in
     uint32_t* hist2 = reinterpret_cast<uint32_t*>(scratch + kTkHistOffset);                 // [2][4096]
     uint32_t* cache = reinterpret_cast<uint32_t*>(scratch);                                  // [kTkCacheKeys] (until the sort)
     static_assert((size_t)kTkCacheKeys * 4 <= kTkHistOffset, "the key cache must end before the histograms");
+    TK_TL(0);
     pdl_launch_dependents();
     if (tid == 0) ctl.n_list = 0;
     pdl_wait();
+    TK_TL(1);
 
     // ---- 1. radix select on the composite (key << 32 | ~index) -----------------------------------------
     uint64_t prefix = 0;               // the resolved leading bits of the K-th composite (== composite >> shift)
@@ -175,7 +185,9 @@ topk_cluster_kernel(const float* __restrict__ scores, int stride, int offset, in
                 if ((c >> pshift) == prefix) atomicAdd(&hist[(uint32_t)(c >> shift) & (uint32_t)(nb - 1)], 1u);
             });
         }
+        TK_TL(2 + 4 * level);
         cluster.sync();  // every CTA's histogram of this level is complete (and nobody reads the other buffer any more)
+        TK_TL(3 + 4 * level);
         // every CTA sums the whole histogram over the cluster: thread t owns bins 4t .. 4t+3
         uint4 tot = make_uint4(0u, 0u, 0u, 0u);
         if (4 * tid < nb) {
@@ -184,6 +196,7 @@ topk_cluster_kernel(const float* __restrict__ scores, int stride, int offset, in
                 tot.x += p.x; tot.y += p.y; tot.z += p.z; tot.w += p.w;
             }
         }
+        TK_TL(4 + 4 * level);
         const uint32_t tsum = tot.x + tot.y + tot.z + tot.w;
         const int before = block_exclusive_scan((int)tsum, ctl.warp_sums, &ctl.scan_total);
         const uint32_t above_t = (uint32_t)ctl.scan_total - (uint32_t)before - tsum;  // bins owned by higher threads
@@ -206,6 +219,7 @@ topk_cluster_kernel(const float* __restrict__ scores, int stride, int offset, in
         prefix = (prefix << bits) | (uint64_t)digit;
         above_total += need - need_left;
         need = need_left;
+        TK_TL(5 + 4 * level);
         if (above_total + in_bin <= (uint32_t)kMaxSort) break;   // certain at the last level: composites are distinct
     }
 
@@ -216,17 +230,78 @@ topk_cluster_kernel(const float* __restrict__ scores, int stride, int offset, in
     });
     __syncthreads();
     const int n_mine = (int)ctl.n_list;
+    TK_TL(26);
 
-    // ---- 3. local sort, exchange of the sorted lists, global ranks ----------------------------------------
-    const int sort_n = max(32, 1 << (32 - __clz(max(n_mine, 1) - 1)));
-    for (int i = n_mine + tid; i < sort_n; i += kTkThreads) list[i] = 0ull;  // padding sorts last
+    TK_TL(27);
+    // ---- 3. every CTA gathers ALL candidate lists (unsorted, <= 8192 entries) and ranks its own by counting ----
+    if (tid < csize) cluster.map_shared_rank(&ctl.cnt[0], tid)[crank] = (uint32_t)n_mine;
+    cluster.sync();  // every list is complete, every length is known everywhere
+    TK_TL(28);
+    uint64_t* all = reinterpret_cast<uint64_t*>(scratch);                 // [total] the peers' lists and this CTA's, back to back
+    uint64_t* byb = reinterpret_cast<uint64_t*>(scratch + kTkListBytes);  // [total] the same, grouped by bin
+    int total = 0;
+    for (int r = 0; r < csize; ++r) {
+        const uint64_t* src = cluster.map_shared_rank(list, r);
+        const int n = (int)ctl.cnt[r];
+        for (int i = tid; i < n; i += kTkThreads) all[total + i] = src[i];
+        total += n;
+    }
+    // this CTA no longer reads its peers' shared memory: arrive now, wait at exit
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     __syncthreads();
-    if (sort_n <= 4096) {
-        block_sort_desc_any(list, sort_n, reinterpret_cast<uint64_t*>(scratch));
-    } else {  // 8192 keys: eight per thread in registers; the exchange buffers start at the (then dead) list itself
+    TK_TL(29);
+    // Order-preserving bins over the candidates' key range [key_lo, 2^32): bin = (key - key_lo) >> s, 4096 bins.  The rank
+    // of a candidate is the number of candidates in higher bins (one scan) plus the number of greater composites in its
+    // own bin (a handful on real score distributions).  A bin with more than kTkBinLimit entries (tie floods: thousands of
+    // equal scores) or a select that had to descend into the index bits sends the whole list through the sorting network
+    // instead -- every CTA takes the same decision from the same histogram.
+    uint32_t* hist = hist2;             // [4096] bin counts, then the bins' first ranks
+    uint32_t* cursor = hist2 + 4096;    // [4096]
+    bool fast = shift >= 32;
+    const uint32_t key_lo = fast ? (uint32_t)(prefix << (shift - 32)) : 0u;
+    int bshift = 0;
+    if (fast) {
+        for (int i = tid; i < 4096; i += kTkThreads) { hist[i] = 0u; cursor[i] = 0u; }
+        if (tid == 0) { ctl.sel[3] = 0u; ctl.sel[2] = 0u; }
+        __syncthreads();
+        uint32_t kmax = 0u;   // the largest key: the bins cover [key_lo, kmax]
+        for (int i = tid; i < total; i += kTkThreads) kmax = max(kmax, composite_key(all[i]));
+        kmax = __reduce_max_sync(0xffffffffu, kmax);
+        if ((tid & 31) == 0) atomicMax(&ctl.sel[2], kmax);
+        __syncthreads();
+        kmax = max(ctl.sel[2], key_lo);
+        while (bshift < 32 && ((kmax - key_lo) >> bshift) >= 4096u) ++bshift;
+        for (int i = tid; i < total; i += kTkThreads) atomicAdd(&hist[(composite_key(all[i]) - key_lo) >> bshift], 1u);
+        __syncthreads();
+        // thread t owns bins 4t .. 4t+3; first rank of a bin = candidates in the bins above it
+        const uint4 c4 = *reinterpret_cast<const uint4*>(hist + 4 * tid);
+        const uint32_t tsum = c4.x + c4.y + c4.z + c4.w;
+        if (max(max(c4.x, c4.y), max(c4.z, c4.w)) > (uint32_t)kTkBinLimit) ctl.sel[3] = 1u;
+        const int before = block_exclusive_scan((int)tsum, ctl.warp_sums, &ctl.scan_total);
+        uint32_t acc = (uint32_t)ctl.scan_total - (uint32_t)before - tsum;   // candidates in the bins of higher threads
+        uint4 st;
+        st.w = acc; acc += c4.w;
+        st.z = acc; acc += c4.z;
+        st.y = acc; acc += c4.y;
+        st.x = acc;
+        __syncthreads();   // every thread has read its counts
+        *reinterpret_cast<uint4*>(hist + 4 * tid) = st;
+        __syncthreads();
+        fast = ctl.sel[3] == 0u;
+    }
+    if (fast) {
+        for (int i = tid; i < total; i += kTkThreads) {
+            const uint64_t v = all[i];
+            const uint32_t bin = (composite_key(v) - key_lo) >> bshift;
+            byb[hist[bin] + atomicAdd(&cursor[bin], 1u)] = v;
+        }
+        __syncthreads();
+    } else {
+        // rare path: all candidates through the sorting network, in every CTA; nobody may still be reading this CTA's list
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
         uint64_t v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = list[tid * 8 + e];
+        for (int e = 0; e < 8; ++e) v[e] = (tid * 8 + e < total) ? all[tid * 8 + e] : 0ull;   // padding sorts last
         __syncthreads();
         block_sort_desc_blocked<8>(v, reinterpret_cast<uint64_t*>(tk_smem));
         __syncthreads();
@@ -234,35 +309,10 @@ topk_cluster_kernel(const float* __restrict__ scores, int stride, int offset, in
         for (int e = 0; e < 8; ++e) list[tid * 8 + e] = v[e];
         __syncthreads();
     }
-    if (tid < csize) cluster.map_shared_rank(&ctl.cnt[0], tid)[crank] = (uint32_t)n_mine;
-    cluster.sync();  // every list is sorted, every length is known everywhere
-    uint64_t* gathered = reinterpret_cast<uint64_t*>(scratch);   // peers' lists, back to back (total <= 8192 entries)
-    int off[8];
-    {
-        int acc = 0;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            off[r] = acc;
-            if (r < csize && r != crank) acc += (int)ctl.cnt[r];
-        }
-    }
-    for (int r = 0; r < csize; ++r) {
-        if (r == crank) continue;
-        const uint64_t* src = cluster.map_shared_rank(list, r);
-        const int n = (int)ctl.cnt[r];
-        for (int i = tid; i < n; i += kTkThreads) gathered[off[r] + i] = src[i];
-    }
-    // this CTA no longer reads its peers' shared memory: arrive now, wait at exit
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    __syncthreads();
+    TK_TL(30);
 
     // ---- 4. emit at the global rank ------------------------------------------------------------------------
-    for (int i = tid; i < n_mine; i += kTkThreads) {
-        const uint64_t v = list[i];
-        int r = i;
-        for (int p = 0; p < csize; ++p)
-            if (p != crank) r += count_greater(gathered + off[p], (int)ctl.cnt[p], v);
-        if (r >= K) continue;
+    auto emit = [&](uint64_t v, int r) {
         const uint32_t a = composite_idx(v);
         if (idx_out) idx_out[(size_t)b * K + r] = (int32_t)a;
         if (vals_out) vals_out[(size_t)b * K + r] = key_score(composite_key(v));
@@ -274,8 +324,23 @@ topk_cluster_kernel(const float* __restrict__ scores, int stride, int offset, in
             dec.boxes_sorted[(size_t)b * K + r] = bx;
             if (dec.pre_nms_boxes) dec.pre_nms_boxes[(size_t)b * K + r] = bx;
         }
+    };
+    if (fast) {
+        // this CTA's own candidates; the order inside a bin of `byb` is whatever the atomics produced: count the bin's
+        // greater composites
+        for (int i = tid; i < n_mine; i += kTkThreads) {
+            const uint64_t v = list[i];
+            const uint32_t bin = (composite_key(v) - key_lo) >> bshift;
+            const int first = (int)hist[bin], n_bin = (int)cursor[bin];
+            int r = first;
+            for (int j = first; j < first + n_bin; ++j) r += (byb[j] > v);
+            if (r < K) emit(v, r);
+        }
+        TK_TL(31);
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // no CTA leaves while a peer may still read its list
+    } else {
+        for (int r = crank + csize * tid; r < min(total, K); r += csize * kTkThreads) emit(list[r], r);
     }
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // no CTA leaves while a peer may still read its list
 }
 
 static size_t tk_smem_bytes() { return kTkListBytes + kTkScratchBytes; }
@@ -328,6 +393,12 @@ int launch_topk(const float* scores, int stride, int offset, int B, int A, int K
 }  // namespace mrcnn
 
 using namespace mrcnn;
+
+#ifdef MRCNN_NMS_PROFILE
+MRCNN_EXPORT int mrcnn_debug_topk_timeline(long long* host_out32) {
+    return (int)cudaMemcpyFromSymbol(host_out32, mrcnn::g_tk_timeline, sizeof(long long) * 32);
+}
+#endif
 
 MRCNN_EXPORT int mrcnn_topk_workspace_bytes(int B, int A, int K, size_t* bytes) {
     if (!bytes) return MRCNN_ERR_NULL;
