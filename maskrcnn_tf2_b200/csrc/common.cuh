@@ -503,6 +503,20 @@ static int pick_cluster_size(const void* kernel, int threads, int B, int max_cs,
     return 1;
 }
 
+// The same over every size a kernel that is generic in its cluster size can take (sizes need not be powers of two;
+// above 8 is the non-portable range, which max_active_clusters opts the kernel into).
+template <typename SmemFn>
+static int pick_cluster_size_any(const void* kernel, int threads, int B, int max_cs, SmemFn smem_for) {
+    static const int kSizes[] = {16, 14, 12, 10, 8, 6, 4, 3, 2};
+    for (int cs : kSizes) {
+        if (cs > max_cs) continue;
+        int active = max_active_clusters(kernel, threads, cs, smem_for(cs));
+        if (active < 0) active = device_props().sms / cs;
+        if (active >= B) return cs;
+    }
+    return 1;
+}
+
 // ---- internal launchers shared between translation units (hidden visibility) -----------------------
 struct NmsEpilogue {
     int mode;                    // 0 = indices, 1 = proposal boxes, 2 = detection rows

@@ -518,17 +518,7 @@ int launch_nms_sweep(const float4* boxes_sorted, const int32_t* valid, int B, in
     if (smem == 0) return -1;
     // Cluster size: the sweep is bound by the alu pipes of the cluster's SMs, so as many SMs per image as can be
     // co-scheduled for the whole batch (one CTA per SM); sizes need not be powers of two, above 8 is the non-portable range
-    int cs = 1;
-    {
-        const int max_cs = tuning_knob("MRCNN_NMS_MAX_CLUSTER", 16);
-        static const int kSizes[] = {16, 14, 12, 10, 8, 6, 4, 3, 2};
-        for (int c : kSizes) {
-            if (c > max_cs) continue;
-            int active = max_active_clusters(kernel, kSwThreads, c, smem);
-            if (active < 0) active = device_props().sms / c;
-            if (active >= B) { cs = c; break; }
-        }
-    }
+    const int cs = pick_cluster_size_any(kernel, kSwThreads, B, tuning_knob("MRCNN_NMS_MAX_CLUSTER", 16), [smem](int) { return smem; });
     const int layout = tuning_knob("MRCNN_SWEEP_LAYOUT", 1);
     int look = tuning_knob("MRCNN_SWEEP_LOOK", 12);
     if (look < 4) look = 4;

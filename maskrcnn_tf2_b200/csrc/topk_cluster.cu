@@ -44,7 +44,7 @@ constexpr int kTkThreads = 1024;
 constexpr size_t kTkListBytes = (size_t)kMaxSort * 8;                 // the CTA's own candidates
 constexpr size_t kTkScratchBytes = block_sort_xch_bytes(8);           // sort exchange buffers / gathered peer lists
 constexpr int kTkBinLimit = 256;                                      // largest bin the counting rank accepts
-constexpr int kTkCacheKeys = 32768;                                   // key cache: the first 128 KB of the scratch
+constexpr int kTkCacheKeys = 30720;                                   // key cache: the first 128 KB of the scratch
 constexpr size_t kTkHistOffset = kTkScratchBytes - 2 * 4096 * sizeof(uint32_t);  // two histograms at the scratch's end,
 // out of reach of every sort's exchange buffers (<= 96 KB from the scratch's start for <= 4096 keys; the 8192-key sort
 // holds the list in registers and uses the list's own 64 KB + the first 96 KB of the scratch): a slow peer may still
@@ -56,6 +56,8 @@ struct TkControl {                 // static shared memory, one per CTA; cnt / c
     uint32_t n_list;
     int warp_sums[32];
     int scan_total;
+    uint32_t group_tot[64];
+    uint32_t fine[64];
 };
 
 __device__ __forceinline__ uint32_t tk_load_key(const float* __restrict__ scores, int stride, int offset, int A, int b,
@@ -78,7 +80,29 @@ __device__ __forceinline__ void for_each_key(const float* __restrict__ scores, i
     const int V = A / PER;                                        // MODE 1 / 2 are only selected when PER divides A
     const int units = (V + 31) >> 5;
     int slot = threadIdx.x;                                       // this thread's vectors sit at slot, slot + 1024, ...
-    if (MODE == 2) {  // two interleaved columns (rpn_probs [B,A,2]): one float4 = two anchors
+    if (MODE == 2 && FIRST) {  // the first pass over rpn_probs [B,A,2] comes from HBM: eight 128-bit loads per thread in
+        const float4* p4 = reinterpret_cast<const float4*>(scores + (size_t)b * A * 2);   // flight before the first use
+        uint2* c2 = reinterpret_cast<uint2*>(cache);   // (measured: the pass is bound by bytes in flight, not by its atomics)
+        constexpr int U = 8;
+        for (int q = warp * csize + crank; q < units; q += 32 * csize * U) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int g = (q + u * 32 * csize) * 32 + lane;
+                v[u] = (g < V) ? __ldg(p4 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u, slot += kTkThreads) {
+                const int g = (q + u * 32 * csize) * 32 + lane;
+                if (g < V) {
+                    const uint2 k = make_uint2(score_key(offset ? v[u].y : v[u].x), score_key(offset ? v[u].w : v[u].z));
+                    if (slot < kSlots) c2[slot] = k;
+                    f(k.x, 2 * g);
+                    f(k.y, 2 * g + 1);
+                }
+            }
+        }
+    } else if (MODE == 2) {  // two interleaved columns (rpn_probs [B,A,2]): one float4 = two anchors
         const float4* p4 = reinterpret_cast<const float4*>(scores + (size_t)b * A * 2);
         uint2* c2 = reinterpret_cast<uint2*>(cache);
 #pragma unroll 4
@@ -157,7 +181,10 @@ topk_cluster_kernel(const float* __restrict__ scores, int stride, int offset, in
     unsigned char* scratch = tk_smem + kTkListBytes;
     uint32_t* hist2 = reinterpret_cast<uint32_t*>(scratch + kTkHistOffset);                 // [2][4096]
     uint32_t* cache = reinterpret_cast<uint32_t*>(scratch);                                  // [kTkCacheKeys] (until the sort)
-    static_assert((size_t)kTkCacheKeys * 4 <= kTkHistOffset, "the key cache must end before the histograms");
+    // [level parity][source CTA][group of nb / 64 bins] coarse sums, written by the peers; between the key cache and the
+    // histograms (static shared memory has no room left next to 224 KB of dynamic)
+    uint32_t* coarse = reinterpret_cast<uint32_t*>(scratch + (size_t)kTkCacheKeys * 4);
+    static_assert((size_t)kTkCacheKeys * 4 + 2 * 16 * 64 * 4 <= kTkHistOffset, "key cache + coarse sums must end before the histograms");
     TK_TL(0);
     pdl_launch_dependents();
     if (tid == 0) ctl.n_list = 0;
@@ -185,32 +212,62 @@ topk_cluster_kernel(const float* __restrict__ scores, int stride, int offset, in
                 if ((c >> pshift) == prefix) atomicAdd(&hist[(uint32_t)(c >> shift) & (uint32_t)(nb - 1)], 1u);
             });
         }
-        TK_TL(2 + 4 * level);
-        cluster.sync();  // every CTA's histogram of this level is complete (and nobody reads the other buffer any more)
-        TK_TL(3 + 4 * level);
-        // every CTA sums the whole histogram over the cluster: thread t owns bins 4t .. 4t+3
-        uint4 tot = make_uint4(0u, 0u, 0u, 0u);
-        if (4 * tid < nb) {
-            for (int r = 0; r < csize; ++r) {
-                const uint4 p = *reinterpret_cast<const uint4*>(cluster.map_shared_rank(hist, r) + 4 * tid);
-                tot.x += p.x; tot.y += p.y; tot.z += p.z; tot.w += p.w;
-            }
-        }
-        TK_TL(4 + 4 * level);
-        const uint32_t tsum = tot.x + tot.y + tot.z + tot.w;
-        const int before = block_exclusive_scan((int)tsum, ctl.warp_sums, &ctl.scan_total);
-        const uint32_t above_t = (uint32_t)ctl.scan_total - (uint32_t)before - tsum;  // bins owned by higher threads
-        if (above_t < need && need <= above_t + tsum) {  // exactly one thread: its bins hold the K-th element
-            const uint32_t c[4] = {tot.x, tot.y, tot.z, tot.w};
-            uint32_t acc = above_t;
+        // Coarse sums first: 64 groups of nb / 64 bins, pushed into every peer BEFORE the cluster barrier, so that after it
+        // every CTA finds the group of the K-th element from local memory and reads only that group's bins from its peers
+        // (2 KB instead of the whole histogram of every peer: 128 KB of distributed-shared-memory reads per CTA and level
+        // took 11 k cycles, measured).
+        __syncthreads();   // this CTA's histogram is complete
+        {
+            const int gsz = nb >> 6;   // bins per group: 64 (12-bit levels) or 4 (8-bit levels)
+            uint32_t part = 0u;
+            if (nb == 4096) {
+                const uint4 c4 = *reinterpret_cast<const uint4*>(hist + 4 * tid);   // 16 threads per group
+                part = c4.x + c4.y + c4.z + c4.w;
 #pragma unroll
-            for (int i = 3; i >= 0; --i) {
-                if (acc < need && need <= acc + c[i]) {
-                    ctl.sel[0] = (uint32_t)(4 * tid + i);
-                    ctl.sel[1] = need - acc;
-                    ctl.sel[2] = c[i];
+                for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            } else if (tid < 64) {
+                for (int i = 0; i < gsz; ++i) part += hist[tid * gsz + i];
+            }
+            const bool owner = (nb == 4096) ? ((tid & 15) == 0) : (tid < 64);
+            const int g = (nb == 4096) ? (tid >> 4) : tid;
+            if (owner)
+                for (int r = 0; r < csize; ++r) cluster.map_shared_rank(coarse + ((level & 1) * 16 + crank) * 64, r)[g] = part;
+        }
+        TK_TL(2 + 4 * level);
+        cluster.sync();  // every CTA's histogram of this level is complete and its coarse sums are everywhere
+        TK_TL(3 + 4 * level);
+        {
+            const int gsz = nb >> 6;
+            if (tid < 64) {
+                uint32_t t = 0u;
+                for (int r = 0; r < csize; ++r) t += coarse[((level & 1) * 16 + r) * 64 + tid];
+                ctl.group_tot[tid] = t;
+            }
+            __syncthreads();
+            if (tid < 64) {   // the group that holds the K-th element (counting from the top)
+                uint32_t above = 0u;
+                for (int g = 63; g > tid; --g) above += ctl.group_tot[g];
+                if (above < need && need <= above + ctl.group_tot[tid]) { ctl.sel[0] = (uint32_t)tid; ctl.sel[1] = need - above; }
+            }
+            __syncthreads();
+            const int grp = (int)ctl.sel[0];
+            const uint32_t need_g = ctl.sel[1];
+            if (tid < gsz) {   // that group's bins, summed over the cluster
+                uint32_t t = 0u;
+                for (int r = 0; r < csize; ++r) t += cluster.map_shared_rank(hist, r)[grp * gsz + tid];
+                ctl.fine[tid] = t;
+            }
+            __syncthreads();
+            TK_TL(4 + 4 * level);
+            if (tid < gsz) {
+                uint32_t above = 0u;
+                for (int i = gsz - 1; i > tid; --i) above += ctl.fine[i];
+                if (above < need_g && need_g <= above + ctl.fine[tid]) {
+                    ctl.sel[0] = (uint32_t)(grp * gsz + tid);   // nobody reads sel[0] as the group any more
+                    ctl.sel[1] = need_g - above;
+                    ctl.sel[2] = ctl.fine[tid];
+                    ctl.sel[3] = (need - need_g) + above;        // candidates above the digit's bin at this level
                 }
-                acc += c[i];
             }
         }
         __syncthreads();
@@ -224,9 +281,10 @@ topk_cluster_kernel(const float* __restrict__ scores, int stride, int offset, in
     }
 
     // ---- 2. compaction of this CTA's candidates into its own list ---------------------------------------
+    const uint64_t bound = prefix << shift;   // (c >> shift) >= prefix  <=>  c >= prefix << shift; shift < 64 here
     for_each_key<MODE, false>(scores, stride, offset, A, b, crank, csize, cache, [&](uint32_t key, int a) {
         const uint64_t c = make_composite(key, (uint32_t)a);
-        if ((c >> shift) >= prefix) list[atomicAdd(&ctl.n_list, 1u)] = c;
+        if (c >= bound) list[atomicAdd(&ctl.n_list, 1u)] = c;
     });
     __syncthreads();
     const int n_mine = (int)ctl.n_list;
@@ -346,7 +404,8 @@ topk_cluster_kernel(const float* __restrict__ scores, int stride, int offset, in
 static size_t tk_smem_bytes() { return kTkListBytes + kTkScratchBytes; }
 
 template <int M> static int tk_cluster_size_for(int B) {
-    return pick_cluster_size((const void*)topk_cluster_kernel<M>, kTkThreads, B, 8, [](int) { return tk_smem_bytes(); });
+    return pick_cluster_size_any((const void*)topk_cluster_kernel<M>, kTkThreads, B, tuning_knob("MRCNN_TOPK_MAX_CLUSTER", 16),
+                                 [](int) { return tk_smem_bytes(); });
 }
 
 size_t topk_ws_bytes(int /*B*/) { return 256; }  // the cluster kernel keeps everything on chip
