@@ -174,7 +174,6 @@ nms_sweep_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ v
     constexpr int kColWords = kJobs * 32;      // u64 words of column masks per tile
     extern __shared__ __align__(16) unsigned char sw_smem[];
     __shared__ int s_done;       // tiles resolved so far (a hint: the release barriers carry the ordering)
-    __shared__ int s_final;      // kept boxes
     __shared__ int s_stop;       // the resolver has left its loop: whatever is still to be sent may be empty
     __shared__ float s_tk[32];   // per resolver lane: largest thr * area among the boxes it has appended to the kept list
     cg::cluster_group cluster = cg::this_cluster();
@@ -328,13 +327,17 @@ nms_sweep_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ v
         SW_TL(120, 4);
         if (lane == 0) *(volatile int*)&s_stop = 1;
         __syncwarp();
+        // every CTA holds the whole kept list: the resolver warps of the cluster share the output rows among themselves
+        // (row r goes to lane r mod 32 csize) while the workers are still completing the unvisited tiles
+        nms_write_outputs(epi, bx, b, M, max_out, nkept, sel, nullptr, crank * 32 + lane, csize * 32);
+        SW_TL(120, 6);
         // stopped before the last tile: wake whoever waits for a later release (they read nk >= max_out and finish with
         // empty sends), then drain every tile barrier of this CTA
         for (int u = t + lane; u < tiles; u += 32) {
             s_nk[u] = max(nkept, max_out);
             mbar_arrive_release(rel_base + 8u * (uint32_t)u);
         }
-        if (lane == 0) { *(volatile int*)&s_done = tiles; s_final = nkept; }
+        if (lane == 0) *(volatile int*)&s_done = tiles;
         for (int u = max(t, 1) + lane; u < tiles; u += 32) mbar_wait_parked(bar_base + 8u * (uint32_t)u, 0u);
         __syncwarp();
         SW_TL(120, 5);
@@ -483,9 +486,6 @@ nms_sweep_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ v
     // every CTA has drained its own tile barriers; the cluster barrier then says that every bulk copy this CTA sourced has
     // been received
     cluster.sync();
-    if (crank != 0) return;
-    nms_write_outputs(epi, bx, b, M, max_out, s_final, sel, nullptr, tid, kSwThreads);
-    SW_TL(120, 6);
 }
 
 template <int DEPTH>
