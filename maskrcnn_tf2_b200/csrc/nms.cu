@@ -149,6 +149,7 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
     const int rel_threads = 32 * (1 + nfar + nrow);  // the release barrier: resolver (arrives) + far and row warps (wait)
     const uint32_t far_bytes = (uint32_t)nsrc * 8u + (grows ? 0u : (uint32_t)kRows * 8u);
     const uint32_t rbar_base = smem_u32(&s_rbar[0]);
+    PROF_TL(100, 0);
     pdl_launch_dependents();
     if (tid == 0) {
         for (int j = 0; j < kRing; ++j) { mbar_init(bar_base + 8u * j, 1); mbar_init(rbar_base + 8u * j, 1); s_nk[j] = 0; }
@@ -157,6 +158,7 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
         s_ncand = 0;
     }
     pdl_wait();  // everything above overlaps the tail of the producing kernel; global memory is touched from here on
+    PROF_TL(100, 1);
     int n = in.valid ? min(max(in.valid[b], 0), M) : M;
     const float4* bx = in.boxes + (size_t)b * M;
     const float4 kNone = make_float4(1.0e18f, 1.0e18f, -1.0e18f, -1.0e18f);  // overlaps nothing, never ambiguous, no inf
@@ -178,6 +180,7 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
             if (key) s_comp[base + __popc(vote & ((1u << lane) - 1u))] = make_composite(key, (uint32_t)i);
         }
         __syncthreads();
+        PROF_TL(100, 2);
         const int nc = s_ncand;
         n = nc;
         if (nc <= 512) {
@@ -220,6 +223,123 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
             sa[i] = a;
         }
     }
+    PROF_TL(100, 3);
+    if (FUSED && n <= kSmallN) {
+        // ---- few candidates (DetectionLayer: ~150 per image): the whole strict-lower-triangle overlap matrix first, all
+        // threads, then ONE warp decides tile after tile from its own columns -- no far / row pipeline, whose fill and
+        // drain cost 14 k cycles for three tiles (measured); the matrix sits in the row ring the pipeline would use
+        uint32_t* colm = reinterpret_cast<uint32_t*>(&s_rows[0][0]);   // [candidate c][8] bit i of word w: candidate 32 w + i < c overlaps c
+        static_assert(sizeof(s_rows) >= (size_t)kSmallN * 8 * 4, "the row ring holds the small-problem matrix");
+        __syncthreads();   // sb / sa staged
+        {
+            // one warp per 32-row job (column tile t, row tile r <= t, half h): lanes own two candidates of tile t and keep
+            // their own masks (bit i = row 64 r + 32 h + i overlaps my candidate), rows are broadcast loads
+            const int T = (n + kTile - 1) / kTile;
+            const float cthr = __fadd_rn(1.0f, thr);
+            const unsigned long long c1_2 = pack_f2(cthr, cthr);
+            for (int job = warp; job < T * (T + 1); job += kNmsWarps) {
+                int t = 0, rem = job >> 1;
+                while (rem > t) { rem -= t + 1; ++t; }   // jobs of tile t: (t + 1) row tiles x 2 halves
+                const int r = rem, h = job & 1;
+                const int c0 = t * kTile + lane, c1 = c0 + 32;
+                const float4 b0 = (c0 < n) ? sb[c0] : kNone, b1 = (c1 < n) ? sb[c1] : kNone;
+                const float a0 = (c0 < n) ? sa[c0] : 1.0f, a1 = (c1 < n) ? sa[c1] : 1.0f;
+                const float tc0 = __fmul_rn(thr, a0), tc1 = __fmul_rn(thr, a1);
+                CandPair cp;
+                cp.y1a = b0.x; cp.x1a = b0.y; cp.y2a = b0.z; cp.x2a = b0.w;
+                cp.y1b = b1.x; cp.x1b = b1.y; cp.y2b = b1.z; cp.x2b = b1.w;
+                cp.ntac = pack_f2(-tc0, -tc1);
+                const int row0 = r * kTile + 32 * h;
+                uint32_t m0 = 0u, m1 = 0u;
+                float amin = 1.0f;   // min over the pairs of |d| - band: <= 0 = some pair within the band
+#pragma unroll 8
+                for (int i = 31; i >= 0; --i) {   // downwards: every row shifts its bit in from the right
+                    const int ri = row0 + i;
+                    const float4 bi = (ri < n) ? sb[ri] : kNone;
+                    const float nti = -__fmul_rn(thr, (ri < n) ? sa[ri] : 1.0f);
+                    float e0, e1;
+                    iou_screen_d2(bi, nti, cp, c1_2, e0, e1);
+                    const float g0 = __fmul_rn(__fsub_rn(tc0, nti), kScreenBand), g1 = __fmul_rn(__fsub_rn(tc1, nti), kScreenBand);
+                    m0 = __funnelshift_l(__float_as_uint(__fsub_rn(g0, e0)), m0, 1);   // sign(band - d) = (d > band)
+                    m1 = __funnelshift_l(__float_as_uint(__fsub_rn(g1, e1)), m1, 1);
+                    amin = fmin3(amin, __fsub_rn(fabsf(e0), g0), __fsub_rn(fabsf(e1), g1));
+                }
+                if (__any_sync(0xffffffffu, amin <= 0.0f)) {   // a pair within 2^-20 of the threshold: exact division
+                    PROF_FALLBACK;
+                    m0 = 0u; m1 = 0u;
+                    for (int i = 0; i < 32; ++i) {
+                        const int ri = row0 + i;
+                        if (ri < n) {
+                            m0 |= iou_gt(sb[ri], sa[ri], b0, a0, thr) ? (1u << i) : 0u;
+                            m1 |= iou_gt(sb[ri], sa[ri], b1, a1, thr) ? (1u << i) : 0u;
+                        }
+                    }
+                }
+                if (r == t) {   // the tile's own block: strictly earlier candidates only
+                    const uint32_t lt = (1u << lane) - 1u;
+                    m0 = h ? 0u : (m0 & lt);
+                    m1 = h ? (m1 & lt) : m1;
+                }
+                if (c0 < n) colm[c0 * 8 + 2 * r + h] = m0;
+                if (c1 < n) colm[c1 * 8 + 2 * r + h] = m1;
+            }
+        }
+        __syncthreads();
+        PROF_TL(100, 4);
+        if (warp == 0) {
+            uint32_t keptw[8];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) keptw[w] = 0u;
+            int nkept = 0;
+#pragma unroll
+            for (int t = 0; t < kSmallN / kTile; ++t) {
+                if (t * kTile < n && nkept < max_out) {
+                    const int c0 = t * kTile + lane, c1 = c0 + 32;
+                    const uint32_t* m0 = colm + c0 * 8;
+                    const uint32_t* m1 = colm + c1 * 8;
+                    uint32_t rem0 = 0u, rem1 = 0u;
+#pragma unroll
+                    for (int w = 0; w < 2 * t; ++w) {   // removed by a box kept in an earlier tile
+                        if (c0 < n) rem0 |= m0[w] & keptw[w];
+                        if (c1 < n) rem1 |= m1[w] & keptw[w];
+                    }
+                    const uint32_t blk0 = (c0 < n) ? m0[2 * t] : 0u;
+                    const uint32_t blk1l = (c1 < n) ? m1[2 * t] : 0u, blk1h = (c1 < n) ? m1[2 * t + 1] : 0u;
+                    uint32_t und_lo = __ballot_sync(0xffffffffu, c0 < n && !rem0), und_hi = __ballot_sync(0xffffffffu, c1 < n && !rem1);
+                    uint32_t kept_lo = 0u, kept_hi = 0u;
+                    while (und_lo | und_hi) {   // fixed point, as the resolver of the pipeline
+                        const bool u0 = (und_lo >> lane) & 1u, u1 = (und_hi >> lane) & 1u;
+                        const bool d0 = u0 && (blk0 & kept_lo), d1 = u1 && ((blk1l & kept_lo) | (blk1h & kept_hi));
+                        const bool k0 = u0 && !d0 && !(blk0 & und_lo), k1 = u1 && !d1 && !((blk1l & und_lo) | (blk1h & und_hi));
+                        const uint32_t nk_lo = __ballot_sync(0xffffffffu, k0), nk_hi = __ballot_sync(0xffffffffu, k1);
+                        const uint32_t nd_lo = __ballot_sync(0xffffffffu, d0), nd_hi = __ballot_sync(0xffffffffu, d1);
+                        kept_lo |= nk_lo; kept_hi |= nk_hi;
+                        und_lo &= ~(nk_lo | nd_lo); und_hi &= ~(nk_hi | nd_hi);
+                    }
+                    const uint32_t lt = (1u << lane) - 1u;
+                    const int room = max_out - nkept;
+                    if (__popc(kept_lo) + __popc(kept_hi) > room) {   // the first `room` of them
+                        const bool f0 = ((kept_lo >> lane) & 1u) && __popc(kept_lo & lt) < room;
+                        const bool f1 = ((kept_hi >> lane) & 1u) && __popc(kept_lo) + __popc(kept_hi & lt) < room;
+                        kept_lo = __ballot_sync(0xffffffffu, f0);
+                        kept_hi = __ballot_sync(0xffffffffu, f1);
+                    }
+                    if ((kept_lo >> lane) & 1u) sel[nkept + __popc(kept_lo & lt)] = c0;
+                    if ((kept_hi >> lane) & 1u) sel[nkept + __popc(kept_lo) + __popc(kept_hi & lt)] = c1;
+                    nkept += __popc(kept_lo) + __popc(kept_hi);
+                    keptw[2 * t] = kept_lo;
+                    keptw[2 * t + 1] = kept_hi;
+                }
+            }
+            if (lane == 0) s_final[1] = nkept;
+        }
+        PROF_TL(100, 5);
+        __syncthreads();
+        PROF_TL(100, 6);
+        nms_write_outputs(epi, bx, b, M, max_out, s_final[1], sel, s_orig, tid, kNmsThreads);
+        PROF_TL(100, 7);
+        return;
+    }
     const int tiles = (n + kTile - 1) / kTile;
     const int tiles_max = (M + kTile - 1) / kTile;
     const unsigned long long* rows_b = grows ? in.rows + (size_t)b * tiles_max * kRows : nullptr;
@@ -244,6 +364,7 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
         }
     }
     cluster.sync();  // every CTA of the cluster is resident and its mbarriers are initialised before any st.async
+    PROF_TL(100, 4);
     // Roles.  Warp 0 resolves; it keeps its scheduler (warps 4, 8, ... share it) to itself, because its per-tile chain
     // is the serial part of the kernel.  The other 24 warps are numbered 0..23 in order: the first nfar are far warps,
     // the next nrow row warps; the rest only helped with the staging and exit (exited threads count as arrived at the
@@ -523,7 +644,9 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
         }
     }
     if (tid == 0) { s_final[0] = t; s_final[1] = nkept; }  // the resolver's loop state, for everybody
+    PROF_TL(100, 5);
     __syncthreads();
+    PROF_TL(100, 6);
     t = s_final[0];
     nkept = s_final[1];
     PROF_DUMP;
@@ -544,6 +667,7 @@ nms_lazy_kernel(NmsInput in, int M, int max_out, float thr, int nfar, int nrow, 
     if (crank != 0) return;
     const int total = nkept;
     nms_write_outputs(epi, bx, b, M, max_out, total, sel, FUSED ? s_orig : nullptr, eidx, rel_threads);
+    PROF_TL(100, 7);
 }
 
 template <bool COMPACT, bool FUSED>

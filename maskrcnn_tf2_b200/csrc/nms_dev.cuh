@@ -38,6 +38,7 @@ static __device__ unsigned long long g_nms_fallbacks;   // exact-division fallba
 #endif
 
 constexpr int kTile = 64;
+constexpr int kSmallN = 256;                        // fused-ordering problems up to this many candidates skip the pipeline
 // Pipeline depth: far(u) covers the boxes kept in tiles <= u - kDepth, so the far warps run kDepth tiles ahead of the
 // resolver; the tiles in between are covered by kDepth - 1 precomputed cross blocks.
 constexpr int kDepth = 2;
