@@ -1,7 +1,13 @@
 // nms.cu -- batched greedy hard NMS with TF NonMaxSuppressionV3 (CPU kernel) semantics.
 // Replaces tf.image.non_max_suppression at mrcnn_layers.py:225 (RPN, thr 0.7) and :455 (detections, thr 0.3).
 //
-// nms_lazy_kernel: a thread-block CLUSTER of 1..16 CTAs per image; every CTA stages the image's candidate boxes
+// Three code paths.  Ordered candidate lists of more than 2048 boxes (ProposalLayer) go to nms_sweep.cu, the round-2
+// redesign of this file's cluster kernel.  Single-CTA problems that order their own candidates and end up with at most
+// 256 of them (DetectionLayer) build the whole strict-lower-triangle overlap matrix and let one warp resolve it
+// (nms_lazy_kernel, "few candidates").  Everything else -- and whatever does not fit the sweep kernel's shared memory --
+// runs the pipeline below.
+//
+// nms_lazy_kernel: a thread-block CLUSTER of 1..8 CTAs per image; every CTA stages the image's candidate boxes
 // (already in candidate order) in its own shared memory and walks the candidates in 64-box tiles.  Only the IoU tests
 // that can matter are evaluated, and neither the cluster nor the CTA blocks on a full barrier inside the loop.  Each CTA
 // is warp-specialised (the other warps only help with the staging and exit):

@@ -4,23 +4,29 @@
 // Round-2 redesign of the cluster path of nms.cu (nms_lazy_kernel stays for single-CTA / fused-ordering problems and as
 // the fallback when this kernel's shared memory does not fit).  Same idea -- walk the candidates in 64-box tiles, test a
 // tile only against what is KEPT, never build the M x M matrix -- but every per-tile fixed cost of the old kernel is
-// gone.  A cluster of 1..16 CTAs per image, 16 warps per CTA:
-//   resolver (warp 0, every CTA for itself, identically): per tile ONE mbarrier wait, six shared-memory loads, two
-//     warp-wide ORs, the ballot fixed point over the tile's own block, and the append to the CTA's copy of the kept list.
-//   far warps: tile u belongs to the far group of CTA (u mod cluster size) -- the group keeps the tile's candidates in
-//     registers for the tile's whole life and screens them against its share of the kept list in THREE instalments
-//     (everything already released when it starts; then through tile u-3; then the boxes kept in tile u-2, the only
-//     work between that release and the send).  One candidate load and one send per far warp and tile, a CTA sends one
-//     tile in `cluster size`.
-//   row warps: what does not depend on the kept list -- the tile's own 64 x 64 block and tile u-1 (rows) x tile u
-//     (columns) -- as 32-row jobs dealt over the cluster.  A lane keeps the masks of ITS two candidates (bit i = row i
-//     overlaps my candidate: no ballots) and sends them to every CTA itself (st.async); the resolver's lane reads them
-//     back as its own columns, so "removed by a box kept in the previous tile" is two ANDs, not a reduction.
+// gone.  A cluster of 1..16 CTAs per image (10 at batch 8 on a B200; sizes need not be powers of two), 20 warps per CTA,
+// roles ordered by the priority the issue arbiter gives them (highest warp id first):
+//   resolver (last warp, alone on its SM sub-partition; every CTA for itself, identically): per tile ONE mbarrier wait,
+//     eight shared-memory loads, two warp-wide ORs, the ballot fixed point over the tile's own block, and the append to
+//     the CTA's copy of the kept list.  ~900 cycles per tile; it also writes the outputs when the sweep is over.
+//   far warps: tile u belongs to the far warps of CTA (u mod cluster size), which keep the tile's candidates in registers
+//     for the tile's whole life.  Two groups: the TAIL group (3 warps, highest priority after the resolver) screens the
+//     boxes kept in the last `cluster size` tiles in two instalments -- through tile u-4, then the boxes kept in tile
+//     u-3, the only work between a release and the tile that needs the result; the BULK group (9 warps, lowest priority)
+//     screens everything kept before that and has cluster-size - 1 resolver periods for it.
+//   row warps (3, between the two): what does not depend on the kept list -- the tile's own 64 x 64 block and the cross
+//     blocks tile u-1 / u-2 (rows) x tile u (columns) -- as 32-row jobs dealt over the cluster.  A lane keeps the masks
+//     of ITS two candidates (bit i = row i overlaps my candidate: a funnel shift of the sign of band - d, no ballots),
+//     the warp stores them into this CTA's slot and sends the slot to every peer as one bulk copy; the resolver's lane
+//     reads them back as its own columns, so "removed by a box kept in the previous tiles" is four ANDs, not a reduction.
 // Every per-tile object (column masks, far partials, the data mbarrier, the release mbarrier, the kept count) has its
-// OWN shared-memory slot -- 1.2 KB per tile, 94 tiles at M = 6000 -- so there is no ring, no phase reuse and no
+// OWN shared-memory slot -- 1.7 KB per tile, 94 tiles at M = 6000 -- so there is no ring, no phase reuse and no
 // flow-control argument: every mbarrier completes exactly one phase.  After the sweep stops (max_out reached) the
-// workers complete the transaction counts of the unvisited tiles with empty sends and every CTA drains all of its tile
-// barriers before it exits, so no st.async is ever in flight towards an exited CTA.
+// workers abandon what they are doing, complete the transaction counts of the unvisited tiles without moving data
+// (mbarrier.complete_tx on the peers' barriers) and every CTA drains all of its tile barriers before the final cluster
+// barrier, so nothing is ever in flight towards an exited CTA and no bulk copy reads from one.
+// What bounds it (ncu): the alu pipes of the cluster's SMs (FMNMX of the IoU screens: 53 % busy
+// on average, saturated late in the sweep) and the resolver's chain.
 #include <cstdlib>
 
 #include "nms_dev.cuh"
@@ -173,7 +179,6 @@ nms_sweep_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ v
     constexpr int kJobs = 2 * DEPTH;           // 32-row jobs per tile: the tile's own block + DEPTH - 1 cross blocks
     constexpr int kColWords = kJobs * 32;      // u64 words of column masks per tile
     extern __shared__ __align__(16) unsigned char sw_smem[];
-    __shared__ int s_done;       // tiles resolved so far (a hint: the release barriers carry the ordering)
     __shared__ int s_stop;       // the resolver has left its loop: whatever is still to be sent may be empty
     __shared__ float s_tk[32];   // per resolver lane: largest thr * area among the boxes it has appended to the kept list
     cg::cluster_group cluster = cg::this_cluster();
@@ -199,7 +204,7 @@ nms_sweep_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ v
         mbar_init(bar_base + 8u * i, 1);
         mbar_init(rel_base + 8u * i, 1);
     }
-    if (tid == 0) { s_done = 0; s_stop = 0; }
+    if (tid == 0) s_stop = 0;
     if (tid < 32) s_tk[tid] = 0.0f;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int i = tid; i < tiles_max; i += kSwThreads)
@@ -319,7 +324,6 @@ nms_sweep_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ v
             __syncwarp();
             if (lane == 0) {
                 s_nk[t] = nkept;
-                *(volatile int*)&s_done = t + 1;
                 mbar_arrive_release(rel_base + 8u * (uint32_t)t);
             }
             SW_TL(t, 3);
@@ -337,7 +341,6 @@ nms_sweep_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ v
             s_nk[u] = max(nkept, max_out);
             mbar_arrive_release(rel_base + 8u * (uint32_t)u);
         }
-        if (lane == 0) *(volatile int*)&s_done = tiles;
         for (int u = max(t, 1) + lane; u < tiles; u += 32) mbar_wait_parked(bar_base + 8u * (uint32_t)u, 0u);
         __syncwarp();
         SW_TL(120, 5);

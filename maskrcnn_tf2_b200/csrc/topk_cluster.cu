@@ -2,28 +2,30 @@
 // Replaces tf.nn.top_k at mrcnn_layers.py:246, the per-image gathers at L:247-250 and (fused epilogue) the box
 // decode / clip of utils.py:830-869.
 //
-// A thread-block cluster of 1..8 CTAs (1024 threads each) owns an image.  The scores are dealt to the CTAs in units of
-// one warp-wide 128-bit load (64 anchors of rpn_probs), round robin -- NOT in contiguous slices: the anchors are
-// level-major and a trained RPN puts most of its top scores on the coarse levels at the end of the list (5000 of the
-// 6000 winners sat in the last eighth on the synthetic COCO-shape input), which would leave one CTA with the whole
-// sort.  Every CTA streams its share (L2-resident after the first pass) and everything else stays on chip:
+// A thread-block cluster of 1..16 CTAs (1024 threads each; 10 at batch 8 on a B200: sizes need not be powers of two) owns
+// an image.  The scores are dealt to the CTAs in units of one warp-wide 128-bit load (64 anchors of rpn_probs), round
+// robin -- NOT in contiguous slices: the anchors are level-major and a trained RPN puts most of its top scores on the
+// coarse levels at the end of the list (5000 of the 6000 winners sat in the last eighth on the synthetic COCO-shape
+// input), which would leave one CTA with all the candidates.  Every CTA streams its share once from HBM (eight 128-bit
+// loads per thread in flight: the pass is bound by bytes in flight) and everything else stays on chip:
 //   1. radix select on the 64-bit composite (order-preserving score key, ~index), 12 + 12 + 8 bits of the key and, only
 //      if more than 8192 candidates share all 32 key bits (tie floods, e.g. saturated probabilities), 12 + 12 + 8 bits
-//      of the index -- lower index first, TopKV2's tie rule, by the same mechanism: per-CTA shared-memory
-//      histogram, ONE cluster barrier per level, after which every CTA sums all the peers' histograms through
-//      distributed shared memory (128-bit loads, four bins per thread) and resolves the digit for itself -- identical
-//      integer sums, so no broadcast of the result is needed; the histograms are double buffered so that the next
-//      level can be zeroed while peers still read the previous one.  The descent stops as soon as "above + boundary
-//      bin" fits the 8192-entry sort;
+//      of the index -- lower index first, TopKV2's tie rule, by the same mechanism: per-CTA shared-memory histogram,
+//      whose 64 coarse group sums every CTA pushes into every peer BEFORE the level's one cluster barrier; after it a
+//      CTA finds the group of the K-th element from local memory and reads only that group's bins from its peers
+//      (2 KB; summing whole histograms through distributed shared memory cost 11 k cycles per level).  Identical integer
+//      sums everywhere, so no broadcast of the result; histograms and coarse sums are double buffered.  The descent stops
+//      as soon as "above + boundary bin" fits 8192 entries;
 //   2. compaction of the CTA's candidates (composite >= the resolved prefix) into its own shared-memory list;
-//   3. every CTA sorts ITS OWN list (register-blocked bitonic network, no cluster traffic), publishes its length, and
-//      after one cluster barrier copies the peers' sorted lists into local shared memory; the global rank of an
-//      element is its local rank plus, per peer, the number of that peer's elements above it (binary search in the
-//      local copy).  The cluster-wide bitonic network this replaces needed six cluster barriers for its cross-CTA
-//      stages alone;
-//   4. epilogue at the element's global rank: indices / values, and for ProposalLayer the gather + std-dev scale +
-//      decode + clip of the winners.
-// Cluster barriers per launch: one per radix level (two on COCO-shape RPN scores) + one before the merge + the exit
+//   3. one cluster barrier, then every CTA copies ALL candidate lists (<= 8192 entries, unsorted) into its shared memory
+//      and ranks by counting: order-preserving bins over [smallest candidate key, largest key], one histogram + scan for
+//      "candidates in higher bins", plus the greater composites inside the own bin (a handful on real score
+//      distributions).  No sorting network, no sorted-list exchange, no binary searches -- they were 45 k of the kernel's
+//      79 k cycles.  A bin with more than 256 entries (tie floods) or a select that went into the index bits sends the
+//      whole list through the register-blocked bitonic network instead, in every CTA, same decision everywhere;
+//   4. epilogue, every CTA for its own candidates at their global rank: indices / values, and for ProposalLayer the
+//      gather + std-dev scale + decode + clip of the winners.
+// Cluster barriers per launch: one per radix level (one on COCO-shape RPN scores) + one before the gather + the exit
 // barrier (split arrive / wait, so it costs no waiting).
 #include <cooperative_groups.h>
 
@@ -44,7 +46,7 @@ constexpr int kTkThreads = 1024;
 constexpr size_t kTkListBytes = (size_t)kMaxSort * 8;                 // the CTA's own candidates
 constexpr size_t kTkScratchBytes = block_sort_xch_bytes(8);           // sort exchange buffers / gathered peer lists
 constexpr int kTkBinLimit = 256;                                      // largest bin the counting rank accepts
-constexpr int kTkCacheKeys = 30720;                                   // key cache: the first 128 KB of the scratch
+constexpr int kTkCacheKeys = 30720;                                   // key cache: the first 120 KB of the scratch
 constexpr size_t kTkHistOffset = kTkScratchBytes - 2 * 4096 * sizeof(uint32_t);  // two histograms at the scratch's end,
 // out of reach of every sort's exchange buffers (<= 96 KB from the scratch's start for <= 4096 keys; the 8192-key sort
 // holds the list in registers and uses the list's own 64 KB + the first 96 KB of the scratch): a slow peer may still
@@ -155,17 +157,6 @@ __device__ __forceinline__ void for_each_key(const float* __restrict__ scores, i
             }
         }
     }
-}
-
-// number of elements of the descending list s[0, n) that are greater than x (all elements are distinct)
-__device__ __forceinline__ int count_greater(const uint64_t* __restrict__ s, int n, uint64_t x) {
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (s[mid] > x) lo = mid + 1;
-        else hi = mid;
-    }
-    return lo;
 }
 
 template <int MODE>

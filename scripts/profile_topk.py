@@ -20,8 +20,8 @@ tl = (ctypes.c_longlong * 32)()
 L.mrcnn_debug_topk_timeline.argtypes = [ctypes.POINTER(ctypes.c_longlong)]
 L.mrcnn_debug_topk_timeline(tl)
 tl = np.array(list(tl), dtype=np.int64)
-names = {0: "entry", 1: "dependency wait over", 26: "compaction done", 27: "local sort done", 28: "cluster barrier (lists)",
-         29: "peer lists gathered", 30: "ranks + epilogue done", 31: "exit barrier"}
+names = {0: "entry", 1: "dependency wait over", 26: "compaction done", 27: "(candidate list complete)", 28: "cluster barrier (lists)",
+         29: "all lists gathered", 30: "ranked by counting", 31: "epilogue done"}
 for lv in range(6):
     names[2 + 4 * lv] = f"level {lv}: histogram pass done"
     names[3 + 4 * lv] = f"level {lv}: cluster barrier"
