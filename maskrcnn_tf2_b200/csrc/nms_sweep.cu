@@ -11,9 +11,9 @@
 //     the CTA's copy of the kept list.  ~900 cycles per tile; it also writes the outputs when the sweep is over.
 //   far warps: tile u belongs to the far warps of CTA (u mod cluster size), which keep the tile's candidates in registers
 //     for the tile's whole life.  Two groups: the TAIL group (3 warps, highest priority after the resolver) screens the
-//     boxes kept in the last `cluster size` tiles in two instalments -- through tile u-4, then the boxes kept in tile
-//     u-3, the only work between a release and the tile that needs the result; the BULK group (9 warps, lowest priority)
-//     screens everything kept before that and has cluster-size - 1 resolver periods for it.
+//     boxes kept in the last `cluster size` tiles in instalments -- after the releases of tiles u-8, u-6, u-4 and then
+//     the boxes kept in tile u-3, the only work between a release and the tile that needs the result; the BULK group
+//     (9 warps, lowest priority) screens everything kept before that and has cluster-size - 1 resolver periods for it.
 //   row warps (3, between the two): what does not depend on the kept list -- the tile's own 64 x 64 block and the cross
 //     blocks tile u-1 / u-2 (rows) x tile u (columns) -- as 32-row jobs dealt over the cluster.  A lane keeps the masks
 //     of ITS two candidates (bit i = row i overlaps my candidate: a funnel shift of the sign of band - d, no ballots),
@@ -175,7 +175,7 @@ __device__ __forceinline__ bool sw_row_job(const float4* __restrict__ bx, int n,
 template <int DEPTH, bool UNIT>
 __global__ void __launch_bounds__(kSwThreads, 1)
 nms_sweep_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ valid, int M, int max_out, float thr,
-                 int nfar, int ntail, int nrow, int layout, int look, NmsEpilogue epi) {
+                 int nfar, int ntail, int nrow, int layout, int look, int sched, NmsEpilogue epi) {
     constexpr int kJobs = 2 * DEPTH;           // 32-row jobs per tile: the tile's own block + DEPTH - 1 cross blocks
     constexpr int kColWords = kJobs * 32;      // u64 words of column masks per tile
     extern __shared__ __align__(16) unsigned char sw_smem[];
@@ -331,17 +331,21 @@ nms_sweep_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ v
         SW_TL(120, 4);
         if (lane == 0) *(volatile int*)&s_stop = 1;
         __syncwarp();
-        // every CTA holds the whole kept list: the resolver warps of the cluster share the output rows among themselves
-        // (row r goes to lane r mod 32 csize) while the workers are still completing the unvisited tiles
-        nms_write_outputs(epi, bx, b, M, max_out, nkept, sel, nullptr, crank * 32 + lane, csize * 32);
-        SW_TL(120, 6);
-        // stopped before the last tile: wake whoever waits for a later release (they read nk >= max_out and finish with
-        // empty sends), then drain every tile barrier of this CTA
+        // stopped before the last tile: wake whoever waits for a later release (they read nk >= max_out or the stop flag
+        // and finish with empty sends) -- first, so that the workers complete the unvisited tiles while the outputs are written
         for (int u = t + lane; u < tiles; u += 32) {
             s_nk[u] = max(nkept, max_out);
             mbar_arrive_release(rel_base + 8u * (uint32_t)u);
         }
+        // every CTA holds the whole kept list: the resolver warps of the cluster share the output rows among themselves
+        // (row r goes to lane r mod 32 csize)
+        nms_write_outputs(epi, bx, b, M, max_out, nkept, sel, nullptr, crank * 32 + lane, csize * 32);
+        SW_TL(120, 6);
+        // then drain every tile barrier of this CTA
         for (int u = max(t, 1) + lane; u < tiles; u += 32) mbar_wait_parked(bar_base + 8u * (uint32_t)u, 0u);
+#ifdef MRCNN_NMS_PROFILE
+        if (blockIdx.x == 0) g_sw_timeline[(64 + lane) * 8 + 7] = clock64();   // when this lane's barriers were complete
+#endif
         __syncwarp();
         SW_TL(120, 5);
     } else if (role <= ntail || (role > ntail + nrow && role <= nfar + nrow)) {
@@ -378,7 +382,7 @@ nms_sweep_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ v
                     if (nk >= max_out) { stop = true; return; }
                     tkmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(s_tk[lane])));   // values >= 0
                     for (; k + 3 * fn < nk; k += 4 * fn) {   // four kept boxes per round: independent chains
-                        if (!tail && *(volatile int*)&s_stop) { stop = true; return; }   // the sweep is over: abandon
+                        if (*(volatile int*)&s_stop) { stop = true; return; }   // the sweep is over: abandon
                         float d0[4], d1[4];
 #pragma unroll
                         for (int qq = 0; qq < 4; ++qq) {
@@ -408,7 +412,11 @@ nms_sweep_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ v
                         const int r = (fi - nb % fn + fn) % fn;
                         k = k_first = nb + r;
                     }
-                    if (!stop && tgt >= 1 && tgt - 1 > split) advance(tgt - 1);
+                    // instalments: bit k of `sched` = one after the release of tile tgt - k (most of the tail's boxes
+                    // early), the last one after the release of tile tgt itself
+#pragma unroll 1
+                    for (int k = 7; k >= 1; --k)
+                        if (!stop && ((sched >> k) & 1) && tgt >= k && tgt - k > split) advance(tgt - k);
                     if (!stop && tgt > split) advance(tgt);
                 }
                 if (!stop) {
@@ -434,13 +442,23 @@ nms_sweep_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ v
                     hit = ballot64(h0, h1);
                 }
             }
-            if (lane < csize) {
-                if (!stop) st_async_u64(mapa_u32(my_far, (uint32_t)lane), hit, mapa_u32(bar_u, (uint32_t)lane));
-                else mbar_complete_tx_cluster(mapa_u32(bar_u, (uint32_t)lane), 8u);   // nobody will read this tile's far set
+            if (stop) {
+                // the sweep is over: this warp's partial of every remaining tile of this CTA is completed without data, all
+                // (tile, peer) pairs spread over the lanes -- a remote mbarrier.complete_tx costs a round trip through the
+                // cluster network, and one per tile in sequence made the drain 4 k cycles long (measured)
+                const int cnt = (tiles - 1 - u) / csize + 1;
+                for (int idx = lane; idx < cnt * csize; idx += 32) {
+                    const int j = idx / csize, p = idx - j * csize;
+                    mbar_complete_tx_cluster(mapa_u32(bar_base + 8u * (uint32_t)(u + j * csize), (uint32_t)p), 8u);
+                }
+                break;
             }
+            if (lane < csize) st_async_u64(mapa_u32(my_far, (uint32_t)lane), hit, mapa_u32(bar_u, (uint32_t)lane));
             if (tail && fi == 0) SW_TL(u, 5);
             if (!tail && fi == 0) SW_TL(u, 4);
         }
+        if (tail && fi == 0) SW_TL(121, 0);
+        if (!tail && fi == 0) SW_TL(121, 1);
     } else if (role > ntail && role <= ntail + nrow) {
         // ================= row warps: 32-row jobs (tile v >= 2, job q), dealt over the cluster =================
         const int rw = role - 1 - ntail;
@@ -479,12 +497,21 @@ nms_sweep_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ v
                         mbar_complete_tx_cluster(mapa_u32(bar_v, (uint32_t)lane), 256u);
                     }
                 }
-            } else if (lane < csize) {
-                mbar_complete_tx_cluster(mapa_u32(bar_v, (uint32_t)lane), 256u);   // nobody will read this tile's rows
+            } else {
+                // the sweep is over: every remaining job of this warp is completed without data, (job, peer) pairs spread
+                // over the lanes (see the far warps)
+                const int stride = nrow * csize, cnt = (njobs - 1 - jb) / stride + 1;
+                for (int idx = lane; idx < cnt * csize; idx += 32) {
+                    const int j = idx / csize, p = idx - j * csize;
+                    const int vv = 2 + (jb + j * stride) / kJobs;
+                    mbar_complete_tx_cluster(mapa_u32(bar_base + 8u * (uint32_t)vv, (uint32_t)p), 256u);
+                }
+                break;
             }
             if (rw == 0) SW_TL(v, 6);
             SW_RTL(rw == 0, v, 3);
         }
+        if (rw == 0) SW_TL(121, 2);
     }
     // every CTA has drained its own tile barriers; the cluster barrier then says that every bulk copy this CTA sourced has
     // been received
@@ -525,6 +552,7 @@ int launch_nms_sweep(const float4* boxes_sorted, const int32_t* valid, int B, in
     const int layout = tuning_knob("MRCNN_SWEEP_LAYOUT", 1);
     int look = tuning_knob("MRCNN_SWEEP_LOOK", 12);
     if (look < 4) look = 4;
+    const int sched = tuning_knob("MRCNN_SWEEP_TAILSCHED", 42) & 0xfe;   // tail instalments after tiles tgt-5, tgt-3, tgt-1 (and tgt)
     {   // per launch: the occupancy cache may have set another problem's (smaller) limit last
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
@@ -542,7 +570,7 @@ int launch_nms_sweep(const float4* boxes_sorted, const int32_t* valid, int B, in
     cfg.attrs = attr;
     cfg.numAttrs = 1 + (unsigned)pdl_attr(attr + 1, stream);
     void* args[] = {(void*)&boxes_sorted, (void*)&valid, (void*)&M, (void*)&max_out, (void*)&thr, (void*)&nfar,
-                    (void*)&ntail, (void*)&nrow, (void*)&layout, (void*)&look, (void*)&epi};
+                    (void*)&ntail, (void*)&nrow, (void*)&layout, (void*)&look, (void*)&sched, (void*)&epi};
     cudaError_t e = cudaLaunchKernelExC(&cfg, kernel, args);
     if (e != cudaSuccess) return (int)e;
     return last_error();

@@ -29,6 +29,10 @@ for i in range(0, last + 1):
 g = tl[120] - t0
 print(f"  kernel entry {g[0]}, after the dependency wait {g[1]}, prologue jobs done {g[2]}, cluster barrier passed {g[3]}, sweep over {g[4]}, "
       f"drained {g[5]}, outputs written {g[6]}")
+e = tl[121] - t0
+lanes = tl[64:96, 7] - t0
+print(f"  CTA 0: tail far warp 0 left its loop at {e[0]}, bulk far warp 0 at {e[1]}, row warp 0 at {e[2]}; the drain's barrier waits "
+      f"ended per lane between {lanes.min()} and {lanes.max()} (lane {int(lanes.argmax())})")
 print(f"  tiles {last + 1}: {(tl[last, 3] - t0) / (last + 1):.0f} cycles per tile")
 
 rt = (ctypes.c_longlong * (128 * 4))()

@@ -38,7 +38,7 @@ KNOBS = [
     {"MRCNN_NMS_MAX_CLUSTER": "1"}, {"MRCNN_NMS_MAX_CLUSTER": "2"}, {"MRCNN_NMS_MAX_CLUSTER": "3"},
     {"MRCNN_NMS_MAX_CLUSTER": "4"}, {"MRCNN_NMS_MAX_CLUSTER": "6"}, {"MRCNN_NMS_MAX_CLUSTER": "8"},
     {"MRCNN_SWEEP_DEPTH": "2"}, {"MRCNN_SWEEP_DEPTH": "2", "MRCNN_NMS_MAX_CLUSTER": "3"},
-    {"MRCNN_SWEEP_LAYOUT": "0"},
+    {"MRCNN_SWEEP_LAYOUT": "0"}, {"MRCNN_SWEEP_TAILSCHED": "2"}, {"MRCNN_SWEEP_TAILSCHED": "254"},
     {"MRCNN_SWEEP_NFAR": "6", "MRCNN_SWEEP_NTAIL": "1", "MRCNN_SWEEP_NROW": "1"},
     {"MRCNN_SWEEP_NFAR": "10", "MRCNN_SWEEP_NTAIL": "5", "MRCNN_SWEEP_NROW": "5", "MRCNN_SWEEP_LOOK": "4"},
 ]
