@@ -606,6 +606,11 @@ def main():
         copy_stream = torch.cuda.Stream(device=dev)
         # two batches in flight: step i+1's ProposalLayer + pixel fetch (the bus) next to step i's ROIAlign / DetectionLayer
         compute_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        # A/B switch BENCH_E2E_STREAMS=2: two batches in flight (step i+1's ProposalLayer + pixel fetch next to step i's
+        # ROIAlign / DetectionLayer).  Measured: +1 % at one GPU (1062 against 1053 images/s), +1 % at two (2129 against
+        # 2107); with the fetch kernel at 4 CTAs per SM +2.5 % at one GPU but unstable at two (1400-1630).  Default: one.
+        if os.environ.get("BENCH_E2E_STREAMS", "1") != "2":
+            compute_streams[1] = compute_streams[0]
         compute_stream = compute_streams[0]
         copied = [torch.cuda.Event(), torch.cuda.Event()]
         consumed = [torch.cuda.Event(), torch.cuda.Event()]
@@ -664,8 +669,7 @@ def main():
                 (sum(s_.fetched_pixels() for s_ in stages) - fetched0) * pixel_bytes / e2e_steps
         e2e_note = ("pinned host inputs copied to HBM and detections read back every step (copy of step i+1 overlaps the "
                     "kernels of step i on a second stream); anchors stay resident" if full_copy else
-                    "pinned host inputs in, detections read back every step, two batches in flight (step i+1's ProposalLayer "
-                    "and pixel fetch next to step i's ROIAlign / DetectionLayer); RPN/head outputs copied to HBM (copy of step "
+                    "pinned host inputs in, detections read back every step; RPN/head outputs copied to HBM (copy of step "
                     "i+1 overlaps step i), feature maps left in pinned host memory and only the pixels the ROIs sample "
                     "fetched over the bus (h2d_bytes_per_step counts them on the device; a full copy of all inputs would "
                     "be %d bytes); rpn_bbox / mrcnn_bbox are read in place, only the rows used; anchors stay resident"

@@ -1220,9 +1220,9 @@ MRCNN_EXPORT int mrcnn_roialign_fetch_hostmaps(const float* boxes, const float* 
                                                             host, ps, N, ph, pw, bins, resident, need);
     int devid = 0, sms = 148;
     if (cudaGetDevice(&devid) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devid);
-    // CTAs per SM of the (persistent) fetch kernel: 4 x 8 warps x 2 KB in flight per SM is far more than the bus needs and
-    // leaves half of the SM's warp slots to whatever runs next to it (another batch's ROIAlign in a pipelined caller)
-    const int grid = min((words + 7) / 8, max(1, min(8, tuning_knob("MRCNN_FETCH_CTAS_PER_SM", 4))) * sms);
+    // CTAs per SM of the (persistent) fetch kernel (MRCNN_FETCH_CTAS_PER_SM for measurements: 4 leaves warp slots to a
+    // second batch's kernels and gave +2.5 % end to end at one GPU, but 1400-1630 instead of 2100 images/s at two)
+    const int grid = min((words + 7) / 8, max(1, min(8, tuning_knob("MRCNN_FETCH_CTAS_PER_SM", 8))) * sms);
 #define MRCNN_FETCH(V) roialign_fetch_kernel<V><<<grid, 256, 0, st>>>(host, dev, ps, C, words, need, resident, fetched)
     if (C == 128) MRCNN_FETCH(1);
     else if (C == 256) MRCNN_FETCH(2);
