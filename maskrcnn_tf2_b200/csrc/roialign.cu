@@ -140,8 +140,11 @@ __device__ __forceinline__ int roi_map_index(int level, const int4& fa, int map_
 // One warp per output ROW (roi f, row y): lanes span the channels with 128-bit accesses, the warp walks the pw
 // bins of its row.  VPL = float4 vectors per lane (C == VPL * 128); VPL == 0 -> any C that is a multiple of 4.
 // XSPLIT: warps per output row (compile-time: the one-warp-per-row code of narrow crops must not change).
+// Occupancy: 5 CTAs/SM (48 registers) for narrow crops, 6 (40 registers, 16 bytes of spill) for wide ones -- the 14x14
+// kernel is bound by the serial load -> lerp -> store chain of a warp's bins, so more resident warps pay (58.4 -> 56.4 us
+// per layer call; 8 CTAs/SM with 32 registers: 66.5 us; the L2-bound 7x7 kernel loses at 6: 140.3 -> 142.2 us).
 template <int VPL, int XSPLIT>
-__global__ void __launch_bounds__(kRoiThreads, 5)
+__global__ void __launch_bounds__(kRoiThreads, XSPLIT > 1 ? 6 : 5)
 roialign_fwd_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ level_ws,
                     const int4* __restrict__ partial, int nparts, int map_mode, MapTable tbl, int C, int N, int ph, int pw,
                     int total_rows, float* __restrict__ out, int32_t* __restrict__ roi_map) {
