@@ -218,7 +218,7 @@ nms_sweep_kernel(const float4* __restrict__ boxes, const int32_t* __restrict__ v
     const float4* bx = boxes + (size_t)b * M;
     const int tiles = (n + kTile - 1) / kTile;
     const float cthr = __fadd_rn(1.0f, thr);
-    // prologue, every CTA for itself: the rows of tiles 0 and 1 as twelve 16-row jobs (warps 1..12): tile 0's own block
+    // prologue, every CTA for itself: the rows of tiles 0 and 1 as twelve 16-row jobs (warps 0..11): tile 0's own block
     // (4), tile 1's own block (4), tile 0 x tile 1 (4); tile 1's second cross block does not exist
     if (warp < 12 && tiles > 0) {
         const int pj = warp;

@@ -280,6 +280,15 @@ topk_cluster_kernel(const float* __restrict__ scores, int stride, int offset, in
     __syncthreads();
     const int n_mine = (int)ctl.n_list;
     TK_TL(26);
+    if (has_dec) {
+        // the epilogue gathers each winner's anchor and delta row from HBM by index: ask the L2 for them now, they arrive
+        // while the lists are exchanged and ranked (a few of the candidates end up below rank K: harmless)
+        for (int i = tid; i < n_mine; i += kTkThreads) {
+            const uint32_t a = composite_idx(list[i]);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(dec.anchors + (size_t)b * A + a));
+            if (dec.deltas) asm volatile("prefetch.global.L2 [%0];" ::"l"(dec.deltas + (size_t)b * A + a));
+        }
+    }
 
     TK_TL(27);
     // ---- 3. every CTA gathers ALL candidate lists (unsorted, <= 8192 entries) and ranks its own by counting ----
